@@ -1,0 +1,261 @@
+// tcgen05 flash-style attention: out = softmax(Q K^T * d^-1/2) V for one (batch, head) and 256 query rows per CTA.
+//
+// Two 128-row query tiles per CTA ping-pong on the tensor pipe (each has its own S/P and O accumulators in TMEM and
+// its own 4-warp softmax group), sharing every K/V tile that TMA streams through a multi-stage smem ring:
+//   S_q   = Q_q K_j^T           tcgen05.mma SS (both operands K-major, 128-byte swizzle)      -> TMEM fp32
+//   P_q   = exp2(S_q*c - m)     softmax warps: tcgen05.ld -> registers -> fp16 pairs -> tcgen05.st (P aliases S)
+//   O_q  += P_q V_j             tcgen05.mma TS (A = P from TMEM, B = V tile, MN-major)        -> TMEM fp32
+// Online softmax keeps a (lazily updated) running max; O is rescaled in TMEM only when the max grows by > 2^8.
+// The S x S score matrix never exists in HBM.  Head dims that are not multiples of 64 (SD-1.5: 40/80/160) are
+// zero-padded by TMA out-of-bounds fill, keys beyond Sk (cross-attention: 77) are masked to -inf.
+//
+// Replaces (reference side): diffusers Attention / F.scaled_dot_product_attention / xformers inside
+// BasicTransformerBlock.attn1/attn2, reached from DiverGen/generation/txt2img_diffusers_stages_from_txt.py:255-259
+// (xformers enabled at :186).
+#pragma once
+#include "common.cuh"
+
+namespace dg {
+
+struct AttnParams {
+  int Sq, Sk;        // query / key tokens per sample
+  int heads;
+  int ldo;           // output row stride (elements) = heads*d
+  float scale_log2;  // d^-1/2 * log2(e)
+  __half* out;       // [B, Sq, heads*d]
+};
+
+template <int kD, int kKV, int kStages>
+struct AttnCfg {
+  static constexpr int kChunks = (kD + 63) / 64;        // 64-wide (128 B) head-dim chunks
+  static constexpr int kDPad = (kD + 15) / 16 * 16;     // MMA-K of QK^T and MMA-N of PV
+  static constexpr int kQTileBytes = kChunks * 128 * 128;
+  static constexpr int kKVChunkBytes = kKV * 128;
+  static constexpr int kKTileBytes = kChunks * kKVChunkBytes;
+  static constexpr int kStageBytes = 2 * kKTileBytes;   // K then V
+  static constexpr int kSmem = 2 * kQTileBytes + kStages * kStageBytes + 1024 + 256;
+  // TMEM columns
+  static constexpr int kS0 = 0, kS1 = kKV;
+  static constexpr int kO0 = 2 * kKV;
+  static constexpr int kOStride = (kDPad <= 128) ? 128 : 192;
+  static constexpr int kO1 = kO0 + kOStride;
+  static_assert(kO1 + kDPad <= 512, "TMEM budget");
+};
+
+template <int kD, int kKV, int kStages>
+__global__ void __launch_bounds__(384, 1)
+attn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
+               const __grid_constant__ CUtensorMap mapV, const AttnParams p) {
+  using C = AttnCfg<kD, kKV, kStages>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sKV = smem + 2 * C::kQTileBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sKV + kStages * C::kStageBytes);
+  uint64_t* q_full = bars;                 // [1]
+  uint64_t* kv_full = bars + 1;            // [kStages]
+  uint64_t* kv_empty = kv_full + kStages;  // [kStages]
+  uint64_t* s_full = kv_empty + kStages;   // [2]
+  uint64_t* p_full = s_full + 2;           // [2]
+  uint64_t* o_done = p_full + 2;           // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_done + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int q_row0 = blockIdx.x * 256;
+  const int head = blockIdx.y;
+  const int batch = blockIdx.z;
+  const int nkv = (p.Sk + kKV - 1) / kKV;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&mapQ); tma_prefetch_desc(&mapK); tma_prefetch_desc(&mapV);
+  }
+  if (warp == 1 && lane == 0) {
+    mbar_init(q_full, 1);
+    for (int i = 0; i < kStages; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 128); mbar_init(&o_done[i], 1); }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (elect_one()) {
+      mbar_arrive_expect_tx(q_full, 2 * C::kQTileBytes);
+      for (int q = 0; q < 2; ++q)
+        for (int c = 0; c < C::kChunks; ++c)
+          tma_load_4d(sQ + q * C::kQTileBytes + c * (128 * 128), &mapQ, q_full, c * 64, head, q_row0 + q * 128, batch);
+      int stage = 0; uint32_t phase = 0;
+      for (int j = 0; j < nkv; ++j) {
+        mbar_wait(&kv_empty[stage], phase ^ 1);
+        uint8_t* sk = sKV + stage * C::kStageBytes;
+        uint8_t* sv = sk + C::kKTileBytes;
+        mbar_arrive_expect_tx(&kv_full[stage], C::kStageBytes);
+        for (int c = 0; c < C::kChunks; ++c) {
+          tma_load_4d(sk + c * C::kKVChunkBytes, &mapK, &kv_full[stage], c * 64, head, j * kKV, batch);
+          tma_load_4d(sv + c * C::kKVChunkBytes, &mapV, &kv_full[stage], c * 64, head, j * kKV, batch);
+        }
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    constexpr uint32_t idesc_s = make_idesc_f16(kKV, false);
+    constexpr uint32_t idesc_o = make_idesc_f16(C::kDPad, true);
+    const uint32_t tS[2] = {tmem_base + C::kS0, tmem_base + C::kS1};
+    const uint32_t tO[2] = {tmem_base + C::kO0, tmem_base + C::kO1};
+    const uint32_t sq_addr = smem_u32(sQ);
+
+    auto issue_S = [&](int q, uint32_t sk_addr) {
+#pragma unroll
+      for (int s = 0; s < C::kDPad / 16; ++s) {
+        const int c = s >> 2, k = s & 3;
+        const uint64_t da = make_smem_desc_sw128(sq_addr + q * C::kQTileBytes + c * (128 * 128) + k * 32, 16, 1024);
+        const uint64_t db = make_smem_desc_sw128(sk_addr + c * C::kKVChunkBytes + k * 32, 16, 1024);
+        umma_ss(tS[q], da, db, idesc_s, s ? 1u : 0u);
+      }
+      umma_commit(&s_full[q]);
+    };
+    auto issue_PV = [&](int q, uint32_t sv_addr, bool accum) {
+#pragma unroll
+      for (int s = 0; s < kKV / 16; ++s) {
+        // V tile: [keys][64-wide d chunk] rows of 128 B => MN-major; 16 keys = 2048 B along K.
+        const uint64_t db = make_smem_desc_sw128(sv_addr + s * 2048, C::kKVChunkBytes, 1024);
+        umma_ts(tO[q], tS[q] + s * 8, db, idesc_o, (accum || s) ? 1u : 0u);
+      }
+    };
+
+    mbar_wait(q_full, 0);
+    int stage = 0; uint32_t phase = 0;
+    // prologue: S_0(0), S_1(0)
+    mbar_wait(&kv_full[0], 0);
+    tc_fence_after();
+    if (elect_one()) { issue_S(0, smem_u32(sKV)); issue_S(1, smem_u32(sKV)); }
+    __syncwarp();
+    for (int j = 0; j < nkv; ++j) {
+      const uint32_t sv_addr = smem_u32(sKV + stage * C::kStageBytes + C::kKTileBytes);
+      int nstage = stage + 1; uint32_t nphase = phase;
+      if (nstage == kStages) { nstage = 0; nphase ^= 1; }
+      const bool has_next = (j + 1 < nkv);
+      if (has_next) mbar_wait(&kv_full[nstage], nphase);
+      const uint32_t sk_next = smem_u32(sKV + nstage * C::kStageBytes);
+      for (int q = 0; q < 2; ++q) {
+        mbar_wait(&p_full[q], j & 1);
+        tc_fence_after();
+        if (elect_one()) {
+          issue_PV(q, sv_addr, j > 0);
+          if (!has_next) umma_commit(&o_done[q]);
+          if (has_next) issue_S(q, sk_next);
+          if (q == 1) umma_commit(&kv_empty[stage]);
+        }
+        __syncwarp();
+      }
+      stage = nstage; phase = nphase;
+    }
+  } else if (warp >= 4) {
+    // ===================== softmax / correction / epilogue =====================
+    const int q = (warp - 4) >> 2;       // query tile handled by this warp group
+    const int quad = warp & 3;           // TMEM lane quadrant
+    const int row = quad * 32 + lane;    // row within the 128-row tile
+    const uint32_t lane_off = (uint32_t)(quad * 32) << 16;
+    const uint32_t tS = tmem_base + (q ? C::kS1 : C::kS0) + lane_off;
+    const uint32_t tO = tmem_base + (q ? C::kO1 : C::kO0) + lane_off;
+    float m_run = -INFINITY;  // running max (log2 domain, already scaled)
+    float l_run = 0.f;
+    for (int j = 0; j < nkv; ++j) {
+      mbar_wait(&s_full[q], j & 1);
+      tc_fence_after();
+      const int kv_valid = min(kKV, p.Sk - j * kKV);
+      // pass 1: row max
+      float mx = -INFINITY;
+#pragma unroll
+      for (int c = 0; c < kKV; c += 32) {
+        uint32_t v[32];
+        tmem_ld32(tS + c, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          float s = __uint_as_float(v[i]);
+          if (c + i >= kv_valid) s = -INFINITY;
+          mx = fmaxf(mx, s);
+        }
+      }
+      const float m_tile = mx * p.scale_log2;
+      if (j == 0) {
+        m_run = m_tile;
+      } else if (m_tile > m_run + 8.0f) {
+        // lazy rescale: only when the max grew enough to threaten fp16/fp32 range of P / O
+        const float alpha = exp2f(m_run - m_tile);
+        m_run = m_tile;
+        l_run *= alpha;
+#pragma unroll
+        for (int c = 0; c < C::kDPad; c += 16) {
+          uint32_t o[16];
+          tmem_ld16(tO + c, o);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+          tmem_st16(tO + c, o);
+        }
+      }
+      // pass 2: P = exp2(S*c - m), packed fp16 over the front half of the S columns
+      float lsum = 0.f;
+#pragma unroll
+      for (int c = 0; c < kKV; c += 32) {
+        uint32_t v[32];
+        tmem_ld32(tS + c, v);
+        tmem_ld_wait();
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          float p0 = (c + i < kv_valid) ? exp2f(__uint_as_float(v[i]) * p.scale_log2 - m_run) : 0.f;
+          float p1 = (c + i + 1 < kv_valid) ? exp2f(__uint_as_float(v[i + 1]) * p.scale_log2 - m_run) : 0.f;
+          __half2 h = __floats2half2_rn(p0, p1);
+          float2 hf = __half22float2(h);  // sum what the tensor core will actually multiply
+          lsum += hf.x + hf.y;
+          pk[i >> 1] = *reinterpret_cast<uint32_t*>(&h);
+        }
+        tmem_st16(tS + (c >> 1), pk);
+      }
+      l_run += lsum;
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(&p_full[q]);
+    }
+    // epilogue: O / l -> fp16 global
+    mbar_wait(&o_done[q], 0);
+    tc_fence_after();
+    const int qrow = q_row0 + q * 128 + row;
+    const float inv_l = 1.0f / l_run;
+    __half* orow = p.out + ((size_t)batch * p.Sq + qrow) * p.ldo + head * kD;
+#pragma unroll
+    for (int c = 0; c < C::kDPad; c += 16) {
+      uint32_t o[16];
+      tmem_ld16(tO + c, o);
+      tmem_ld_wait();
+      if (qrow < p.Sq) {
+        uint4 w0, w1;
+        w0.x = pack_half2(__uint_as_float(o[0]) * inv_l, __uint_as_float(o[1]) * inv_l);
+        w0.y = pack_half2(__uint_as_float(o[2]) * inv_l, __uint_as_float(o[3]) * inv_l);
+        w0.z = pack_half2(__uint_as_float(o[4]) * inv_l, __uint_as_float(o[5]) * inv_l);
+        w0.w = pack_half2(__uint_as_float(o[6]) * inv_l, __uint_as_float(o[7]) * inv_l);
+        w1.x = pack_half2(__uint_as_float(o[8]) * inv_l, __uint_as_float(o[9]) * inv_l);
+        w1.y = pack_half2(__uint_as_float(o[10]) * inv_l, __uint_as_float(o[11]) * inv_l);
+        w1.z = pack_half2(__uint_as_float(o[12]) * inv_l, __uint_as_float(o[13]) * inv_l);
+        w1.w = pack_half2(__uint_as_float(o[14]) * inv_l, __uint_as_float(o[15]) * inv_l);
+        if (c + 8 <= kD) *reinterpret_cast<uint4*>(orow + c) = w0;
+        if (c + 16 <= kD) *reinterpret_cast<uint4*>(orow + c + 8) = w1;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) { tc_fence_after(); tmem_dealloc<512>(tmem_base); }
+}
+
+}  // namespace dg

@@ -1,0 +1,827 @@
+// C-ABI translation unit (include/divergen_b200.h): context, UNet2DConditionModel graph, denoise loop, operator
+// entry points.  Host C++ only enqueues the hand-written sm_100a kernels; there is no CPU or library compute path.
+#include <algorithm>
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "host_common.cuh"
+
+using namespace dg;
+
+struct dg_ctx {
+  int device = 0;
+  int num_sms = 0;
+  float* gn_stats = nullptr;  // scratch for the stand-alone groupnorm op (tests)
+};
+
+// ================================================================== arena allocator (deterministic, graph friendly)
+struct Arena {
+  uint8_t* base = nullptr;
+  size_t size = 0;
+  struct Blk { size_t off, len; bool used; };
+  std::vector<Blk> blks;
+  size_t high_water = 0;
+  void reset() { blks.clear(); blks.push_back({0, size, false}); }
+  void* alloc(size_t bytes) {
+    bytes = (bytes + 1023) & ~size_t(1023);
+    for (size_t i = 0; i < blks.size(); ++i) {
+      if (!blks[i].used && blks[i].len >= bytes) {
+        if (blks[i].len > bytes) {
+          Blk rest{blks[i].off + bytes, blks[i].len - bytes, false};
+          blks[i].len = bytes;
+          blks.insert(blks.begin() + i + 1, rest);
+        }
+        blks[i].used = true;
+        high_water = std::max(high_water, blks[i].off + bytes);
+        return base + blks[i].off;
+      }
+    }
+    return nullptr;
+  }
+  void release(void* p) {
+    if (!p) return;
+    size_t off = (uint8_t*)p - base;
+    for (size_t i = 0; i < blks.size(); ++i) {
+      if (blks[i].off == off && blks[i].used) {
+        blks[i].used = false;
+        if (i + 1 < blks.size() && !blks[i + 1].used) { blks[i].len += blks[i + 1].len; blks.erase(blks.begin() + i + 1); }
+        if (i > 0 && !blks[i - 1].used) { blks[i - 1].len += blks[i].len; blks.erase(blks.begin() + i); }
+        return;
+      }
+    }
+  }
+};
+
+// ================================================================== weights
+enum PackKind { PK_COPY, PK_CONV3, PK_CONV_IN, PK_GEGLU_W, PK_GEGLU_B, PK_ROWS };
+
+struct Slot {
+  std::string key;
+  std::vector<int64_t> shape;  // expected PyTorch shape
+  PackKind kind;
+  __half* dst = nullptr;       // destination base
+  int64_t row_off = 0;         // PK_ROWS: destination row offset (fused QKV / KV / time_emb_proj tables)
+  int a = 0, b = 0;            // kind-specific dims
+  bool set = false;
+};
+
+struct Norm { __half* g = nullptr; __half* b = nullptr; int c = 0; };
+struct Lin { __half* w = nullptr; __half* b = nullptr; int in = 0, out = 0; int rows = 0; };
+struct Res { Norm n1, n2; Lin c1, c2, sc; bool has_sc = false; int cin = 0, cout = 0; int temb_off = 0; };
+struct Xf {
+  Norm gn, ln1, ln2, ln3;
+  Lin proj_in, qkv, o1, q2, kv2, o2, ff1, ff2, proj_out;
+  int c = 0, heads = 0, ff_inner = 0;
+};
+struct DownBlk { std::vector<Res> res; std::vector<Xf> xf; bool has_down = false; Lin down; };
+struct UpBlk { std::vector<Res> res; std::vector<Xf> xf; bool has_up = false; Lin up; };
+
+struct T4 { __half* p = nullptr; int B = 0, H = 0, W = 0, C = 0; size_t bytes() const { return (size_t)B * H * W * C * 2; } };
+
+struct GraphKey {
+  int batch, h, w, tokens; const void* sample; const void* ehs; void* out;
+  bool operator==(const GraphKey& o) const {
+    return batch == o.batch && h == o.h && w == o.w && tokens == o.tokens && sample == o.sample && ehs == o.ehs && out == o.out;
+  }
+};
+
+struct dg_unet {
+  dg_ctx* ctx = nullptr;
+  dg_unet_config cfg{};
+  std::vector<Slot> slots;
+  std::map<std::string, int> slot_index;
+  std::vector<void*> owned;  // cudaMalloc'd weight buffers
+  // modules
+  Lin conv_in, conv_out, time1, time2;
+  Norm norm_out;
+  __half* temb_proj_w = nullptr; __half* temb_proj_b = nullptr; int temb_total = 0;
+  std::vector<DownBlk> down;
+  Res mid_r0, mid_r1; Xf mid_xf;
+  std::vector<UpBlk> up;
+  int temb_dim = 0;
+  // workspace
+  Arena arena;
+  int max_batch = 0, ws_h = 0, ws_w = 0, ws_tokens = 0;
+  float* d_t = nullptr;       // [max_batch] timesteps (device)
+  float* gn_stats = nullptr;  // [max_batch, groups, 2]
+  float4* d_coef = nullptr;   // DDIM coefficient table (per step)
+  int* d_step = nullptr;      // current step index (device)
+  __half* loop_in = nullptr;  // [2B,4,h,w] CFG-duplicated UNet input
+  __half* loop_out = nullptr; // [2B,4,h,w] noise prediction
+  int coef_cap = 0;
+  // graphs
+  bool use_graphs = true;
+  struct CachedGraph { GraphKey key; cudaGraphExec_t exec; long long launches; };
+  std::vector<CachedGraph> graphs;
+  long long last_launches = 0;
+};
+
+namespace {
+
+int dev_alloc(dg_unet* u, void** p, size_t bytes) {
+  cudaError_t e = cudaMalloc(p, bytes);
+  if (e != cudaSuccess) return fail(DG_E_NOMEM, "cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
+  cudaMemset(*p, 0, bytes);
+  u->owned.push_back(*p);
+  return DG_OK;
+}
+
+int add_slot(dg_unet* u, const std::string& key, std::vector<int64_t> shape, PackKind kind, __half* dst,
+             int64_t row_off = 0, int a = 0, int b = 0) {
+  Slot s; s.key = key; s.shape = std::move(shape); s.kind = kind; s.dst = dst; s.row_off = row_off; s.a = a; s.b = b;
+  u->slot_index[key] = (int)u->slots.size();
+  u->slots.push_back(std::move(s));
+  return DG_OK;
+}
+
+int make_norm(dg_unet* u, const std::string& pfx, int c, Norm* n) {
+  n->c = c;
+  DG_TRY(dev_alloc(u, (void**)&n->g, c * 2));
+  DG_TRY(dev_alloc(u, (void**)&n->b, c * 2));
+  add_slot(u, pfx + ".weight", {c}, PK_COPY, n->g);
+  add_slot(u, pfx + ".bias", {c}, PK_COPY, n->b);
+  return DG_OK;
+}
+int make_linear(dg_unet* u, const std::string& pfx, int in, int out, bool bias, Lin* l, bool conv1x1 = false) {
+  l->in = in; l->out = out; l->rows = out;
+  DG_TRY(dev_alloc(u, (void**)&l->w, (size_t)in * out * 2));
+  if (conv1x1) add_slot(u, pfx + ".weight", {out, in, 1, 1}, PK_COPY, l->w);
+  else add_slot(u, pfx + ".weight", {out, in}, PK_COPY, l->w);
+  if (bias) {
+    DG_TRY(dev_alloc(u, (void**)&l->b, out * 2));
+    add_slot(u, pfx + ".bias", {out}, PK_COPY, l->b);
+  }
+  return DG_OK;
+}
+int make_conv3(dg_unet* u, const std::string& pfx, int in, int out, Lin* l) {
+  l->in = in; l->out = out; l->rows = out;
+  DG_TRY(dev_alloc(u, (void**)&l->w, (size_t)in * 9 * out * 2));
+  DG_TRY(dev_alloc(u, (void**)&l->b, out * 2));
+  add_slot(u, pfx + ".weight", {out, in, 3, 3}, PK_CONV3, l->w, 0, out, in);
+  add_slot(u, pfx + ".bias", {out}, PK_COPY, l->b);
+  return DG_OK;
+}
+int make_res(dg_unet* u, const std::string& pfx, int cin, int cout, Res* r, int* temb_off) {
+  r->cin = cin; r->cout = cout;
+  DG_TRY(make_norm(u, pfx + ".norm1", cin, &r->n1));
+  DG_TRY(make_conv3(u, pfx + ".conv1", cin, cout, &r->c1));
+  r->temb_off = *temb_off; *temb_off += cout;
+  DG_TRY(make_norm(u, pfx + ".norm2", cout, &r->n2));
+  DG_TRY(make_conv3(u, pfx + ".conv2", cout, cout, &r->c2));
+  r->has_sc = cin != cout;
+  if (r->has_sc) DG_TRY(make_linear(u, pfx + ".conv_shortcut", cin, cout, true, &r->sc, true));
+  return DG_OK;
+}
+int make_fused_rows(dg_unet* u, const std::vector<std::string>& keys, int in, int out_each, Lin* l) {
+  l->in = in; l->out = out_each * (int)keys.size(); l->rows = l->out;
+  DG_TRY(dev_alloc(u, (void**)&l->w, (size_t)in * l->out * 2));
+  for (size_t i = 0; i < keys.size(); ++i) add_slot(u, keys[i], {out_each, in}, PK_ROWS, l->w, (int64_t)i * out_each, out_each, in);
+  return DG_OK;
+}
+int geglu_rows(int inner) { return ((inner + kGemmBlockN / 2 - 1) / (kGemmBlockN / 2)) * kGemmBlockN; }
+int make_xf(dg_unet* u, const std::string& pfx, int c, int heads, Xf* x) {
+  const dg_unet_config& cf = u->cfg;
+  x->c = c; x->heads = heads; x->ff_inner = 4 * c;
+  const bool lin = cf.use_linear_projection != 0;
+  DG_TRY(make_norm(u, pfx + ".norm", c, &x->gn));
+  DG_TRY(make_linear(u, pfx + ".proj_in", c, c, true, &x->proj_in, !lin));
+  const std::string tb = pfx + ".transformer_blocks.0";
+  DG_TRY(make_norm(u, tb + ".norm1", c, &x->ln1));
+  DG_TRY(make_fused_rows(u, {tb + ".attn1.to_q.weight", tb + ".attn1.to_k.weight", tb + ".attn1.to_v.weight"}, c, c, &x->qkv));
+  DG_TRY(make_linear(u, tb + ".attn1.to_out.0", c, c, true, &x->o1));
+  DG_TRY(make_norm(u, tb + ".norm2", c, &x->ln2));
+  DG_TRY(make_fused_rows(u, {tb + ".attn2.to_q.weight"}, c, c, &x->q2));
+  DG_TRY(make_fused_rows(u, {tb + ".attn2.to_k.weight", tb + ".attn2.to_v.weight"}, cf.cross_attention_dim, c, &x->kv2));
+  DG_TRY(make_linear(u, tb + ".attn2.to_out.0", c, c, true, &x->o2));
+  DG_TRY(make_norm(u, tb + ".norm3", c, &x->ln3));
+  // GEGLU projection, packed in tiles of [value | gate]
+  x->ff1.in = c; x->ff1.out = x->ff_inner; x->ff1.rows = geglu_rows(x->ff_inner);
+  DG_TRY(dev_alloc(u, (void**)&x->ff1.w, (size_t)x->ff1.rows * c * 2));
+  DG_TRY(dev_alloc(u, (void**)&x->ff1.b, (size_t)x->ff1.rows * 2));
+  add_slot(u, tb + ".ff.net.0.proj.weight", {2 * x->ff_inner, c}, PK_GEGLU_W, x->ff1.w, 0, x->ff_inner, c);
+  add_slot(u, tb + ".ff.net.0.proj.bias", {2 * x->ff_inner}, PK_GEGLU_B, x->ff1.b, 0, x->ff_inner, 1);
+  DG_TRY(make_linear(u, tb + ".ff.net.2", x->ff_inner, c, true, &x->ff2));
+  DG_TRY(make_linear(u, pfx + ".proj_out", c, c, true, &x->proj_out, !lin));
+  return DG_OK;
+}
+
+int build_modules(dg_unet* u) {
+  const dg_unet_config& cf = u->cfg;
+  const int* ch = cf.block_out_channels;
+  u->temb_dim = ch[0] * 4;
+  // conv_in: im2col K padded to 64
+  u->conv_in.in = 64; u->conv_in.out = ch[0]; u->conv_in.rows = ch[0];
+  if (cf.in_channels * 9 > 64) return fail(DG_E_UNSUPPORTED, "in_channels %d too large for the conv_in gather", cf.in_channels);
+  DG_TRY(dev_alloc(u, (void**)&u->conv_in.w, (size_t)64 * ch[0] * 2));
+  DG_TRY(dev_alloc(u, (void**)&u->conv_in.b, ch[0] * 2));
+  add_slot(u, "conv_in.weight", {ch[0], cf.in_channels, 3, 3}, PK_CONV_IN, u->conv_in.w, 0, ch[0], cf.in_channels);
+  add_slot(u, "conv_in.bias", {ch[0]}, PK_COPY, u->conv_in.b);
+  DG_TRY(make_linear(u, "time_embedding.linear_1", ch[0], u->temb_dim, true, &u->time1));
+  DG_TRY(make_linear(u, "time_embedding.linear_2", u->temb_dim, u->temb_dim, true, &u->time2));
+
+  int temb_off = 0;
+  const int L = cf.layers_per_block;
+  int cout = ch[0];
+  u->down.resize(4);
+  for (int i = 0; i < 4; ++i) {
+    const int cin = cout; cout = ch[i];
+    DownBlk& d = u->down[i];
+    d.res.resize(L);
+    if (cf.down_has_attn[i]) d.xf.resize(L);
+    const std::string pfx = "down_blocks." + std::to_string(i);
+    for (int j = 0; j < L; ++j) {
+      DG_TRY(make_res(u, pfx + ".resnets." + std::to_string(j), j == 0 ? cin : cout, cout, &d.res[j], &temb_off));
+      if (cf.down_has_attn[i]) DG_TRY(make_xf(u, pfx + ".attentions." + std::to_string(j), cout, cf.num_heads[i], &d.xf[j]));
+    }
+    d.has_down = i != 3;
+    if (d.has_down) DG_TRY(make_conv3(u, pfx + ".downsamplers.0.conv", cout, cout, &d.down));
+  }
+  DG_TRY(make_res(u, "mid_block.resnets.0", ch[3], ch[3], &u->mid_r0, &temb_off));
+  DG_TRY(make_xf(u, "mid_block.attentions.0", ch[3], cf.num_heads[3], &u->mid_xf));
+  DG_TRY(make_res(u, "mid_block.resnets.1", ch[3], ch[3], &u->mid_r1, &temb_off));
+  u->up.resize(4);
+  cout = ch[3];
+  for (int i = 0; i < 4; ++i) {
+    const int prev = cout; cout = ch[3 - i];
+    const int cin = ch[std::max(3 - i - 1, 0)];
+    const bool attn = cf.down_has_attn[3 - i] != 0;
+    UpBlk& b = u->up[i];
+    b.res.resize(L + 1);
+    if (attn) b.xf.resize(L + 1);
+    const std::string pfx = "up_blocks." + std::to_string(i);
+    for (int j = 0; j < L + 1; ++j) {
+      const int skip = (j == L) ? cin : cout;
+      const int rin = (j == 0) ? prev : cout;
+      DG_TRY(make_res(u, pfx + ".resnets." + std::to_string(j), rin + skip, cout, &b.res[j], &temb_off));
+      if (attn) DG_TRY(make_xf(u, pfx + ".attentions." + std::to_string(j), cout, cf.num_heads[3 - i], &b.xf[j]));
+    }
+    b.has_up = i != 3;
+    if (b.has_up) DG_TRY(make_conv3(u, pfx + ".upsamplers.0.conv", cout, cout, &b.up));
+  }
+  DG_TRY(make_norm(u, "conv_norm_out", ch[0], &u->norm_out));
+  DG_TRY(make_conv3(u, "conv_out", ch[0], cf.out_channels, &u->conv_out));
+
+  // all 22 time_emb_proj layers live in one [sum(Cout), temb_dim] table so a single GEMV serves a forward
+  u->temb_total = temb_off;
+  DG_TRY(dev_alloc(u, (void**)&u->temb_proj_w, (size_t)temb_off * u->temb_dim * 2));
+  DG_TRY(dev_alloc(u, (void**)&u->temb_proj_b, (size_t)temb_off * 2));
+  auto reg = [&](const std::string& pfx, const Res& r) {
+    add_slot(u, pfx + ".time_emb_proj.weight", {r.cout, u->temb_dim}, PK_ROWS, u->temb_proj_w, r.temb_off, r.cout, u->temb_dim);
+    add_slot(u, pfx + ".time_emb_proj.bias", {r.cout}, PK_ROWS, u->temb_proj_b, r.temb_off, r.cout, 1);
+  };
+  for (int i = 0; i < 4; ++i)
+    for (size_t j = 0; j < u->down[i].res.size(); ++j) reg("down_blocks." + std::to_string(i) + ".resnets." + std::to_string(j), u->down[i].res[j]);
+  reg("mid_block.resnets.0", u->mid_r0);
+  reg("mid_block.resnets.1", u->mid_r1);
+  for (int i = 0; i < 4; ++i)
+    for (size_t j = 0; j < u->up[i].res.size(); ++j) reg("up_blocks." + std::to_string(i) + ".resnets." + std::to_string(j), u->up[i].res[j]);
+  return DG_OK;
+}
+
+// ================================================================== forward
+struct Fwd {
+  dg_unet* u; cudaStream_t s; int sms; int B; int tokens; const __half* ehs; __half* temb_all;
+  int err = DG_OK;
+
+  __half* alloc(size_t bytes) {
+    void* p = u->arena.alloc(bytes);
+    if (!p && err == DG_OK) err = fail(DG_E_NOMEM, "activation arena exhausted (%zu bytes requested); call dg_unet_prepare with a larger batch", bytes);
+    return (__half*)p;
+  }
+  T4 talloc(int B_, int H, int W, int C) { T4 t; t.B = B_; t.H = H; t.W = W; t.C = C; t.p = alloc(t.bytes()); return t; }
+  void free_(T4& t) { u->arena.release(t.p); t.p = nullptr; }
+  void free_(__half* p) { u->arena.release(p); }
+
+#define FW(expr) do { if (err == DG_OK) err = (expr); } while (0)
+
+  void gn(const T4& x0, const T4* x1, const Norm& n, float eps, int silu, T4& out) {
+    FW(launch_groupnorm(s, sms, x0.p, x0.C, x1 ? x1->p : nullptr, x1 ? x1->C : 0, n.g, n.b, out.p, u->gn_stats, x0.B,
+                        x0.H * x0.W, u->cfg.norm_num_groups, eps, silu));
+  }
+  void conv3(const T4& x, const Lin& w, const __half* rowvec, const __half* residual, T4& out) {
+    GemmArgs a; a.a0 = x.p; a.c0 = x.C; a.B = x.B; a.H = x.H; a.W = x.W; a.taps = 9; a.w = w.w; a.n_w = w.rows;
+    a.n_out = w.out; a.bias = w.b; a.rowvec = rowvec; a.ld_rowvec = u->temb_total; a.residual = residual; a.ld_res = w.out;
+    a.out = out.p; a.ldo = w.out;
+    FW(launch_gemm(s, sms, a));
+  }
+  // plain GEMM over rows = B*H*W of x (optionally 2-source concat along channels)
+  void linear(const __half* x0, int c0, const __half* x1, int c1, int rows, const Lin& w, const __half* residual, int geglu,
+              __half* out) {
+    GemmArgs a; a.a0 = x0; a.c0 = c0; a.a1 = x1; a.c1 = c1; a.B = 1; a.H = 1; a.W = rows; a.taps = 1; a.w = w.w; a.n_w = w.rows;
+    a.n_out = w.out; a.bias = w.b; a.residual = residual; a.ld_res = w.out; a.geglu = geglu; a.out = out; a.ldo = w.out;
+    FW(launch_gemm(s, sms, a));
+  }
+
+  T4 resnet(const Res& r, const T4& x0, const T4* x1) {
+    const int B_ = x0.B, H = x0.H, W = x0.W;
+    T4 hn = talloc(B_, H, W, r.cin);
+    gn(x0, x1, r.n1, u->cfg.norm_eps, 1, hn);
+    T4 h1 = talloc(B_, H, W, r.cout);
+    conv3(hn, r.c1, temb_all + r.temb_off, nullptr, h1);
+    free_(hn);
+    T4 h2n = talloc(B_, H, W, r.cout);
+    gn(h1, nullptr, r.n2, u->cfg.norm_eps, 1, h2n);
+    free_(h1);
+    T4 out = talloc(B_, H, W, r.cout);
+    const __half* resid = x0.p;
+    T4 sc{};
+    if (r.has_sc) {
+      sc = talloc(B_, H, W, r.cout);
+      linear(x0.p, x0.C, x1 ? x1->p : nullptr, x1 ? x1->C : 0, B_ * H * W, r.sc, nullptr, 0, sc.p);
+      resid = sc.p;
+    }
+    conv3(h2n, r.c2, nullptr, resid, out);
+    free_(h2n);
+    if (r.has_sc) free_(sc);
+    return out;
+  }
+
+  T4 transformer(const Xf& x, const T4& in) {
+    const int B_ = in.B, S = in.H * in.W, C = x.c, rows = B_ * S;
+    const int d = C / x.heads;
+    T4 xn = talloc(B_, in.H, in.W, C);
+    gn(in, nullptr, x.gn, 1e-6f, 0, xn);
+    T4 h = talloc(B_, in.H, in.W, C);
+    linear(xn.p, C, nullptr, 0, rows, x.proj_in, nullptr, 0, h.p);
+    // self-attention
+    FW(launch_layernorm(s, h.p, x.ln1.g, x.ln1.b, xn.p, rows, C, 1e-5f));
+    __half* qkv = alloc((size_t)rows * 3 * C * 2);
+    linear(xn.p, C, nullptr, 0, rows, x.qkv, nullptr, 0, qkv);
+    if (err == DG_OK) FW(launch_attention(s, qkv, 3 * C, qkv + C, 3 * C, qkv + 2 * C, 3 * C, xn.p, B_, x.heads, S, S, d));
+    free_(qkv);
+    linear(xn.p, C, nullptr, 0, rows, x.o1, h.p, 0, h.p);
+    // cross-attention
+    FW(launch_layernorm(s, h.p, x.ln2.g, x.ln2.b, xn.p, rows, C, 1e-5f));
+    __half* q = alloc((size_t)rows * C * 2);
+    linear(xn.p, C, nullptr, 0, rows, x.q2, nullptr, 0, q);
+    __half* kv = alloc((size_t)B_ * tokens * 2 * C * 2);
+    linear(ehs, u->cfg.cross_attention_dim, nullptr, 0, B_ * tokens, x.kv2, nullptr, 0, kv);
+    if (err == DG_OK) FW(launch_attention(s, q, C, kv, 2 * C, kv + C, 2 * C, xn.p, B_, x.heads, S, tokens, d));
+    free_(q); free_(kv);
+    linear(xn.p, C, nullptr, 0, rows, x.o2, h.p, 0, h.p);
+    // feed-forward (GEGLU)
+    FW(launch_layernorm(s, h.p, x.ln3.g, x.ln3.b, xn.p, rows, C, 1e-5f));
+    __half* g = alloc((size_t)rows * x.ff_inner * 2);
+    linear(xn.p, C, nullptr, 0, rows, x.ff1, nullptr, 1, g);
+    linear(g, x.ff_inner, nullptr, 0, rows, x.ff2, h.p, 0, h.p);
+    free_(g);
+    // proj_out + residual with the block input
+    T4 out = talloc(B_, in.H, in.W, C);
+    linear(h.p, C, nullptr, 0, rows, x.proj_out, in.p, 0, out.p);
+    free_(xn); free_(h);
+    return out;
+  }
+};
+
+int run_forward(dg_unet* u, cudaStream_t s, const __half* sample, const __half* ehs, int tokens, __half* out, int B, int h, int w) {
+  const dg_unet_config& cf = u->cfg;
+  const int sms = u->ctx->num_sms;
+  u->arena.reset();
+  Fwd f{u, s, sms, B, tokens, ehs, nullptr};
+
+  // ---- time embedding: sinusoid -> MLP -> all time_emb_proj(SiLU(emb)) in one GEMV
+  const int c0 = cf.block_out_channels[0];
+  __half* tsin = f.alloc((size_t)B * c0 * 2);
+  __half* t1 = f.alloc((size_t)B * u->temb_dim * 2);
+  __half* emb = f.alloc((size_t)B * u->temb_dim * 2);
+  f.temb_all = f.alloc((size_t)B * u->temb_total * 2);
+  if (f.err) return f.err;
+  timestep_sinusoid_kernel<<<(B * c0 / 2 + 127) / 128, 128, 0, s>>>(u->d_t, tsin, B, c0, cf.freq_shift, cf.flip_sin_to_cos);
+  DG_LAUNCH_CHECK();
+  for (int b0 = 0; b0 < B; b0 += 8) {
+    const int nb = std::min(8, B - b0);
+    DG_TRY(launch_gemv(s, tsin + (size_t)b0 * c0, c0, u->time1.w, u->time1.b, t1 + (size_t)b0 * u->temb_dim, u->temb_dim, nb, u->temb_dim, c0, 0, 1));
+    DG_TRY(launch_gemv(s, t1 + (size_t)b0 * u->temb_dim, u->temb_dim, u->time2.w, u->time2.b, emb + (size_t)b0 * u->temb_dim, u->temb_dim, nb, u->temb_dim, u->temb_dim, 0, 0));
+    DG_TRY(launch_gemv(s, emb + (size_t)b0 * u->temb_dim, u->temb_dim, u->temb_proj_w, u->temb_proj_b, f.temb_all + (size_t)b0 * u->temb_total, u->temb_total, nb, u->temb_total, u->temb_dim, 1, 0));
+  }
+
+  // ---- conv_in (4-channel NCHW gather -> K=64 GEMM)
+  __half* col = f.alloc((size_t)B * h * w * 64 * 2);
+  T4 x = f.talloc(B, h, w, c0);
+  if (f.err) return f.err;
+  {
+    const size_t items = (size_t)B * h * w * 64;
+    im2col_conv_in_kernel<<<grid_for(items, 256, sms), 256, 0, s>>>(sample, col, B, cf.in_channels, h, w, 64);
+    DG_LAUNCH_CHECK();
+    f.linear(col, 64, nullptr, 0, B * h * w, u->conv_in, nullptr, 0, x.p);
+    f.free_(col);
+  }
+  std::vector<T4> skips;
+  skips.push_back(x);
+  // ---- down
+  for (int i = 0; i < 4 && !f.err; ++i) {
+    DownBlk& d = u->down[i];
+    for (size_t j = 0; j < d.res.size(); ++j) {
+      T4 y = f.resnet(d.res[j], x, nullptr);
+      if (!d.xf.empty()) { T4 z = f.transformer(d.xf[j], y); f.free_(y); y = z; }
+      x = y; skips.push_back(x);
+    }
+    if (d.has_down) {
+      const int Ho = (x.H - 1) / 2 + 1, Wo = (x.W - 1) / 2 + 1;
+      __half* c2 = f.alloc((size_t)x.B * Ho * Wo * 9 * x.C * 2);
+      T4 y = f.talloc(x.B, Ho, Wo, x.C);
+      if (f.err) break;
+      const size_t items = (size_t)x.B * Ho * Wo * 9 * (x.C / 8);
+      im2col3x3_nhwc_kernel<<<grid_for(items, 256, sms), 256, 0, s>>>(x.p, c2, x.B, x.H, x.W, x.C, 2, Ho, Wo);
+      DG_LAUNCH_CHECK();
+      f.linear(c2, 9 * x.C, nullptr, 0, x.B * Ho * Wo, d.down, nullptr, 0, y.p);
+      f.free_(c2);
+      x = y; skips.push_back(x);
+    }
+  }
+  // ---- mid
+  if (!f.err) {
+    T4 a = f.resnet(u->mid_r0, x, nullptr);
+    T4 b = f.transformer(u->mid_xf, a); f.free_(a);
+    T4 c = f.resnet(u->mid_r1, b, nullptr); f.free_(b);
+    x = c;  // the last skip (== previous x) stays alive on the stack
+  }
+  // ---- up
+  for (int i = 0; i < 4 && !f.err; ++i) {
+    UpBlk& b = u->up[i];
+    for (size_t j = 0; j < b.res.size(); ++j) {
+      T4 skip = skips.back(); skips.pop_back();
+      T4 y = f.resnet(b.res[j], x, &skip);
+      f.free_(x); f.free_(skip);
+      if (!b.xf.empty()) { T4 z = f.transformer(b.xf[j], y); f.free_(y); y = z; }
+      x = y;
+    }
+    if (b.has_up) {
+      T4 upx = f.talloc(x.B, x.H * 2, x.W * 2, x.C);
+      T4 y = f.talloc(x.B, x.H * 2, x.W * 2, x.C);
+      if (f.err) break;
+      const size_t items = (size_t)x.B * 4 * x.H * x.W * (x.C / 8);
+      upsample2x_nhwc_kernel<<<grid_for(items, 256, sms), 256, 0, s>>>(x.p, upx.p, x.B, x.H, x.W, x.C);
+      DG_LAUNCH_CHECK();
+      f.conv3(upx, b.up, nullptr, nullptr, y);
+      f.free_(upx); f.free_(x);
+      x = y;
+    }
+  }
+  if (f.err) return f.err;
+  // ---- out
+  T4 xn = f.talloc(B, h, w, c0);
+  f.gn(x, nullptr, u->norm_out, cf.norm_eps, 1, xn);
+  T4 o = f.talloc(B, h, w, cf.out_channels);
+  f.conv3(xn, u->conv_out, nullptr, nullptr, o);
+  if (f.err) return f.err;
+  {
+    const size_t n = (size_t)B * cf.out_channels * h * w;
+    nhwc_to_nchw_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(o.p, out, B, cf.out_channels, h * w);
+    DG_LAUNCH_CHECK();
+  }
+  return DG_OK;
+}
+
+__global__ void set_timesteps_kernel(float* dst, int n, float t0, float t1, float t2, float t3, float t4, float t5, float t6, float t7, int bcast) {
+  const float v[8] = {t0, t1, t2, t3, t4, t5, t6, t7};
+  for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = bcast ? t0 : v[i & 7];
+}
+__global__ void set_step_kernel(int* step, float* d_t, const float* t_table, int idx, int n) {
+  if (threadIdx.x == 0) *step = idx;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) d_t[i] = t_table[idx];
+}
+__global__ void dup_latents_kernel(const __half* __restrict__ lat, __half* __restrict__ dst, size_t n_vec8, int copies) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n_vec8; i += (size_t)gridDim.x * blockDim.x) {
+    const Half8 v = *reinterpret_cast<const Half8*>(lat + i * 8);
+    for (int c = 0; c < copies; ++c) *reinterpret_cast<Half8*>(dst + (c * n_vec8 + i) * 8) = v;
+  }
+}
+
+int forward_maybe_graph(dg_unet* u, cudaStream_t s, const __half* sample, const __half* ehs, int tokens, __half* out, int B, int h, int w) {
+  if (!u->use_graphs) {
+    const long long c0 = g_launch_counter;
+    DG_TRY(run_forward(u, s, sample, ehs, tokens, out, B, h, w));
+    u->last_launches += g_launch_counter - c0;
+    return DG_OK;
+  }
+  GraphKey key{B, h, w, tokens, sample, ehs, out};
+  for (auto& g : u->graphs) {
+    if (g.key == key) {
+      DG_CUDA(cudaGraphLaunch(g.exec, s));
+      u->last_launches += g.launches;
+      return DG_OK;
+    }
+  }
+  // capture
+  cudaGraph_t graph = nullptr;
+  const long long c0 = g_launch_counter;
+  DG_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+  int r = run_forward(u, s, sample, ehs, tokens, out, B, h, w);
+  cudaError_t e = cudaStreamEndCapture(s, &graph);
+  if (r != DG_OK) { if (graph) cudaGraphDestroy(graph); return r; }
+  if (e != cudaSuccess) return fail(DG_E_CUDA, "graph capture failed: %s", cudaGetErrorString(e));
+  cudaGraphExec_t exec = nullptr;
+  DG_CUDA(cudaGraphInstantiate(&exec, graph, 0));
+  cudaGraphDestroy(graph);
+  if (u->graphs.size() >= 8) { cudaGraphExecDestroy(u->graphs.front().exec); u->graphs.erase(u->graphs.begin()); }
+  u->graphs.push_back({key, exec, g_launch_counter - c0});
+  DG_CUDA(cudaGraphLaunch(exec, s));
+  u->last_launches += g_launch_counter - c0;
+  return DG_OK;
+}
+
+int check_prepared(dg_unet* u, int batch, int h, int w, int tokens) {
+  if (!u->arena.base) return fail(DG_E_STATE, "dg_unet_prepare has not been called");
+  if (batch > u->max_batch || h * w > u->ws_h * u->ws_w || tokens > u->ws_tokens)
+    return fail(DG_E_SHAPE, "forward (batch %d, %dx%d, %d tokens) exceeds prepared workspace (batch %d, %dx%d, %d tokens)",
+                batch, h, w, tokens, u->max_batch, u->ws_h, u->ws_w, u->ws_tokens);
+  if (h % 8 || w % 8) return fail(DG_E_SHAPE, "latent size %dx%d must be a multiple of 8", h, w);
+  int missing = 0;
+  for (auto& sl : u->slots) missing += sl.set ? 0 : 1;
+  if (missing) return fail(DG_E_STATE, "%d weights have not been set", missing);
+  return DG_OK;
+}
+
+}  // namespace
+
+// ================================================================== C ABI
+extern "C" {
+
+int32_t dg_version(void) { return 100; }
+const char* dg_last_error(void) { return g_last_error.c_str(); }
+
+int32_t dg_ctx_create(int32_t device, dg_ctx** out) {
+  if (!out) return fail(DG_E_ARG, "out is null");
+  int n = 0;
+  DG_CUDA(cudaGetDeviceCount(&n));
+  if (device < 0 || device >= n) return fail(DG_E_ARG, "device %d out of range (%d devices)", device, n);
+  cudaDeviceProp prop;
+  DG_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) return fail(DG_E_ARCH, "device %d is sm_%d%d; this library contains sm_100a code only (no fallback)", device, prop.major, prop.minor);
+  DG_CUDA(cudaSetDevice(device));
+  if (!get_encode_fn()) return fail(DG_E_CUDA, "driver entry point cuTensorMapEncodeTiled not found");
+  DG_TRY(init_kernel_attributes());
+  dg_ctx* c = new dg_ctx();
+  c->device = device;
+  c->num_sms = prop.multiProcessorCount;
+  DG_CUDA(cudaMalloc(&c->gn_stats, sizeof(float) * 2 * 64 * 64));
+  *out = c;
+  return DG_OK;
+}
+void dg_ctx_destroy(dg_ctx* ctx) {
+  if (!ctx) return;
+  cudaFree(ctx->gn_stats);
+  delete ctx;
+}
+
+int32_t dg_unet_create(dg_ctx* ctx, const dg_unet_config* cfg, dg_unet** out) {
+  if (!ctx || !cfg || !out) return fail(DG_E_ARG, "null argument");
+  for (int i = 0; i < 4; ++i) {
+    if (cfg->block_out_channels[i] % 64) return fail(DG_E_UNSUPPORTED, "block_out_channels[%d]=%d must be a multiple of 64", i, cfg->block_out_channels[i]);
+    if (cfg->num_heads[i] <= 0 || cfg->block_out_channels[i] % cfg->num_heads[i]) return fail(DG_E_SHAPE, "heads[%d]=%d", i, cfg->num_heads[i]);
+  }
+  if (cfg->cross_attention_dim % 64) return fail(DG_E_UNSUPPORTED, "cross_attention_dim must be a multiple of 64");
+  if (cfg->norm_num_groups > 64) return fail(DG_E_UNSUPPORTED, "norm_num_groups > 64");
+  DG_CUDA(cudaSetDevice(ctx->device));
+  std::unique_ptr<dg_unet> u(new dg_unet());
+  u->ctx = ctx; u->cfg = *cfg;
+  int r = build_modules(u.get());
+  if (r != DG_OK) { for (void* p : u->owned) cudaFree(p); return r; }
+  *out = u.release();
+  return DG_OK;
+}
+void dg_unet_destroy(dg_unet* u) {
+  if (!u) return;
+  for (auto& g : u->graphs) cudaGraphExecDestroy(g.exec);
+  for (void* p : u->owned) cudaFree(p);
+  cudaFree(u->arena.base); cudaFree(u->d_t); cudaFree(u->gn_stats); cudaFree(u->d_coef); cudaFree(u->d_step);
+  cudaFree(u->loop_in); cudaFree(u->loop_out);
+  delete u;
+}
+int32_t dg_unet_num_weights(dg_unet* u) { return u ? (int32_t)u->slots.size() : 0; }
+const char* dg_unet_weight_name(dg_unet* u, int32_t i) {
+  if (!u || i < 0 || i >= (int)u->slots.size()) return nullptr;
+  return u->slots[i].key.c_str();
+}
+int32_t dg_unet_weight_shape(dg_unet* u, int32_t i, int64_t* shape4, int32_t* ndim) {
+  if (!u || i < 0 || i >= (int)u->slots.size() || !shape4 || !ndim) return fail(DG_E_ARG, "bad argument");
+  *ndim = (int32_t)u->slots[i].shape.size();
+  for (int k = 0; k < *ndim; ++k) shape4[k] = u->slots[i].shape[k];
+  return DG_OK;
+}
+int32_t dg_unet_missing_weights(dg_unet* u) {
+  int m = 0;
+  if (u) for (auto& s : u->slots) m += s.set ? 0 : 1;
+  return m;
+}
+
+int32_t dg_unet_set_weight(dg_unet* u, const char* key, const void* src, int32_t ndim, const int64_t* shape) {
+  if (!u || !key || !src || !shape) return fail(DG_E_ARG, "null argument");
+  auto it = u->slot_index.find(key);
+  if (it == u->slot_index.end()) return fail(DG_E_ARG, "unexpected state-dict key '%s'", key);
+  Slot& s = u->slots[it->second];
+  bool ok = (int)s.shape.size() == ndim;
+  for (int i = 0; ok && i < ndim; ++i) ok = s.shape[i] == shape[i];
+  if (!ok) return fail(DG_E_SHAPE, "shape mismatch for '%s'", key);
+  DG_CUDA(cudaSetDevice(u->ctx->device));
+  const __half* w = (const __half*)src;
+  size_t n = 1;
+  for (auto d : s.shape) n *= (size_t)d;
+  const int sms = u->ctx->num_sms;
+  switch (s.kind) {
+    case PK_COPY: DG_CUDA(cudaMemcpy(s.dst, w, n * 2, cudaMemcpyDeviceToDevice)); break;
+    case PK_ROWS: DG_CUDA(cudaMemcpy(s.dst + (size_t)s.row_off * s.b, w, n * 2, cudaMemcpyDeviceToDevice)); break;
+    case PK_CONV3:
+      pack_conv3x3_kernel<<<grid_for(n, 256, sms), 256>>>(w, s.dst, s.a, s.b, s.b);
+      DG_LAUNCH_CHECK();
+      break;
+    case PK_CONV_IN:
+      pack_conv_in_kernel<<<grid_for((size_t)s.a * 64, 256, sms), 256>>>(w, s.dst, s.a, s.b, 64);
+      DG_LAUNCH_CHECK();
+      break;
+    case PK_GEGLU_W:
+    case PK_GEGLU_B: {
+      const int tiles = geglu_rows(s.a) / kGemmBlockN;
+      pack_geglu_kernel<<<grid_for((size_t)tiles * kGemmBlockN * s.b, 256, sms), 256>>>(w, s.dst, s.a, s.b, kGemmBlockN, tiles);
+      DG_LAUNCH_CHECK();
+      break;
+    }
+  }
+  DG_CUDA(cudaDeviceSynchronize());
+  s.set = true;
+  return DG_OK;
+}
+
+int32_t dg_unet_prepare(dg_unet* u, int32_t max_batch, int32_t h, int32_t w, int32_t ctx_tokens) {
+  if (!u || max_batch <= 0 || h <= 0 || w <= 0 || ctx_tokens <= 0) return fail(DG_E_ARG, "bad argument");
+  DG_CUDA(cudaSetDevice(u->ctx->device));
+  for (auto& g : u->graphs) cudaGraphExecDestroy(g.exec);
+  u->graphs.clear();
+  cudaFree(u->arena.base); cudaFree(u->d_t); cudaFree(u->gn_stats); cudaFree(u->loop_in); cudaFree(u->loop_out);
+  u->arena.base = nullptr; u->d_t = nullptr; u->gn_stats = nullptr; u->loop_in = nullptr; u->loop_out = nullptr;
+  // Peak live activation set: generous closed-form bound (skips + the widest transformer intermediates).
+  const size_t c0 = u->cfg.block_out_channels[0];
+  const size_t pix = (size_t)max_batch * h * w;
+  size_t bytes = pix * c0 * 2 * 40 + ((size_t)64 << 20);
+  u->arena.size = bytes;
+  cudaError_t e = cudaMalloc((void**)&u->arena.base, bytes);
+  if (e != cudaSuccess) return fail(DG_E_NOMEM, "workspace cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
+  DG_CUDA(cudaMalloc((void**)&u->d_t, sizeof(float) * max_batch));
+  DG_CUDA(cudaMalloc((void**)&u->gn_stats, sizeof(float) * 2 * u->cfg.norm_num_groups * max_batch));
+  const size_t lat = (size_t)max_batch * u->cfg.in_channels * h * w * 2;
+  DG_CUDA(cudaMalloc((void**)&u->loop_in, lat));
+  DG_CUDA(cudaMalloc((void**)&u->loop_out, lat));
+  if (!u->d_step) DG_CUDA(cudaMalloc((void**)&u->d_step, sizeof(int)));
+  u->max_batch = max_batch; u->ws_h = h; u->ws_w = w; u->ws_tokens = ctx_tokens;
+  return DG_OK;
+}
+
+int32_t dg_unet_set_graphs(dg_unet* u, int32_t enabled) {
+  if (!u) return fail(DG_E_ARG, "null");
+  u->use_graphs = enabled != 0;
+  return DG_OK;
+}
+int64_t dg_unet_last_launch_count(dg_unet* u) { return u ? u->last_launches : 0; }
+
+int32_t dg_unet_forward(dg_unet* u, const void* sample, const float* t_host, int32_t n_t, const void* ehs,
+                        int32_t tokens, void* out, int32_t batch, int32_t h, int32_t w, void* stream) {
+  if (!u || !sample || !t_host || !ehs || !out) return fail(DG_E_ARG, "null argument");
+  if (n_t != 1 && n_t != batch) return fail(DG_E_SHAPE, "n_timesteps must be 1 or batch");
+  if (n_t > 8) {
+    bool same = true;
+    for (int i = 1; i < n_t; ++i) same = same && t_host[i] == t_host[0];
+    if (!same) return fail(DG_E_UNSUPPORTED, "more than 8 distinct per-sample timesteps");
+    n_t = 1;
+  }
+  DG_TRY(check_prepared(u, batch, h, w, tokens));
+  DG_CUDA(cudaSetDevice(u->ctx->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  u->last_launches = 0;
+  float t[8] = {0};
+  for (int i = 0; i < n_t; ++i) t[i] = t_host[i];
+  set_timesteps_kernel<<<1, 32, 0, s>>>(u->d_t, batch, t[0], t[1], t[2], t[3], t[4], t[5], t[6], t[7], n_t == 1);
+  DG_LAUNCH_CHECK();
+  u->last_launches += 1;
+  return forward_maybe_graph(u, s, (const __half*)sample, (const __half*)ehs, tokens, (__half*)out, batch, h, w);
+}
+
+int32_t dg_cfg_ddim_step(dg_ctx* ctx, const void* noise, void* latents, int32_t n_images, int64_t elems, float a_t,
+                         float a_prev, float guidance, int32_t pred_type, void* stream) {
+  if (!ctx || !noise || !latents) return fail(DG_E_ARG, "null argument");
+  const size_t n = (size_t)n_images * elems;
+  if (n % 8) return fail(DG_E_SHAPE, "element count must be a multiple of 8");
+  if (pred_type != 0 && pred_type != 1) return fail(DG_E_ARG, "prediction_type must be 0 (epsilon) or 1 (v_prediction)");
+  cudaStream_t s = (cudaStream_t)stream;
+  // coefficient passed through a small device table owned by the context scratch (first 4 floats of gn_stats)
+  const float4 cf = make_float4(sqrtf(a_t), sqrtf(1.f - a_t), sqrtf(a_prev), sqrtf(1.f - a_prev));
+  DG_CUDA(cudaMemcpyAsync(ctx->gn_stats, &cf, sizeof(cf), cudaMemcpyHostToDevice, s));
+  cfg_ddim_step_kernel<<<grid_for(n / 8, 256, ctx->num_sms), 256, 0, s>>>((const __half*)noise, (__half*)latents, n / 8, n,
+                                                                         guidance, guidance > 1.0f, pred_type,
+                                                                         (const float4*)ctx->gn_stats, nullptr);
+  DG_LAUNCH_CHECK();
+  return DG_OK;
+}
+
+int32_t dg_denoise_loop(dg_unet* u, void* latents, const void* ehs, int32_t tokens, int32_t n_images, int32_t h, int32_t w,
+                        const float* t_host, const float* a_t, const float* a_prev, int32_t n_steps, float guidance,
+                        int32_t pred_type, void* stream) {
+  if (!u || !latents || !ehs || !t_host || !a_t || !a_prev || n_steps <= 0) return fail(DG_E_ARG, "bad argument");
+  const bool cfg_on = guidance > 1.0f;
+  const int B = cfg_on ? 2 * n_images : n_images;
+  DG_TRY(check_prepared(u, B, h, w, tokens));
+  DG_CUDA(cudaSetDevice(u->ctx->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  const size_t elems = (size_t)n_images * u->cfg.in_channels * h * w;
+  if (elems % 8) return fail(DG_E_SHAPE, "latent element count must be a multiple of 8");
+  // per-step tables (device): coefficients + timestep values
+  if (u->coef_cap < n_steps) {
+    cudaFree(u->d_coef);
+    DG_CUDA(cudaMalloc((void**)&u->d_coef, (sizeof(float4) + sizeof(float)) * n_steps));
+    u->coef_cap = n_steps;
+  }
+  std::vector<float4> cf(n_steps);
+  for (int i = 0; i < n_steps; ++i) cf[i] = make_float4(sqrtf(a_t[i]), sqrtf(1.f - a_t[i]), sqrtf(a_prev[i]), sqrtf(1.f - a_prev[i]));
+  float* d_ttab = (float*)(u->d_coef + n_steps);
+  DG_CUDA(cudaMemcpyAsync(u->d_coef, cf.data(), sizeof(float4) * n_steps, cudaMemcpyHostToDevice, s));
+  DG_CUDA(cudaMemcpyAsync(d_ttab, t_host, sizeof(float) * n_steps, cudaMemcpyHostToDevice, s));
+  DG_CUDA(cudaStreamSynchronize(s));  // host staging buffers go out of scope
+  u->last_launches = 0;
+  for (int i = 0; i < n_steps; ++i) {
+    set_step_kernel<<<1, 32, 0, s>>>(u->d_step, u->d_t, d_ttab, i, B);
+    DG_LAUNCH_CHECK();
+    dup_latents_kernel<<<grid_for(elems / 8, 256, u->ctx->num_sms), 256, 0, s>>>((const __half*)latents, u->loop_in, elems / 8, cfg_on ? 2 : 1);
+    DG_LAUNCH_CHECK();
+    u->last_launches += 2;
+    DG_TRY(forward_maybe_graph(u, s, u->loop_in, (const __half*)ehs, tokens, u->loop_out, B, h, w));
+    cfg_ddim_step_kernel<<<grid_for(elems / 8, 256, u->ctx->num_sms), 256, 0, s>>>(u->loop_out, (__half*)latents, elems / 8, elems,
+                                                                                 guidance, cfg_on, pred_type, u->d_coef, u->d_step);
+    DG_LAUNCH_CHECK();
+    u->last_launches += 1;
+  }
+  return DG_OK;
+}
+
+// ------------------------------------------------------------------ single operators
+int32_t dg_op_gemm(dg_ctx* ctx, const void* A, const void* W, const void* bias, const void* residual, void* out, int32_t M,
+                   int32_t K, int32_t n_w, int32_t n_out, int32_t geglu, void* stream) {
+  if (!ctx || !A || !W || !out) return fail(DG_E_ARG, "null argument");
+  GemmArgs a; a.a0 = (const __half*)A; a.c0 = K; a.B = 1; a.H = 1; a.W = M; a.taps = 1; a.w = (const __half*)W; a.n_w = n_w;
+  a.n_out = n_out; a.bias = (const __half*)bias; a.residual = (const __half*)residual; a.ld_res = n_out; a.geglu = geglu;
+  a.out = (__half*)out; a.ldo = n_out;
+  return launch_gemm((cudaStream_t)stream, ctx->num_sms, a);
+}
+int32_t dg_op_geglu_packed_rows(int32_t inner) { return geglu_rows(inner); }
+int32_t dg_op_pack_geglu(dg_ctx* ctx, const void* w, const void* b, void* w_out, void* b_out, int32_t inner, int32_t K, void* stream) {
+  if (!ctx || !w || !b || !w_out || !b_out) return fail(DG_E_ARG, "null argument");
+  const int tiles = geglu_rows(inner) / kGemmBlockN;
+  cudaStream_t s = (cudaStream_t)stream;
+  pack_geglu_kernel<<<grid_for((size_t)tiles * kGemmBlockN * K, 256, ctx->num_sms), 256, 0, s>>>((const __half*)w, (__half*)w_out, inner, K, kGemmBlockN, tiles);
+  DG_LAUNCH_CHECK();
+  pack_geglu_kernel<<<grid_for((size_t)tiles * kGemmBlockN, 256, ctx->num_sms), 256, 0, s>>>((const __half*)b, (__half*)b_out, inner, 1, kGemmBlockN, tiles);
+  DG_LAUNCH_CHECK();
+  return DG_OK;
+}
+int32_t dg_op_pack_conv3x3(dg_ctx* ctx, const void* w, void* w_out, int32_t O, int32_t I, void* stream) {
+  if (!ctx || !w || !w_out) return fail(DG_E_ARG, "null argument");
+  pack_conv3x3_kernel<<<grid_for((size_t)O * 9 * I, 256, ctx->num_sms), 256, 0, (cudaStream_t)stream>>>((const __half*)w, (__half*)w_out, O, I, I);
+  DG_LAUNCH_CHECK();
+  return DG_OK;
+}
+int32_t dg_op_conv3x3(dg_ctx* ctx, const void* x0, int32_t C0, const void* x1, int32_t C1, const void* Wp, const void* bias,
+                      const void* rowvec, int32_t ld_rowvec, const void* residual, void* out, int32_t B, int32_t H, int32_t Wd,
+                      int32_t N, void* stream) {
+  if (!ctx || !x0 || !Wp || !out) return fail(DG_E_ARG, "null argument");
+  GemmArgs a; a.a0 = (const __half*)x0; a.c0 = C0; a.a1 = (const __half*)x1; a.c1 = C1; a.B = B; a.H = H; a.W = Wd; a.taps = 9;
+  a.w = (const __half*)Wp; a.n_w = N; a.n_out = N; a.bias = (const __half*)bias; a.rowvec = (const __half*)rowvec; a.ld_rowvec = ld_rowvec;
+  a.residual = (const __half*)residual; a.ld_res = N; a.out = (__half*)out; a.ldo = N;
+  return launch_gemm((cudaStream_t)stream, ctx->num_sms, a);
+}
+int32_t dg_op_attention(dg_ctx* ctx, const void* q, int32_t ldq, const void* k, int32_t ldk, const void* v, int32_t ldv, void* out,
+                        int32_t B, int32_t heads, int32_t Sq, int32_t Sk, int32_t d, void* stream) {
+  if (!ctx || !q || !k || !v || !out) return fail(DG_E_ARG, "null argument");
+  return launch_attention((cudaStream_t)stream, (const __half*)q, ldq, (const __half*)k, ldk, (const __half*)v, ldv, (__half*)out, B, heads, Sq, Sk, d);
+}
+int32_t dg_op_groupnorm(dg_ctx* ctx, const void* x0, int32_t C0, const void* x1, int32_t C1, const void* gamma, const void* beta,
+                        void* out, int32_t B, int32_t HW, int32_t groups, float eps, int32_t silu, void* stream) {
+  if (!ctx || !x0 || !gamma || !beta || !out) return fail(DG_E_ARG, "null argument");
+  if (B * groups > 64 * 64) return fail(DG_E_SHAPE, "groupnorm op: B*groups too large for the context scratch");
+  return launch_groupnorm((cudaStream_t)stream, ctx->num_sms, (const __half*)x0, C0, (const __half*)x1, C1, (const __half*)gamma,
+                          (const __half*)beta, (__half*)out, ctx->gn_stats, B, HW, groups, eps, silu);
+}
+int32_t dg_op_layernorm(dg_ctx* ctx, const void* x, const void* gamma, const void* beta, void* out, int32_t rows, int32_t C, float eps, void* stream) {
+  if (!ctx || !x || !gamma || !beta || !out) return fail(DG_E_ARG, "null argument");
+  return launch_layernorm((cudaStream_t)stream, (const __half*)x, (const __half*)gamma, (const __half*)beta, (__half*)out, rows, C, eps);
+}
+int32_t dg_op_time_embedding(dg_ctx* ctx, const float* t_host, int32_t B, int32_t dim, int32_t temb_dim, const void* w1, const void* b1,
+                             const void* w2, const void* b2, void* out, void* stream) {
+  if (!ctx || !t_host || !w1 || !w2 || !out) return fail(DG_E_ARG, "null argument");
+  if (B > 8) return fail(DG_E_SHAPE, "time embedding op: B <= 8");
+  cudaStream_t s = (cudaStream_t)stream;
+  float* d_t = nullptr; __half* tsin = nullptr; __half* t1 = nullptr;
+  DG_CUDA(cudaMalloc((void**)&d_t, sizeof(float) * B));
+  DG_CUDA(cudaMalloc((void**)&tsin, (size_t)B * dim * 2));
+  DG_CUDA(cudaMalloc((void**)&t1, (size_t)B * temb_dim * 2));
+  DG_CUDA(cudaMemcpyAsync(d_t, t_host, sizeof(float) * B, cudaMemcpyHostToDevice, s));
+  timestep_sinusoid_kernel<<<(B * dim / 2 + 127) / 128, 128, 0, s>>>(d_t, tsin, B, dim, 0.f, 1);
+  DG_LAUNCH_CHECK();
+  int r = launch_gemv(s, tsin, dim, (const __half*)w1, (const __half*)b1, t1, temb_dim, B, temb_dim, dim, 0, 1);
+  if (r == DG_OK) r = launch_gemv(s, t1, temb_dim, (const __half*)w2, (const __half*)b2, (__half*)out, temb_dim, B, temb_dim, temb_dim, 0, 0);
+  cudaStreamSynchronize(s);
+  cudaFree(d_t); cudaFree(tsin); cudaFree(t1);
+  return r;
+}
+
+}  // extern "C"

@@ -1,0 +1,354 @@
+// HBM-bound kernels of the path: layout changes, GroupNorm / LayerNorm, timestep embedding + small-batch GEMV,
+// nearest-neighbour upsample, im2col gathers for the few convolutions TMA cannot tile (4-channel conv_in, stride-2
+// downsamplers), and the fused classifier-free-guidance + DDIM step.  All are coalesced, 16-byte vectorised, fp32 math.
+#pragma once
+#include "common.cuh"
+
+namespace dg {
+
+__device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
+
+struct alignas(16) Half8 { __half2 h[4]; };
+
+__device__ __forceinline__ void load8(const __half* p, float* f) {
+  Half8 v = *reinterpret_cast<const Half8*>(p);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { float2 t = __half22float2(v.h[i]); f[2 * i] = t.x; f[2 * i + 1] = t.y; }
+}
+__device__ __forceinline__ void store8(__half* p, const float* f) {
+  Half8 v;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) v.h[i] = __floats2half2_rn(f[2 * i], f[2 * i + 1]);
+  *reinterpret_cast<Half8*>(p) = v;
+}
+
+// ------------------------------------------------------------------ layout
+// NCHW fp16 -> NHWC fp16 (tiny tensors only: latents in, noise prediction out).
+__global__ void nchw_to_nhwc_kernel(const __half* __restrict__ in, __half* __restrict__ out, int B, int C, int HW) {
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  size_t n = (size_t)B * C * HW;
+  if (i >= n) return;
+  int c = i % C; size_t t = i / C; int p = t % HW; int b = t / HW;
+  out[i] = in[((size_t)b * C + c) * HW + p];
+}
+__global__ void nhwc_to_nchw_kernel(const __half* __restrict__ in, __half* __restrict__ out, int B, int C, int HW) {
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  size_t n = (size_t)B * C * HW;
+  if (i >= n) return;
+  int p = i % HW; size_t t = i / HW; int c = t % C; int b = t / C;
+  out[i] = in[((size_t)b * HW + p) * C + c];
+}
+
+// ------------------------------------------------------------------ GroupNorm (NHWC, optional 2-source concat)
+// stats[b][g] = {sum, sumsq}; block = 256 threads over a strip of pixels of one sample.
+__global__ void gn_stats_kernel(const __half* __restrict__ x0, int C0, const __half* __restrict__ x1, int C1, int HW,
+                                int groups, int pix_per_block, float* __restrict__ stats) {
+  extern __shared__ float sh[];  // [groups*2]
+  const int C = C0 + C1, cpg = C / groups, nvec = C / 8;
+  const int b = blockIdx.y;
+  for (int i = threadIdx.x; i < groups * 2; i += blockDim.x) sh[i] = 0.f;
+  __syncthreads();
+  const int p0 = blockIdx.x * pix_per_block;
+  const int p1 = min(HW, p0 + pix_per_block);
+  const int lanes_per_pix = nvec;  // one thread = one 8-channel vector
+  const int pix_stride = blockDim.x / lanes_per_pix > 0 ? blockDim.x / lanes_per_pix : 1;
+  if (blockDim.x >= lanes_per_pix) {
+    const int v = threadIdx.x % lanes_per_pix;
+    const int pofs = threadIdx.x / lanes_per_pix;
+    if (pofs < pix_stride) {
+      float s[8], ss[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { s[i] = 0.f; ss[i] = 0.f; }
+      const int c = v * 8;
+      for (int p = p0 + pofs; p < p1; p += pix_stride) {
+        float f[8];
+        const size_t pix = (size_t)b * HW + p;
+        if (c < C0) load8(x0 + pix * C0 + c, f); else load8(x1 + pix * C1 + (c - C0), f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { s[i] += f[i]; ss[i] += f[i] * f[i]; }
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int g = (c + i) / cpg;
+        atomicAdd(&sh[2 * g], s[i]);
+        atomicAdd(&sh[2 * g + 1], ss[i]);
+      }
+    }
+  } else {
+    // very wide C (more vectors than threads): thread loops over vectors too
+    for (int v = threadIdx.x; v < nvec; v += blockDim.x) {
+      float s[8], ss[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { s[i] = 0.f; ss[i] = 0.f; }
+      const int c = v * 8;
+      for (int p = p0; p < p1; ++p) {
+        float f[8];
+        const size_t pix = (size_t)b * HW + p;
+        if (c < C0) load8(x0 + pix * C0 + c, f); else load8(x1 + pix * C1 + (c - C0), f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { s[i] += f[i]; ss[i] += f[i] * f[i]; }
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int g = (c + i) / cpg;
+        atomicAdd(&sh[2 * g], s[i]);
+        atomicAdd(&sh[2 * g + 1], ss[i]);
+      }
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < groups * 2; i += blockDim.x) atomicAdd(&stats[(size_t)b * groups * 2 + i], sh[i]);
+}
+
+// y = act((x - mean) * rstd * gamma + beta), written as one concatenated NHWC tensor.
+__global__ void gn_apply_kernel(const __half* __restrict__ x0, int C0, const __half* __restrict__ x1, int C1, int HW,
+                                int B, int groups, float eps, const float* __restrict__ stats,
+                                const __half* __restrict__ gamma, const __half* __restrict__ beta, int do_silu,
+                                __half* __restrict__ out) {
+  const int C = C0 + C1, cpg = C / groups, nvec = C / 8;
+  const size_t total = (size_t)B * HW * nvec;
+  const float inv_n = 1.0f / ((float)cpg * (float)HW);
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int v = i % nvec;
+    const size_t pix = i / nvec;
+    const int b = pix / HW;
+    const int c = v * 8;
+    float f[8], g[8], be[8];
+    if (c < C0) load8(x0 + pix * C0 + c, f); else load8(x1 + pix * C1 + (c - C0), f);
+    load8(gamma + c, g);
+    load8(beta + c, be);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int grp = (c + k) / cpg;
+      const float sum = stats[((size_t)b * groups + grp) * 2];
+      const float sq = stats[((size_t)b * groups + grp) * 2 + 1];
+      const float mean = sum * inv_n;
+      const float var = fmaxf(sq * inv_n - mean * mean, 0.f);
+      const float rstd = rsqrtf(var + eps);
+      float y = (f[k] - mean) * rstd * g[k] + be[k];
+      f[k] = do_silu ? silu_f(y) : y;
+    }
+    store8(out + pix * C + c, f);
+  }
+}
+
+// ------------------------------------------------------------------ LayerNorm over the last dim (one warp per row)
+template <int kMaxVec>
+__global__ void layernorm_kernel(const __half* __restrict__ x, const __half* __restrict__ gamma,
+                                 const __half* __restrict__ beta, __half* __restrict__ out, int rows, int C, float eps) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const int nvec = C / 8;
+  float f[kMaxVec][8];
+  float s = 0.f;
+#pragma unroll
+  for (int j = 0; j < kMaxVec; ++j) {
+    const int v = lane + j * 32;
+    if (v < nvec) {
+      load8(x + (size_t)row * C + v * 8, f[j]);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) s += f[j][k];
+    }
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float mean = s / (float)C;
+  float ss = 0.f;
+#pragma unroll
+  for (int j = 0; j < kMaxVec; ++j) {
+    const int v = lane + j * 32;
+    if (v < nvec) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { const float d = f[j][k] - mean; ss += d * d; }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  const float rstd = rsqrtf(ss / (float)C + eps);
+#pragma unroll
+  for (int j = 0; j < kMaxVec; ++j) {
+    const int v = lane + j * 32;
+    if (v < nvec) {
+      float g[8], b[8], y[8];
+      load8(gamma + v * 8, g);
+      load8(beta + v * 8, b);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) y[k] = (f[j][k] - mean) * rstd * g[k] + b[k];
+      store8(out + (size_t)row * C + v * 8, y);
+    }
+  }
+}
+
+// ------------------------------------------------------------------ timestep embedding + GEMV
+// diffusers get_timestep_embedding(flip_sin_to_cos=True): [cos | sin], fp32 math, rounded to fp16 like `.to(dtype)`.
+__global__ void timestep_sinusoid_kernel(const float* __restrict__ t, __half* __restrict__ out, int B, int dim,
+                                         float freq_shift, int flip) {
+  const int half_dim = dim / 2;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * half_dim) return;
+  const int b = i / half_dim, k = i % half_dim;
+  const float freq = expf(-logf(10000.0f) * (float)k / ((float)half_dim - freq_shift));
+  const float a = t[b] * freq;
+  const float s = sinf(a), c = cosf(a);
+  __half* o = out + (size_t)b * dim;
+  if (flip) { o[k] = __float2half_rn(c); o[half_dim + k] = __float2half_rn(s); }
+  else      { o[k] = __float2half_rn(s); o[half_dim + k] = __float2half_rn(c); }
+}
+
+// out[b, n] = act_out( sum_k act_in(x[b,k]) * W[n,k] + bias[n] ), B <= 8.  One warp per output row: the weight matrix
+// is streamed exactly once with 16-byte loads (HBM-bound; the time-embedding MLP and the 22 time_emb_proj layers).
+__global__ void gemv_small_batch_kernel(const __half* __restrict__ x, int ldx, const __half* __restrict__ W,
+                                        const __half* __restrict__ bias, __half* __restrict__ out, int ldo, int B,
+                                        int N, int K, int silu_in, int silu_out) {
+  extern __shared__ float xs[];  // [B][K]
+  for (int i = threadIdx.x; i < B * K; i += blockDim.x) {
+    float v = __half2float(x[(size_t)(i / K) * ldx + (i % K)]);
+    xs[i] = silu_in ? silu_f(v) : v;
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (n >= N) return;
+  float acc[8];
+#pragma unroll
+  for (int b = 0; b < 8; ++b) acc[b] = 0.f;
+  for (int k = lane * 8; k < K; k += 32 * 8) {
+    float w[8];
+    load8(W + (size_t)n * K + k, w);
+#pragma unroll
+    for (int b = 0; b < 8; ++b) {
+      if (b < B) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[b] += w[i] * xs[b * K + k + i];
+      }
+    }
+  }
+#pragma unroll
+  for (int b = 0; b < 8; ++b) {
+#pragma unroll
+    for (int o = 16; o; o >>= 1) acc[b] += __shfl_xor_sync(0xffffffffu, acc[b], o);
+  }
+  if (lane == 0) {
+    for (int b = 0; b < B; ++b) {
+      float v = acc[b] + (bias ? __half2float(bias[n]) : 0.f);
+      out[(size_t)b * ldo + n] = __float2half_rn(silu_out ? silu_f(v) : v);
+    }
+  }
+}
+
+// ------------------------------------------------------------------ resampling / gathers
+__global__ void upsample2x_nhwc_kernel(const __half* __restrict__ in, __half* __restrict__ out, int B, int H, int W,
+                                       int C) {
+  const int nvec = C / 8;
+  const size_t total = (size_t)B * (2 * H) * (2 * W) * nvec;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int v = i % nvec; size_t t = i / nvec;
+    const int x = t % (2 * W); t /= (2 * W);
+    const int y = t % (2 * H); const int b = t / (2 * H);
+    const Half8 val = *reinterpret_cast<const Half8*>(in + (((size_t)b * H + (y >> 1)) * W + (x >> 1)) * C + v * 8);
+    *reinterpret_cast<Half8*>(out + i * 8) = val;
+  }
+}
+
+// im2col for 3x3 / pad 1 / stride s on NHWC (C % 8 == 0): out[(b,yo,xo), tap*C + c].
+__global__ void im2col3x3_nhwc_kernel(const __half* __restrict__ in, __half* __restrict__ out, int B, int H, int W,
+                                      int C, int stride, int Ho, int Wo) {
+  const int nvec = C / 8;
+  const size_t total = (size_t)B * Ho * Wo * 9 * nvec;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int v = i % nvec; size_t t = i / nvec;
+    const int tap = t % 9; t /= 9;
+    const int xo = t % Wo; t /= Wo;
+    const int yo = t % Ho; const int b = t / Ho;
+    const int y = yo * stride + tap / 3 - 1, x = xo * stride + tap % 3 - 1;
+    Half8 val;
+    if (y >= 0 && y < H && x >= 0 && x < W)
+      val = *reinterpret_cast<const Half8*>(in + (((size_t)b * H + y) * W + x) * C + v * 8);
+    else {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) val.h[k] = __floats2half2_rn(0.f, 0.f);
+    }
+    *reinterpret_cast<Half8*>(out + i * 8) = val;
+  }
+}
+
+// conv_in gather: NCHW fp16 sample [B,C,H,W] (C small, e.g. 4) -> [B*H*W, Kpad] with k = tap*C + c, zero padded.
+__global__ void im2col_conv_in_kernel(const __half* __restrict__ in, __half* __restrict__ out, int B, int C, int H, int W,
+                                      int Kpad) {
+  const size_t total = (size_t)B * H * W * Kpad;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int k = i % Kpad; size_t t = i / Kpad;
+    const int x = t % W; t /= W;
+    const int y = t % H; const int b = t / H;
+    __half val = __float2half_rn(0.f);
+    if (k < 9 * C) {
+      const int tap = k / C, c = k % C;
+      const int yy = y + tap / 3 - 1, xx = x + tap % 3 - 1;
+      if (yy >= 0 && yy < H && xx >= 0 && xx < W) val = in[(((size_t)b * C + c) * H + yy) * W + xx];
+    }
+    out[i] = val;
+  }
+}
+
+// ------------------------------------------------------------------ CFG combine + DDIM step (eta = 0)
+// noise: [2*n_img, E] (rows [0,n_img) uncond, [n_img, 2 n_img) cond) or [n_img, E] when guidance is off.
+// coef = {sqrt(a_t), sqrt(1-a_t), sqrt(a_prev), sqrt(1-a_prev)} read from device memory at index *step_idx so the
+// kernel is CUDA-graph replayable.  prediction_type: 0 = epsilon, 1 = v_prediction.
+__global__ void cfg_ddim_step_kernel(const __half* __restrict__ noise, __half* __restrict__ latents, size_t n_vec8,
+                                     size_t half_offset_elems, float guidance, int use_cfg, int prediction_type,
+                                     const float4* __restrict__ coef_table, const int* __restrict__ step_idx) {
+  const float4 cf = coef_table[step_idx ? *step_idx : 0];
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n_vec8; i += (size_t)gridDim.x * blockDim.x) {
+    float u[8], c[8], x[8];
+    load8(noise + i * 8, u);
+    load8(latents + i * 8, x);
+    if (use_cfg) load8(noise + half_offset_elems + i * 8, c);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float m = use_cfg ? (u[k] + guidance * (c[k] - u[k])) : u[k];
+      float x0, eps;
+      if (prediction_type == 0) { eps = m; x0 = (x[k] - cf.y * m) / cf.x; }
+      else { x0 = cf.x * x[k] - cf.y * m; eps = cf.x * m + cf.y * x[k]; }
+      x[k] = cf.z * x0 + cf.w * eps;
+    }
+    store8(latents + i * 8, x);
+  }
+}
+
+// ------------------------------------------------------------------ weight packing (one-off, at load time)
+// OIHW [O, I, 3, 3] -> [O, 9*Ipad] with k = tap*Ipad + c  (Ipad >= I, zero filled).
+__global__ void pack_conv3x3_kernel(const __half* __restrict__ w, __half* __restrict__ out, int O, int I, int Ipad) {
+  const size_t total = (size_t)O * 9 * Ipad;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int c = i % Ipad; size_t t = i / Ipad;
+    const int tap = t % 9; const int o = t / 9;
+    out[i] = (c < I) ? w[((size_t)o * I + c) * 9 + tap] : __float2half_rn(0.f);
+  }
+}
+// conv_in: OIHW [O, I, 3, 3] -> [O, Kpad] with k = tap*I + c.
+__global__ void pack_conv_in_kernel(const __half* __restrict__ w, __half* __restrict__ out, int O, int I, int Kpad) {
+  const size_t total = (size_t)O * Kpad;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int k = i % Kpad; const int o = i / Kpad;
+    __half v = __float2half_rn(0.f);
+    if (k < 9 * I) { const int tap = k / I, c = k % I; v = w[((size_t)o * I + c) * 9 + tap]; }
+    out[i] = v;
+  }
+}
+// GEGLU interleave: proj [2*inner, K] (rows [0,inner) value, [inner,2 inner) gate) -> tiles of `tile` rows:
+// [value(half rows) | gate(half rows)], zero padded to n_tiles*tile rows.  `vec_k == 1` packs a bias vector.
+__global__ void pack_geglu_kernel(const __half* __restrict__ w, __half* __restrict__ out, int inner, int K, int tile,
+                                  int n_tiles) {
+  const int hf = tile / 2;
+  const size_t total = (size_t)n_tiles * tile * K;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int k = i % K; const int r = i / K;
+    const int t = r / tile, rr = r % tile;
+    const int j = t * hf + (rr % hf);
+    const bool gate = rr >= hf;
+    out[i] = (j < inner) ? w[((size_t)(gate ? inner + j : j)) * K + k] : __float2half_rn(0.f);
+  }
+}
+
+}  // namespace dg

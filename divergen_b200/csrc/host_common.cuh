@@ -1,0 +1,287 @@
+// Host-side plumbing shared by the C-ABI translation unit: error reporting, TMA tensor-map construction through the
+// driver entry point (no link-time libcuda dependency), kernel launchers for the tcgen05 GEMM/conv and attention
+// kernels and for the HBM-bound elementwise kernels.
+#pragma once
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <cudaTypedefs.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+
+#include "../../include/divergen_b200.h"
+#include "attn_tc.cuh"
+#include "elementwise.cuh"
+#include "gemm_tc.cuh"
+
+namespace dg {
+
+inline thread_local std::string g_last_error;
+inline thread_local long long g_launch_counter = 0;
+
+inline int fail(int code, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_last_error = buf;
+  return code;
+}
+
+#define DG_CUDA(expr)                                                                                      \
+  do {                                                                                                     \
+    cudaError_t _e = (expr);                                                                               \
+    if (_e != cudaSuccess) return ::dg::fail(DG_E_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), \
+                                             __FILE__, __LINE__);                                          \
+  } while (0)
+#define DG_TRY(expr)            \
+  do {                          \
+    int _r = (expr);            \
+    if (_r != DG_OK) return _r; \
+  } while (0)
+#define DG_LAUNCH_CHECK()                                                                                   \
+  do {                                                                                                      \
+    ++::dg::g_launch_counter;                                                                               \
+    cudaError_t _e = cudaGetLastError();                                                                    \
+    if (_e != cudaSuccess) return ::dg::fail(DG_E_CUDA, "kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e), \
+                                             __FILE__, __LINE__);                                           \
+  } while (0)
+
+// ------------------------------------------------------------------ tensor maps
+inline PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess ||
+        qres != cudaDriverEntryPointSuccess)
+      return nullptr;
+    fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
+  }
+  return fn;
+}
+
+// rank-4 fp16 map, 128-byte swizzle, zero OOB fill.  dims/box innermost first; strides (bytes) for dims 1..3.
+inline int make_map_4d(CUtensorMap* m, const void* ptr, const uint64_t dims[4], const uint64_t strides[3],
+                       const uint32_t box[4], bool weights = false) {
+  auto fn = get_encode_fn();
+  if (!fn) return fail(DG_E_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
+  cuuint64_t gd[4] = {dims[0], dims[1], dims[2], dims[3]};
+  cuuint64_t gs[3] = {strides[0], strides[1], strides[2]};
+  cuuint32_t bx[4] = {box[0], box[1], box[2], box[3]};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(ptr), gd, gs, bx, es,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  weights ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fail(DG_E_CUDA,
+                "cuTensorMapEncodeTiled(4d) failed: %d ptr=%p dims={%llu,%llu,%llu,%llu} strides={%llu,%llu,%llu} "
+                "box={%u,%u,%u,%u}",
+                (int)r, ptr, (unsigned long long)dims[0], (unsigned long long)dims[1], (unsigned long long)dims[2],
+                (unsigned long long)dims[3], (unsigned long long)strides[0], (unsigned long long)strides[1],
+                (unsigned long long)strides[2], box[0], box[1], box[2], box[3]);
+  return DG_OK;
+}
+inline int make_map_2d(CUtensorMap* m, const void* ptr, uint64_t inner, uint64_t outer, uint64_t stride_bytes,
+                       uint32_t box_inner, uint32_t box_outer, bool weights = true) {
+  auto fn = get_encode_fn();
+  if (!fn) return fail(DG_E_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
+  cuuint64_t gd[2] = {inner, outer};
+  cuuint64_t gs[1] = {stride_bytes};
+  cuuint32_t bx[2] = {box_inner, box_outer};
+  cuuint32_t es[2] = {1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(ptr), gd, gs, bx, es,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  weights ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fail(DG_E_CUDA, "cuTensorMapEncodeTiled(2d) failed: %d ptr=%p dims={%llu,%llu} stride=%llu box={%u,%u}",
+                (int)r, ptr, (unsigned long long)inner, (unsigned long long)outer, (unsigned long long)stride_bytes,
+                box_inner, box_outer);
+  return DG_OK;
+}
+
+// ------------------------------------------------------------------ GEMM / conv launcher
+constexpr int kGemmBlockN = 160;  // divides every channel count of SD-1.x/2.x (320, 640, 1280, ... 10240)
+constexpr int kGemmStages = 6;
+
+struct GemmArgs {
+  const __half* a0 = nullptr; int c0 = 0;  // source 0: NHWC [B,H,W,c0]
+  const __half* a1 = nullptr; int c1 = 0;  // optional source 1 (channel concat)
+  int B = 1, H = 1, W = 1;                 // plain GEMM: B = H = 1, W = M
+  int taps = 1;                            // 1 (Linear / 1x1) or 9 (3x3, stride 1, pad 1)
+  const __half* w = nullptr;               // packed [n_w, taps*(c0+c1)]
+  int n_w = 0;                             // rows of w
+  int n_out = 0;                           // output columns
+  const __half* bias = nullptr;
+  const __half* rowvec = nullptr; int ld_rowvec = 0;
+  const __half* residual = nullptr; int ld_res = 0;
+  int geglu = 0;
+  __half* out = nullptr; int ldo = 0;
+};
+
+inline int largest_pow2_divisor(int x, int cap) {
+  int p = 1;
+  while (p * 2 <= cap && x % (p * 2) == 0) p *= 2;
+  return p;
+}
+
+inline int launch_gemm(cudaStream_t stream, int num_sms, const GemmArgs& a) {
+  using S = GemmSmem<kGemmBlockN, kGemmStages>;
+  if (a.c0 % 64 || a.c1 % 64 || a.c0 <= 0) return fail(DG_E_SHAPE, "gemm: channel counts must be multiples of 64 (%d,%d)", a.c0, a.c1);
+  if (a.taps != 1 && a.taps != 9) return fail(DG_E_ARG, "gemm: taps must be 1 or 9");
+  if ((reinterpret_cast<uintptr_t>(a.a0) | reinterpret_cast<uintptr_t>(a.w) | reinterpret_cast<uintptr_t>(a.out)) & 15)
+    return fail(DG_E_ARG, "gemm: pointers must be 16-byte aligned");
+  GemmParams p{};
+  int W = a.W, H = a.H, B = a.B;
+  if (a.taps == 1) { W = a.B * a.H * a.W; H = 1; B = 1; }
+  p.W = W; p.H = H; p.B = B;
+  p.bw = largest_pow2_divisor(W, 128);
+  if (a.taps == 1) p.bw = 128;
+  p.bh = (a.taps == 1) ? 1 : largest_pow2_divisor(H, 128 / p.bw);
+  p.bn = 128 / (p.bw * p.bh);
+  p.tiles_x = (W + p.bw - 1) / p.bw;
+  p.tiles_y = (H + p.bh - 1) / p.bh;
+  p.tiles_b = (B + p.bn - 1) / p.bn;
+  p.n_gemm = a.n_w;
+  p.tiles_n = (a.n_w + kGemmBlockN - 1) / kGemmBlockN;
+  p.n_out = a.n_out;
+  p.ldo = a.ldo;
+  p.taps = a.taps;
+  p.kb0 = a.c0 / 64; p.kb1 = a.c1 / 64;
+  p.bias = a.bias; p.rowvec = a.rowvec; p.ld_rowvec = a.ld_rowvec;
+  p.residual = a.residual; p.ld_res = a.ld_res;
+  p.geglu = a.geglu; p.out = a.out;
+  if (a.geglu && !a.bias) return fail(DG_E_ARG, "gemm: geglu epilogue needs a packed bias");
+
+  CUtensorMap mA0, mA1, mW;
+  {
+    uint64_t dims[4] = {(uint64_t)a.c0, (uint64_t)W, (uint64_t)H, (uint64_t)B};
+    uint64_t st[3] = {(uint64_t)a.c0 * 2, (uint64_t)W * a.c0 * 2, (uint64_t)H * W * a.c0 * 2};
+    uint32_t box[4] = {64, (uint32_t)p.bw, (uint32_t)p.bh, (uint32_t)p.bn};
+    DG_TRY(make_map_4d(&mA0, a.a0, dims, st, box));
+    if (a.c1 > 0) {
+      uint64_t d1[4] = {(uint64_t)a.c1, (uint64_t)W, (uint64_t)H, (uint64_t)B};
+      uint64_t s1[3] = {(uint64_t)a.c1 * 2, (uint64_t)W * a.c1 * 2, (uint64_t)H * W * a.c1 * 2};
+      DG_TRY(make_map_4d(&mA1, a.a1, d1, s1, box));
+    } else {
+      mA1 = mA0;
+    }
+    const uint64_t ktot = (uint64_t)a.taps * (a.c0 + a.c1);
+    DG_TRY(make_map_2d(&mW, a.w, ktot, (uint64_t)a.n_w, ktot * 2, 64, kGemmBlockN));
+  }
+  const int total_tiles = p.tiles_x * p.tiles_y * p.tiles_b * p.tiles_n;
+  const int grid = total_tiles < num_sms ? total_tiles : num_sms;
+  auto kern = gemm_tc_kernel<kGemmBlockN, kGemmStages>;
+  kern<<<grid, 256, S::kTotal, stream>>>(mA0, mA1, mW, p);
+  DG_LAUNCH_CHECK();
+  return DG_OK;
+}
+
+// ------------------------------------------------------------------ attention launcher
+template <int kD, int kKV, int kStages>
+inline int launch_attn_t(cudaStream_t stream, const __half* q, int ldq, const __half* k, int ldk, const __half* v,
+                         int ldv, __half* out, int B, int heads, int Sq, int Sk) {
+  using C = AttnCfg<kD, kKV, kStages>;
+  CUtensorMap mQ, mK, mV;
+  auto mk = [&](CUtensorMap* m, const __half* ptr, int ld, int S, int rows) -> int {
+    uint64_t dims[4] = {(uint64_t)kD, (uint64_t)heads, (uint64_t)S, (uint64_t)B};
+    uint64_t st[3] = {(uint64_t)kD * 2, (uint64_t)ld * 2, (uint64_t)S * ld * 2};
+    uint32_t box[4] = {64, 1, (uint32_t)rows, 1};
+    return make_map_4d(m, ptr, dims, st, box);
+  };
+  DG_TRY(mk(&mQ, q, ldq, Sq, 128));
+  DG_TRY(mk(&mK, k, ldk, Sk, kKV));
+  DG_TRY(mk(&mV, v, ldv, Sk, kKV));
+  AttnParams p{};
+  p.Sq = Sq; p.Sk = Sk; p.heads = heads; p.ldo = heads * kD; p.out = out;
+  p.scale_log2 = (1.0f / sqrtf((float)kD)) * 1.4426950408889634f;
+  auto kern = attn_tc_kernel<kD, kKV, kStages>;
+  dim3 grid((Sq + 255) / 256, heads, B);
+  kern<<<grid, 384, C::kSmem, stream>>>(mQ, mK, mV, p);
+  DG_LAUNCH_CHECK();
+  return DG_OK;
+}
+
+inline int launch_attention(cudaStream_t stream, const __half* q, int ldq, const __half* k, int ldk, const __half* v,
+                            int ldv, __half* out, int B, int heads, int Sq, int Sk, int d) {
+  if ((ldq | ldk | ldv) % 8) return fail(DG_E_SHAPE, "attention: row strides must be multiples of 8 elements");
+  switch (d) {
+    case 32: return launch_attn_t<32, 128, 4>(stream, q, ldq, k, ldk, v, ldv, out, B, heads, Sq, Sk);
+    case 40: return launch_attn_t<40, 128, 4>(stream, q, ldq, k, ldk, v, ldv, out, B, heads, Sq, Sk);
+    case 64: return launch_attn_t<64, 128, 3>(stream, q, ldq, k, ldk, v, ldv, out, B, heads, Sq, Sk);
+    case 80: return launch_attn_t<80, 128, 2>(stream, q, ldq, k, ldk, v, ldv, out, B, heads, Sq, Sk);
+    case 160: return launch_attn_t<160, 64, 2>(stream, q, ldq, k, ldk, v, ldv, out, B, heads, Sq, Sk);
+    default: return fail(DG_E_UNSUPPORTED, "attention: head dim %d not built (32/40/64/80/160)", d);
+  }
+}
+
+// Opt every tcgen05 kernel into its dynamic shared-memory size once per device (never during graph capture).
+template <int kD, int kKV, int kStages>
+inline int init_attn_attr() {
+  DG_CUDA(cudaFuncSetAttribute(attn_tc_kernel<kD, kKV, kStages>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               AttnCfg<kD, kKV, kStages>::kSmem));
+  return DG_OK;
+}
+inline int init_kernel_attributes() {
+  DG_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<kGemmBlockN, kGemmStages>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               GemmSmem<kGemmBlockN, kGemmStages>::kTotal));
+  DG_TRY((init_attn_attr<32, 128, 4>()));
+  DG_TRY((init_attn_attr<40, 128, 4>()));
+  DG_TRY((init_attn_attr<64, 128, 3>()));
+  DG_TRY((init_attn_attr<80, 128, 2>()));
+  DG_TRY((init_attn_attr<160, 64, 2>()));
+  return DG_OK;
+}
+
+// ------------------------------------------------------------------ elementwise launchers
+inline int grid_for(size_t work_items, int block, int num_sms, int waves = 8) {
+  size_t g = (work_items + block - 1) / block;
+  size_t cap = (size_t)num_sms * waves;
+  return (int)(g < cap ? (g ? g : 1) : cap);
+}
+
+inline int launch_groupnorm(cudaStream_t s, int num_sms, const __half* x0, int C0, const __half* x1, int C1,
+                            const __half* gamma, const __half* beta, __half* out, float* stats, int B, int HW,
+                            int groups, float eps, int silu) {
+  const int C = C0 + C1;
+  if (C % groups || C0 % 8 || C1 % 8) return fail(DG_E_SHAPE, "groupnorm: C=%d+%d groups=%d", C0, C1, groups);
+  DG_CUDA(cudaMemsetAsync(stats, 0, sizeof(float) * 2 * groups * B, s));
+  int ppb = 64;
+  while (ppb > 8 && (size_t)B * ((HW + ppb - 1) / ppb) < (size_t)2 * num_sms) ppb /= 2;
+  dim3 grid((HW + ppb - 1) / ppb, B);
+  gn_stats_kernel<<<grid, 256, sizeof(float) * 2 * groups, s>>>(x0, C0, x1, C1, HW, groups, ppb, stats);
+  DG_LAUNCH_CHECK();
+  const size_t items = (size_t)B * HW * (C / 8);
+  gn_apply_kernel<<<grid_for(items, 256, num_sms), 256, 0, s>>>(x0, C0, x1, C1, HW, B, groups, eps, stats, gamma, beta,
+                                                               silu, out);
+  DG_LAUNCH_CHECK();
+  return DG_OK;
+}
+
+inline int launch_layernorm(cudaStream_t s, const __half* x, const __half* gamma, const __half* beta, __half* out,
+                            int rows, int C, float eps) {
+  if (C % 8 || C > 5 * 256) return fail(DG_E_SHAPE, "layernorm: C=%d unsupported", C);
+  const int warps = 8;
+  layernorm_kernel<5><<<(rows + warps - 1) / warps, warps * 32, 0, s>>>(x, gamma, beta, out, rows, C, eps);
+  DG_LAUNCH_CHECK();
+  return DG_OK;
+}
+
+inline int launch_gemv(cudaStream_t s, const __half* x, int ldx, const __half* W, const __half* bias, __half* out,
+                       int ldo, int B, int N, int K, int silu_in, int silu_out) {
+  if (B > 8 || K % 8) return fail(DG_E_SHAPE, "gemv: B=%d K=%d unsupported", B, K);
+  const int warps = 8;
+  const size_t smem = sizeof(float) * B * K;
+  gemv_small_batch_kernel<<<(N + warps - 1) / warps, warps * 32, smem, s>>>(x, ldx, W, bias, out, ldo, B, N, K, silu_in,
+                                                                           silu_out);
+  DG_LAUNCH_CHECK();
+  return DG_OK;
+}
+
+}  // namespace dg

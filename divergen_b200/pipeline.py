@@ -1,0 +1,120 @@
+"""`StableDiffusionPipeline` surface: `pipe(prompt_embeds=, negative_prompt_embeds=, generator=, output_type=,
+num_images_per_prompt=, num_inference_steps=, guidance_scale=).images` as called by the reference driver
+(DiverGen/generation/txt2img_diffusers_stages_from_txt.py:242,255-259), semantics per SURVEY.md 3.2.
+
+In scope: latent preparation, the 50-step UNet + CFG + DDIM loop (one C-ABI call, CUDA-graph replayed).
+Out of scope this round ("next" rows f1/f2): VAE decode and the CLIP text encoder -- `output_type='latent'` is the
+native output; other output types need a `vae_decode` callable supplied by the caller and otherwise raise.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Callable, List, Optional, Union
+
+import torch
+
+from .scheduler import DDIMScheduler
+from .unet import UNet2DConditionModel
+
+
+@dataclass
+class StableDiffusionPipelineOutput:
+    images: Union[torch.Tensor, list]
+    nsfw_content_detected: Optional[List[bool]] = None
+
+
+def pt_to_pil(images: torch.Tensor):
+    """diffusers.utils.pt_to_pil: [B,3,H,W] in [-1,1] -> list of PIL images (txt2img_...py:267)."""
+    from PIL import Image
+    images = (images / 2 + 0.5).clamp(0, 1)
+    arr = (images.cpu().permute(0, 2, 3, 1).float().numpy() * 255).round().astype("uint8")
+    return [Image.fromarray(a) for a in arr]
+
+
+class StableDiffusionPipeline:
+    def __init__(self, unet: UNet2DConditionModel, scheduler: DDIMScheduler,
+                 text_encoder: Optional[Callable] = None, vae_decode: Optional[Callable] = None,
+                 vae_scale_factor: int = 8):
+        self.unet, self.scheduler = unet, scheduler
+        self.text_encoder, self.vae_decode = text_encoder, vae_decode
+        self.vae_scale_factor = vae_scale_factor
+        self.device = unet.device
+        self.feature_extractor = None
+        self.safety_checker = None
+
+    def to(self, device):
+        return self
+
+    def enable_model_cpu_offload(self, gpu_id=None):
+        """Accepted for call compatibility (txt2img_...py:143); weights stay resident in HBM (1.7 GB of 180 GB)."""
+
+    def enable_xformers_memory_efficient_attention(self):
+        """Accepted for call compatibility (txt2img_...py:186); attention is always the fused tcgen05 kernel."""
+
+    def encode_prompt(self, prompt, device=None, num_images_per_prompt: int = 1, do_classifier_free_guidance: bool = True,
+                      negative_prompt=None):
+        if self.text_encoder is None:
+            raise ValueError("no text_encoder attached: pass prompt_embeds/negative_prompt_embeds (CLIP is row f2, next)")
+        pos = self.text_encoder(prompt)
+        neg = self.text_encoder(negative_prompt if negative_prompt is not None else "")
+        return pos, neg
+
+    @torch.no_grad()
+    def __call__(self, prompt=None, height: Optional[int] = None, width: Optional[int] = None,
+                 num_inference_steps: int = 50, guidance_scale: float = 7.5, negative_prompt=None,
+                 num_images_per_prompt: int = 1, eta: float = 0.0, generator=None, latents: Optional[torch.Tensor] = None,
+                 prompt_embeds: Optional[torch.Tensor] = None, negative_prompt_embeds: Optional[torch.Tensor] = None,
+                 output_type: str = "pil", return_dict: bool = True, cross_attention_kwargs=None):
+        if eta != 0.0:
+            raise ValueError("only eta=0 (deterministic DDIM) is supported")
+        if cross_attention_kwargs is not None:
+            raise ValueError("cross_attention_kwargs is not supported")
+        cfg = self.unet.config
+        height = height or cfg.sample_size * self.vae_scale_factor
+        width = width or cfg.sample_size * self.vae_scale_factor
+        if height % 64 or width % 64:
+            raise ValueError("height and width must be multiples of 64")
+        do_cfg = guidance_scale > 1.0
+        if prompt_embeds is None:
+            if prompt is None:
+                raise ValueError("provide `prompt` or `prompt_embeds`")
+            prompt_embeds, negative_prompt_embeds = self.encode_prompt(prompt, negative_prompt=negative_prompt)
+        if do_cfg and negative_prompt_embeds is None:
+            raise ValueError("classifier-free guidance needs negative_prompt_embeds")
+        dev = self.device
+        pe = prompt_embeds.to(dev, torch.float16)
+        bsz = pe.shape[0] * num_images_per_prompt
+        pe = pe.repeat_interleave(num_images_per_prompt, dim=0)
+        if do_cfg:
+            ne = negative_prompt_embeds.to(dev, torch.float16).repeat_interleave(num_images_per_prompt, dim=0)
+            ehs = torch.cat([ne, pe], dim=0).contiguous()
+        else:
+            ehs = pe.contiguous()
+        h, w = height // self.vae_scale_factor, width // self.vae_scale_factor
+        shape = (bsz, cfg.in_channels, h, w)
+        if latents is None:
+            # diffusers randn_tensor: a CPU generator draws on the CPU and moves (the reference passes
+            # torch.manual_seed(seed + rank), a CPU generator: txt2img_...py:200)
+            gdev = generator.device if generator is not None else torch.device("cpu")
+            latents = torch.randn(shape, generator=generator, device=gdev, dtype=torch.float16).to(dev)
+        else:
+            latents = latents.to(dev, torch.float16)
+        latents = (latents * self.scheduler.init_noise_sigma).contiguous().clone()
+        self.scheduler.set_timesteps(num_inference_steps)
+        ts = [int(t) for t in self.scheduler.timesteps]
+        al = [self.scheduler.alphas_for(t) for t in ts]
+        self.unet.denoise_loop(latents, ehs, ts, [a for a, _ in al], [p for _, p in al], guidance_scale,
+                               self.scheduler.config.prediction_type)
+        if output_type == "latent":
+            images = latents
+        else:
+            if self.vae_decode is None:
+                raise ValueError("output_type != 'latent' needs a vae_decode callable (VAE decode is row f1, next)")
+            images = self.vae_decode(latents / 0.18215)
+            if output_type == "pt":
+                images = (images / 2 + 0.5).clamp(0, 1)
+            elif output_type == "pil":
+                images = pt_to_pil(images)
+            else:
+                raise ValueError(output_type)
+        return StableDiffusionPipelineOutput(images=images) if return_dict else (images, None)

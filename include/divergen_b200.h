@@ -1,0 +1,133 @@
+/* divergen_b200 -- C ABI of the B200-native Stable-Diffusion denoising hot path.
+ *
+ * The reference (aim-uofa/DiverGen) has no FFI of its own: its boundary for this path is the diffusers Python class
+ * surface used at DiverGen/generation/txt2img_diffusers_stages_from_txt.py:139-143, :242, :255-259.
+ * This header is the C ABI that sits directly beneath that surface; each entry point names the diffusers call it
+ * replaces.  Plain C: raw device pointers, sizes, a cudaStream_t passed as void*.  No torch types.
+ *
+ * Conventions
+ *   - every function returns 0 on success or a negative DG_E_* code; dg_last_error() gives the message
+ *     (thread-local).  No C++ exception crosses the ABI.
+ *   - all tensors are fp16, contiguous, 16-byte aligned, owned by the caller; NCHW at this surface
+ *     (kernel-internal NHWC is private).  The library owns packed weights, workspaces, TMA descriptors, CUDA graphs.
+ *   - work is enqueued asynchronously on the supplied stream.  A handle is not thread-safe (one per process per GPU,
+ *     the reference's process model: txt2img_diffusers_stages_from_txt.py:14-23,122).
+ *   - creating a context on a device that is not sm_100 fails with DG_E_ARCH: there is no fallback path.
+ */
+#ifndef DIVERGEN_B200_H
+#define DIVERGEN_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DG_OK 0
+#define DG_E_ARG (-1)
+#define DG_E_SHAPE (-2)
+#define DG_E_UNSUPPORTED (-3)
+#define DG_E_CUDA (-4)
+#define DG_E_NOMEM (-5)
+#define DG_E_ARCH (-6)
+#define DG_E_STATE (-7)
+
+typedef struct dg_ctx dg_ctx;
+typedef struct dg_unet dg_unet;
+
+/* Mirrors the fields of diffusers' unet/config.json that SD-1.x / SD-2.x use. */
+typedef struct dg_unet_config {
+  int32_t in_channels;            /* 4 */
+  int32_t out_channels;           /* 4 */
+  int32_t sample_size;            /* 64 (SD-1.5) / 96 (SD-2.1-768) */
+  int32_t block_out_channels[4];  /* 320, 640, 1280, 1280 */
+  int32_t layers_per_block;       /* 2 */
+  int32_t num_heads[4];           /* diffusers `attention_head_dim` (a head COUNT): 8,8,8,8 / 5,10,20,20 */
+  int32_t cross_attention_dim;    /* 768 / 1024 */
+  int32_t norm_num_groups;        /* 32 */
+  float norm_eps;                 /* 1e-5 */
+  int32_t use_linear_projection;  /* 0 / 1 : proj_in/proj_out are Conv1x1 or Linear (same arithmetic) */
+  int32_t upcast_attention;       /* softmax is always fp32 here; accepted for config parity */
+  int32_t down_has_attn[4];       /* 1,1,1,0 */
+  int32_t flip_sin_to_cos;        /* 1 */
+  float freq_shift;               /* 0 */
+} dg_unet_config;
+
+int32_t dg_version(void);
+const char* dg_last_error(void);
+
+/* ---- context --------------------------------------------------------------------------------------------------- */
+int32_t dg_ctx_create(int32_t device_ordinal, dg_ctx** out);
+void dg_ctx_destroy(dg_ctx* ctx);
+
+/* ---- UNet2DConditionModel ------------------------------------------------------------------------------------------
+ * dg_unet_create      <- UNet2DConditionModel.__init__ / from_pretrained (txt2img_...py:139)
+ * dg_unet_set_weight  <- load_state_dict: one call per diffusers state-dict key (686 for SD-1.5/2.1).  `src` is a device
+ *                        pointer to the fp16 tensor in PyTorch layout; it is repacked into kernel layout and may be freed
+ *                        by the caller afterwards.
+ * dg_unet_prepare     <- .to(device): allocates the activation workspace for up to max_batch samples of latent h x w.
+ * dg_unet_forward     <- UNet2DConditionModel.forward(sample, timestep, encoder_hidden_states).sample
+ *                        sample/out: [batch, C, h, w]; ehs: [batch, tokens, cross_attention_dim];
+ *                        timesteps: host array of n_timesteps values (1 = broadcast, or one per sample).
+ */
+int32_t dg_unet_create(dg_ctx* ctx, const dg_unet_config* cfg, dg_unet** out);
+void dg_unet_destroy(dg_unet* unet);
+int32_t dg_unet_num_weights(dg_unet* unet);
+const char* dg_unet_weight_name(dg_unet* unet, int32_t index);
+int32_t dg_unet_weight_shape(dg_unet* unet, int32_t index, int64_t* shape4, int32_t* ndim);
+int32_t dg_unet_set_weight(dg_unet* unet, const char* key, const void* src, int32_t ndim, const int64_t* shape);
+int32_t dg_unet_missing_weights(dg_unet* unet); /* number of keys not yet set */
+int32_t dg_unet_prepare(dg_unet* unet, int32_t max_batch, int32_t h, int32_t w, int32_t ctx_tokens);
+int32_t dg_unet_forward(dg_unet* unet, const void* sample, const float* timesteps_host, int32_t n_timesteps,
+                        const void* ehs, int32_t ctx_tokens, void* out, int32_t batch, int32_t h, int32_t w,
+                        void* stream);
+/* 1 (default): the forward is captured into a CUDA graph per (batch, pointers) and replayed; 0: eager launches. */
+int32_t dg_unet_set_graphs(dg_unet* unet, int32_t enabled);
+/* kernels launched by the last dg_unet_forward / dg_denoise_loop call (graph replays count their kernel nodes). */
+int64_t dg_unet_last_launch_count(dg_unet* unet);
+
+/* ---- StableDiffusionPipeline.__call__ steps 4-7 -----------------------------------------------------
+ * dg_cfg_ddim_step <- `u + g*(c-u)` + DDIMScheduler.step(...).prev_sample (eta = 0), fused, in place on `latents`.
+ *    noise_pred: [2*n_images (cfg) or n_images, elems_per_image]; prediction_type 0 = epsilon, 1 = v_prediction.
+ * dg_denoise_loop  <- the whole loop: for t in timesteps: unet(cat([x,x]), t, cat([neg,pos])) -> CFG -> step.
+ *    latents [n_images,4,h,w] are updated in place; ehs is [2*n_images, tokens, D] (uncond rows first) when
+ *    guidance_scale > 1 else [n_images, tokens, D].  alphas: host arrays a_t[i], a_prev[i] per step.
+ */
+int32_t dg_cfg_ddim_step(dg_ctx* ctx, const void* noise_pred, void* latents, int32_t n_images, int64_t elems_per_image,
+                         float alpha_t, float alpha_prev, float guidance_scale, int32_t prediction_type, void* stream);
+int32_t dg_denoise_loop(dg_unet* unet, void* latents, const void* ehs, int32_t ctx_tokens, int32_t n_images, int32_t h,
+                        int32_t w, const float* timesteps_host, const float* alpha_t_host, const float* alpha_prev_host,
+                        int32_t n_steps, float guidance_scale, int32_t prediction_type, void* stream);
+
+/* ---- single operators (exported for the parity tests; the same launchers the UNet uses) ---------------------------
+ * dg_op_gemm: out[M, n_out] = epi(A[M, K] * W[n_w, K]^T)      <- torch.nn.Linear / Conv2d 1x1
+ *    bias [n_w] / residual [M, n_out] optional; geglu: W is GEGLU-packed (see dg_op_pack_geglu), n_out = inner dim.
+ * dg_op_conv3x3: NHWC x[B,H,W,C0] (++ x1[B,H,W,C1]) * Wp[N, 9*(C0+C1)] <- Conv2d 3x3 stride 1 pad 1
+ *    rowvec [B, ld_rowvec] optional per-sample additive vector (time embedding).
+ * dg_op_attention: out[B,Sq,heads*d] = softmax(Q K^T / sqrt(d)) V  <- diffusers Attention core
+ *    q/k/v are base pointers of [B, S, ld] fp16 matrices (head h at columns [h*d, (h+1)*d)).
+ */
+int32_t dg_op_gemm(dg_ctx* ctx, const void* A, const void* W, const void* bias, const void* residual, void* out,
+                   int32_t M, int32_t K, int32_t n_w, int32_t n_out, int32_t geglu, void* stream);
+int32_t dg_op_pack_geglu(dg_ctx* ctx, const void* w, const void* b, void* w_out, void* b_out, int32_t inner, int32_t K,
+                         void* stream);
+int32_t dg_op_geglu_packed_rows(int32_t inner);
+int32_t dg_op_pack_conv3x3(dg_ctx* ctx, const void* w_oihw, void* w_out, int32_t O, int32_t I, void* stream);
+int32_t dg_op_conv3x3(dg_ctx* ctx, const void* x0, int32_t C0, const void* x1, int32_t C1, const void* Wp,
+                      const void* bias, const void* rowvec, int32_t ld_rowvec, const void* residual, void* out,
+                      int32_t B, int32_t H, int32_t Wd, int32_t N, void* stream);
+int32_t dg_op_attention(dg_ctx* ctx, const void* q, int32_t ldq, const void* k, int32_t ldk, const void* v, int32_t ldv,
+                        void* out, int32_t B, int32_t heads, int32_t Sq, int32_t Sk, int32_t d, void* stream);
+int32_t dg_op_groupnorm(dg_ctx* ctx, const void* x0, int32_t C0, const void* x1, int32_t C1, const void* gamma,
+                        const void* beta, void* out, int32_t B, int32_t HW, int32_t groups, float eps, int32_t silu,
+                        void* stream);
+int32_t dg_op_layernorm(dg_ctx* ctx, const void* x, const void* gamma, const void* beta, void* out, int32_t rows,
+                        int32_t C, float eps, void* stream);
+/* Timesteps(dim) sinusoid -> Linear -> SiLU -> Linear  <- diffusers Timesteps + TimestepEmbedding */
+int32_t dg_op_time_embedding(dg_ctx* ctx, const float* timesteps_host, int32_t B, int32_t dim, int32_t temb_dim,
+                             const void* w1, const void* b1, const void* w2, const void* b2, void* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DIVERGEN_B200_H */

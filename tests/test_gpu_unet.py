@@ -1,0 +1,158 @@
+"""GPU parity of the whole UNet forward and of the denoise loop, through the diffusers-shaped surface, against the
+oracle on identical seeded weights / latents / timesteps / embeddings.
+
+Parity statement ("parity unpinned": upstream diffusers is unavailable, the oracle is the checker):
+  E_new   = || kernel_fp16 - oracle_fp32 ||,  E_torch = || oracle run in fp16 eager on the GPU - oracle_fp32 ||
+  require max|err| <= 2e-2 * max|ref| + 1e-3, cosine >= 0.999, and rms(E_new) <= 2 * rms(E_torch) + 1e-4.
+"""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _need_gpu():
+    if not torch.cuda.is_available():
+        pytest.skip("no GPU")
+
+
+def _models(cfg, seed=0):
+    from divergen_b200 import UNet2DConditionModel
+    from oracle.unet_oracle import UNet2DConditionOracle, seeded_state_dict
+    sd = seeded_state_dict(cfg, seed)
+    # fp16-round the weights once so oracle and kernel see the same values
+    sd = {k: v.half().float() for k, v in sd.items()}
+    oracle = UNet2DConditionOracle(cfg).eval()
+    oracle.load_state_dict(sd)
+    unet = UNet2DConditionModel(device=DEV, in_channels=cfg.in_channels, out_channels=cfg.out_channels,
+                                sample_size=cfg.sample_size, block_out_channels=cfg.block_out_channels,
+                                layers_per_block=cfg.layers_per_block, attention_head_dim=cfg.attention_head_dim,
+                                cross_attention_dim=cfg.cross_attention_dim, use_linear_projection=cfg.use_linear_projection,
+                                upcast_attention=cfg.upcast_attention)
+    res = unet.load_state_dict(sd)
+    assert not res.missing_keys and not res.unexpected_keys
+    return oracle, unet
+
+
+def _check(got, ref32, ref16=None, name="unet"):
+    got32 = got.float().cpu()
+    err = (got32 - ref32).abs()
+    cos = torch.nn.functional.cosine_similarity(got32.flatten(), ref32.flatten(), dim=0).item()
+    lim = 2e-2 * ref32.abs().max().item() + 1e-3
+    msg = f"{name}: max err {err.max().item():.4g} (limit {lim:.4g}), cosine {cos:.6f}, ref absmax {ref32.abs().max().item():.4g}"
+    if ref16 is not None:
+        e_new = err.pow(2).mean().sqrt().item()
+        e_torch = (ref16.float().cpu() - ref32).pow(2).mean().sqrt().item()
+        msg += f", rms E_new {e_new:.4g} vs E_torch {e_torch:.4g}"
+    print(msg)
+    assert torch.isfinite(got32).all(), msg
+    assert err.max().item() <= lim and cos >= 0.999, msg
+    if ref16 is not None:
+        assert e_new <= 2 * e_torch + 1e-4, msg
+
+
+@pytest.mark.parametrize("linear,B,hw,graphs", [(False, 2, 16, False), (True, 3, 16, True), (False, 2, 32, True)])
+def test_tiny_unet_forward(linear, B, hw, graphs):
+    _need_gpu()
+    from oracle.unet_oracle import UNetConfig
+    cfg = UNetConfig.tiny(cross_attention_dim=64, linear=linear)
+    oracle, unet = _models(cfg)
+    unet.set_graphs(graphs)
+    g = torch.Generator().manual_seed(42)
+    x = torch.randn(B, 4, hw, hw, generator=g)
+    ehs = torch.randn(B, 77, 64, generator=g)
+    with torch.no_grad():
+        ref32 = oracle(x.half().float(), 981, ehs.half().float()).sample
+        o16 = oracle.to(DEV).half()
+        ref16 = o16(x.to(DEV).half(), torch.tensor([981], device=DEV), ehs.to(DEV).half()).sample
+    for rep in range(2):  # second call replays the captured graph
+        got = unet(x.to(DEV).half(), 981, ehs.to(DEV).half()).sample
+        torch.cuda.synchronize()
+        _check(got, ref32, ref16, f"tiny unet linear={linear} B={B} rep={rep}")
+    assert unet.last_launch_count > 100
+
+
+def test_per_sample_timesteps():
+    _need_gpu()
+    from oracle.unet_oracle import UNetConfig
+    cfg = UNetConfig.tiny()
+    oracle, unet = _models(cfg, seed=3)
+    g = torch.Generator().manual_seed(7)
+    x, ehs = torch.randn(2, 4, 16, 16, generator=g), torch.randn(2, 77, 64, generator=g)
+    t = torch.tensor([981, 21])
+    with torch.no_grad():
+        ref32 = oracle(x.half().float(), t, ehs.half().float()).sample
+    got = unet(x.to(DEV).half(), t.to(DEV), ehs.to(DEV).half()).sample
+    _check(got, ref32, None, "per-sample timesteps")
+
+
+def test_unsupported_arguments_raise():
+    _need_gpu()
+    from oracle.unet_oracle import UNetConfig
+    _, unet = _models(UNetConfig.tiny(), seed=1)
+    x, ehs = torch.zeros(1, 4, 16, 16, device=DEV, dtype=torch.half), torch.zeros(1, 77, 64, device=DEV, dtype=torch.half)
+    with pytest.raises(ValueError):
+        unet(x, 1, ehs, class_labels=torch.zeros(1))
+    with pytest.raises(ValueError):
+        unet(x, 1, ehs, cross_attention_kwargs={"scale": 0.5})
+    with pytest.raises(ValueError):
+        unet(x[:, :3], 1, ehs)
+
+
+@pytest.mark.parametrize("pred", ["epsilon", "v_prediction"])
+def test_tiny_denoise_loop(pred):
+    """A 5-step CFG loop: device loop (dg_denoise_loop) vs the oracle loop, plus the same loop driven step by step
+    through the Python surface (UNet.forward + scheduler.step) -- the two product paths must agree closely."""
+    _need_gpu()
+    from divergen_b200 import DDIMScheduler, StableDiffusionPipeline
+    from oracle.ddim_oracle import DDIMOracle, denoise_loop
+    from oracle.unet_oracle import UNetConfig
+    cfg = UNetConfig.tiny()
+    oracle, unet = _models(cfg, seed=5)
+    g = torch.Generator().manual_seed(11)
+    lat = torch.randn(2, 4, 16, 16, generator=g).half()
+    pos, neg = torch.randn(2, 77, 64, generator=g).half(), torch.randn(2, 77, 64, generator=g).half()
+    ref = denoise_loop(oracle, DDIMOracle(prediction_type=pred), lat.float(), pos.float(), neg.float(),
+                       num_inference_steps=5, guidance_scale=7.5)
+    pipe = StableDiffusionPipeline(unet, DDIMScheduler(prediction_type=pred))
+    out = pipe(prompt_embeds=pos, negative_prompt_embeds=neg, latents=lat, num_inference_steps=5, guidance_scale=7.5,
+               height=128, width=128, output_type="latent").images
+    torch.cuda.synchronize()
+    got = out.float().cpu()
+    cos = torch.nn.functional.cosine_similarity(got.flatten(), ref.flatten(), dim=0).item()
+    err = (got - ref).abs().max().item()
+    print(f"loop {pred}: max err {err:.4g}, cosine {cos:.6f}, ref absmax {ref.abs().max().item():.4g}")
+    assert cos >= 0.998 and err <= 5e-2 * ref.abs().max().item() + 5e-3
+    # step-by-step through the class surface
+    sch = DDIMScheduler(prediction_type=pred)
+    sch.set_timesteps(5)
+    x = lat.to(DEV).clone()
+    ehs = torch.cat([neg, pos]).to(DEV)
+    for t in sch.timesteps:
+        n = unet(torch.cat([x, x]), t, ehs).sample
+        u, c = n.chunk(2)
+        x = sch.step((u.float() + 7.5 * (c.float() - u.float())).half(), t, x).prev_sample
+    d = (x.float().cpu() - got).abs().max().item()
+    print(f"loop {pred}: device loop vs step-by-step max diff {d:.4g}")
+    assert d <= 3e-2 * ref.abs().max().item() + 5e-3
+
+
+def test_sd15_forward_full_width():
+    """SD-1.5 at full width, batch 2 (one CFG pair) at 64x64 latent -- BASELINE config 2's per-sample shape.
+    The fp32 oracle runs on the GPU here (CPU takes minutes); it is the checker, never the thing measured."""
+    _need_gpu()
+    from oracle.unet_oracle import UNetConfig
+    cfg = UNetConfig.sd15()
+    oracle, unet = _models(cfg, seed=0)
+    g = torch.Generator().manual_seed(42)
+    x, ehs = torch.randn(2, 4, 64, 64, generator=g).half(), torch.randn(2, 77, 768, generator=g).half()
+    with torch.no_grad():
+        o = oracle.to(DEV)
+        ref32 = o(x.to(DEV).float(), torch.tensor([981], device=DEV), ehs.to(DEV).float()).sample.cpu()
+        o = o.half()
+        ref16 = o(x.to(DEV), torch.tensor([981], device=DEV), ehs.to(DEV)).sample.cpu()
+        del o
+    got = unet(x.to(DEV), 981, ehs.to(DEV)).sample
+    torch.cuda.synchronize()
+    _check(got, ref32, ref16, "sd15 full width")
