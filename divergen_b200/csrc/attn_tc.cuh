@@ -187,19 +187,22 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
       const float m_tile = mx * p.scale_log2;
       if (j == 0) {
         m_run = m_tile;
-      } else if (m_tile > m_run + 8.0f) {
-        // lazy rescale: only when the max grew enough to threaten fp16/fp32 range of P / O
-        const float alpha = exp2f(m_run - m_tile);
-        m_run = m_tile;
-        l_run *= alpha;
+      } else {
+        // lazy rescale: only when the max grew enough to threaten the fp16 range of P.  tcgen05.ld/st are warp-wide
+        // (.sync.aligned), so the decision is made per warp and rows that do not need it scale by exactly 1.
+        const bool need = m_tile > m_run + 8.0f;
+        if (__any_sync(0xffffffffu, need)) {
+          const float alpha = need ? exp2f(m_run - m_tile) : 1.0f;
+          if (need) { m_run = m_tile; l_run *= alpha; }
 #pragma unroll
-        for (int c = 0; c < C::kDPad; c += 16) {
-          uint32_t o[16];
-          tmem_ld16(tO + c, o);
-          tmem_ld_wait();
+          for (int c = 0; c < C::kDPad; c += 16) {
+            uint32_t o[16];
+            tmem_ld16(tO + c, o);
+            tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-          tmem_st16(tO + c, o);
+            for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            tmem_st16(tO + c, o);
+          }
         }
       }
       // pass 2: P = exp2(S*c - m), packed fp16 over the front half of the S columns

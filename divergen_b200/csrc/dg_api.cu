@@ -113,6 +113,7 @@ struct dg_unet {
   int coef_cap = 0;
   // graphs
   bool use_graphs = true;
+  cudaStream_t cap_stream = nullptr;
   struct CachedGraph { GraphKey key; cudaGraphExec_t exec; long long launches; };
   std::vector<CachedGraph> graphs;
   long long last_launches = 0;
@@ -506,11 +507,15 @@ int forward_maybe_graph(dg_unet* u, cudaStream_t s, const __half* sample, const 
     }
   }
   // capture
+  // Capture on a private stream (the caller's stream may be the legacy default stream, which cannot capture); the
+  // instantiated graph is then launched into the caller's stream.
   cudaGraph_t graph = nullptr;
   const long long c0 = g_launch_counter;
-  DG_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
-  int r = run_forward(u, s, sample, ehs, tokens, out, B, h, w);
-  cudaError_t e = cudaStreamEndCapture(s, &graph);
+  if (!u->cap_stream) DG_CUDA(cudaStreamCreateWithFlags(&u->cap_stream, cudaStreamNonBlocking));
+  cudaStream_t cs = u->cap_stream;
+  DG_CUDA(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
+  int r = run_forward(u, cs, sample, ehs, tokens, out, B, h, w);
+  cudaError_t e = cudaStreamEndCapture(cs, &graph);
   if (r != DG_OK) { if (graph) cudaGraphDestroy(graph); return r; }
   if (e != cudaSuccess) return fail(DG_E_CUDA, "graph capture failed: %s", cudaGetErrorString(e));
   cudaGraphExec_t exec = nullptr;
@@ -586,6 +591,7 @@ int32_t dg_unet_create(dg_ctx* ctx, const dg_unet_config* cfg, dg_unet** out) {
 void dg_unet_destroy(dg_unet* u) {
   if (!u) return;
   for (auto& g : u->graphs) cudaGraphExecDestroy(g.exec);
+  if (u->cap_stream) cudaStreamDestroy(u->cap_stream);
   for (void* p : u->owned) cudaFree(p);
   cudaFree(u->arena.base); cudaFree(u->d_t); cudaFree(u->gn_stats); cudaFree(u->d_coef); cudaFree(u->d_step);
   cudaFree(u->loop_in); cudaFree(u->loop_out);
@@ -696,6 +702,41 @@ int32_t dg_unet_forward(dg_unet* u, const void* sample, const float* t_host, int
   DG_LAUNCH_CHECK();
   u->last_launches += 1;
   return forward_maybe_graph(u, s, (const __half*)sample, (const __half*)ehs, tokens, (__half*)out, batch, h, w);
+}
+
+int32_t dg_unet_profile_forward(dg_unet* u, const void* sample, const float* t_host, int32_t n_t, const void* ehs,
+                                int32_t tokens, void* out, int32_t batch, int32_t h, int32_t w, void* stream,
+                                double* ms_by_family, double* flops_by_family, double* bytes_by_family,
+                                int64_t* launches_by_family, double* total_ms) {
+  if (!u || !ms_by_family || !flops_by_family || !bytes_by_family || !launches_by_family || !total_ms) return fail(DG_E_ARG, "null argument");
+  const bool graphs = u->use_graphs;
+  u->use_graphs = false;
+  Profiler prof;
+  cudaStream_t s = (cudaStream_t)stream;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  cudaEventRecord(e0, s);
+  g_prof = &prof;
+  int r = dg_unet_forward(u, sample, t_host, n_t, ehs, tokens, out, batch, h, w, stream);
+  g_prof = nullptr;
+  u->use_graphs = graphs;
+  cudaEventRecord(e1, s);
+  cudaError_t e = cudaStreamSynchronize(s);
+  for (int i = 0; i < FAM_COUNT; ++i) { ms_by_family[i] = 0; flops_by_family[i] = 0; bytes_by_family[i] = 0; launches_by_family[i] = 0; }
+  float ms = 0.f;
+  if (e == cudaSuccess) { cudaEventElapsedTime(&ms, e0, e1); *total_ms = ms; }
+  for (auto& rec : prof.recs) {
+    if (e == cudaSuccess && rec.a && rec.b) {
+      cudaEventElapsedTime(&ms, rec.a, rec.b);
+      ms_by_family[rec.fam] += ms; flops_by_family[rec.fam] += rec.flops; bytes_by_family[rec.fam] += rec.bytes;
+      launches_by_family[rec.fam] += 1;
+    }
+    cudaEventDestroy(rec.a); cudaEventDestroy(rec.b);
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  if (r != DG_OK) return r;
+  if (e != cudaSuccess) return fail(DG_E_CUDA, "profile forward failed: %s", cudaGetErrorString(e));
+  return DG_OK;
 }
 
 int32_t dg_cfg_ddim_step(dg_ctx* ctx, const void* noise, void* latents, int32_t n_images, int64_t elems, float a_t,

@@ -11,6 +11,7 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <vector>
 
 #include "../../include/divergen_b200.h"
 #include "attn_tc.cuh"
@@ -50,6 +51,27 @@ inline int fail(int code, const char* fmt, ...) {
     if (_e != cudaSuccess) return ::dg::fail(DG_E_CUDA, "kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e), \
                                              __FILE__, __LINE__);                                           \
   } while (0)
+
+// ------------------------------------------------------------------ per-launch profiler (bench.py roofline numbers)
+// When active, every launcher below brackets its kernel with a CUDA-event pair on the launch stream and records the
+// algorithmic FLOPs / bytes of that launch.  Never active during graph capture or the timed bench region.
+enum Family { FAM_GEMM = 0, FAM_ATTN = 1, FAM_NORM = 2, FAM_OTHER = 3, FAM_COUNT = 4 };
+struct Profiler {
+  struct Rec { int fam; cudaEvent_t a, b; double flops, bytes; };
+  std::vector<Rec> recs;
+};
+inline thread_local Profiler* g_prof = nullptr;
+struct ProfScope {
+  cudaStream_t s; bool on;
+  ProfScope(int fam, cudaStream_t s_, double flops, double bytes) : s(s_), on(g_prof != nullptr) {
+    if (!on) return;
+    Profiler::Rec r{fam, nullptr, nullptr, flops, bytes};
+    cudaEventCreate(&r.a); cudaEventCreate(&r.b);
+    cudaEventRecord(r.a, s);
+    g_prof->recs.push_back(r);
+  }
+  ~ProfScope() { if (on) cudaEventRecord(g_prof->recs.back().b, s); }
+};
 
 // ------------------------------------------------------------------ tensor maps
 inline PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
@@ -178,6 +200,9 @@ inline int launch_gemm(cudaStream_t stream, int num_sms, const GemmArgs& a) {
   const int total_tiles = p.tiles_x * p.tiles_y * p.tiles_b * p.tiles_n;
   const int grid = total_tiles < num_sms ? total_tiles : num_sms;
   auto kern = gemm_tc_kernel<kGemmBlockN, kGemmStages>;
+  const double rows_ = (double)a.B * a.H * a.W, ktot_ = (double)a.taps * (a.c0 + a.c1);
+  ProfScope prof_(FAM_GEMM, stream, 2.0 * rows_ * ktot_ * (double)a.n_w,
+                  2.0 * (rows_ * (a.c0 + a.c1) + ktot_ * a.n_w + rows_ * a.n_out));
   kern<<<grid, 256, S::kTotal, stream>>>(mA0, mA1, mW, p);
   DG_LAUNCH_CHECK();
   return DG_OK;
@@ -203,6 +228,8 @@ inline int launch_attn_t(cudaStream_t stream, const __half* q, int ldq, const __
   p.scale_log2 = (1.0f / sqrtf((float)kD)) * 1.4426950408889634f;
   auto kern = attn_tc_kernel<kD, kKV, kStages>;
   dim3 grid((Sq + 255) / 256, heads, B);
+  ProfScope prof_(FAM_ATTN, stream, 4.0 * B * heads * (double)Sq * Sk * kD,
+                  2.0 * B * heads * kD * (2.0 * Sq + 2.0 * Sk));
   kern<<<grid, 384, C::kSmem, stream>>>(mQ, mK, mV, p);
   DG_LAUNCH_CHECK();
   return DG_OK;
@@ -251,6 +278,7 @@ inline int launch_groupnorm(cudaStream_t s, int num_sms, const __half* x0, int C
                             int groups, float eps, int silu) {
   const int C = C0 + C1;
   if (C % groups || C0 % 8 || C1 % 8) return fail(DG_E_SHAPE, "groupnorm: C=%d+%d groups=%d", C0, C1, groups);
+  ProfScope prof_(FAM_NORM, s, 0.0, 2.0 * 3.0 * B * HW * (double)C);
   DG_CUDA(cudaMemsetAsync(stats, 0, sizeof(float) * 2 * groups * B, s));
   int ppb = 64;
   while (ppb > 8 && (size_t)B * ((HW + ppb - 1) / ppb) < (size_t)2 * num_sms) ppb /= 2;
@@ -268,6 +296,7 @@ inline int launch_layernorm(cudaStream_t s, const __half* x, const __half* gamma
                             int rows, int C, float eps) {
   if (C % 8 || C > 5 * 256) return fail(DG_E_SHAPE, "layernorm: C=%d unsupported", C);
   const int warps = 8;
+  ProfScope prof_(FAM_NORM, s, 0.0, 2.0 * 2.0 * rows * (double)C);
   layernorm_kernel<5><<<(rows + warps - 1) / warps, warps * 32, 0, s>>>(x, gamma, beta, out, rows, C, eps);
   DG_LAUNCH_CHECK();
   return DG_OK;
@@ -278,6 +307,7 @@ inline int launch_gemv(cudaStream_t s, const __half* x, int ldx, const __half* W
   if (B > 8 || K % 8) return fail(DG_E_SHAPE, "gemv: B=%d K=%d unsupported", B, K);
   const int warps = 8;
   const size_t smem = sizeof(float) * B * K;
+  ProfScope prof_(FAM_OTHER, s, 2.0 * B * (double)N * K, 2.0 * ((double)N * K + B * (double)(N + K)));
   gemv_small_batch_kernel<<<(N + warps - 1) / warps, warps * 32, smem, s>>>(x, ldx, W, bias, out, ldo, B, N, K, silu_in,
                                                                            silu_out);
   DG_LAUNCH_CHECK();

@@ -86,6 +86,14 @@ int32_t dg_unet_set_graphs(dg_unet* unet, int32_t enabled);
 /* kernels launched by the last dg_unet_forward / dg_denoise_loop call (graph replays count their kernel nodes). */
 int64_t dg_unet_last_launch_count(dg_unet* unet);
 
+/* One eager (non-graph) forward with a CUDA-event pair around every launch: per kernel family
+ * {0: tcgen05 GEMM/conv, 1: tcgen05 attention, 2: Group/LayerNorm, 3: other} accumulated device ms, algorithmic FLOPs,
+ * algorithmic bytes and launch count (arrays of 4), plus the whole-forward device ms.  bench.py's roofline source. */
+int32_t dg_unet_profile_forward(dg_unet* unet, const void* sample, const float* timesteps_host, int32_t n_timesteps,
+                                const void* ehs, int32_t ctx_tokens, void* out, int32_t batch, int32_t h, int32_t w,
+                                void* stream, double* ms_by_family, double* flops_by_family, double* bytes_by_family,
+                                int64_t* launches_by_family, double* total_ms);
+
 /* ---- StableDiffusionPipeline.__call__ steps 4-7 -----------------------------------------------------
  * dg_cfg_ddim_step <- `u + g*(c-u)` + DDIMScheduler.step(...).prev_sample (eta = 0), fused, in place on `latents`.
  *    noise_pred: [2*n_images (cfg) or n_images, elems_per_image]; prediction_type 0 = epsilon, 1 = v_prediction.
