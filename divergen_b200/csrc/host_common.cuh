@@ -9,6 +9,7 @@
 
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -72,6 +73,13 @@ struct ProfScope {
   }
   ~ProfScope() { if (on) cudaEventRecord(g_prof->recs.back().b, s); }
 };
+
+// DG_TRACE=1: one stderr line per tcgen05 launch (shape census that lines up with an ncu launch list).
+inline bool trace_on() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("DG_TRACE"); v = (e && e[0] == '1') ? 1 : 0; }
+  return v == 1;
+}
 
 // ------------------------------------------------------------------ tensor maps
 inline PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
@@ -200,6 +208,9 @@ inline int launch_gemm(cudaStream_t stream, int num_sms, const GemmArgs& a) {
   const int total_tiles = p.tiles_x * p.tiles_y * p.tiles_b * p.tiles_n;
   const int grid = total_tiles < num_sms ? total_tiles : num_sms;
   auto kern = gemm_tc_kernel<kGemmBlockN, kGemmStages>;
+  if (trace_on())
+    fprintf(stderr, "DG_TRACE gemm M=%d N=%d K=%d taps=%d c0=%d c1=%d tiles=%d grid=%d geglu=%d\n", a.B * a.H * a.W, a.n_w,
+            a.taps * (a.c0 + a.c1), a.taps, a.c0, a.c1, total_tiles, grid, a.geglu);
   const double rows_ = (double)a.B * a.H * a.W, ktot_ = (double)a.taps * (a.c0 + a.c1);
   ProfScope prof_(FAM_GEMM, stream, 2.0 * rows_ * ktot_ * (double)a.n_w,
                   2.0 * (rows_ * (a.c0 + a.c1) + ktot_ * a.n_w + rows_ * a.n_out));
@@ -228,6 +239,7 @@ inline int launch_attn_t(cudaStream_t stream, const __half* q, int ldq, const __
   p.scale_log2 = (1.0f / sqrtf((float)kD)) * 1.4426950408889634f;
   auto kern = attn_tc_kernel<kD, kKV, kStages>;
   dim3 grid((Sq + 255) / 256, heads, B);
+  if (trace_on()) fprintf(stderr, "DG_TRACE attn B=%d heads=%d Sq=%d Sk=%d d=%d\n", B, heads, Sq, Sk, kD);
   ProfScope prof_(FAM_ATTN, stream, 4.0 * B * heads * (double)Sq * Sk * kD,
                   2.0 * B * heads * kD * (2.0 * Sq + 2.0 * Sk));
   kern<<<grid, 384, C::kSmem, stream>>>(mQ, mK, mV, p);
