@@ -170,20 +170,30 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
       mbar_wait(&s_full[q], j & 1);
       tc_fence_after();
       const int kv_valid = min(kKV, p.Sk - j * kKV);
-      // pass 1: row max
-      float mx = -INFINITY;
+      const bool full_tile = kv_valid == kKV;
+      // pass 1: row max (FMNMX3: two columns per instruction, two independent chains)
+      float mx = -INFINITY, mx_b = -INFINITY;
 #pragma unroll
       for (int c = 0; c < kKV; c += 32) {
         uint32_t v[32];
         tmem_ld32(tS + c, v);
         tmem_ld_wait();
+        if (full_tile) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          float s = __uint_as_float(v[i]);
-          if (c + i >= kv_valid) s = -INFINITY;
-          mx = fmaxf(mx, s);
+          for (int i = 0; i < 32; i += 4) {
+            mx = max3f(mx, __uint_as_float(v[i]), __uint_as_float(v[i + 1]));
+            mx_b = max3f(mx_b, __uint_as_float(v[i + 2]), __uint_as_float(v[i + 3]));
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            float s = __uint_as_float(v[i]);
+            if (c + i >= kv_valid) s = -INFINITY;
+            mx = fmaxf(mx, s);
+          }
         }
       }
+      mx = fmaxf(mx, mx_b);
       const float m_tile = mx * p.scale_log2;
       if (j == 0) {
         m_run = m_tile;
@@ -205,24 +215,49 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
           }
         }
       }
-      // pass 2: P = exp2(S*c - m), packed fp16 over the front half of the S columns
+      // pass 2: P = exp2(S*c - m), packed fp16 over the front half of the S columns.
+      // Per pair of columns: 1 FFMA2 + 2 MUFU.EX2 + 1 F2FP + 1 FADD2 -- the MUFU pipe (16/clk/SM) is the bound.
       float lsum = 0.f;
+      if (full_tile) {
+        const uint64_t sc2 = pack_f32x2(p.scale_log2, p.scale_log2);
+        const uint64_t nm2 = pack_f32x2(-m_run, -m_run);
+        uint64_t sum2 = pack_f32x2(0.f, 0.f);
 #pragma unroll
-      for (int c = 0; c < kKV; c += 32) {
-        uint32_t v[32];
-        tmem_ld32(tS + c, v);
-        tmem_ld_wait();
-        uint32_t pk[16];
+        for (int c = 0; c < kKV; c += 32) {
+          uint32_t v[32];
+          tmem_ld32(tS + c, v);
+          tmem_ld_wait();
+          uint32_t pk[16];
 #pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          float p0 = (c + i < kv_valid) ? exp2f(__uint_as_float(v[i]) * p.scale_log2 - m_run) : 0.f;
-          float p1 = (c + i + 1 < kv_valid) ? exp2f(__uint_as_float(v[i + 1]) * p.scale_log2 - m_run) : 0.f;
-          __half2 h = __floats2half2_rn(p0, p1);
-          float2 hf = __half22float2(h);  // sum what the tensor core will actually multiply
-          lsum += hf.x + hf.y;
-          pk[i >> 1] = *reinterpret_cast<uint32_t*>(&h);
+          for (int i = 0; i < 32; i += 2) {
+            const uint64_t x2 = fma_f32x2(pack_f32x2(__uint_as_float(v[i]), __uint_as_float(v[i + 1])), sc2, nm2);
+            float x0, x1;
+            unpack_f32x2(x2, x0, x1);
+            const float p0 = fast_exp2(x0), p1 = fast_exp2(x1);
+            pk[i >> 1] = cvt_pack_half2(p0, p1);
+            sum2 = add_f32x2(sum2, pack_f32x2(p0, p1));
+          }
+          tmem_st16(tS + (c >> 1), pk);
         }
-        tmem_st16(tS + (c >> 1), pk);
+        float s0, s1;
+        unpack_f32x2(sum2, s0, s1);
+        lsum = s0 + s1;
+      } else {
+#pragma unroll
+        for (int c = 0; c < kKV; c += 32) {
+          uint32_t v[32];
+          tmem_ld32(tS + c, v);
+          tmem_ld_wait();
+          uint32_t pk[16];
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            const float p0 = (c + i < kv_valid) ? fast_exp2(__uint_as_float(v[i]) * p.scale_log2 - m_run) : 0.f;
+            const float p1 = (c + i + 1 < kv_valid) ? fast_exp2(__uint_as_float(v[i + 1]) * p.scale_log2 - m_run) : 0.f;
+            pk[i >> 1] = cvt_pack_half2(p0, p1);
+            lsum += p0 + p1;
+          }
+          tmem_st16(tS + (c >> 1), pk);
+        }
       }
       l_run += lsum;
       tmem_st_wait();

@@ -40,95 +40,105 @@ __global__ void nhwc_to_nchw_kernel(const __half* __restrict__ in, __half* __res
 }
 
 // ------------------------------------------------------------------ GroupNorm (NHWC, optional 2-source concat)
-// stats[b][g] = {sum, sumsq}; block = 256 threads over a strip of pixels of one sample.
-__global__ void gn_stats_kernel(const __half* __restrict__ x0, int C0, const __half* __restrict__ x1, int C1, int HW,
-                                int groups, int pix_per_block, float* __restrict__ stats) {
-  extern __shared__ float sh[];  // [groups*2]
-  const int C = C0 + C1, cpg = C / groups, nvec = C / 8;
-  const int b = blockIdx.y;
-  for (int i = threadIdx.x; i < groups * 2; i += blockDim.x) sh[i] = 0.f;
-  __syncthreads();
-  const int p0 = blockIdx.x * pix_per_block;
-  const int p1 = min(HW, p0 + pix_per_block);
-  const int lanes_per_pix = nvec;  // one thread = one 8-channel vector
-  const int pix_stride = blockDim.x / lanes_per_pix > 0 ? blockDim.x / lanes_per_pix : 1;
-  if (blockDim.x >= lanes_per_pix) {
-    const int v = threadIdx.x % lanes_per_pix;
-    const int pofs = threadIdx.x / lanes_per_pix;
-    if (pofs < pix_stride) {
-      float s[8], ss[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) { s[i] = 0.f; ss[i] = 0.f; }
-      const int c = v * 8;
-      for (int p = p0 + pofs; p < p1; p += pix_stride) {
-        float f[8];
-        const size_t pix = (size_t)b * HW + p;
-        if (c < C0) load8(x0 + pix * C0 + c, f); else load8(x1 + pix * C1 + (c - C0), f);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) { s[i] += f[i]; ss[i] += f[i] * f[i]; }
-      }
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int g = (c + i) / cpg;
-        atomicAdd(&sh[2 * g], s[i]);
-        atomicAdd(&sh[2 * g + 1], ss[i]);
-      }
-    }
-  } else {
-    // very wide C (more vectors than threads): thread loops over vectors too
-    for (int v = threadIdx.x; v < nvec; v += blockDim.x) {
-      float s[8], ss[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) { s[i] = 0.f; ss[i] = 0.f; }
-      const int c = v * 8;
-      for (int p = p0; p < p1; ++p) {
-        float f[8];
-        const size_t pix = (size_t)b * HW + p;
-        if (c < C0) load8(x0 + pix * C0 + c, f); else load8(x1 + pix * C1 + (c - C0), f);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) { s[i] += f[i]; ss[i] += f[i] * f[i]; }
-      }
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int g = (c + i) / cpg;
-        atomicAdd(&sh[2 * g], s[i]);
-        atomicAdd(&sh[2 * g + 1], ss[i]);
-      }
+// Work decomposition shared by both kernels: a block owns a strip of `pix_per_block` pixels of one sample; a thread owns
+// one 8-channel (16-byte) vector position and walks the strip, so every global access is a coalesced 16-byte load of a
+// contiguous NHWC row segment and per-channel constants are computed once per thread, not once per element.
+struct GnThreadMap {
+  int v0, vstep, pofs, pstride;
+  __device__ GnThreadMap(int nvec) {
+    if (nvec <= (int)blockDim.x) {
+      pstride = blockDim.x / nvec;
+      v0 = threadIdx.x % nvec; vstep = nvec;
+      pofs = threadIdx.x / nvec;
+      if (pofs >= pstride) { v0 = nvec; }  // idle tail threads
+    } else {
+      pstride = 1; pofs = 0; v0 = threadIdx.x; vstep = blockDim.x;
     }
   }
+};
+
+// stats[b][g] = {sum, sumsq} (fp32, atomically accumulated over strips; zeroed by the launcher).
+__global__ void gn_stats_kernel(const __half* __restrict__ x0, int C0, const __half* __restrict__ x1, int C1, int HW,
+                                int groups, int pix_per_block, float* __restrict__ stats) {
+  extern __shared__ float sh[];  // [pstride][C][2] partials, then [C][2] channel sums
+  const int C = C0 + C1, cpg = C / groups, nvec = C / 8;
+  const int b = blockIdx.y;
+  const int p0 = blockIdx.x * pix_per_block;
+  const int p1 = min(HW, p0 + pix_per_block);
+  const GnThreadMap tm(nvec);
+  for (int v = tm.v0; v < nvec; v += tm.vstep) {
+    float s[8], ss[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { s[i] = 0.f; ss[i] = 0.f; }
+    const int c = v * 8;
+    const __half* src = (c < C0) ? x0 + c : x1 + (c - C0);
+    const int ld = (c < C0) ? C0 : C1;
+#pragma unroll 4
+    for (int p = p0 + tm.pofs; p < p1; p += tm.pstride) {
+      float f[8];
+      load8(src + ((size_t)b * HW + p) * ld, f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { s[i] += f[i]; ss[i] = fmaf(f[i], f[i], ss[i]); }
+    }
+    float* dst = sh + ((size_t)tm.pofs * C + c) * 2;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { dst[2 * i] = s[i]; dst[2 * i + 1] = ss[i]; }
+  }
   __syncthreads();
-  for (int i = threadIdx.x; i < groups * 2; i += blockDim.x) atomicAdd(&stats[(size_t)b * groups * 2 + i], sh[i]);
+  // per-channel totals over the pixel sub-strips (into slab 0)
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float a = 0.f, q = 0.f;
+    for (int j = 0; j < tm.pstride; ++j) { a += sh[((size_t)j * C + c) * 2]; q += sh[((size_t)j * C + c) * 2 + 1]; }
+    sh[(size_t)c * 2] = a; sh[(size_t)c * 2 + 1] = q;
+  }
+  __syncthreads();
+  for (int g = threadIdx.x; g < groups; g += blockDim.x) {
+    float a = 0.f, q = 0.f;
+    for (int c = g * cpg; c < (g + 1) * cpg; ++c) { a += sh[(size_t)c * 2]; q += sh[(size_t)c * 2 + 1]; }
+    atomicAdd(&stats[((size_t)b * groups + g) * 2], a);
+    atomicAdd(&stats[((size_t)b * groups + g) * 2 + 1], q);
+  }
 }
 
-// y = act((x - mean) * rstd * gamma + beta), written as one concatenated NHWC tensor.
+// y = act((x - mean) * rstd * gamma + beta) = act(x * scale + shift), written as one concatenated NHWC tensor.
 __global__ void gn_apply_kernel(const __half* __restrict__ x0, int C0, const __half* __restrict__ x1, int C1, int HW,
-                                int B, int groups, float eps, const float* __restrict__ stats,
+                                int groups, float eps, int pix_per_block, const float* __restrict__ stats,
                                 const __half* __restrict__ gamma, const __half* __restrict__ beta, int do_silu,
                                 __half* __restrict__ out) {
   const int C = C0 + C1, cpg = C / groups, nvec = C / 8;
-  const size_t total = (size_t)B * HW * nvec;
+  const int b = blockIdx.y;
+  const int p0 = blockIdx.x * pix_per_block;
+  const int p1 = min(HW, p0 + pix_per_block);
   const float inv_n = 1.0f / ((float)cpg * (float)HW);
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    const int v = i % nvec;
-    const size_t pix = i / nvec;
-    const int b = pix / HW;
+  const GnThreadMap tm(nvec);
+  for (int v = tm.v0; v < nvec; v += tm.vstep) {
     const int c = v * 8;
-    float f[8], g[8], be[8];
-    if (c < C0) load8(x0 + pix * C0 + c, f); else load8(x1 + pix * C1 + (c - C0), f);
+    float sc[8], sf[8], g[8], be[8];
     load8(gamma + c, g);
     load8(beta + c, be);
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
       const int grp = (c + k) / cpg;
-      const float sum = stats[((size_t)b * groups + grp) * 2];
-      const float sq = stats[((size_t)b * groups + grp) * 2 + 1];
-      const float mean = sum * inv_n;
-      const float var = fmaxf(sq * inv_n - mean * mean, 0.f);
+      const float mean = stats[((size_t)b * groups + grp) * 2] * inv_n;
+      const float var = fmaxf(stats[((size_t)b * groups + grp) * 2 + 1] * inv_n - mean * mean, 0.f);
       const float rstd = rsqrtf(var + eps);
-      float y = (f[k] - mean) * rstd * g[k] + be[k];
-      f[k] = do_silu ? silu_f(y) : y;
+      sc[k] = rstd * g[k];
+      sf[k] = be[k] - mean * sc[k];
     }
-    store8(out + pix * C + c, f);
+    const __half* src = (c < C0) ? x0 + c : x1 + (c - C0);
+    const int ld = (c < C0) ? C0 : C1;
+#pragma unroll 4
+    for (int p = p0 + tm.pofs; p < p1; p += tm.pstride) {
+      const size_t pix = (size_t)b * HW + p;
+      float f[8];
+      load8(src + pix * ld, f);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const float y = fmaf(f[k], sc[k], sf[k]);
+        f[k] = do_silu ? __fdividef(y, 1.0f + __expf(-y)) : y;
+      }
+      store8(out + pix * C + c, f);
+    }
   }
 }
 
@@ -196,8 +206,10 @@ __global__ void timestep_sinusoid_kernel(const float* __restrict__ t, __half* __
   else      { o[k] = __float2half_rn(s); o[half_dim + k] = __float2half_rn(c); }
 }
 
-// out[b, n] = act_out( sum_k act_in(x[b,k]) * W[n,k] + bias[n] ), B <= 8.  One warp per output row: the weight matrix
-// is streamed exactly once with 16-byte loads (HBM-bound; the time-embedding MLP and the 22 time_emb_proj layers).
+// out[b, n] = act_out( sum_k act_in(x[b,k]) * W[n,k] + bias[n] ), B <= 8.  A warp owns kRowsPerWarp consecutive output
+// rows; the weight matrix is streamed exactly once with 16-byte loads (HBM-bound: the time-embedding MLP and the 22
+// time_emb_proj layers); the activated input vector is staged once per block in shared memory as fp32.
+constexpr int kGemvRowsPerWarp = 8;
 __global__ void gemv_small_batch_kernel(const __half* __restrict__ x, int ldx, const __half* __restrict__ W,
                                         const __half* __restrict__ bias, __half* __restrict__ out, int ldo, int B,
                                         int N, int K, int silu_in, int silu_out) {
@@ -208,31 +220,36 @@ __global__ void gemv_small_batch_kernel(const __half* __restrict__ x, int ldx, c
   }
   __syncthreads();
   const int lane = threadIdx.x & 31;
-  const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (n >= N) return;
-  float acc[8];
+  const int n_base = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * kGemvRowsPerWarp;
+#pragma unroll 2
+  for (int r = 0; r < kGemvRowsPerWarp; ++r) {
+    const int n = n_base + r;
+    if (n >= N) break;
+    float acc[8];
 #pragma unroll
-  for (int b = 0; b < 8; ++b) acc[b] = 0.f;
-  for (int k = lane * 8; k < K; k += 32 * 8) {
-    float w[8];
-    load8(W + (size_t)n * K + k, w);
+    for (int b = 0; b < 8; ++b) acc[b] = 0.f;
+    for (int k = lane * 8; k < K; k += 32 * 8) {
+      float w[8];
+      load8(W + (size_t)n * K + k, w);
 #pragma unroll
-    for (int b = 0; b < 8; ++b) {
-      if (b < B) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) acc[b] += w[i] * xs[b * K + k + i];
+      for (int b = 0; b < 8; ++b) {
+        if (b < B) {
+          const float4 xa = *reinterpret_cast<const float4*>(xs + b * K + k);
+          const float4 xb = *reinterpret_cast<const float4*>(xs + b * K + k + 4);
+          acc[b] += w[0] * xa.x + w[1] * xa.y + w[2] * xa.z + w[3] * xa.w + w[4] * xb.x + w[5] * xb.y + w[6] * xb.z + w[7] * xb.w;
+        }
       }
     }
-  }
 #pragma unroll
-  for (int b = 0; b < 8; ++b) {
+    for (int b = 0; b < 8; ++b) {
 #pragma unroll
-    for (int o = 16; o; o >>= 1) acc[b] += __shfl_xor_sync(0xffffffffu, acc[b], o);
-  }
-  if (lane == 0) {
-    for (int b = 0; b < B; ++b) {
-      float v = acc[b] + (bias ? __half2float(bias[n]) : 0.f);
-      out[(size_t)b * ldo + n] = __float2half_rn(silu_out ? silu_f(v) : v);
+      for (int o = 16; o; o >>= 1) acc[b] += __shfl_xor_sync(0xffffffffu, acc[b], o);
+    }
+    if (lane == 0) {
+      for (int b = 0; b < B; ++b) {
+        const float v = acc[b] + (bias ? __half2float(bias[n]) : 0.f);
+        out[(size_t)b * ldo + n] = __float2half_rn(silu_out ? silu_f(v) : v);
+      }
     }
   }
 }

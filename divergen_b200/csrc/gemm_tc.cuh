@@ -9,7 +9,7 @@
 // Wt is the K-major packed weight [N, taps*C] behind a 2-D tensor map.
 //
 // Warp roles (256 threads): warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane), warp 2 = TMEM allocator,
-// warps 4..7 = epilogue (TMEM -> registers -> fp16 global).  Persistent over tiles, kStages-deep smem ring, two TMEM
+// warps 4..7 = epilogue (TMEM -> registers -> smem staging -> coalesced fp16 global).  Persistent over tiles, kStages-deep smem ring, two TMEM
 // accumulator stages so the epilogue of tile i overlaps the main loop of tile i+1.
 //
 // Replaces (reference side): torch.nn.Conv2d / Linear inside diffusers ResnetBlock2D, Attention, FeedForward,
@@ -49,7 +49,9 @@ struct GemmSmem {
   static constexpr int kABytes = kBlockM * kBlockK * 2;
   static constexpr int kBBytes = kBlockN * kBlockK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kTotal = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int kOutRowBytes = kBlockN * 2 + 16;  // +16 B pad: conflict-free 16-byte row-strided stores
+  static constexpr int kOutBytes = kBlockM * kOutRowBytes + kBlockM * 8 /*row -> pixel table*/;
+  static constexpr int kTotal = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ + kOutBytes;
 };
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
@@ -155,9 +157,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     }
   } else if (warp >= 4) {
     // ===================== epilogue =====================
+    // pass 1 (thread = accumulator row): TMEM -> registers -> +bias (+time-embedding vector) -> fp16 -> padded smem tile;
+    //         the TMEM stage is released as soon as it has been drained.
+    // pass 2 (coalesced): the 128 threads sweep the staged tile in 16-byte vectors, add the residual (independent,
+    //         batched global loads) and store full 32-byte sectors.
     const int q = warp - 4;          // TMEM lane quadrant
     const int r = q * 32 + lane;     // row within the tile
+    const int et = threadIdx.x - 128;  // 0..127
     const int box_xy = p.bw * p.bh;
+    uint8_t* sOut = smem + kStages * S::kStageBytes + 256;
+    long long* sRow = reinterpret_cast<long long*>(sOut + kBlockM * S::kOutRowBytes);
     int acc = 0; uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int nt = tile % p.tiles_n;
@@ -169,101 +178,144 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
       const int yy = ty * p.bh + (r / p.bw) % p.bh;
       const int bb = tb * p.bn + r / box_xy;
       const bool row_ok = (xx < p.W) && (yy < p.H) && (bb < p.B);
-      const size_t pix = ((size_t)bb * p.H + yy) * p.W + xx;
+      const long long pix = ((long long)bb * p.H + yy) * p.W + xx;
 
       mbar_wait(&acc_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + acc * kAccStride + ((uint32_t)(q * 32) << 16);
+      // previous tile's pass 2 must be done with the staging tile
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      sRow[r] = row_ok ? pix : -1;
+      uint8_t* my_row = sOut + r * S::kOutRowBytes;
 
       if (!p.geglu) {
         const int n0 = nt * kBlockN;
-#pragma unroll 1
+#pragma unroll 2
         for (int c = 0; c < kBlockN; c += 16) {
           uint32_t v[16];
           tmem_ld16(t_row + c, v);
           tmem_ld_wait();
           const int col = n0 + c;
-          if (row_ok && col < p.n_out) {
-            float f[16];
+          float f[16];
 #pragma unroll
-            for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]);
-            if (col + 16 <= p.n_out) {
-              if (p.bias) {
-                const uint4* bp = reinterpret_cast<const uint4*>(p.bias + col);
-                uint4 b0 = __ldg(bp), b1 = __ldg(bp + 1);
-                const uint32_t bw_[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+          for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]);
+          if (col + 16 <= p.n_gemm) {
+            if (p.bias) {
+              const uint4* bp = reinterpret_cast<const uint4*>(p.bias + col);
+              const uint4 b0 = __ldg(bp), b1 = __ldg(bp + 1);
+              float2 t;
+              t = unpack_half2(b0.x); f[0] += t.x; f[1] += t.y;   t = unpack_half2(b0.y); f[2] += t.x; f[3] += t.y;
+              t = unpack_half2(b0.z); f[4] += t.x; f[5] += t.y;   t = unpack_half2(b0.w); f[6] += t.x; f[7] += t.y;
+              t = unpack_half2(b1.x); f[8] += t.x; f[9] += t.y;   t = unpack_half2(b1.y); f[10] += t.x; f[11] += t.y;
+              t = unpack_half2(b1.z); f[12] += t.x; f[13] += t.y; t = unpack_half2(b1.w); f[14] += t.x; f[15] += t.y;
+            }
+            if (p.rowvec && row_ok) {
+              const uint4* rp = reinterpret_cast<const uint4*>(p.rowvec + (size_t)bb * p.ld_rowvec + col);
+              const uint4 b0 = __ldg(rp), b1 = __ldg(rp + 1);
+              float2 t;
+              t = unpack_half2(b0.x); f[0] += t.x; f[1] += t.y;   t = unpack_half2(b0.y); f[2] += t.x; f[3] += t.y;
+              t = unpack_half2(b0.z); f[4] += t.x; f[5] += t.y;   t = unpack_half2(b0.w); f[6] += t.x; f[7] += t.y;
+              t = unpack_half2(b1.x); f[8] += t.x; f[9] += t.y;   t = unpack_half2(b1.y); f[10] += t.x; f[11] += t.y;
+              t = unpack_half2(b1.z); f[12] += t.x; f[13] += t.y; t = unpack_half2(b1.w); f[14] += t.x; f[15] += t.y;
+            }
+          } else {
+            // ragged N tail (e.g. conv_out: 4 channels): guarded scalar loads
 #pragma unroll
-                for (int i = 0; i < 8; ++i) { float2 t = unpack_half2(bw_[i]); f[2 * i] += t.x; f[2 * i + 1] += t.y; }
-              }
-              if (p.rowvec) {
-                const uint4* rp = reinterpret_cast<const uint4*>(p.rowvec + (size_t)bb * p.ld_rowvec + col);
-                uint4 b0 = __ldg(rp), b1 = __ldg(rp + 1);
-                const uint32_t bw_[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-#pragma unroll
-                for (int i = 0; i < 8; ++i) { float2 t = unpack_half2(bw_[i]); f[2 * i] += t.x; f[2 * i + 1] += t.y; }
-              }
-              if (p.residual) {
-                const uint4* rp = reinterpret_cast<const uint4*>(p.residual + pix * p.ld_res + col);
-                uint4 b0 = rp[0], b1 = rp[1];  // plain loads: the residual may alias `out` (in-place add)
-                const uint32_t bw_[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-#pragma unroll
-                for (int i = 0; i < 8; ++i) { float2 t = unpack_half2(bw_[i]); f[2 * i] += t.x; f[2 * i + 1] += t.y; }
-              }
-              uint4 o0, o1;
-              o0.x = pack_half2(f[0], f[1]);   o0.y = pack_half2(f[2], f[3]);
-              o0.z = pack_half2(f[4], f[5]);   o0.w = pack_half2(f[6], f[7]);
-              o1.x = pack_half2(f[8], f[9]);   o1.y = pack_half2(f[10], f[11]);
-              o1.z = pack_half2(f[12], f[13]); o1.w = pack_half2(f[14], f[15]);
-              uint4* op = reinterpret_cast<uint4*>(p.out + pix * p.ldo + col);
-              op[0] = o0; op[1] = o1;
-            } else {
-              // ragged N tail (e.g. conv_out with 4 channels): scalar path
-              for (int i = 0; i < 16 && col + i < p.n_out; ++i) {
-                float x = f[i];
-                if (p.bias) x += __half2float(p.bias[col + i]);
-                if (p.rowvec) x += __half2float(p.rowvec[(size_t)bb * p.ld_rowvec + col + i]);
-                if (p.residual) x += __half2float(p.residual[pix * p.ld_res + col + i]);
-                p.out[pix * p.ldo + col + i] = __float2half_rn(x);
+            for (int i = 0; i < 16; ++i) {
+              if (col + i < p.n_gemm) {
+                if (p.bias) f[i] += __half2float(p.bias[col + i]);
+                if (p.rowvec && row_ok) f[i] += __half2float(p.rowvec[(size_t)bb * p.ld_rowvec + col + i]);
               }
             }
           }
+          uint4 o0, o1;
+          o0.x = pack_half2(f[0], f[1]);   o0.y = pack_half2(f[2], f[3]);
+          o0.z = pack_half2(f[4], f[5]);   o0.w = pack_half2(f[6], f[7]);
+          o1.x = pack_half2(f[8], f[9]);   o1.y = pack_half2(f[10], f[11]);
+          o1.z = pack_half2(f[12], f[13]); o1.w = pack_half2(f[14], f[15]);
+          uint4* sp = reinterpret_cast<uint4*>(my_row + c * 2);
+          sp[0] = o0; sp[1] = o1;
         }
       } else {
         // GEGLU: columns [0, kBlockN/2) = value, [kBlockN/2, kBlockN) = gate, same output channels.
         constexpr int kHalf = kBlockN / 2;
-        const int n0 = nt * kHalf;
 #pragma unroll 1
         for (int c = 0; c < kHalf; c += 16) {
           uint32_t va[16], vg[16];
           tmem_ld16(t_row + c, va);
           tmem_ld16(t_row + kHalf + c, vg);
           tmem_ld_wait();
-          const int col = n0 + c;
-          if (row_ok && col < p.n_out) {
-            float o[16];
+          float o[16];
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              float a = __uint_as_float(va[i]) + __half2float(__ldg(p.bias + nt * kBlockN + c + i));
-              float g = __uint_as_float(vg[i]) + __half2float(__ldg(p.bias + nt * kBlockN + kHalf + c + i));
-              o[i] = a * gelu_erf(g);
+          for (int i = 0; i < 16; ++i) {
+            const float a = __uint_as_float(va[i]) + __half2float(__ldg(p.bias + nt * kBlockN + c + i));
+            const float g = __uint_as_float(vg[i]) + __half2float(__ldg(p.bias + nt * kBlockN + kHalf + c + i));
+            o[i] = a * gelu_erf(g);
+          }
+          uint4 o0, o1;
+          o0.x = pack_half2(o[0], o[1]);   o0.y = pack_half2(o[2], o[3]);
+          o0.z = pack_half2(o[4], o[5]);   o0.w = pack_half2(o[6], o[7]);
+          o1.x = pack_half2(o[8], o[9]);   o1.y = pack_half2(o[10], o[11]);
+          o1.z = pack_half2(o[12], o[13]); o1.w = pack_half2(o[14], o[15]);
+          uint4* sp = reinterpret_cast<uint4*>(my_row + c * 2);
+          sp[0] = o0; sp[1] = o1;
+        }
+      }
+      // accumulator drained: hand the TMEM stage back to the MMA warp before the global-memory pass
+      tc_fence_before();
+      mbar_arrive(&acc_empty[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+
+      // ---- pass 2
+      const int tile_cols = p.geglu ? kBlockN / 2 : kBlockN;
+      const int n0 = nt * tile_cols;
+      const int vec_per_row = tile_cols / 8;
+      const int total_vec = kBlockM * vec_per_row;
+      constexpr int kBatch = 5;
+      for (int base = et; base < total_vec; base += 128 * kBatch) {
+        uint4 val[kBatch], res[kBatch];
+        long long gofs[kBatch];
+        int colv[kBatch];
+#pragma unroll
+        for (int b = 0; b < kBatch; ++b) {
+          const int v = base + b * 128;
+          gofs[b] = -1; colv[b] = 0;
+          res[b] = make_uint4(0u, 0u, 0u, 0u);
+          if (v < total_vec) {
+            const int row = v / vec_per_row, cv = v - row * vec_per_row;
+            const long long px = sRow[row];
+            const int col = n0 + cv * 8;
+            if (px >= 0 && col < p.n_out) {
+              gofs[b] = px; colv[b] = col;
+              val[b] = *reinterpret_cast<const uint4*>(sOut + row * S::kOutRowBytes + cv * 16);
+              if (p.residual && col + 8 <= p.n_out) res[b] = *reinterpret_cast<const uint4*>(p.residual + px * p.ld_res + col);
             }
-            if (col + 16 <= p.n_out) {
-              uint4 o0, o1;
-              o0.x = pack_half2(o[0], o[1]);   o0.y = pack_half2(o[2], o[3]);
-              o0.z = pack_half2(o[4], o[5]);   o0.w = pack_half2(o[6], o[7]);
-              o1.x = pack_half2(o[8], o[9]);   o1.y = pack_half2(o[10], o[11]);
-              o1.z = pack_half2(o[12], o[13]); o1.w = pack_half2(o[14], o[15]);
-              uint4* op = reinterpret_cast<uint4*>(p.out + pix * p.ldo + col);
-              op[0] = o0; op[1] = o1;
-            } else {
-              for (int i = 0; i < 16 && col + i < p.n_out; ++i) p.out[pix * p.ldo + col + i] = __float2half_rn(o[i]);
+          }
+        }
+#pragma unroll
+        for (int b = 0; b < kBatch; ++b) {
+          if (gofs[b] < 0) continue;
+          const int col = colv[b];
+          if (col + 8 <= p.n_out) {
+            uint4 o = val[b];
+            if (p.residual) {
+              const float2 a0 = unpack_half2(o.x), a1 = unpack_half2(o.y), a2 = unpack_half2(o.z), a3 = unpack_half2(o.w);
+              const float2 r0 = unpack_half2(res[b].x), r1 = unpack_half2(res[b].y), r2 = unpack_half2(res[b].z), r3 = unpack_half2(res[b].w);
+              o.x = pack_half2(a0.x + r0.x, a0.y + r0.y); o.y = pack_half2(a1.x + r1.x, a1.y + r1.y);
+              o.z = pack_half2(a2.x + r2.x, a2.y + r2.y); o.w = pack_half2(a3.x + r3.x, a3.y + r3.y);
+            }
+            *reinterpret_cast<uint4*>(p.out + gofs[b] * p.ldo + col) = o;
+          } else {
+            const __half* hv = reinterpret_cast<const __half*>(&val[b]);
+            for (int i = 0; i < 8 && col + i < p.n_out; ++i) {
+              float x = __half2float(hv[i]);
+              if (p.residual) x += __half2float(p.residual[gofs[b] * p.ld_res + col + i]);
+              p.out[gofs[b] * p.ldo + col + i] = __float2half_rn(x);
             }
           }
         }
       }
-      tc_fence_before();
-      mbar_arrive(&acc_empty[acc]);
-      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   }
 

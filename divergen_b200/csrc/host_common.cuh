@@ -138,7 +138,7 @@ inline int make_map_2d(CUtensorMap* m, const void* ptr, uint64_t inner, uint64_t
 
 // ------------------------------------------------------------------ GEMM / conv launcher
 constexpr int kGemmBlockN = 160;  // divides every channel count of SD-1.x/2.x (320, 640, 1280, ... 10240)
-constexpr int kGemmStages = 6;
+constexpr int kGemmStages = 5;  // 5 x 36 KB ring + 43 KB epilogue staging tile <= 227 KB
 
 struct GemmArgs {
   const __half* a0 = nullptr; int c0 = 0;  // source 0: NHWC [B,H,W,c0]
@@ -292,14 +292,16 @@ inline int launch_groupnorm(cudaStream_t s, int num_sms, const __half* x0, int C
   if (C % groups || C0 % 8 || C1 % 8) return fail(DG_E_SHAPE, "groupnorm: C=%d+%d groups=%d", C0, C1, groups);
   ProfScope prof_(FAM_NORM, s, 0.0, 2.0 * 3.0 * B * HW * (double)C);
   DG_CUDA(cudaMemsetAsync(stats, 0, sizeof(float) * 2 * groups * B, s));
-  int ppb = 64;
-  while (ppb > 8 && (size_t)B * ((HW + ppb - 1) / ppb) < (size_t)2 * num_sms) ppb /= 2;
+  const int nvec = C / 8;
+  const int pstride = nvec <= 256 ? 256 / nvec : 1;
+  // strip length: enough blocks to fill the chip (>= 4 per SM when the tensor allows), >= 8 pixel iterations per thread
+  int ppb = 8 * pstride;
+  while (ppb * 2 <= HW && (size_t)B * ((HW + ppb - 1) / ppb) > (size_t)8 * num_sms) ppb *= 2;
   dim3 grid((HW + ppb - 1) / ppb, B);
-  gn_stats_kernel<<<grid, 256, sizeof(float) * 2 * groups, s>>>(x0, C0, x1, C1, HW, groups, ppb, stats);
+  const size_t smem = sizeof(float) * 2 * (size_t)pstride * C;
+  gn_stats_kernel<<<grid, 256, smem, s>>>(x0, C0, x1, C1, HW, groups, ppb, stats);
   DG_LAUNCH_CHECK();
-  const size_t items = (size_t)B * HW * (C / 8);
-  gn_apply_kernel<<<grid_for(items, 256, num_sms), 256, 0, s>>>(x0, C0, x1, C1, HW, B, groups, eps, stats, gamma, beta,
-                                                               silu, out);
+  gn_apply_kernel<<<grid, 256, 0, s>>>(x0, C0, x1, C1, HW, groups, eps, ppb, stats, gamma, beta, silu, out);
   DG_LAUNCH_CHECK();
   return DG_OK;
 }
@@ -317,10 +319,10 @@ inline int launch_layernorm(cudaStream_t s, const __half* x, const __half* gamma
 inline int launch_gemv(cudaStream_t s, const __half* x, int ldx, const __half* W, const __half* bias, __half* out,
                        int ldo, int B, int N, int K, int silu_in, int silu_out) {
   if (B > 8 || K % 8) return fail(DG_E_SHAPE, "gemv: B=%d K=%d unsupported", B, K);
-  const int warps = 8;
+  const int warps = 8, rows_per_block = warps * kGemvRowsPerWarp;
   const size_t smem = sizeof(float) * B * K;
   ProfScope prof_(FAM_OTHER, s, 2.0 * B * (double)N * K, 2.0 * ((double)N * K + B * (double)(N + K)));
-  gemv_small_batch_kernel<<<(N + warps - 1) / warps, warps * 32, smem, s>>>(x, ldx, W, bias, out, ldo, B, N, K, silu_in,
+  gemv_small_batch_kernel<<<(N + rows_per_block - 1) / rows_per_block, warps * 32, smem, s>>>(x, ldx, W, bias, out, ldo, B, N, K, silu_in,
                                                                            silu_out);
   DG_LAUNCH_CHECK();
   return DG_OK;
