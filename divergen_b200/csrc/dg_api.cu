@@ -181,7 +181,7 @@ int make_fused_rows(dg_unet* u, const std::vector<std::string>& keys, int in, in
   for (size_t i = 0; i < keys.size(); ++i) add_slot(u, keys[i], {out_each, in}, PK_ROWS, l->w, (int64_t)i * out_each, out_each, in);
   return DG_OK;
 }
-int geglu_rows(int inner) { return ((inner + kGemmBlockN / 2 - 1) / (kGemmBlockN / 2)) * kGemmBlockN; }
+int geglu_rows(int inner) { return ((inner + kGegluBlockN / 2 - 1) / (kGegluBlockN / 2)) * kGegluBlockN; }
 int make_xf(dg_unet* u, const std::string& pfx, int c, int heads, Xf* x) {
   const dg_unet_config& cf = u->cfg;
   x->c = c; x->heads = heads; x->ff_inner = 4 * c;
@@ -465,12 +465,18 @@ int run_forward(dg_unet* u, cudaStream_t s, const __half* sample, const __half* 
   // ---- out
   T4 xn = f.talloc(B, h, w, c0);
   f.gn(x, nullptr, u->norm_out, cf.norm_eps, 1, xn);
-  T4 o = f.talloc(B, h, w, cf.out_channels);
-  f.conv3(xn, u->conv_out, nullptr, nullptr, o);
+  // conv_out writes rows padded to 8 channels (TMA store needs a 16-byte row pitch); the NCHW exit kernel reads that pitch
+  const int opitch = (cf.out_channels + 7) / 8 * 8;
+  T4 o = f.talloc(B, h, w, opitch);
+  {
+    GemmArgs a; a.a0 = xn.p; a.c0 = xn.C; a.B = B; a.H = h; a.W = w; a.taps = 9; a.w = u->conv_out.w; a.n_w = u->conv_out.rows;
+    a.n_out = cf.out_channels; a.bias = u->conv_out.b; a.out = o.p; a.ldo = opitch;
+    if (f.err == DG_OK) f.err = launch_gemm(s, sms, a);
+  }
   if (f.err) return f.err;
   {
     const size_t n = (size_t)B * cf.out_channels * h * w;
-    nhwc_to_nchw_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(o.p, out, B, cf.out_channels, h * w);
+    nhwc_to_nchw_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(o.p, out, B, cf.out_channels, h * w, opitch);
     DG_LAUNCH_CHECK();
   }
   return DG_OK;
@@ -640,8 +646,8 @@ int32_t dg_unet_set_weight(dg_unet* u, const char* key, const void* src, int32_t
       break;
     case PK_GEGLU_W:
     case PK_GEGLU_B: {
-      const int tiles = geglu_rows(s.a) / kGemmBlockN;
-      pack_geglu_kernel<<<grid_for((size_t)tiles * kGemmBlockN * s.b, 256, sms), 256>>>(w, s.dst, s.a, s.b, kGemmBlockN, tiles);
+      const int tiles = geglu_rows(s.a) / kGegluBlockN;
+      pack_geglu_kernel<<<grid_for((size_t)tiles * kGegluBlockN * s.b, 256, sms), 256>>>(w, s.dst, s.a, s.b, kGegluBlockN, tiles);
       DG_LAUNCH_CHECK();
       break;
     }
@@ -807,11 +813,11 @@ int32_t dg_op_gemm(dg_ctx* ctx, const void* A, const void* W, const void* bias, 
 int32_t dg_op_geglu_packed_rows(int32_t inner) { return geglu_rows(inner); }
 int32_t dg_op_pack_geglu(dg_ctx* ctx, const void* w, const void* b, void* w_out, void* b_out, int32_t inner, int32_t K, void* stream) {
   if (!ctx || !w || !b || !w_out || !b_out) return fail(DG_E_ARG, "null argument");
-  const int tiles = geglu_rows(inner) / kGemmBlockN;
+  const int tiles = geglu_rows(inner) / kGegluBlockN;
   cudaStream_t s = (cudaStream_t)stream;
-  pack_geglu_kernel<<<grid_for((size_t)tiles * kGemmBlockN * K, 256, ctx->num_sms), 256, 0, s>>>((const __half*)w, (__half*)w_out, inner, K, kGemmBlockN, tiles);
+  pack_geglu_kernel<<<grid_for((size_t)tiles * kGegluBlockN * K, 256, ctx->num_sms), 256, 0, s>>>((const __half*)w, (__half*)w_out, inner, K, kGegluBlockN, tiles);
   DG_LAUNCH_CHECK();
-  pack_geglu_kernel<<<grid_for((size_t)tiles * kGemmBlockN, 256, ctx->num_sms), 256, 0, s>>>((const __half*)b, (__half*)b_out, inner, 1, kGemmBlockN, tiles);
+  pack_geglu_kernel<<<grid_for((size_t)tiles * kGegluBlockN, 256, ctx->num_sms), 256, 0, s>>>((const __half*)b, (__half*)b_out, inner, 1, kGegluBlockN, tiles);
   DG_LAUNCH_CHECK();
   return DG_OK;
 }
@@ -823,11 +829,12 @@ int32_t dg_op_pack_conv3x3(dg_ctx* ctx, const void* w, void* w_out, int32_t O, i
 }
 int32_t dg_op_conv3x3(dg_ctx* ctx, const void* x0, int32_t C0, const void* x1, int32_t C1, const void* Wp, const void* bias,
                       const void* rowvec, int32_t ld_rowvec, const void* residual, void* out, int32_t B, int32_t H, int32_t Wd,
-                      int32_t N, void* stream) {
+                      int32_t N, int32_t ldo, void* stream) {
   if (!ctx || !x0 || !Wp || !out) return fail(DG_E_ARG, "null argument");
+  if (ldo <= 0) ldo = N;
   GemmArgs a; a.a0 = (const __half*)x0; a.c0 = C0; a.a1 = (const __half*)x1; a.c1 = C1; a.B = B; a.H = H; a.W = Wd; a.taps = 9;
   a.w = (const __half*)Wp; a.n_w = N; a.n_out = N; a.bias = (const __half*)bias; a.rowvec = (const __half*)rowvec; a.ld_rowvec = ld_rowvec;
-  a.residual = (const __half*)residual; a.ld_res = N; a.out = (__half*)out; a.ldo = N;
+  a.residual = (const __half*)residual; a.ld_res = ldo; a.out = (__half*)out; a.ldo = ldo;
   return launch_gemm((cudaStream_t)stream, ctx->num_sms, a);
 }
 int32_t dg_op_attention(dg_ctx* ctx, const void* q, int32_t ldq, const void* k, int32_t ldk, const void* v, int32_t ldv, void* out,

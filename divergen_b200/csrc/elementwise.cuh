@@ -31,12 +31,13 @@ __global__ void nchw_to_nhwc_kernel(const __half* __restrict__ in, __half* __res
   int c = i % C; size_t t = i / C; int p = t % HW; int b = t / HW;
   out[i] = in[((size_t)b * C + c) * HW + p];
 }
-__global__ void nhwc_to_nchw_kernel(const __half* __restrict__ in, __half* __restrict__ out, int B, int C, int HW) {
+__global__ void nhwc_to_nchw_kernel(const __half* __restrict__ in, __half* __restrict__ out, int B, int C, int HW,
+                                    int in_pitch) {
   size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
   size_t n = (size_t)B * C * HW;
   if (i >= n) return;
   int p = i % HW; size_t t = i / HW; int c = t % C; int b = t / C;
-  out[i] = in[((size_t)b * HW + p) * C + c];
+  out[i] = in[((size_t)b * HW + p) * in_pitch + c];
 }
 
 // ------------------------------------------------------------------ GroupNorm (NHWC, optional 2-source concat)

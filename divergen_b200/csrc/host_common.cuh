@@ -97,7 +97,7 @@ inline PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
 
 // rank-4 fp16 map, 128-byte swizzle, zero OOB fill.  dims/box innermost first; strides (bytes) for dims 1..3.
 inline int make_map_4d(CUtensorMap* m, const void* ptr, const uint64_t dims[4], const uint64_t strides[3],
-                       const uint32_t box[4], bool weights = false) {
+                       const uint32_t box[4], bool weights = false, bool swizzle64 = false) {
   auto fn = get_encode_fn();
   if (!fn) return fail(DG_E_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
   cuuint64_t gd[4] = {dims[0], dims[1], dims[2], dims[3]};
@@ -105,7 +105,7 @@ inline int make_map_4d(CUtensorMap* m, const void* ptr, const uint64_t dims[4], 
   cuuint32_t bx[4] = {box[0], box[1], box[2], box[3]};
   cuuint32_t es[4] = {1, 1, 1, 1};
   CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(ptr), gd, gs, bx, es,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
                   weights ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)
@@ -137,8 +137,10 @@ inline int make_map_2d(CUtensorMap* m, const void* ptr, uint64_t inner, uint64_t
 }
 
 // ------------------------------------------------------------------ GEMM / conv launcher
-constexpr int kGemmBlockN = 160;  // divides every channel count of SD-1.x/2.x (320, 640, 1280, ... 10240)
-constexpr int kGemmStages = 5;  // 5 x 36 KB ring + 43 KB epilogue staging tile <= 227 KB
+constexpr int kGemmBlockN = 160;   // divides every channel count of SD-1.x/2.x (320, 640, 1280, ... 10240)
+constexpr int kGemmStages = 5;     // 5 x 36 KB ring + 40 KB staging tile
+constexpr int kGegluBlockN = 128;  // GEGLU tiles: [64 value | 64 gate] -> 64 outputs
+constexpr int kGegluStages = 6;
 
 struct GemmArgs {
   const __half* a0 = nullptr; int c0 = 0;  // source 0: NHWC [B,H,W,c0]
@@ -162,11 +164,13 @@ inline int largest_pow2_divisor(int x, int cap) {
 }
 
 inline int launch_gemm(cudaStream_t stream, int num_sms, const GemmArgs& a) {
-  using S = GemmSmem<kGemmBlockN, kGemmStages>;
   if (a.c0 % 64 || a.c1 % 64 || a.c0 <= 0) return fail(DG_E_SHAPE, "gemm: channel counts must be multiples of 64 (%d,%d)", a.c0, a.c1);
   if (a.taps != 1 && a.taps != 9) return fail(DG_E_ARG, "gemm: taps must be 1 or 9");
-  if ((reinterpret_cast<uintptr_t>(a.a0) | reinterpret_cast<uintptr_t>(a.w) | reinterpret_cast<uintptr_t>(a.out)) & 15)
+  if ((reinterpret_cast<uintptr_t>(a.a0) | reinterpret_cast<uintptr_t>(a.w) | reinterpret_cast<uintptr_t>(a.out) |
+       reinterpret_cast<uintptr_t>(a.residual) | reinterpret_cast<uintptr_t>(a.a1)) & 15)
     return fail(DG_E_ARG, "gemm: pointers must be 16-byte aligned");
+  if (a.ldo % 8 || (a.residual && a.ld_res % 8)) return fail(DG_E_SHAPE, "gemm: output / residual row pitch must be a multiple of 8 elements");
+  const int block_n = a.geglu ? kGegluBlockN : kGemmBlockN;
   GemmParams p{};
   int W = a.W, H = a.H, B = a.B;
   if (a.taps == 1) { W = a.B * a.H * a.W; H = 1; B = 1; }
@@ -179,17 +183,15 @@ inline int launch_gemm(cudaStream_t stream, int num_sms, const GemmArgs& a) {
   p.tiles_y = (H + p.bh - 1) / p.bh;
   p.tiles_b = (B + p.bn - 1) / p.bn;
   p.n_gemm = a.n_w;
-  p.tiles_n = (a.n_w + kGemmBlockN - 1) / kGemmBlockN;
+  p.tiles_n = (a.n_w + block_n - 1) / block_n;
   p.n_out = a.n_out;
-  p.ldo = a.ldo;
   p.taps = a.taps;
   p.kb0 = a.c0 / 64; p.kb1 = a.c1 / 64;
   p.bias = a.bias; p.rowvec = a.rowvec; p.ld_rowvec = a.ld_rowvec;
-  p.residual = a.residual; p.ld_res = a.ld_res;
-  p.geglu = a.geglu; p.out = a.out;
+  p.has_residual = a.residual != nullptr;
   if (a.geglu && !a.bias) return fail(DG_E_ARG, "gemm: geglu epilogue needs a packed bias");
 
-  CUtensorMap mA0, mA1, mW;
+  CUtensorMap mA0, mA1, mW, mO, mR;
   {
     uint64_t dims[4] = {(uint64_t)a.c0, (uint64_t)W, (uint64_t)H, (uint64_t)B};
     uint64_t st[3] = {(uint64_t)a.c0 * 2, (uint64_t)W * a.c0 * 2, (uint64_t)H * W * a.c0 * 2};
@@ -203,18 +205,33 @@ inline int launch_gemm(cudaStream_t stream, int num_sms, const GemmArgs& a) {
       mA1 = mA0;
     }
     const uint64_t ktot = (uint64_t)a.taps * (a.c0 + a.c1);
-    DG_TRY(make_map_2d(&mW, a.w, ktot, (uint64_t)a.n_w, ktot * 2, 64, kGemmBlockN));
+    DG_TRY(make_map_2d(&mW, a.w, ktot, (uint64_t)a.n_w, ktot * 2, 64, block_n));
+    // output / residual tiles: {n_out, W, H, B} boxes of 32 columns x 128 pixels, 64-byte swizzle in smem
+    uint64_t od[4] = {(uint64_t)a.n_out, (uint64_t)W, (uint64_t)H, (uint64_t)B};
+    uint64_t os[3] = {(uint64_t)a.ldo * 2, (uint64_t)W * a.ldo * 2, (uint64_t)H * W * a.ldo * 2};
+    uint32_t obox[4] = {32, (uint32_t)p.bw, (uint32_t)p.bh, (uint32_t)p.bn};
+    DG_TRY(make_map_4d(&mO, a.out, od, os, obox, false, true));
+    if (a.residual) {
+      uint64_t rs[3] = {(uint64_t)a.ld_res * 2, (uint64_t)W * a.ld_res * 2, (uint64_t)H * W * a.ld_res * 2};
+      DG_TRY(make_map_4d(&mR, a.residual, od, rs, obox, false, true));
+    } else {
+      mR = mO;
+    }
   }
   const int total_tiles = p.tiles_x * p.tiles_y * p.tiles_b * p.tiles_n;
   const int grid = total_tiles < num_sms ? total_tiles : num_sms;
-  auto kern = gemm_tc_kernel<kGemmBlockN, kGemmStages>;
   if (trace_on())
     fprintf(stderr, "DG_TRACE gemm M=%d N=%d K=%d taps=%d c0=%d c1=%d tiles=%d grid=%d geglu=%d\n", a.B * a.H * a.W, a.n_w,
             a.taps * (a.c0 + a.c1), a.taps, a.c0, a.c1, total_tiles, grid, a.geglu);
   const double rows_ = (double)a.B * a.H * a.W, ktot_ = (double)a.taps * (a.c0 + a.c1);
   ProfScope prof_(FAM_GEMM, stream, 2.0 * rows_ * ktot_ * (double)a.n_w,
                   2.0 * (rows_ * (a.c0 + a.c1) + ktot_ * a.n_w + rows_ * a.n_out));
-  kern<<<grid, 256, S::kTotal, stream>>>(mA0, mA1, mW, p);
+  if (a.geglu)
+    gemm_tc_kernel<kGegluBlockN, kGegluStages, true>
+        <<<grid, 384, GemmSmem<kGegluBlockN, kGegluStages, true>::kTotal, stream>>>(mA0, mA1, mW, mO, mR, p);
+  else
+    gemm_tc_kernel<kGemmBlockN, kGemmStages, false>
+        <<<grid, 384, GemmSmem<kGemmBlockN, kGemmStages, false>::kTotal, stream>>>(mA0, mA1, mW, mO, mR, p);
   DG_LAUNCH_CHECK();
   return DG_OK;
 }
@@ -268,8 +285,10 @@ inline int init_attn_attr() {
   return DG_OK;
 }
 inline int init_kernel_attributes() {
-  DG_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<kGemmBlockN, kGemmStages>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               GemmSmem<kGemmBlockN, kGemmStages>::kTotal));
+  DG_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<kGemmBlockN, kGemmStages, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               GemmSmem<kGemmBlockN, kGemmStages, false>::kTotal));
+  DG_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<kGegluBlockN, kGegluStages, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               GemmSmem<kGegluBlockN, kGegluStages, true>::kTotal));
   DG_TRY((init_attn_attr<32, 128, 4>()));
   DG_TRY((init_attn_attr<40, 128, 4>()));
   DG_TRY((init_attn_attr<64, 128, 3>()));

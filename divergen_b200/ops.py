@@ -64,11 +64,14 @@ def conv3x3_nhwc(x, weight_oihw, bias=None, x1=None, rowvec=None, residual=None)
     assert I == C0 + C1
     wp = torch.empty((O, 9 * I), dtype=torch.float16, device=x.device)
     _lib.check(lib.dg_op_pack_conv3x3(ctx, _p(weight_oihw), _p(wp), O, I, s), "dg_op_pack_conv3x3")
-    out = torch.empty((B, H, W, O), dtype=torch.float16, device=x.device)
+    ldo = (O + 7) // 8 * 8   # TMA store needs a 16-byte row pitch
+    if residual is not None and ldo != O:
+        raise ValueError("residual needs an output width that is a multiple of 8")
+    out = torch.zeros((B, H, W, ldo), dtype=torch.float16, device=x.device)
     _lib.check(lib.dg_op_conv3x3(ctx, _p(x), C0, _p(x1), C1, _p(wp), _p(bias), _p(rowvec),
-                                 rowvec.shape[1] if rowvec is not None else 0, _p(residual), _p(out), B, H, W, O, s),
+                                 rowvec.stride(0) if rowvec is not None else 0, _p(residual), _p(out), B, H, W, O, ldo, s),
                "dg_op_conv3x3")
-    return out
+    return out[..., :O]
 
 
 def attention(q, k, v, heads: int):

@@ -111,7 +111,8 @@ int32_t dg_denoise_loop(dg_unet* unet, void* latents, const void* ehs, int32_t c
  * dg_op_gemm: out[M, n_out] = epi(A[M, K] * W[n_w, K]^T)      <- torch.nn.Linear / Conv2d 1x1
  *    bias [n_w] / residual [M, n_out] optional; geglu: W is GEGLU-packed (see dg_op_pack_geglu), n_out = inner dim.
  * dg_op_conv3x3: NHWC x[B,H,W,C0] (++ x1[B,H,W,C1]) * Wp[N, 9*(C0+C1)] <- Conv2d 3x3 stride 1 pad 1
- *    rowvec [B, ld_rowvec] optional per-sample additive vector (time embedding).
+ *    rowvec [B, ld_rowvec] optional per-sample additive vector (time embedding).  ldo: row pitch of out / residual in
+ *    elements (0 = N); must be a multiple of 8 (TMA store needs 16-byte pitches), so N = 4 (conv_out) uses ldo = 8.
  * dg_op_attention: out[B,Sq,heads*d] = softmax(Q K^T / sqrt(d)) V  <- diffusers Attention core
  *    q/k/v are base pointers of [B, S, ld] fp16 matrices (head h at columns [h*d, (h+1)*d)).
  */
@@ -123,7 +124,7 @@ int32_t dg_op_geglu_packed_rows(int32_t inner);
 int32_t dg_op_pack_conv3x3(dg_ctx* ctx, const void* w_oihw, void* w_out, int32_t O, int32_t I, void* stream);
 int32_t dg_op_conv3x3(dg_ctx* ctx, const void* x0, int32_t C0, const void* x1, int32_t C1, const void* Wp,
                       const void* bias, const void* rowvec, int32_t ld_rowvec, const void* residual, void* out,
-                      int32_t B, int32_t H, int32_t Wd, int32_t N, void* stream);
+                      int32_t B, int32_t H, int32_t Wd, int32_t N, int32_t ldo, void* stream);
 int32_t dg_op_attention(dg_ctx* ctx, const void* q, int32_t ldq, const void* k, int32_t ldk, const void* v, int32_t ldv,
                         void* out, int32_t B, int32_t heads, int32_t Sq, int32_t Sk, int32_t d, void* stream);
 int32_t dg_op_groupnorm(dg_ctx* ctx, const void* x0, int32_t C0, const void* x1, int32_t C1, const void* gamma,

@@ -169,7 +169,7 @@ def test_conv3x3_temb_residual(ops):
     _lib.check(lib.dg_op_pack_conv3x3(ctx, w.data_ptr(), wp.data_ptr(), N, C, s))
     out = torch.empty((B, H, W, N), dtype=torch.float16, device=DEV)
     _lib.check(lib.dg_op_conv3x3(ctx, x.data_ptr(), C, None, 0, wp.data_ptr(), bias.data_ptr(), rv.data_ptr(), 1000,
-                                 res.data_ptr(), out.data_ptr(), B, H, W, N, s))
+                                 res.data_ptr(), out.data_ptr(), B, H, W, N, N, s))
     ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.float(), bias.float(), padding=1).permute(0, 2, 3, 1)
     ref = ref + rv.float()[:, None, None, :] + res.float()
     _report("conv3x3+temb+res", out, ref, 6e-3, 4e-3)
