@@ -68,6 +68,12 @@ SIGNATURES = {
     "dg_op_gemm": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "dg_op_pack_geglu": (_I, [_P, _P, _P, _P, _P, _I, _I, _P]),
     "dg_op_geglu_packed_rows": (_I, [_I]),
+    "dg_op_gemm_row_parts": (_I, [_I]),
+    "dg_op_gemm_fused": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _F, _P, _P, _I, _I, _I, _I, _I, _P, _P, _I, _I, _P]),
+    "dg_op_fold_layernorm": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _P]),
+    "dg_op_row_stats": (_I, [_P, _P, _P, _I, _I, _I, _P]),
+    "dg_op_conv3x3_stats": (_I, [_P, _P, _I, _P, _P, _P, _I, _I, _I, _I, _P, _I, _P]),
+    "dg_op_groupnorm_fused": (_I, [_P, _P, _I, _P, _P, _I, _P, _I, _P, _P, _P, _I, _I, _I, _F, _I, _P]),
     "dg_op_pack_conv3x3": (_I, [_P, _P, _P, _I, _I, _P]),
     "dg_op_conv3x3": (_I, [_P, _P, _I, _P, _I, _P, _P, _P, _I, _P, _P, _I, _I, _I, _I, _I, _P]),
     "dg_op_attention": (_I, [_P, _P, _I, _P, _I, _P, _I, _P, _I, _I, _I, _I, _I, _P]),

@@ -14,6 +14,9 @@ struct dg_ctx {
   int device = 0;
   int num_sms = 0;
   float* gn_stats = nullptr;  // scratch for the stand-alone groupnorm op (tests)
+  GemmRes gemm;               // split-K workspace, tickets, persistent grid size
+  int fuse_ln = 1;            // DG_FUSE_LN=0: stand-alone LayerNorm kernels instead of the folded GEMM epilogue
+  int fuse_gn = 1;            // DG_FUSE_GN=0: stand-alone GroupNorm statistics kernels instead of epilogue sums
 };
 
 // ================================================================== arena allocator (deterministic, graph friendly)
@@ -68,7 +71,11 @@ struct Slot {
 };
 
 struct Norm { __half* g = nullptr; __half* b = nullptr; int c = 0; };
-struct Lin { __half* w = nullptr; __half* b = nullptr; int in = 0, out = 0; int rows = 0; };
+struct Lin {
+  __half* w = nullptr; __half* b = nullptr; int in = 0, out = 0; int rows = 0;
+  // LayerNorm-folded copy (finalize_weights): wf = w * gamma, cs = row sums of wf, b32 = b + w . beta
+  __half* wf = nullptr; float* cs = nullptr; float* b32 = nullptr;
+};
 struct Res { Norm n1, n2; Lin c1, c2, sc; bool has_sc = false; int cin = 0, cout = 0; int temb_off = 0; };
 struct Xf {
   Norm gn, ln1, ln2, ln3;
@@ -78,7 +85,11 @@ struct Xf {
 struct DownBlk { std::vector<Res> res; std::vector<Xf> xf; bool has_down = false; Lin down; };
 struct UpBlk { std::vector<Res> res; std::vector<Xf> xf; bool has_up = false; Lin up; };
 
-struct T4 { __half* p = nullptr; int B = 0, H = 0, W = 0, C = 0; size_t bytes() const { return (size_t)B * H * W * C * 2; } };
+struct T4 {
+  __half* p = nullptr; int B = 0, H = 0, W = 0, C = 0;
+  float* gst = nullptr;   // fused GroupNorm block sums [B][C/blk][2] written by the producing GEMM (nullptr: none)
+  size_t bytes() const { return (size_t)B * H * W * C * 2; }
+};
 
 struct GraphKey {
   int batch, h, w, tokens; const void* sample; const void* ehs; void* out;
@@ -111,6 +122,11 @@ struct dg_unet {
   __half* loop_in = nullptr;  // [2B,4,h,w] CFG-duplicated UNet input
   __half* loop_out = nullptr; // [2B,4,h,w] noise prediction
   int coef_cap = 0;
+  // fused-statistics scratch: bump-allocated per forward in launch order (graph-stable addresses)
+  float* gn_arena = nullptr; size_t gn_cap = 0, gn_off = 0;   // GroupNorm block sums (zeroed at the top of a forward)
+  float* ln_arena = nullptr; size_t ln_cap = 0, ln_off = 0;   // LayerNorm row partials (fully overwritten, never zeroed)
+  int gn_blk = 0;             // channel-block width of the fused GroupNorm sums (block_out_channels[0] / groups), 0 = off
+  bool finalized = false;     // LayerNorm folds are up to date with the loaded weights
   // graphs
   bool use_graphs = true;
   cudaStream_t cap_stream = nullptr;
@@ -181,7 +197,7 @@ int make_fused_rows(dg_unet* u, const std::vector<std::string>& keys, int in, in
   for (size_t i = 0; i < keys.size(); ++i) add_slot(u, keys[i], {out_each, in}, PK_ROWS, l->w, (int64_t)i * out_each, out_each, in);
   return DG_OK;
 }
-int geglu_rows(int inner) { return ((inner + kGegluBlockN / 2 - 1) / (kGegluBlockN / 2)) * kGegluBlockN; }
+int geglu_rows(int inner) { return ((inner + kGemmTileN / 2 - 1) / (kGemmTileN / 2)) * kGemmTileN; }
 int make_xf(dg_unet* u, const std::string& pfx, int c, int heads, Xf* x) {
   const dg_unet_config& cf = u->cfg;
   x->c = c; x->heads = heads; x->ff_inner = 4 * c;
@@ -297,22 +313,63 @@ struct Fwd {
 
 #define FW(expr) do { if (err == DG_OK) err = (expr); } while (0)
 
-  void gn(const T4& x0, const T4* x1, const Norm& n, float eps, int silu, T4& out) {
-    FW(launch_groupnorm(s, sms, x0.p, x0.C, x1 ? x1->p : nullptr, x1 ? x1->C : 0, n.g, n.b, out.p, u->gn_stats, x0.B,
-                        x0.H * x0.W, u->cfg.norm_num_groups, eps, silu));
+  bool fuse_gn() const { return u->gn_blk > 0; }
+  bool fuse_ln() const { return u->ctx->fuse_ln != 0; }
+  // fused GroupNorm block sums for a [B_, *, *, C] tensor about to be produced (zeroed by the memset at the top of the forward)
+  float* gn_alloc(int B_, int C) {
+    if (!fuse_gn()) return nullptr;
+    const size_t n = (size_t)B_ * (C / u->gn_blk) * 2;
+    if (u->gn_off + n > u->gn_cap) { if (err == DG_OK) err = fail(DG_E_NOMEM, "GroupNorm statistics arena exhausted"); return nullptr; }
+    float* p = u->gn_arena + u->gn_off;
+    u->gn_off += (n + 3) & ~size_t(3);
+    return p;
   }
+  // LayerNorm row partials [rows][gemm_row_parts(C)][2] for a token matrix about to be produced
+  float* ln_alloc(int rows, int C) {
+    if (!fuse_ln()) return nullptr;
+    const size_t n = (size_t)rows * gemm_row_parts(C) * 2;
+    if (u->ln_off + n > u->ln_cap) { if (err == DG_OK) err = fail(DG_E_NOMEM, "LayerNorm statistics arena exhausted"); return nullptr; }
+    float* p = u->ln_arena + u->ln_off;
+    u->ln_off += (n + 3) & ~size_t(3);
+    return p;
+  }
+
+  void gn(const T4& x0, const T4* x1, const Norm& n, float eps, int silu, T4& out) {
+    if (fuse_gn() && x0.gst && (!x1 || x1->gst))
+      FW(launch_groupnorm_fused(s, sms, x0.p, x0.C, x0.gst, x1 ? x1->p : nullptr, x1 ? x1->C : 0, x1 ? x1->gst : nullptr,
+                                u->gn_blk, n.g, n.b, out.p, x0.B, x0.H * x0.W, u->cfg.norm_num_groups, eps, silu));
+    else
+      FW(launch_groupnorm(s, sms, x0.p, x0.C, x1 ? x1->p : nullptr, x1 ? x1->C : 0, n.g, n.b, out.p, u->gn_stats, x0.B,
+                          x0.H * x0.W, u->cfg.norm_num_groups, eps, silu));
+  }
+  // 3x3 conv; `out.gst` (if the caller allocated it) receives the fused GroupNorm sums of the result
   void conv3(const T4& x, const Lin& w, const __half* rowvec, const __half* residual, T4& out) {
     GemmArgs a; a.a0 = x.p; a.c0 = x.C; a.B = x.B; a.H = x.H; a.W = x.W; a.taps = 9; a.w = w.w; a.n_w = w.rows;
     a.n_out = w.out; a.bias = w.b; a.rowvec = rowvec; a.ld_rowvec = u->temb_total; a.residual = residual; a.ld_res = w.out;
-    a.out = out.p; a.ldo = w.out;
-    FW(launch_gemm(s, sms, a));
+    a.out = out.p; a.ldo = w.out; a.gn_stats_out = out.gst; a.gn_blk = u->gn_blk;
+    FW(launch_gemm(s, u->ctx->gemm, a));
   }
+  struct LinOpt {
+    const __half* residual = nullptr; int geglu = 0;
+    float* gn_out = nullptr; int hw = 0;         // fused GroupNorm sums of the result (rows per sample = hw)
+    float* rows_out = nullptr;                   // LayerNorm row partials of the result
+    const float* ln_in = nullptr; int ln_c = 0;  // LayerNorm-folded GEMM: row partials of the input (w must carry wf/cs/b32)
+  };
   // plain GEMM over rows = B*H*W of x (optionally 2-source concat along channels)
+  void linear(const __half* x0, int c0, const __half* x1, int c1, int rows, const Lin& w, __half* out, const LinOpt& o) {
+    GemmArgs a; a.a0 = x0; a.c0 = c0; a.a1 = x1; a.c1 = c1; a.B = 1; a.H = 1; a.W = rows; a.taps = 1; a.w = w.w; a.n_w = w.rows;
+    a.n_out = w.out; a.bias = w.b; a.residual = o.residual; a.ld_res = w.out; a.geglu = o.geglu; a.out = out; a.ldo = w.out;
+    a.gn_stats_out = o.gn_out; a.gn_blk = u->gn_blk; a.hw = o.hw; a.row_stats_out = o.rows_out;
+    if (o.ln_in) {
+      a.w = w.wf; a.bias = nullptr; a.bias32 = w.b32; a.colsum = w.cs; a.ln_stats = o.ln_in; a.ln_parts = gemm_row_parts(o.ln_c);
+      a.ln_c = o.ln_c; a.ln_eps = 1e-5f;
+    }
+    FW(launch_gemm(s, u->ctx->gemm, a));
+  }
   void linear(const __half* x0, int c0, const __half* x1, int c1, int rows, const Lin& w, const __half* residual, int geglu,
               __half* out) {
-    GemmArgs a; a.a0 = x0; a.c0 = c0; a.a1 = x1; a.c1 = c1; a.B = 1; a.H = 1; a.W = rows; a.taps = 1; a.w = w.w; a.n_w = w.rows;
-    a.n_out = w.out; a.bias = w.b; a.residual = residual; a.ld_res = w.out; a.geglu = geglu; a.out = out; a.ldo = w.out;
-    FW(launch_gemm(s, sms, a));
+    LinOpt o; o.residual = residual; o.geglu = geglu;
+    linear(x0, c0, x1, c1, rows, w, out, o);
   }
 
   T4 resnet(const Res& r, const T4& x0, const T4* x1) {
@@ -320,12 +377,14 @@ struct Fwd {
     T4 hn = talloc(B_, H, W, r.cin);
     gn(x0, x1, r.n1, u->cfg.norm_eps, 1, hn);
     T4 h1 = talloc(B_, H, W, r.cout);
+    h1.gst = gn_alloc(B_, r.cout);
     conv3(hn, r.c1, temb_all + r.temb_off, nullptr, h1);
     free_(hn);
     T4 h2n = talloc(B_, H, W, r.cout);
     gn(h1, nullptr, r.n2, u->cfg.norm_eps, 1, h2n);
     free_(h1);
     T4 out = talloc(B_, H, W, r.cout);
+    out.gst = gn_alloc(B_, r.cout);
     const __half* resid = x0.p;
     T4 sc{};
     if (r.has_sc) {
@@ -342,35 +401,49 @@ struct Fwd {
   T4 transformer(const Xf& x, const T4& in) {
     const int B_ = in.B, S = in.H * in.W, C = x.c, rows = B_ * S;
     const int d = C / x.heads;
+    const bool fl = fuse_ln();
     T4 xn = talloc(B_, in.H, in.W, C);
     gn(in, nullptr, x.gn, 1e-6f, 0, xn);
     T4 h = talloc(B_, in.H, in.W, C);
-    linear(xn.p, C, nullptr, 0, rows, x.proj_in, nullptr, 0, h.p);
-    // self-attention
-    FW(launch_layernorm(s, h.p, x.ln1.g, x.ln1.b, xn.p, rows, C, 1e-5f));
+    float* rs = ln_alloc(rows, C);
+    { LinOpt o; o.rows_out = rs; linear(xn.p, C, nullptr, 0, rows, x.proj_in, h.p, o); }
+    // self-attention: LayerNorm folded into the QKV projection (or a stand-alone LayerNorm pass when fusion is off)
     __half* qkv = alloc((size_t)rows * 3 * C * 2);
-    linear(xn.p, C, nullptr, 0, rows, x.qkv, nullptr, 0, qkv);
+    if (fl) { LinOpt o; o.ln_in = rs; o.ln_c = C; linear(h.p, C, nullptr, 0, rows, x.qkv, qkv, o); }
+    else {
+      FW(launch_layernorm(s, h.p, x.ln1.g, x.ln1.b, xn.p, rows, C, 1e-5f));
+      linear(xn.p, C, nullptr, 0, rows, x.qkv, nullptr, 0, qkv);
+    }
     if (err == DG_OK) FW(launch_attention(s, qkv, 3 * C, qkv + C, 3 * C, qkv + 2 * C, 3 * C, xn.p, B_, x.heads, S, S, d));
     free_(qkv);
-    linear(xn.p, C, nullptr, 0, rows, x.o1, h.p, 0, h.p);
+    rs = ln_alloc(rows, C);
+    { LinOpt o; o.residual = h.p; o.rows_out = rs; linear(xn.p, C, nullptr, 0, rows, x.o1, h.p, o); }
     // cross-attention
-    FW(launch_layernorm(s, h.p, x.ln2.g, x.ln2.b, xn.p, rows, C, 1e-5f));
     __half* q = alloc((size_t)rows * C * 2);
-    linear(xn.p, C, nullptr, 0, rows, x.q2, nullptr, 0, q);
+    if (fl) { LinOpt o; o.ln_in = rs; o.ln_c = C; linear(h.p, C, nullptr, 0, rows, x.q2, q, o); }
+    else {
+      FW(launch_layernorm(s, h.p, x.ln2.g, x.ln2.b, xn.p, rows, C, 1e-5f));
+      linear(xn.p, C, nullptr, 0, rows, x.q2, nullptr, 0, q);
+    }
     __half* kv = alloc((size_t)B_ * tokens * 2 * C * 2);
     linear(ehs, u->cfg.cross_attention_dim, nullptr, 0, B_ * tokens, x.kv2, nullptr, 0, kv);
     if (err == DG_OK) FW(launch_attention(s, q, C, kv, 2 * C, kv + C, 2 * C, xn.p, B_, x.heads, S, tokens, d));
     free_(q); free_(kv);
-    linear(xn.p, C, nullptr, 0, rows, x.o2, h.p, 0, h.p);
+    rs = ln_alloc(rows, C);
+    { LinOpt o; o.residual = h.p; o.rows_out = rs; linear(xn.p, C, nullptr, 0, rows, x.o2, h.p, o); }
     // feed-forward (GEGLU)
-    FW(launch_layernorm(s, h.p, x.ln3.g, x.ln3.b, xn.p, rows, C, 1e-5f));
     __half* g = alloc((size_t)rows * x.ff_inner * 2);
-    linear(xn.p, C, nullptr, 0, rows, x.ff1, nullptr, 1, g);
+    if (fl) { LinOpt o; o.ln_in = rs; o.ln_c = C; o.geglu = 1; linear(h.p, C, nullptr, 0, rows, x.ff1, g, o); }
+    else {
+      FW(launch_layernorm(s, h.p, x.ln3.g, x.ln3.b, xn.p, rows, C, 1e-5f));
+      linear(xn.p, C, nullptr, 0, rows, x.ff1, nullptr, 1, g);
+    }
     linear(g, x.ff_inner, nullptr, 0, rows, x.ff2, h.p, 0, h.p);
     free_(g);
     // proj_out + residual with the block input
     T4 out = talloc(B_, in.H, in.W, C);
-    linear(h.p, C, nullptr, 0, rows, x.proj_out, in.p, 0, out.p);
+    out.gst = gn_alloc(B_, C);
+    { LinOpt o; o.residual = in.p; o.gn_out = out.gst; o.hw = S; linear(h.p, C, nullptr, 0, rows, x.proj_out, out.p, o); }
     free_(xn); free_(h);
     return out;
   }
@@ -380,7 +453,9 @@ int run_forward(dg_unet* u, cudaStream_t s, const __half* sample, const __half* 
   const dg_unet_config& cf = u->cfg;
   const int sms = u->ctx->num_sms;
   u->arena.reset();
+  u->gn_off = 0; u->ln_off = 0;
   Fwd f{u, s, sms, B, tokens, ehs, nullptr};
+  if (u->gn_blk > 0) DG_CUDA(cudaMemsetAsync(u->gn_arena, 0, u->gn_cap * sizeof(float), s));
 
   // ---- time embedding: sinusoid -> MLP -> all time_emb_proj(SiLU(emb)) in one GEMV
   const int c0 = cf.block_out_channels[0];
@@ -406,7 +481,8 @@ int run_forward(dg_unet* u, cudaStream_t s, const __half* sample, const __half* 
     const size_t items = (size_t)B * h * w * 64;
     im2col_conv_in_kernel<<<grid_for(items, 256, sms), 256, 0, s>>>(sample, col, B, cf.in_channels, h, w, 64);
     DG_LAUNCH_CHECK();
-    f.linear(col, 64, nullptr, 0, B * h * w, u->conv_in, nullptr, 0, x.p);
+    x.gst = f.gn_alloc(B, c0);
+    { Fwd::LinOpt o; o.gn_out = x.gst; o.hw = h * w; f.linear(col, 64, nullptr, 0, B * h * w, u->conv_in, x.p, o); }
     f.free_(col);
   }
   std::vector<T4> skips;
@@ -427,7 +503,8 @@ int run_forward(dg_unet* u, cudaStream_t s, const __half* sample, const __half* 
       const size_t items = (size_t)x.B * Ho * Wo * 9 * (x.C / 8);
       im2col3x3_nhwc_kernel<<<grid_for(items, 256, sms), 256, 0, s>>>(x.p, c2, x.B, x.H, x.W, x.C, 2, Ho, Wo);
       DG_LAUNCH_CHECK();
-      f.linear(c2, 9 * x.C, nullptr, 0, x.B * Ho * Wo, d.down, nullptr, 0, y.p);
+      y.gst = f.gn_alloc(x.B, x.C);
+      { Fwd::LinOpt o; o.gn_out = y.gst; o.hw = Ho * Wo; f.linear(c2, 9 * x.C, nullptr, 0, x.B * Ho * Wo, d.down, y.p, o); }
       f.free_(c2);
       x = y; skips.push_back(x);
     }
@@ -456,6 +533,7 @@ int run_forward(dg_unet* u, cudaStream_t s, const __half* sample, const __half* 
       const size_t items = (size_t)x.B * 4 * x.H * x.W * (x.C / 8);
       upsample2x_nhwc_kernel<<<grid_for(items, 256, sms), 256, 0, s>>>(x.p, upx.p, x.B, x.H, x.W, x.C);
       DG_LAUNCH_CHECK();
+      y.gst = f.gn_alloc(x.B, x.C);
       f.conv3(upx, b.up, nullptr, nullptr, y);
       f.free_(upx); f.free_(x);
       x = y;
@@ -471,7 +549,7 @@ int run_forward(dg_unet* u, cudaStream_t s, const __half* sample, const __half* 
   {
     GemmArgs a; a.a0 = xn.p; a.c0 = xn.C; a.B = B; a.H = h; a.W = w; a.taps = 9; a.w = u->conv_out.w; a.n_w = u->conv_out.rows;
     a.n_out = cf.out_channels; a.bias = u->conv_out.b; a.out = o.p; a.ldo = opitch;
-    if (f.err == DG_OK) f.err = launch_gemm(s, sms, a);
+    if (f.err == DG_OK) f.err = launch_gemm(s, u->ctx->gemm, a);
   }
   if (f.err) return f.err;
   {
@@ -534,6 +612,36 @@ int forward_maybe_graph(dg_unet* u, cudaStream_t s, const __half* sample, const 
   return DG_OK;
 }
 
+// LayerNorm folds of the three GEMMs that consume a LayerNorm output in every transformer block (qkv, to_q of the
+// cross-attention, GEGLU projection).  Runs once after load_state_dict, outside any graph capture.
+int fold_lin(dg_unet* u, Lin* l, const Norm& n) {
+  if (!l->wf) {
+    DG_TRY(dev_alloc(u, (void**)&l->wf, (size_t)l->rows * l->in * 2));
+    DG_TRY(dev_alloc(u, (void**)&l->cs, (size_t)l->rows * 4));
+    DG_TRY(dev_alloc(u, (void**)&l->b32, (size_t)l->rows * 4));
+  }
+  fold_layernorm_kernel<<<(l->rows + 7) / 8, 256>>>(l->w, l->b, n.g, n.b, l->wf, l->cs, l->b32, l->rows, l->in);
+  DG_LAUNCH_CHECK();
+  return DG_OK;
+}
+int finalize_weights(dg_unet* u) {
+  if (u->finalized) return DG_OK;
+  auto fold_xf = [&](Xf& x) -> int {
+    DG_TRY(fold_lin(u, &x.qkv, x.ln1));
+    DG_TRY(fold_lin(u, &x.q2, x.ln2));
+    DG_TRY(fold_lin(u, &x.ff1, x.ln3));
+    return DG_OK;
+  };
+  for (auto& d : u->down) for (auto& x : d.xf) DG_TRY(fold_xf(x));
+  DG_TRY(fold_xf(u->mid_xf));
+  for (auto& b : u->up) for (auto& x : b.xf) DG_TRY(fold_xf(x));
+  DG_CUDA(cudaDeviceSynchronize());
+  for (auto& g : u->graphs) cudaGraphExecDestroy(g.exec);   // captured graphs point at stale folds
+  u->graphs.clear();
+  u->finalized = true;
+  return DG_OK;
+}
+
 int check_prepared(dg_unet* u, int batch, int h, int w, int tokens) {
   if (!u->arena.base) return fail(DG_E_STATE, "dg_unet_prepare has not been called");
   if (batch > u->max_batch || h * w > u->ws_h * u->ws_w || tokens > u->ws_tokens)
@@ -543,7 +651,7 @@ int check_prepared(dg_unet* u, int batch, int h, int w, int tokens) {
   int missing = 0;
   for (auto& sl : u->slots) missing += sl.set ? 0 : 1;
   if (missing) return fail(DG_E_STATE, "%d weights have not been set", missing);
-  return DG_OK;
+  return finalize_weights(u);
 }
 
 }  // namespace
@@ -569,12 +677,22 @@ int32_t dg_ctx_create(int32_t device, dg_ctx** out) {
   c->device = device;
   c->num_sms = prop.multiProcessorCount;
   DG_CUDA(cudaMalloc(&c->gn_stats, sizeof(float) * 2 * 64 * 64));
+  c->gemm.num_sms = c->num_sms;
+  DG_TRY(query_max_pairs(&c->gemm.max_pairs));
+  DG_CUDA(cudaMalloc(&c->gemm.ws, kSplitWsFloats * sizeof(float)));
+  DG_CUDA(cudaMalloc(&c->gemm.tickets, kSplitTickets * sizeof(int)));
+  DG_CUDA(cudaMemset(c->gemm.tickets, 0, kSplitTickets * sizeof(int)));
+  auto env_int = [](const char* name, int dflt) { const char* e = getenv(name); return e && e[0] ? atoi(e) : dflt; };
+  c->gemm.cta_mode = env_int("DG_GEMM_CTA", 2) == 1 ? 1 : 2;
+  if (env_int("DG_SPLITK", 1) == 0) { cudaFree(c->gemm.ws); c->gemm.ws = nullptr; }
+  c->fuse_ln = env_int("DG_FUSE_LN", 1);
+  c->fuse_gn = env_int("DG_FUSE_GN", 1);
   *out = c;
   return DG_OK;
 }
 void dg_ctx_destroy(dg_ctx* ctx) {
   if (!ctx) return;
-  cudaFree(ctx->gn_stats);
+  cudaFree(ctx->gn_stats); cudaFree(ctx->gemm.ws); cudaFree(ctx->gemm.tickets);
   delete ctx;
 }
 
@@ -589,6 +707,16 @@ int32_t dg_unet_create(dg_ctx* ctx, const dg_unet_config* cfg, dg_unet** out) {
   DG_CUDA(cudaSetDevice(ctx->device));
   std::unique_ptr<dg_unet> u(new dg_unet());
   u->ctx = ctx; u->cfg = *cfg;
+  {
+    // fused GroupNorm sums are kept per (sample, blk-channel block); every channel count of the UNet is a multiple of
+    // block_out_channels[0], so blk = block_out_channels[0] / groups tiles every (concatenated) group exactly.
+    const int c0 = cfg->block_out_channels[0], g = cfg->norm_num_groups;
+    bool ok = ctx->fuse_gn && g > 0 && c0 % g == 0;
+    const int blk = ok ? c0 / g : 0;
+    ok = ok && blk % 2 == 0 && 160 % blk == 0;
+    for (int i = 0; ok && i < 4; ++i) ok = cfg->block_out_channels[i] % c0 == 0;
+    u->gn_blk = ok ? blk : 0;
+  }
   int r = build_modules(u.get());
   if (r != DG_OK) { for (void* p : u->owned) cudaFree(p); return r; }
   *out = u.release();
@@ -600,7 +728,7 @@ void dg_unet_destroy(dg_unet* u) {
   if (u->cap_stream) cudaStreamDestroy(u->cap_stream);
   for (void* p : u->owned) cudaFree(p);
   cudaFree(u->arena.base); cudaFree(u->d_t); cudaFree(u->gn_stats); cudaFree(u->d_coef); cudaFree(u->d_step);
-  cudaFree(u->loop_in); cudaFree(u->loop_out);
+  cudaFree(u->loop_in); cudaFree(u->loop_out); cudaFree(u->gn_arena); cudaFree(u->ln_arena);
   delete u;
 }
 int32_t dg_unet_num_weights(dg_unet* u) { return u ? (int32_t)u->slots.size() : 0; }
@@ -646,14 +774,15 @@ int32_t dg_unet_set_weight(dg_unet* u, const char* key, const void* src, int32_t
       break;
     case PK_GEGLU_W:
     case PK_GEGLU_B: {
-      const int tiles = geglu_rows(s.a) / kGegluBlockN;
-      pack_geglu_kernel<<<grid_for((size_t)tiles * kGegluBlockN * s.b, 256, sms), 256>>>(w, s.dst, s.a, s.b, kGegluBlockN, tiles);
+      const int tiles = geglu_rows(s.a) / kGemmTileN;
+      pack_geglu_kernel<<<grid_for((size_t)tiles * kGemmTileN * s.b, 256, sms), 256>>>(w, s.dst, s.a, s.b, kGemmTileN, tiles);
       DG_LAUNCH_CHECK();
       break;
     }
   }
   DG_CUDA(cudaDeviceSynchronize());
   s.set = true;
+  u->finalized = false;
   return DG_OK;
 }
 
@@ -677,6 +806,16 @@ int32_t dg_unet_prepare(dg_unet* u, int32_t max_batch, int32_t h, int32_t w, int
   DG_CUDA(cudaMalloc((void**)&u->loop_in, lat));
   DG_CUDA(cudaMalloc((void**)&u->loop_out, lat));
   if (!u->d_step) DG_CUDA(cudaMalloc((void**)&u->d_step, sizeof(int)));
+  cudaFree(u->gn_arena); cudaFree(u->ln_arena);
+  u->gn_arena = nullptr; u->ln_arena = nullptr;
+  {
+    // ~70 GroupNorm inputs of at most 4*c0 channels; 48 LayerNorm inputs of at most pix rows x 8 partials
+    const int blk = u->gn_blk > 0 ? u->gn_blk : 2;
+    u->gn_cap = (size_t)96 * max_batch * (4 * c0 / blk + 4) * 2;
+    u->ln_cap = (size_t)pix * 64 * (2 + c0 / 80) + ((size_t)1 << 20);   // >= 3x the sum over blocks of rows*parts*2
+    DG_CUDA(cudaMalloc((void**)&u->gn_arena, u->gn_cap * sizeof(float)));
+    DG_CUDA(cudaMalloc((void**)&u->ln_arena, u->ln_cap * sizeof(float)));
+  }
   u->max_batch = max_batch; u->ws_h = h; u->ws_w = w; u->ws_tokens = ctx_tokens;
   return DG_OK;
 }
@@ -808,16 +947,59 @@ int32_t dg_op_gemm(dg_ctx* ctx, const void* A, const void* W, const void* bias, 
   GemmArgs a; a.a0 = (const __half*)A; a.c0 = K; a.B = 1; a.H = 1; a.W = M; a.taps = 1; a.w = (const __half*)W; a.n_w = n_w;
   a.n_out = n_out; a.bias = (const __half*)bias; a.residual = (const __half*)residual; a.ld_res = n_out; a.geglu = geglu;
   a.out = (__half*)out; a.ldo = n_out;
-  return launch_gemm((cudaStream_t)stream, ctx->num_sms, a);
+  return launch_gemm((cudaStream_t)stream, ctx->gemm, a);
 }
 int32_t dg_op_geglu_packed_rows(int32_t inner) { return geglu_rows(inner); }
+int32_t dg_op_gemm_row_parts(int32_t n_out) { return gemm_row_parts(n_out); }
+int32_t dg_op_gemm_fused(dg_ctx* ctx, const void* A, const void* W, const void* bias, const float* bias32, const float* colsum,
+                         const float* ln_stats, int32_t ln_c, float ln_eps, const void* residual, void* out, int32_t M, int32_t K,
+                         int32_t n_w, int32_t n_out, int32_t geglu, float* row_stats_out, float* gn_stats_out, int32_t gn_blk,
+                         int32_t hw, void* stream) {
+  if (!ctx || !A || !W || !out) return fail(DG_E_ARG, "null argument");
+  GemmArgs a; a.a0 = (const __half*)A; a.c0 = K; a.B = 1; a.H = 1; a.W = M; a.taps = 1; a.w = (const __half*)W; a.n_w = n_w;
+  a.n_out = n_out; a.bias = (const __half*)bias; a.bias32 = bias32; a.colsum = colsum; a.ln_stats = ln_stats;
+  a.ln_parts = gemm_row_parts(ln_c); a.ln_c = ln_c; a.ln_eps = ln_eps;
+  a.residual = (const __half*)residual; a.ld_res = n_out; a.geglu = geglu; a.out = (__half*)out; a.ldo = n_out;
+  a.row_stats_out = row_stats_out; a.gn_stats_out = gn_stats_out; a.gn_blk = gn_blk; a.hw = hw;
+  return launch_gemm((cudaStream_t)stream, ctx->gemm, a);
+}
+int32_t dg_op_fold_layernorm(dg_ctx* ctx, const void* W, const void* bias, const void* gamma, const void* beta, void* Wf,
+                             float* colsum, float* b32, int32_t N, int32_t K, void* stream) {
+  if (!ctx || !W || !gamma || !beta || !Wf || !colsum || !b32) return fail(DG_E_ARG, "null argument");
+  fold_layernorm_kernel<<<(N + 7) / 8, 256, 0, (cudaStream_t)stream>>>((const __half*)W, (const __half*)bias, (const __half*)gamma,
+                                                                      (const __half*)beta, (__half*)Wf, colsum, b32, N, K);
+  DG_LAUNCH_CHECK();
+  return DG_OK;
+}
+int32_t dg_op_row_stats(dg_ctx* ctx, const void* x, float* stats, int32_t rows, int32_t C, int32_t parts, void* stream) {
+  if (!ctx || !x || !stats || parts <= 0) return fail(DG_E_ARG, "bad argument");
+  row_stats_kernel<<<(rows + 7) / 8, 256, 0, (cudaStream_t)stream>>>((const __half*)x, stats, rows, C, parts);
+  DG_LAUNCH_CHECK();
+  return DG_OK;
+}
+int32_t dg_op_conv3x3_stats(dg_ctx* ctx, const void* x0, int32_t C0, const void* Wp, const void* bias, void* out, int32_t B,
+                            int32_t H, int32_t Wd, int32_t N, float* gn_stats_out, int32_t gn_blk, void* stream) {
+  if (!ctx || !x0 || !Wp || !out || !gn_stats_out) return fail(DG_E_ARG, "null argument");
+  GemmArgs a; a.a0 = (const __half*)x0; a.c0 = C0; a.B = B; a.H = H; a.W = Wd; a.taps = 9;
+  a.w = (const __half*)Wp; a.n_w = N; a.n_out = N; a.bias = (const __half*)bias; a.out = (__half*)out; a.ldo = N;
+  a.gn_stats_out = gn_stats_out; a.gn_blk = gn_blk;
+  return launch_gemm((cudaStream_t)stream, ctx->gemm, a);
+}
+int32_t dg_op_groupnorm_fused(dg_ctx* ctx, const void* x0, int32_t C0, const float* stats0, const void* x1, int32_t C1,
+                              const float* stats1, int32_t blk, const void* gamma, const void* beta, void* out, int32_t B,
+                              int32_t HW, int32_t groups, float eps, int32_t silu, void* stream) {
+  if (!ctx || !x0 || !stats0 || !gamma || !beta || !out || (x1 && !stats1)) return fail(DG_E_ARG, "null argument");
+  return launch_groupnorm_fused((cudaStream_t)stream, ctx->num_sms, (const __half*)x0, C0, stats0, (const __half*)x1, C1, stats1,
+                                blk, (const __half*)gamma, (const __half*)beta, (__half*)out, B, HW, groups, eps, silu);
+}
+
 int32_t dg_op_pack_geglu(dg_ctx* ctx, const void* w, const void* b, void* w_out, void* b_out, int32_t inner, int32_t K, void* stream) {
   if (!ctx || !w || !b || !w_out || !b_out) return fail(DG_E_ARG, "null argument");
-  const int tiles = geglu_rows(inner) / kGegluBlockN;
+  const int tiles = geglu_rows(inner) / kGemmTileN;
   cudaStream_t s = (cudaStream_t)stream;
-  pack_geglu_kernel<<<grid_for((size_t)tiles * kGegluBlockN * K, 256, ctx->num_sms), 256, 0, s>>>((const __half*)w, (__half*)w_out, inner, K, kGegluBlockN, tiles);
+  pack_geglu_kernel<<<grid_for((size_t)tiles * kGemmTileN * K, 256, ctx->num_sms), 256, 0, s>>>((const __half*)w, (__half*)w_out, inner, K, kGemmTileN, tiles);
   DG_LAUNCH_CHECK();
-  pack_geglu_kernel<<<grid_for((size_t)tiles * kGegluBlockN, 256, ctx->num_sms), 256, 0, s>>>((const __half*)b, (__half*)b_out, inner, 1, kGegluBlockN, tiles);
+  pack_geglu_kernel<<<grid_for((size_t)tiles * kGemmTileN, 256, ctx->num_sms), 256, 0, s>>>((const __half*)b, (__half*)b_out, inner, 1, kGemmTileN, tiles);
   DG_LAUNCH_CHECK();
   return DG_OK;
 }
@@ -835,7 +1017,7 @@ int32_t dg_op_conv3x3(dg_ctx* ctx, const void* x0, int32_t C0, const void* x1, i
   GemmArgs a; a.a0 = (const __half*)x0; a.c0 = C0; a.a1 = (const __half*)x1; a.c1 = C1; a.B = B; a.H = H; a.W = Wd; a.taps = 9;
   a.w = (const __half*)Wp; a.n_w = N; a.n_out = N; a.bias = (const __half*)bias; a.rowvec = (const __half*)rowvec; a.ld_rowvec = ld_rowvec;
   a.residual = (const __half*)residual; a.ld_res = ldo; a.out = (__half*)out; a.ldo = ldo;
-  return launch_gemm((cudaStream_t)stream, ctx->num_sms, a);
+  return launch_gemm((cudaStream_t)stream, ctx->gemm, a);
 }
 int32_t dg_op_attention(dg_ctx* ctx, const void* q, int32_t ldq, const void* k, int32_t ldk, const void* v, int32_t ldv, void* out,
                         int32_t B, int32_t heads, int32_t Sq, int32_t Sk, int32_t d, void* stream) {

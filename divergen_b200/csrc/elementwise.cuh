@@ -143,6 +143,101 @@ __global__ void gn_apply_kernel(const __half* __restrict__ x0, int C0, const __h
   }
 }
 
+// Same apply pass, statistics taken from the producers' fused epilogue sums: stats{0,1}[b][C{0,1}/blk][2] hold
+// (sum, sum of squares) over blk-channel blocks of each source (gemm2_tc.cuh); a group of the concatenated tensor is a
+// union of whole blocks, so each CTA first folds them into 32 (mean, rstd) pairs in shared memory.
+__global__ void gn_apply_blk_kernel(const __half* __restrict__ x0, int C0, const __half* __restrict__ x1, int C1, int HW,
+                                    int groups, float eps, int pix_per_block, const float* __restrict__ stats0,
+                                    const float* __restrict__ stats1, int blk, const __half* __restrict__ gamma,
+                                    const __half* __restrict__ beta, int do_silu, __half* __restrict__ out) {
+  __shared__ float s_mean[64], s_rstd[64];
+  const int C = C0 + C1, cpg = C / groups, nvec = C / 8;
+  const int b = blockIdx.y;
+  const int p0 = blockIdx.x * pix_per_block;
+  const int p1 = min(HW, p0 + pix_per_block);
+  const float inv_n = 1.0f / ((float)cpg * (float)HW);
+  if ((int)threadIdx.x < groups) {
+    const int g = threadIdx.x;
+    const int nb0 = C0 / blk, nb1 = C1 / blk, bpg = cpg / blk;
+    float a = 0.f, q = 0.f;
+    for (int i = 0; i < bpg; ++i) {
+      const int cb = g * bpg + i;
+      const float* sp = (cb < nb0) ? stats0 + ((size_t)b * nb0 + cb) * 2 : stats1 + ((size_t)b * nb1 + (cb - nb0)) * 2;
+      a += sp[0]; q += sp[1];
+    }
+    const float mean = a * inv_n;
+    const float var = fmaxf(q * inv_n - mean * mean, 0.f);
+    s_mean[g] = mean; s_rstd[g] = rsqrtf(var + eps);
+  }
+  __syncthreads();
+  const GnThreadMap tm(nvec);
+  for (int v = tm.v0; v < nvec; v += tm.vstep) {
+    const int c = v * 8;
+    float sc[8], sf[8], g[8], be[8];
+    load8(gamma + c, g);
+    load8(beta + c, be);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int grp = (c + k) / cpg;
+      sc[k] = s_rstd[grp] * g[k];
+      sf[k] = be[k] - s_mean[grp] * sc[k];
+    }
+    const __half* src = (c < C0) ? x0 + c : x1 + (c - C0);
+    const int ld = (c < C0) ? C0 : C1;
+#pragma unroll 4
+    for (int p = p0 + tm.pofs; p < p1; p += tm.pstride) {
+      const size_t pix = (size_t)b * HW + p;
+      float f[8];
+      load8(src + pix * ld, f);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const float y = fmaf(f[k], sc[k], sf[k]);
+        f[k] = do_silu ? __fdividef(y, 1.0f + __expf(-y)) : y;
+      }
+      store8(out + pix * C + c, f);
+    }
+  }
+}
+
+// ------------------------------------------------------------------ LayerNorm fold (one-off, at weight finalisation)
+// LN(x) W^T + b  ==  rstd * (x Wf^T - mean * colsum) + b32   with  Wf[n,c] = W[n,c]*gamma[c],
+// colsum[n] = sum_c Wf[n,c] (of the ROUNDED fp16 Wf, so the mean term cancels exactly what the GEMM accumulates),
+// b32[n] = b[n] + sum_c beta[c]*W[n,c].  One warp per weight row.
+__global__ void fold_layernorm_kernel(const __half* __restrict__ W, const __half* __restrict__ bias,
+                                      const __half* __restrict__ gamma, const __half* __restrict__ beta,
+                                      __half* __restrict__ Wf, float* __restrict__ colsum, float* __restrict__ b32,
+                                      int N, int K) {
+  const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (n >= N) return;
+  float cs = 0.f, bs = 0.f;
+  for (int k = lane; k < K; k += 32) {
+    const float w = __half2float(W[(size_t)n * K + k]);
+    const __half wf = __float2half_rn(w * __half2float(gamma[k]));
+    Wf[(size_t)n * K + k] = wf;
+    cs += __half2float(wf);
+    bs = fmaf(__half2float(beta[k]), w, bs);
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) { cs += __shfl_xor_sync(0xffffffffu, cs, o); bs += __shfl_xor_sync(0xffffffffu, bs, o); }
+  if (lane == 0) { colsum[n] = cs; b32[n] = bs + (bias ? __half2float(bias[n]) : 0.f); }
+}
+
+// Per-row (sum, sumsq) of a [rows, C] fp16 matrix in the layout the GEMM epilogue produces ([rows][parts][2], part 0
+// carries everything): used by the operator-level tests when no producing GEMM exists.
+__global__ void row_stats_kernel(const __half* __restrict__ x, float* __restrict__ stats, int rows, int C, int parts) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  float s = 0.f, ss = 0.f;
+  for (int k = lane; k < C; k += 32) { const float v = __half2float(x[(size_t)row * C + k]); s += v; ss = fmaf(v, v, ss); }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); ss += __shfl_xor_sync(0xffffffffu, ss, o); }
+  if (lane == 0) {
+    for (int i = 0; i < parts; ++i) { stats[((size_t)row * parts + i) * 2] = i ? 0.f : s; stats[((size_t)row * parts + i) * 2 + 1] = i ? 0.f : ss; }
+  }
+}
+
 // ------------------------------------------------------------------ LayerNorm over the last dim (one warp per row)
 template <int kMaxVec>
 __global__ void layernorm_kernel(const __half* __restrict__ x, const __half* __restrict__ gamma,

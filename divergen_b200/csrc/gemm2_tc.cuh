@@ -1,0 +1,631 @@
+// tcgen05 implicit-GEMM kernel, second generation: CTA-pair (cta_group::2) 256 x 320 tiles, split-K, fused statistics.
+//
+//   out[pixel, n] = epilogue( sum_{tap, c} A[pixel + tap_offset, c] * Wt[n, tap*C + c] )
+//
+// One kernel serves every Linear, 1x1 conv and 3x3 (stride-1, pad-1) conv of the UNet.  A is an NHWC fp16 activation
+// tensor behind a 4-D TMA map {C, W, H, B}: a 128-row M tile is a {bw x bh x bn} box of pixels, each 3x3 tap is the same
+// box shifted by (dx, dy) with TMA out-of-bounds zero fill as the padding; a plain [M, K] GEMM is {K, M, 1, 1} with one
+// tap.  Up to two A sources split the channel range (`cat([x, skip])` is never materialised).  Wt is the K-major packed
+// weight [N, taps*C] behind a 2-D map.
+//
+// Why CTA pairs: a 128 x 160 tile moves 36 KB of operands per 64-wide k-block for 1.3 MMAC, 115 B/clk/SM at the tensor
+// pipe's rate -- measured tensor-pipe utilisation 63 % (profiles/r01_ncu_gemm_v3.txt).  Two CTAs of a cluster each load
+// their own 128 pixels of A and HALF of each 160-row weight block; tcgen05.mma.cta_group::2 (M = 256) reads the other
+// half from the peer's shared memory.  Per CTA: the same 36 KB per k-block now feeds 128 x 320 outputs (57 B/clk/SM).
+//
+// Warp roles (384 threads per CTA): warp 0 = TMA producer (one lane), warp 1 = MMA issuer (one lane, leader CTA only),
+// warp 2 = TMEM allocator, warps 4..11 = epilogue.  Persistent over work units (tile x K-split), kStages-deep smem ring.
+// Barrier protocol for a pair: both producers' TMA bytes complete on the LEADER's full barrier (peer-bit-masked barrier
+// address); the leader's tcgen05.commit multicasts stage-free / accumulator-ready arrivals to both CTAs; every epilogue
+// warp of either CTA arrives remotely on the leader's accumulator-free barrier.
+//
+// Epilogue (per CTA: its own 128 rows x 320 columns, fp32 in TMEM), in chunks of 32 columns per thread:
+//   tcgen05.ld -> [LayerNorm fold: rstd*(acc - mean*colsum[n])] + bias (+ time-embedding vector) (+ residual, prefetched
+//   one chunk ahead with 16-byte loads) [GEGLU: value * gelu(gate)] -> fp16 -> 64-byte-swizzled staging ring -> TMA store.
+//   Fused statistics on the rounded outputs: per-row (sum, sum of squares) partials for the LayerNorm that consumes this
+//   tensor, and per-(sample, channel-block) sums for the next GroupNorm (warp shuffle reduce + fp32 atomics).
+// Split-K (small-M layers at the bottom of the U): each split writes its fp32 partial tile to an L2-resident workspace;
+//   the last arriver (atomic ticket) sums the partials in split order (deterministic) and runs the epilogue.
+//
+// Replaces (reference side): torch.nn.Conv2d / Linear / LayerNorm / GroupNorm statistics inside diffusers ResnetBlock2D,
+// Attention, FeedForward, Transformer2DModel, reached from DiverGen/generation/txt2img_diffusers_stages_from_txt.py:255-259.
+#pragma once
+#include "common.cuh"
+
+namespace dg {
+
+struct Gemm2Params {
+  // problem
+  int n_out;        // valid output columns (after GEGLU halving if enabled)
+  int n_gemm;       // rows of Wt that are meaningful
+  int taps;         // 1 or 9
+  int kb0, kb1;     // 64-channel k-blocks taken from source 0 / source 1 per tap
+  int splits;       // K splits per tile (>= 1)
+  // M tiling (pixels)
+  int W, H, B;      // logical A dims (plain GEMM: W = M, H = B = 1)
+  int bw, bh, bn;   // box; bw*bh*bn == 128
+  int tiles_x, tiles_y, tiles_b, tiles_n;
+  int hw;           // plain GEMM only: rows per sample (0 = unknown / not needed)
+  // epilogue
+  const __half* bias;      // [n_gemm] fp16 or nullptr
+  const float* bias32;     // [n_gemm] fp32 (LayerNorm-folded layers) or nullptr
+  const float* colsum;     // [n_gemm] fp32: sum_c gamma[c]*W[n,c]   (LayerNorm fold; needs ln_stats)
+  const float* ln_stats;   // [rows][ln_parts][2] (sum, sumsq) partials of the A rows
+  int ln_parts;
+  float ln_inv_c, ln_eps;
+  const __half* rowvec;    // [B, ld_rowvec] per-sample additive vector (time embedding) or nullptr
+  int ld_rowvec;
+  const __half* residual;  // same geometry as out (row pitch ld_res) or nullptr
+  int ld_res;
+  float* row_stats_out;    // [rows][row_parts][2]; this launch writes part nt*2 + hf   (plain GEMM only)
+  int row_parts;
+  float* gn_stats_out;     // [B][gn_nblk][2] fp32 atomics: sums over gn_blk-channel blocks
+  int gn_blk, gn_nblk;
+  float* ws;               // split-K workspace: [m_tile*tiles_n + nt][split][128][320] fp32
+  int* tickets;            // [m_tile*tiles_n + nt], zero on entry, zero on exit
+};
+
+template <int kCta, int kStages>
+struct Gemm2Cfg {
+  static constexpr int kNI = 160;                       // N of one MMA instruction
+  static constexpr int kBN = 320;                       // tile N = two accumulators
+  static constexpr int kABytes = 128 * 64 * 2;          // 16 KB: 128 pixels x 64 channels
+  static constexpr int kBRows = kNI / kCta;             // weight rows this CTA loads per accumulator
+  static constexpr int kBHalfBytes = kBRows * 128;
+  static constexpr int kBBytes = 2 * kBHalfBytes;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kSubBytes = 128 * 64;            // staging sub-tile [128 rows][32 cols fp16], 64-byte swizzle
+  static constexpr int kRingBytes = 2 * 2 * kSubBytes;  // two buffers x two sub-tiles (one per column half)
+  static constexpr int kVecBytes = 2 * kBN * 4;         // bias + colsum, fp32
+  static constexpr int kBarBytes = 256;
+  static constexpr int kTotal = kStages * kStageBytes + kRingBytes + kVecBytes + kBarBytes + 1024 /*align slack*/;
+  static_assert(kBHalfBytes % 1024 == 0, "B halves must keep 1024-byte alignment");
+  static_assert(kTotal <= 232448, "shared memory budget");
+};
+
+// erf via Abramowitz-Stegun 7.1.26 (|err| < 1.5e-7, far below fp16 resolution): 2 MUFU + ~10 FMA instead of erff().
+__device__ __forceinline__ float gelu_erf_fast(float x) {
+  const float z = fabsf(x) * 0.70710678118654752f;
+  const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  const float e = 1.0f - poly * t * __expf(-z * z);
+  return 0.5f * x * (1.0f + copysignf(e, x));
+}
+
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, const void* src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+// ---- CTA-pair primitives ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// Address of `local_smem_addr` in CTA `rank` of this cluster (shared::cluster window).
+__device__ __forceinline__ uint32_t mapa_rank(uint32_t local_smem_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_smem_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// The barrier of the even (leader) CTA of the pair at the same offset, as a shared::cluster address.
+__device__ __forceinline__ uint32_t leader_bar_addr(const uint64_t* bar) { return mapa_rank(smem_u32(bar), 0); }
+
+template <int kCta>
+__device__ __forceinline__ void tma_load_4d_pair(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2, int c3) {
+  if constexpr (kCta == 1) {
+    tma_load_4d(dst, m, bar, c0, c1, c2, c3);
+  } else {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(leader_bar_addr(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+  }
+}
+template <int kCta>
+__device__ __forceinline__ void tma_load_2d_pair(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1) {
+  if constexpr (kCta == 1) {
+    tma_load_2d(dst, m, bar, c0, c1);
+  } else {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(leader_bar_addr(bar)), "r"(c0), "r"(c1)
+        : "memory");
+  }
+}
+template <int kCta>
+__device__ __forceinline__ void umma_ss_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accum) {
+  if constexpr (kCta == 1) {
+    umma_ss(d_tmem, a_desc, b_desc, idesc, accum);
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accum)
+        : "memory");
+  }
+}
+// Arrive (once every earlier MMA of this thread has completed) on the barrier at this offset in every CTA of the pair.
+template <int kCta>
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
+  if constexpr (kCta == 1) {
+    umma_commit(bar);
+  } else {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                     smem_u32(bar)),
+                 "h"((uint16_t)3)
+                 : "memory");
+  }
+}
+template <int kCta, uint32_t kCols>
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t* dst_smem) {
+  if constexpr (kCta == 1) {
+    tmem_alloc<kCols>(dst_smem);
+  } else {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "n"(kCols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+}
+template <int kCta, uint32_t kCols>
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr) {
+  if constexpr (kCta == 1) {
+    tmem_dealloc<kCols>(taddr);
+  } else {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(kCols) : "memory");
+  }
+}
+
+// ---- work decomposition ----------------------------------------------------------------------------------------------
+struct Unit { int nt, x0, y0, b0, kb_begin, kb_end, split, ctile; bool valid_m; };
+
+template <int kCta>
+__device__ __forceinline__ Unit unit_coord(const Gemm2Params& p, int u, int cta_rank, int m_tiles, int num_kb) {
+  Unit t;
+  t.split = u % p.splits;
+  int r = u / p.splits;
+  t.nt = r % p.tiles_n;
+  int mt = (r / p.tiles_n) * kCta + cta_rank;
+  t.valid_m = mt < m_tiles;
+  t.ctile = mt * p.tiles_n + t.nt;
+  t.x0 = (mt % p.tiles_x) * p.bw; mt /= p.tiles_x;
+  t.y0 = (mt % p.tiles_y) * p.bh;
+  t.b0 = (mt / p.tiles_y) * p.bn;    // mt >= m_tiles => b0 >= B: every TMA box of this CTA is out of bounds (zeros)
+  t.kb_begin = (int)(((long long)t.split * num_kb) / p.splits);
+  t.kb_end = (int)(((long long)(t.split + 1) * num_kb) / p.splits);
+  return t;
+}
+
+template <int kCta, int kStages, bool kGeglu>
+__global__ void __launch_bounds__(384, 1)
+gemm2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
+             const __grid_constant__ CUtensorMap mapW, const __grid_constant__ CUtensorMap mapO, const Gemm2Params p) {
+  using S = Gemm2Cfg<kCta, kStages>;
+  constexpr uint32_t kTmemCols = 512;
+  constexpr int kEpiThreads = 256;
+  constexpr int kChunks = 5;   // 32-column chunks per column half (plain) / 32-output chunks (GEGLU)
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sRing = smem + kStages * S::kStageBytes;                       // 1024-aligned
+  float* sBias = reinterpret_cast<float*>(sRing + S::kRingBytes);          // [320]
+  float* sCs = sBias + S::kBN;                                             // [320]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sRing + S::kRingBytes + S::kVecBytes);
+  uint64_t* full = bars;                    // [kStages]  (leader's are the live ones)
+  uint64_t* empty = bars + kStages;         // [kStages]
+  uint64_t* acc_full = bars + 2 * kStages;  // [1]
+  uint64_t* acc_empty = acc_full + 1;       // [1]  (leader's is the live one)
+  uint64_t* buf_free = acc_empty + 1;       // [2]  staging ring buffer reusable
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(buf_free + 2);
+  volatile uint32_t* ticket_slot = tmem_slot + 1;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int cta_rank = (kCta == 2) ? (int)cluster_ctarank() : 0;
+  const bool leader = cta_rank == 0;
+  const int pair_id = blockIdx.x / kCta;
+  const int num_pairs = gridDim.x / kCta;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&mapA0); tma_prefetch_desc(&mapA1); tma_prefetch_desc(&mapW); tma_prefetch_desc(&mapO);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < kStages; ++i) { mbar_init(&full[i], kCta); mbar_init(&empty[i], 1); }
+    mbar_init(acc_full, 1);
+    mbar_init(acc_empty, kCta * 8);
+    mbar_init(&buf_free[0], 1); mbar_init(&buf_free[1], 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc_pair<kCta, kTmemCols>(tmem_slot);
+  tc_fence_before();
+  if constexpr (kCta == 2) cluster_sync_all(); else __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int m_tiles = p.tiles_x * p.tiles_y * p.tiles_b;
+  const int m_pairs = (m_tiles + kCta - 1) / kCta;
+  const int total_units = m_pairs * p.tiles_n * p.splits;
+  const int kb_per_tap = p.kb0 + p.kb1;
+  const int num_kb = p.taps * kb_per_tap;
+
+  if (warp == 0) {
+    // ===================== TMA producer (one lane) =====================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      const uint32_t full0_leader = mapa_rank(smem_u32(&full[0]), 0);
+      for (int u = pair_id; u < total_units; u += num_pairs) {
+        const Unit t = unit_coord<kCta>(p, u, cta_rank, m_tiles, num_kb);
+        int tap = t.kb_begin / kb_per_tap;
+        int kb = t.kb_begin - tap * kb_per_tap;
+        const int wrow = t.nt * S::kBN + cta_rank * S::kBRows;
+        for (int kbi = t.kb_begin; kbi < t.kb_end; ++kbi) {
+          const int dx = (p.taps == 9) ? (tap % 3 - 1) : 0;
+          const int dy = (p.taps == 9) ? (tap / 3 - 1) : 0;
+          mbar_wait(&empty[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * S::kStageBytes;
+          uint8_t* sb = sa + S::kABytes;
+          if (leader) mbar_arrive_expect_tx(&full[stage], kCta * S::kStageBytes);
+          else mbar_arrive_cluster(full0_leader + stage * 8);
+          if (kb < p.kb0) tma_load_4d_pair<kCta>(sa, &mapA0, &full[stage], kb * 64, t.x0 + dx, t.y0 + dy, t.b0);
+          else            tma_load_4d_pair<kCta>(sa, &mapA1, &full[stage], (kb - p.kb0) * 64, t.x0 + dx, t.y0 + dy, t.b0);
+          const int kcol = kbi * 64;
+          tma_load_2d_pair<kCta>(sb, &mapW, &full[stage], kcol, wrow);
+          tma_load_2d_pair<kCta>(sb + S::kBHalfBytes, &mapW, &full[stage], kcol, wrow + S::kNI);
+          if (++kb == kb_per_tap) { kb = 0; ++tap; }
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (one lane of the leader CTA) =====================
+    if (leader && lane == 0) {
+      constexpr uint32_t idesc = make_idesc_f16(S::kNI, false, 128 * kCta);
+      const uint64_t descA0 = make_smem_desc_sw128(smem_u32(smem), 16, 1024);
+      const uint64_t descB0 = make_smem_desc_sw128(smem_u32(smem) + S::kABytes, 16, 1024);
+      int stage = 0; uint32_t phase = 0, acc_phase = 0;
+      for (int u = pair_id; u < total_units; u += num_pairs) {
+        const int split = u % p.splits;
+        const int kb_begin = (int)(((long long)split * num_kb) / p.splits);
+        const int kb_end = (int)(((long long)(split + 1) * num_kb) / p.splits);
+        mbar_wait(acc_empty, acc_phase ^ 1);
+        tc_fence_after();
+        for (int kbi = kb_begin; kbi < kb_end; ++kbi) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint64_t da = descA0 + (uint64_t)(stage * (S::kStageBytes >> 4));
+          const uint64_t db0 = descB0 + (uint64_t)(stage * (S::kStageBytes >> 4));
+          const uint64_t db1 = db0 + (uint64_t)(S::kBHalfBytes >> 4);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint32_t acc = (kbi > kb_begin || k > 0) ? 1u : 0u;
+            umma_ss_pair<kCta>(tmem_base, da + 2 * k, db0 + 2 * k, idesc, acc);
+            umma_ss_pair<kCta>(tmem_base + S::kNI, da + 2 * k, db1 + 2 * k, idesc, acc);
+          }
+          umma_commit_pair<kCta>(&empty[stage]);
+          if (kbi == kb_end - 1) umma_commit_pair<kCta>(acc_full);
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+        acc_phase ^= 1;
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue (8 warps) =====================
+    const int ew = warp - 4;
+    const int q = ew & 3;               // TMEM lane quadrant (== warp index % 4)
+    const int hf = ew >> 2;             // column half owned by this warp
+    const int r = q * 32 + lane;        // accumulator row within this CTA's tile
+    const int et = threadIdx.x - 128;   // 0..255
+    const int box_xy = p.bw * p.bh;
+    const uint32_t row_sw = (uint32_t)((r >> 1) & 3);   // 64-byte swizzle phase of this row
+    const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16);
+    const uint32_t acc_empty_leader = mapa_rank(smem_u32(acc_empty), 0);
+    uint32_t acc_phase = 0;
+    uint32_t chunk_ctr = 0;             // staging-ring chunk counter (final epilogues only)
+    if (et == 0) mbar_arrive(&buf_free[0]);   // buffer 0 starts free; buffer 1 is freed after the first store is issued
+
+    for (int u = pair_id; u < total_units; u += num_pairs) {
+      const Unit t = unit_coord<kCta>(p, u, cta_rank, m_tiles, num_kb);
+      const int nt = t.nt;
+      // ---- this thread's output row
+      int bb, yy = 0, xx = 0;
+      size_t grow;                      // global row index (pixel index in [B*H*W))
+      bool row_ok;
+      if (p.taps == 1 && p.H == 1 && p.B == 1) {
+        grow = (size_t)t.x0 + r;
+        row_ok = t.valid_m && grow < (size_t)p.W;
+        bb = p.hw > 0 ? (int)(grow / p.hw) : 0;
+      } else {
+        const int rb = r / box_xy, rin = r - rb * box_xy;
+        bb = t.b0 + rb; yy = t.y0 + rin / p.bw; xx = t.x0 + rin % p.bw;
+        row_ok = t.valid_m && bb < p.B && yy < p.H && xx < p.W;
+        grow = ((size_t)bb * p.H + yy) * p.W + xx;
+      }
+      const int bbc = row_ok ? bb : 0;
+
+      // ---- per-unit vectors -> smem (previous unit's readers are past that unit's last bar.sync)
+      for (int i = et; i < S::kBN; i += kEpiThreads) {
+        const int n = nt * S::kBN + i;
+        float bv = 0.f, cv = 0.f;
+        if (n < p.n_gemm) {
+          if (p.bias32) bv = __ldg(p.bias32 + n);
+          else if (p.bias) bv = __half2float(__ldg(p.bias + n));
+          if (p.colsum) cv = __ldg(p.colsum + n);
+        }
+        sBias[i] = bv; sCs[i] = cv;
+      }
+      // ---- LayerNorm fold: this row's mean / rstd from the producer's partials
+      float ln_a = 1.f, ln_b = 0.f;     // value = ln_a * acc + ln_b * colsum[n] + bias[n]
+      if (p.ln_stats) {
+        float s = 0.f, ss = 0.f;
+        if (row_ok) {
+          const float2* sp = reinterpret_cast<const float2*>(p.ln_stats) + grow * p.ln_parts;
+          for (int i = 0; i < p.ln_parts; ++i) { const float2 v = __ldg(sp + i); s += v.x; ss += v.y; }
+        }
+        const float mean = s * p.ln_inv_c;
+        const float var = fmaxf(ss * p.ln_inv_c - mean * mean, 0.f);
+        ln_a = rsqrtf(var + p.ln_eps);
+        ln_b = -mean * ln_a;
+      }
+      // residual prefetch registers (one chunk ahead)
+      uint4 res_cur[4], res_nxt[4];
+      const __half* res_row = p.residual ? p.residual + grow * p.ld_res + (size_t)nt * (kGeglu ? S::kNI : S::kBN) : nullptr;
+      auto load_res = [&](int j, uint4* dst) {
+        const int c = hf * S::kNI + j * 32;   // plain layout only (GEGLU has no residual)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int col = nt * S::kBN + c + i * 8;
+          dst[i] = (row_ok && col + 8 <= p.n_out) ? __ldg(reinterpret_cast<const uint4*>(res_row + c + i * 8)) : make_uint4(0, 0, 0, 0);
+        }
+      };
+      if (p.residual) load_res(0, res_cur);
+
+      mbar_wait(acc_full, acc_phase);
+      acc_phase ^= 1;
+      tc_fence_after();
+      asm volatile("bar.sync 1, 256;" ::: "memory");   // sBias / sCs visible
+
+      bool do_final = true;
+      if (p.splits > 1) {
+        // ---- split-K: park this split's fp32 partial in the workspace; the last arriver finishes the tile
+        float* wrow = p.ws + (((size_t)t.ctile * p.splits + t.split) * 128 + r) * S::kBN + hf * S::kNI;
+#pragma unroll
+        for (int j = 0; j < kChunks; ++j) {
+          uint32_t v[32];
+          tmem_ld32(t_row + hf * S::kNI + j * 32, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; i += 4)
+            __stcg(reinterpret_cast<uint4*>(wrow + j * 32 + i), make_uint4(v[i], v[i + 1], v[i + 2], v[i + 3]));
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(acc_empty_leader);
+        __threadfence();
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (et == 0) *ticket_slot = (uint32_t)atomicAdd(p.tickets + t.ctile, 1);
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        do_final = (*ticket_slot == (uint32_t)(p.splits - 1));
+        if (do_final) {
+          __threadfence();
+          if (et == 0) p.tickets[t.ctile] = 0;   // ready for the next launch
+        }
+      }
+
+      if (do_final) {
+        // GroupNorm block statistics carried across chunks (this thread's columns are contiguous: hf*160 + [0,160))
+        float gs = 0.f, gss = 0.f;
+        int gcnt = 0, gblk = 0;
+        const bool gn_on = p.gn_stats_out != nullptr;
+        const bool warp_uniform = __all_sync(0xffffffffu, bbc == __shfl_sync(0xffffffffu, bbc, 0)) != 0;
+        if (gn_on) gblk = (nt * S::kBN + hf * S::kNI) / p.gn_blk;
+        float rs = 0.f, rss = 0.f;     // LayerNorm row statistics of this thread's 160 output columns
+        const float* wsrow = p.ws + ((size_t)t.ctile * p.splits * 128 + r) * S::kBN;
+
+#pragma unroll 1
+        for (int j = 0; j < kChunks; ++j) {
+          float f[32];
+          int ncols;          // outputs produced by this thread in this chunk
+          int ocol;           // first output column within the tile's output range
+          if constexpr (!kGeglu) {
+            ncols = 32; ocol = hf * S::kNI + j * 32;
+            const int c = ocol;
+            if (p.splits == 1) {
+              uint32_t v[32];
+              tmem_ld32(t_row + c, v);
+              if (p.residual && j + 1 < kChunks) load_res(j + 1, res_nxt);
+              tmem_ld_wait();
+              if (j == kChunks - 1) {
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(acc_empty_leader);
+              }
+#pragma unroll
+              for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
+            } else {
+              if (p.residual && j + 1 < kChunks) load_res(j + 1, res_nxt);
+#pragma unroll
+              for (int i = 0; i < 32; ++i) f[i] = 0.f;
+              for (int s = 0; s < p.splits; ++s) {
+                const float* src = wsrow + (size_t)s * 128 * S::kBN + c;
+#pragma unroll
+                for (int i = 0; i < 32; i += 4) {
+                  const float4 v4 = __ldcg(reinterpret_cast<const float4*>(src + i));
+                  f[i] += v4.x; f[i + 1] += v4.y; f[i + 2] += v4.z; f[i + 3] += v4.w;
+                }
+              }
+            }
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+              const float4 b4 = *reinterpret_cast<const float4*>(sBias + c + i);
+              const float4 c4 = *reinterpret_cast<const float4*>(sCs + c + i);
+              f[i] = fmaf(ln_a, f[i], fmaf(ln_b, c4.x, b4.x));
+              f[i + 1] = fmaf(ln_a, f[i + 1], fmaf(ln_b, c4.y, b4.y));
+              f[i + 2] = fmaf(ln_a, f[i + 2], fmaf(ln_b, c4.z, b4.z));
+              f[i + 3] = fmaf(ln_a, f[i + 3], fmaf(ln_b, c4.w, b4.w));
+            }
+            if (p.rowvec) {
+              const int col = nt * S::kBN + c;
+              const __half* rv = p.rowvec + (size_t)bbc * p.ld_rowvec + col;
+#pragma unroll
+              for (int i = 0; i < 32; i += 8) {
+                if (col + i + 8 <= p.n_out) {
+                  const uint4 b0 = __ldg(reinterpret_cast<const uint4*>(rv + i));
+                  float2 tt;
+                  tt = unpack_half2(b0.x); f[i] += tt.x; f[i + 1] += tt.y;
+                  tt = unpack_half2(b0.y); f[i + 2] += tt.x; f[i + 3] += tt.y;
+                  tt = unpack_half2(b0.z); f[i + 4] += tt.x; f[i + 5] += tt.y;
+                  tt = unpack_half2(b0.w); f[i + 6] += tt.x; f[i + 7] += tt.y;
+                }
+              }
+            }
+            if (p.residual) {
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                float2 tt;
+                tt = unpack_half2(res_cur[i].x); f[i * 8] += tt.x; f[i * 8 + 1] += tt.y;
+                tt = unpack_half2(res_cur[i].y); f[i * 8 + 2] += tt.x; f[i * 8 + 3] += tt.y;
+                tt = unpack_half2(res_cur[i].z); f[i * 8 + 4] += tt.x; f[i * 8 + 5] += tt.y;
+                tt = unpack_half2(res_cur[i].w); f[i * 8 + 6] += tt.x; f[i * 8 + 7] += tt.y;
+              }
+#pragma unroll
+              for (int i = 0; i < 4; ++i) res_cur[i] = res_nxt[i];
+            }
+          } else {
+            // GEGLU: accumulator 0 = value columns, accumulator 1 = gate columns of the same 160 outputs
+            ncols = 16; ocol = j * 32 + hf * 16;
+            float a[16], g[16];
+            if (p.splits == 1) {
+              uint32_t va[16], vg[16];
+              tmem_ld16(t_row + ocol, va);
+              tmem_ld16(t_row + S::kNI + ocol, vg);
+              tmem_ld_wait();
+              if (j == kChunks - 1) {
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(acc_empty_leader);
+              }
+#pragma unroll
+              for (int i = 0; i < 16; ++i) { a[i] = __uint_as_float(va[i]); g[i] = __uint_as_float(vg[i]); }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) { a[i] = 0.f; g[i] = 0.f; }
+              for (int s = 0; s < p.splits; ++s) {
+                const float* src = wsrow + (size_t)s * 128 * S::kBN + ocol;
+#pragma unroll
+                for (int i = 0; i < 16; i += 4) {
+                  const float4 v4 = __ldcg(reinterpret_cast<const float4*>(src + i));
+                  const float4 g4 = __ldcg(reinterpret_cast<const float4*>(src + S::kNI + i));
+                  a[i] += v4.x; a[i + 1] += v4.y; a[i + 2] += v4.z; a[i + 3] += v4.w;
+                  g[i] += g4.x; g[i + 1] += g4.y; g[i + 2] += g4.z; g[i + 3] += g4.w;
+                }
+              }
+            }
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const float av = fmaf(ln_a, a[i], fmaf(ln_b, sCs[ocol + i], sBias[ocol + i]));
+              const float gv = fmaf(ln_a, g[i], fmaf(ln_b, sCs[S::kNI + ocol + i], sBias[S::kNI + ocol + i]));
+              f[i] = av * gelu_erf_fast(gv);
+            }
+#pragma unroll
+            for (int i = 16; i < 32; ++i) f[i] = 0.f;
+          }
+
+          // ---- round to fp16, statistics on the rounded values, write the staging row
+          uint32_t pk[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) pk[i] = cvt_pack_half2(f[2 * i], f[2 * i + 1]);
+          if (p.row_stats_out || gn_on) {
+            const int out_w = kGeglu ? S::kNI : S::kBN;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              if (2 * i < ncols) {
+                const float2 v = unpack_half2(pk[i]);
+                const int col = nt * out_w + ocol + 2 * i;
+                const bool ok0 = row_ok && col < p.n_out, ok1 = row_ok && col + 1 < p.n_out;
+                const float v0 = ok0 ? v.x : 0.f, v1 = ok1 ? v.y : 0.f;
+                rs += v0 + v1; rss = fmaf(v0, v0, fmaf(v1, v1, rss));
+                if (gn_on) {
+                  // two columns per step; gn_blk is even for every supported config (checked on the host)
+                  gs += v0 + v1; gss = fmaf(v0, v0, fmaf(v1, v1, gss));
+                  gcnt += 2;
+                  if (gcnt == p.gn_blk) {
+                    float a0 = gs, a1 = gss;
+                    if (warp_uniform) {
+#pragma unroll
+                      for (int o = 16; o; o >>= 1) { a0 += __shfl_xor_sync(0xffffffffu, a0, o); a1 += __shfl_xor_sync(0xffffffffu, a1, o); }
+                      if (lane == 0 && gblk < p.gn_nblk) {
+                        atomicAdd(p.gn_stats_out + ((size_t)bbc * p.gn_nblk + gblk) * 2, a0);
+                        atomicAdd(p.gn_stats_out + ((size_t)bbc * p.gn_nblk + gblk) * 2 + 1, a1);
+                      }
+                    } else if (row_ok && gblk < p.gn_nblk) {
+                      atomicAdd(p.gn_stats_out + ((size_t)bbc * p.gn_nblk + gblk) * 2, a0);
+                      atomicAdd(p.gn_stats_out + ((size_t)bbc * p.gn_nblk + gblk) * 2 + 1, a1);
+                    }
+                    gs = 0.f; gss = 0.f; gcnt = 0; ++gblk;
+                  }
+                }
+              }
+            }
+          }
+          const uint32_t buf = chunk_ctr & 1;
+          mbar_wait(&buf_free[buf], (chunk_ctr >> 1) & 1);
+          uint8_t* sub = sRing + (buf * 2 + (kGeglu ? 0 : hf)) * S::kSubBytes + r * 64;
+          if constexpr (!kGeglu) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              *reinterpret_cast<uint4*>(sub + (((uint32_t)i ^ row_sw) << 4)) = make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
+              *reinterpret_cast<uint4*>(sub + (((uint32_t)(hf * 2 + i) ^ row_sw) << 4)) = make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
+          }
+          fence_proxy_async();                              // generic-proxy smem writes -> visible to the TMA store
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+          if (et == 0) {
+            if (t.valid_m) {
+              if constexpr (!kGeglu) {
+#pragma unroll
+                for (int h2 = 0; h2 < 2; ++h2) {
+                  const int col = nt * S::kBN + h2 * S::kNI + j * 32;
+                  if (col < p.n_out) tma_store_4d(&mapO, sRing + (buf * 2 + h2) * S::kSubBytes, col, t.x0, t.y0, t.b0);
+                }
+              } else {
+                const int col = nt * S::kNI + j * 32;
+                if (col < p.n_out) tma_store_4d(&mapO, sRing + (buf * 2) * S::kSubBytes, col, t.x0, t.y0, t.b0);
+              }
+            }
+            tma_store_commit();
+            tma_store_wait_read1();          // the store issued one chunk ago has drained its buffer ...
+            mbar_arrive(&buf_free[buf ^ 1]); // ... so the OTHER buffer is reusable by chunk_ctr + 1
+          }
+          ++chunk_ctr;
+        }
+        if (p.row_stats_out && row_ok)
+          reinterpret_cast<float2*>(p.row_stats_out)[grow * p.row_parts + nt * 2 + hf] = make_float2(rs, rss);
+      }
+    }
+    if (et == 0) tma_store_wait_all();
+  }
+
+  __syncwarp();
+  tc_fence_before();
+  if constexpr (kCta == 2) cluster_sync_all(); else __syncthreads();
+  if (warp == 2) { tc_fence_after(); tmem_dealloc_pair<kCta, kTmemCols>(tmem_base); }
+}
+
+}  // namespace dg

@@ -17,7 +17,7 @@
 #include "../../include/divergen_b200.h"
 #include "attn_tc.cuh"
 #include "elementwise.cuh"
-#include "gemm_tc.cuh"
+#include "gemm2_tc.cuh"
 
 namespace dg {
 
@@ -137,25 +137,43 @@ inline int make_map_2d(CUtensorMap* m, const void* ptr, uint64_t inner, uint64_t
 }
 
 // ------------------------------------------------------------------ GEMM / conv launcher
-constexpr int kGemmBlockN = 160;   // divides every channel count of SD-1.x/2.x (320, 640, 1280, ... 10240)
-constexpr int kGemmStages = 5;     // 5 x 36 KB ring + 40 KB staging tile
-constexpr int kGegluBlockN = 128;  // GEGLU tiles: [64 value | 64 gate] -> 64 outputs
-constexpr int kGegluStages = 6;
+constexpr int kGemmTileN = 320;     // output columns per tile (two 160-wide accumulators)
+constexpr int kGemmStages1 = 3;     // single-CTA variant: 3 x 56 KB
+constexpr int kGemmStages2 = 5;     // CTA-pair variant:   5 x 36 KB per CTA
+constexpr size_t kSplitWsFloats = (size_t)24 << 20;   // 96 MB fp32 split-K workspace (L2-resident slices in practice)
+constexpr int kSplitTickets = 1 << 16;
+
+// Device resources shared by every GEMM launch of a context.
+struct GemmRes {
+  int num_sms = 0;
+  int max_pairs = 0;        // co-resident 2-CTA clusters of the pair kernel (cudaOccupancyMaxActiveClusters)
+  int cta_mode = 2;         // 2 = CTA pairs (default), 1 = single-CTA tiles (DG_GEMM_CTA=1, bring-up / A-B runs)
+  float* ws = nullptr;      // split-K partials
+  int* tickets = nullptr;   // split-K arrival counters (self-resetting)
+};
 
 struct GemmArgs {
   const __half* a0 = nullptr; int c0 = 0;  // source 0: NHWC [B,H,W,c0]
   const __half* a1 = nullptr; int c1 = 0;  // optional source 1 (channel concat)
   int B = 1, H = 1, W = 1;                 // plain GEMM: B = H = 1, W = M
   int taps = 1;                            // 1 (Linear / 1x1) or 9 (3x3, stride 1, pad 1)
+  int hw = 0;                              // plain GEMM: rows per sample (needed for gn_stats)
   const __half* w = nullptr;               // packed [n_w, taps*(c0+c1)]
   int n_w = 0;                             // rows of w
   int n_out = 0;                           // output columns
   const __half* bias = nullptr;
+  const float* bias32 = nullptr;           // fp32 bias (LayerNorm-folded layers)
+  const float* colsum = nullptr;           // LayerNorm fold
+  const float* ln_stats = nullptr; int ln_parts = 0; int ln_c = 0; float ln_eps = 1e-5f;
   const __half* rowvec = nullptr; int ld_rowvec = 0;
   const __half* residual = nullptr; int ld_res = 0;
   int geglu = 0;
+  float* row_stats_out = nullptr;          // [rows][2*tiles_n][2]
+  float* gn_stats_out = nullptr; int gn_blk = 0;   // [B][n_out/gn_blk][2]
   __half* out = nullptr; int ldo = 0;
 };
+
+inline int gemm_row_parts(int n_out) { return 2 * ((n_out + kGemmTileN - 1) / kGemmTileN); }
 
 inline int largest_pow2_divisor(int x, int cap) {
   int p = 1;
@@ -163,15 +181,50 @@ inline int largest_pow2_divisor(int x, int cap) {
   return p;
 }
 
-inline int launch_gemm(cudaStream_t stream, int num_sms, const GemmArgs& a) {
+// K-split factor: minimise waves x k-blocks-per-split (+ a fixed fix-up cost per extra split).
+inline int choose_splits(int units, int num_kb, int slots, size_t ws_floats_per_unit_split, size_t ws_cap) {
+  if (units >= slots || num_kb < 16) return 1;
+  int best = 1;
+  double best_cost = 1e30;
+  for (int s = 1; s <= 16 && s * 4 <= num_kb; ++s) {
+    if (s > 1 && (size_t)units * s * ws_floats_per_unit_split > ws_cap) break;
+    const int waves = (units * s + slots - 1) / slots;
+    const double cost = (double)waves * ((num_kb + s - 1) / s + 3) + (s > 1 ? 4.0 + 1.5 * s : 0.0);
+    if (cost < best_cost - 1e-9) { best_cost = cost; best = s; }
+  }
+  return best;
+}
+
+template <int kCta, int kStages, bool kGeglu>
+inline cudaError_t launch_gemm2_t(cudaStream_t stream, int grid_ctas, const CUtensorMap& mA0, const CUtensorMap& mA1,
+                                  const CUtensorMap& mW, const CUtensorMap& mO, const Gemm2Params& p) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)grid_ctas);
+  cfg.blockDim = dim3(384);
+  cfg.dynamicSmemBytes = Gemm2Cfg<kCta, kStages>::kTotal;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = kCta; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, gemm2_kernel<kCta, kStages, kGeglu>, mA0, mA1, mW, mO, p);
+}
+
+inline int launch_gemm(cudaStream_t stream, const GemmRes& res, const GemmArgs& a) {
   if (a.c0 % 64 || a.c1 % 64 || a.c0 <= 0) return fail(DG_E_SHAPE, "gemm: channel counts must be multiples of 64 (%d,%d)", a.c0, a.c1);
   if (a.taps != 1 && a.taps != 9) return fail(DG_E_ARG, "gemm: taps must be 1 or 9");
   if ((reinterpret_cast<uintptr_t>(a.a0) | reinterpret_cast<uintptr_t>(a.w) | reinterpret_cast<uintptr_t>(a.out) |
-       reinterpret_cast<uintptr_t>(a.residual) | reinterpret_cast<uintptr_t>(a.a1)) & 15)
+       reinterpret_cast<uintptr_t>(a.residual) | reinterpret_cast<uintptr_t>(a.a1) | reinterpret_cast<uintptr_t>(a.rowvec)) & 15)
     return fail(DG_E_ARG, "gemm: pointers must be 16-byte aligned");
-  if (a.ldo % 8 || (a.residual && a.ld_res % 8)) return fail(DG_E_SHAPE, "gemm: output / residual row pitch must be a multiple of 8 elements");
-  const int block_n = a.geglu ? kGegluBlockN : kGemmBlockN;
-  GemmParams p{};
+  if (a.ldo % 8 || (a.residual && a.ld_res % 8) || (a.rowvec && a.ld_rowvec % 8))
+    return fail(DG_E_SHAPE, "gemm: output / residual / rowvec row pitch must be a multiple of 8 elements");
+  if (a.geglu && (a.residual || a.rowvec || a.row_stats_out || a.gn_stats_out)) return fail(DG_E_ARG, "gemm: geglu epilogue takes bias / LayerNorm fold only");
+  if (a.colsum && (!a.ln_stats || !a.bias32 || a.ln_c <= 0)) return fail(DG_E_ARG, "gemm: LayerNorm fold needs ln_stats, bias32 and ln_c");
+  if (a.row_stats_out && a.taps != 1) return fail(DG_E_ARG, "gemm: row statistics are produced by plain GEMMs only");
+  if (a.gn_stats_out && (a.gn_blk <= 0 || a.gn_blk % 2 || 160 % a.gn_blk || a.n_out % a.gn_blk))
+    return fail(DG_E_SHAPE, "gemm: fused GroupNorm statistics need an even channel block dividing 160 and n_out (blk %d, n_out %d)", a.gn_blk, a.n_out);
+  const int kcta = res.cta_mode == 1 ? 1 : 2;
+  Gemm2Params p{};
   int W = a.W, H = a.H, B = a.B;
   if (a.taps == 1) { W = a.B * a.H * a.W; H = 1; B = 1; }
   p.W = W; p.H = H; p.B = B;
@@ -182,16 +235,31 @@ inline int launch_gemm(cudaStream_t stream, int num_sms, const GemmArgs& a) {
   p.tiles_x = (W + p.bw - 1) / p.bw;
   p.tiles_y = (H + p.bh - 1) / p.bh;
   p.tiles_b = (B + p.bn - 1) / p.bn;
+  p.hw = a.taps == 1 ? (a.hw > 0 ? a.hw : a.H * a.W) : 0;
   p.n_gemm = a.n_w;
-  p.tiles_n = (a.n_w + block_n - 1) / block_n;
+  p.tiles_n = (a.n_w + kGemmTileN - 1) / kGemmTileN;
   p.n_out = a.n_out;
   p.taps = a.taps;
   p.kb0 = a.c0 / 64; p.kb1 = a.c1 / 64;
-  p.bias = a.bias; p.rowvec = a.rowvec; p.ld_rowvec = a.ld_rowvec;
-  p.has_residual = a.residual != nullptr;
-  if (a.geglu && !a.bias) return fail(DG_E_ARG, "gemm: geglu epilogue needs a packed bias");
+  p.bias = a.bias; p.bias32 = a.bias32; p.colsum = a.colsum;
+  p.ln_stats = a.ln_stats; p.ln_parts = a.ln_parts; p.ln_inv_c = a.ln_c > 0 ? 1.0f / (float)a.ln_c : 0.f; p.ln_eps = a.ln_eps;
+  p.rowvec = a.rowvec; p.ld_rowvec = a.ld_rowvec;
+  p.residual = a.residual; p.ld_res = a.ld_res;
+  p.row_stats_out = a.row_stats_out; p.row_parts = 2 * p.tiles_n;
+  p.gn_stats_out = a.gn_stats_out; p.gn_blk = a.gn_blk; p.gn_nblk = a.gn_blk > 0 ? a.n_out / a.gn_blk : 0;
+  p.ws = res.ws; p.tickets = res.tickets;
+  if (a.geglu && !a.bias && !a.bias32) return fail(DG_E_ARG, "gemm: geglu epilogue needs a packed bias");
 
-  CUtensorMap mA0, mA1, mW, mO, mR;
+  const int m_tiles = p.tiles_x * p.tiles_y * p.tiles_b;
+  const int m_units = (m_tiles + kcta - 1) / kcta;
+  const int units = m_units * p.tiles_n;
+  const int slots = kcta == 2 ? res.max_pairs : res.num_sms;
+  const int num_kb = a.taps * (p.kb0 + p.kb1);
+  p.splits = 1;
+  if (res.ws && res.tickets && m_tiles * p.tiles_n <= kSplitTickets)
+    p.splits = choose_splits(units, num_kb, slots, (size_t)kcta * 128 * kGemmTileN, kSplitWsFloats);
+
+  CUtensorMap mA0, mA1, mW, mO;
   {
     uint64_t dims[4] = {(uint64_t)a.c0, (uint64_t)W, (uint64_t)H, (uint64_t)B};
     uint64_t st[3] = {(uint64_t)a.c0 * 2, (uint64_t)W * a.c0 * 2, (uint64_t)H * W * a.c0 * 2};
@@ -205,34 +273,32 @@ inline int launch_gemm(cudaStream_t stream, int num_sms, const GemmArgs& a) {
       mA1 = mA0;
     }
     const uint64_t ktot = (uint64_t)a.taps * (a.c0 + a.c1);
-    DG_TRY(make_map_2d(&mW, a.w, ktot, (uint64_t)a.n_w, ktot * 2, 64, block_n));
-    // output / residual tiles: {n_out, W, H, B} boxes of 32 columns x 128 pixels, 64-byte swizzle in smem
+    DG_TRY(make_map_2d(&mW, a.w, ktot, (uint64_t)a.n_w, ktot * 2, 64, 160 / kcta));
+    // output tiles: {n_out, W, H, B} boxes of 32 columns x 128 pixels, 64-byte swizzle in smem
     uint64_t od[4] = {(uint64_t)a.n_out, (uint64_t)W, (uint64_t)H, (uint64_t)B};
     uint64_t os[3] = {(uint64_t)a.ldo * 2, (uint64_t)W * a.ldo * 2, (uint64_t)H * W * a.ldo * 2};
     uint32_t obox[4] = {32, (uint32_t)p.bw, (uint32_t)p.bh, (uint32_t)p.bn};
     DG_TRY(make_map_4d(&mO, a.out, od, os, obox, false, true));
-    if (a.residual) {
-      uint64_t rs[3] = {(uint64_t)a.ld_res * 2, (uint64_t)W * a.ld_res * 2, (uint64_t)H * W * a.ld_res * 2};
-      DG_TRY(make_map_4d(&mR, a.residual, od, rs, obox, false, true));
-    } else {
-      mR = mO;
-    }
   }
-  const int total_tiles = p.tiles_x * p.tiles_y * p.tiles_b * p.tiles_n;
-  const int grid = total_tiles < num_sms ? total_tiles : num_sms;
+  const int total_units = units * p.splits;
+  const int grid_units = total_units < slots ? total_units : slots;
   if (trace_on())
-    fprintf(stderr, "DG_TRACE gemm M=%d N=%d K=%d taps=%d c0=%d c1=%d tiles=%d grid=%d geglu=%d\n", a.B * a.H * a.W, a.n_w,
-            a.taps * (a.c0 + a.c1), a.taps, a.c0, a.c1, total_tiles, grid, a.geglu);
+    fprintf(stderr, "DG_TRACE gemm M=%d N=%d K=%d taps=%d c0=%d c1=%d units=%d splits=%d grid=%dx%d geglu=%d ln=%d res=%d gn=%d rs=%d\n",
+            a.B * a.H * a.W, a.n_w, a.taps * (a.c0 + a.c1), a.taps, a.c0, a.c1, units, p.splits, grid_units, kcta, a.geglu,
+            a.colsum != nullptr, a.residual != nullptr, a.gn_stats_out != nullptr, a.row_stats_out != nullptr);
   const double rows_ = (double)a.B * a.H * a.W, ktot_ = (double)a.taps * (a.c0 + a.c1);
   ProfScope prof_(FAM_GEMM, stream, 2.0 * rows_ * ktot_ * (double)a.n_w,
                   2.0 * (rows_ * (a.c0 + a.c1) + ktot_ * a.n_w + rows_ * a.n_out));
-  if (a.geglu)
-    gemm_tc_kernel<kGegluBlockN, kGegluStages, true>
-        <<<grid, 384, GemmSmem<kGegluBlockN, kGegluStages, true>::kTotal, stream>>>(mA0, mA1, mW, mO, mR, p);
-  else
-    gemm_tc_kernel<kGemmBlockN, kGemmStages, false>
-        <<<grid, 384, GemmSmem<kGemmBlockN, kGemmStages, false>::kTotal, stream>>>(mA0, mA1, mW, mO, mR, p);
-  DG_LAUNCH_CHECK();
+  cudaError_t e;
+  if (kcta == 2) {
+    e = a.geglu ? launch_gemm2_t<2, kGemmStages2, true>(stream, grid_units * 2, mA0, mA1, mW, mO, p)
+                : launch_gemm2_t<2, kGemmStages2, false>(stream, grid_units * 2, mA0, mA1, mW, mO, p);
+  } else {
+    e = a.geglu ? launch_gemm2_t<1, kGemmStages1, true>(stream, grid_units, mA0, mA1, mW, mO, p)
+                : launch_gemm2_t<1, kGemmStages1, false>(stream, grid_units, mA0, mA1, mW, mO, p);
+  }
+  ++g_launch_counter;
+  if (e != cudaSuccess) return fail(DG_E_CUDA, "gemm2 launch failed: %s", cudaGetErrorString(e));
   return DG_OK;
 }
 
@@ -284,11 +350,32 @@ inline int init_attn_attr() {
                                AttnCfg<kD, kKV, kStages>::kSmem));
   return DG_OK;
 }
+template <int kCta, int kStages, bool kGeglu>
+inline int init_gemm_attr() {
+  DG_CUDA(cudaFuncSetAttribute(gemm2_kernel<kCta, kStages, kGeglu>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               Gemm2Cfg<kCta, kStages>::kTotal));
+  return DG_OK;
+}
+// Co-resident CTA pairs of the pair kernel (persistent grid size).
+inline int query_max_pairs(int* out) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(2 * 148); cfg.blockDim = dim3(384);
+  cfg.dynamicSmemBytes = Gemm2Cfg<2, kGemmStages2>::kTotal;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  int n = 0;
+  DG_CUDA(cudaOccupancyMaxActiveClusters(&n, gemm2_kernel<2, kGemmStages2, false>, &cfg));
+  if (n <= 0) return fail(DG_E_CUDA, "no co-resident CTA pair fits (cudaOccupancyMaxActiveClusters = %d)", n);
+  *out = n;
+  return DG_OK;
+}
 inline int init_kernel_attributes() {
-  DG_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<kGemmBlockN, kGemmStages, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               GemmSmem<kGemmBlockN, kGemmStages, false>::kTotal));
-  DG_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<kGegluBlockN, kGegluStages, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               GemmSmem<kGegluBlockN, kGegluStages, true>::kTotal));
+  DG_TRY((init_gemm_attr<1, kGemmStages1, false>()));
+  DG_TRY((init_gemm_attr<1, kGemmStages1, true>()));
+  DG_TRY((init_gemm_attr<2, kGemmStages2, false>()));
+  DG_TRY((init_gemm_attr<2, kGemmStages2, true>()));
   DG_TRY((init_attn_attr<32, 128, 4>()));
   DG_TRY((init_attn_attr<40, 128, 4>()));
   DG_TRY((init_attn_attr<64, 128, 3>()));
@@ -304,6 +391,15 @@ inline int grid_for(size_t work_items, int block, int num_sms, int waves = 8) {
   return (int)(g < cap ? (g ? g : 1) : cap);
 }
 
+inline void gn_launch_geometry(int C, int B, int HW, int num_sms, int* ppb_out, int* pstride_out) {
+  const int nvec = C / 8;
+  const int pstride = nvec <= 256 ? 256 / nvec : 1;
+  // strip length: enough blocks to fill the chip (>= 4 per SM when the tensor allows), >= 8 pixel iterations per thread
+  int ppb = 8 * pstride;
+  while (ppb * 2 <= HW && (size_t)B * ((HW + ppb - 1) / ppb) > (size_t)8 * num_sms) ppb *= 2;
+  *ppb_out = ppb; *pstride_out = pstride;
+}
+
 inline int launch_groupnorm(cudaStream_t s, int num_sms, const __half* x0, int C0, const __half* x1, int C1,
                             const __half* gamma, const __half* beta, __half* out, float* stats, int B, int HW,
                             int groups, float eps, int silu) {
@@ -311,16 +407,29 @@ inline int launch_groupnorm(cudaStream_t s, int num_sms, const __half* x0, int C
   if (C % groups || C0 % 8 || C1 % 8) return fail(DG_E_SHAPE, "groupnorm: C=%d+%d groups=%d", C0, C1, groups);
   ProfScope prof_(FAM_NORM, s, 0.0, 2.0 * 3.0 * B * HW * (double)C);
   DG_CUDA(cudaMemsetAsync(stats, 0, sizeof(float) * 2 * groups * B, s));
-  const int nvec = C / 8;
-  const int pstride = nvec <= 256 ? 256 / nvec : 1;
-  // strip length: enough blocks to fill the chip (>= 4 per SM when the tensor allows), >= 8 pixel iterations per thread
-  int ppb = 8 * pstride;
-  while (ppb * 2 <= HW && (size_t)B * ((HW + ppb - 1) / ppb) > (size_t)8 * num_sms) ppb *= 2;
+  int ppb, pstride;
+  gn_launch_geometry(C, B, HW, num_sms, &ppb, &pstride);
   dim3 grid((HW + ppb - 1) / ppb, B);
   const size_t smem = sizeof(float) * 2 * (size_t)pstride * C;
   gn_stats_kernel<<<grid, 256, smem, s>>>(x0, C0, x1, C1, HW, groups, ppb, stats);
   DG_LAUNCH_CHECK();
   gn_apply_kernel<<<grid, 256, 0, s>>>(x0, C0, x1, C1, HW, groups, eps, ppb, stats, gamma, beta, silu, out);
+  DG_LAUNCH_CHECK();
+  return DG_OK;
+}
+
+// GroupNorm apply with statistics already accumulated by the producing GEMM epilogues (block sums per source).
+inline int launch_groupnorm_fused(cudaStream_t s, int num_sms, const __half* x0, int C0, const float* st0, const __half* x1,
+                                  int C1, const float* st1, int blk, const __half* gamma, const __half* beta, __half* out,
+                                  int B, int HW, int groups, float eps, int silu) {
+  const int C = C0 + C1;
+  if (C % groups || C0 % 8 || C1 % 8 || groups > 64) return fail(DG_E_SHAPE, "groupnorm: C=%d+%d groups=%d", C0, C1, groups);
+  if (blk <= 0 || (C / groups) % blk || C0 % blk || C1 % blk) return fail(DG_E_SHAPE, "groupnorm: block %d does not tile C=%d+%d", blk, C0, C1);
+  ProfScope prof_(FAM_NORM, s, 0.0, 2.0 * 2.0 * B * HW * (double)C);
+  int ppb, pstride;
+  gn_launch_geometry(C, B, HW, num_sms, &ppb, &pstride);
+  dim3 grid((HW + ppb - 1) / ppb, B);
+  gn_apply_blk_kernel<<<grid, 256, 0, s>>>(x0, C0, x1, C1, HW, groups, eps, ppb, st0, st1, blk, gamma, beta, silu, out);
   DG_LAUNCH_CHECK();
   return DG_OK;
 }

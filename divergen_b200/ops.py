@@ -133,3 +133,86 @@ def cfg_ddim_step(noise_pred, latents, alpha_t: float, alpha_prev: float, guidan
                                     guidance_scale, {"epsilon": 0, "v_prediction": 1}[prediction_type], s),
                "dg_cfg_ddim_step")
     return latents
+
+
+# ------------------------------------------------------------------ fused-epilogue forms (what the UNet launches)
+def _pf(t: Optional[torch.Tensor]):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def row_parts(n_out: int) -> int:
+    return int(_lib.load().dg_op_gemm_row_parts(n_out))
+
+
+def linear_stats(x, weight, bias=None, residual=None, gn_blk: int = 0, hw: int = 0):
+    """linear() that also returns the fused statistics of its fp16 result: per-row (sum, sumsq) [M, 2] (partials already
+    added up) and, when gn_blk > 0, GroupNorm block sums [M // hw, N // gn_blk, 2]."""
+    _chk16(x, weight, bias, residual)
+    lib, ctx, s = _env(x)
+    M, K = x.shape
+    N = weight.shape[0]
+    out = torch.empty((M, N), dtype=torch.float16, device=x.device)
+    parts = row_parts(N)
+    rs = torch.full((M, parts, 2), float("nan"), dtype=torch.float32, device=x.device)
+    gs = torch.zeros((M // hw, N // gn_blk, 2), dtype=torch.float32, device=x.device) if gn_blk else None
+    _lib.check(lib.dg_op_gemm_fused(ctx, _p(x), _p(weight), _p(bias), _pf(None), _pf(None), _pf(None), 0, 0.0,
+                                    _p(residual), _p(out), M, K, N, N, 0, _pf(rs), _pf(gs), gn_blk, hw, s),
+               "dg_op_gemm_fused(stats)")
+    return out, rs.sum(1), gs
+
+
+def layernorm_linear(x, gamma, beta, weight, bias=None, eps: float = 1e-5, geglu: bool = False, row_stats=None):
+    """LayerNorm(x) @ weight^T + bias with the normalisation folded into the GEMM epilogue.  `row_stats` [M, parts, 2]
+    may come from the GEMM that produced x (linear_stats' raw partials); otherwise dg_op_row_stats computes them."""
+    _chk16(x, gamma, beta, weight, bias)
+    lib, ctx, s = _env(x)
+    M, K = x.shape
+    if geglu:
+        inner = weight.shape[0] // 2
+        rows = lib.dg_op_geglu_packed_rows(inner)
+        wp = torch.empty((rows, K), dtype=torch.float16, device=x.device)
+        bp = torch.empty((rows,), dtype=torch.float16, device=x.device)
+        _lib.check(lib.dg_op_pack_geglu(ctx, _p(weight), _p(bias), _p(wp), _p(bp), inner, K, s), "dg_op_pack_geglu")
+        weight, bias, n_w, n_out = wp, bp, rows, inner
+    else:
+        n_w = n_out = weight.shape[0]
+    wf = torch.empty_like(weight)
+    cs = torch.empty((n_w,), dtype=torch.float32, device=x.device)
+    b32 = torch.empty((n_w,), dtype=torch.float32, device=x.device)
+    _lib.check(lib.dg_op_fold_layernorm(ctx, _p(weight), _p(bias), _p(gamma), _p(beta), _p(wf), _pf(cs), _pf(b32), n_w, K, s),
+               "dg_op_fold_layernorm")
+    if row_stats is None:
+        parts = row_parts(K)
+        row_stats = torch.empty((M, parts, 2), dtype=torch.float32, device=x.device)
+        _lib.check(lib.dg_op_row_stats(ctx, _p(x), _pf(row_stats), M, K, parts, s), "dg_op_row_stats")
+    out = torch.empty((M, n_out), dtype=torch.float16, device=x.device)
+    _lib.check(lib.dg_op_gemm_fused(ctx, _p(x), _p(wf), _p(None), _pf(b32), _pf(cs), _pf(row_stats), K, eps, _p(None), _p(out),
+                                    M, K, n_w, n_out, int(geglu), _pf(None), _pf(None), 0, 0, s), "dg_op_gemm_fused(ln)")
+    return out
+
+
+def conv3x3_stats(x, weight_oihw, bias, gn_blk: int):
+    """conv3x3_nhwc() that also returns the GroupNorm block sums [B, N // gn_blk, 2] of its fp16 result."""
+    _chk16(x, weight_oihw, bias)
+    lib, ctx, s = _env(x)
+    B, H, W, C0 = x.shape
+    O = weight_oihw.shape[0]
+    wp = torch.empty((O, 9 * C0), dtype=torch.float16, device=x.device)
+    _lib.check(lib.dg_op_pack_conv3x3(ctx, _p(weight_oihw), _p(wp), O, C0, s), "dg_op_pack_conv3x3")
+    out = torch.empty((B, H, W, O), dtype=torch.float16, device=x.device)
+    gs = torch.zeros((B, O // gn_blk, 2), dtype=torch.float32, device=x.device)
+    _lib.check(lib.dg_op_conv3x3_stats(ctx, _p(x), C0, _p(wp), _p(bias), _p(out), B, H, W, O, _pf(gs), gn_blk, s),
+               "dg_op_conv3x3_stats")
+    return out, gs
+
+
+def groupnorm_fused_nhwc(x, stats, gamma, beta, groups: int, eps: float, silu: bool, blk: int, x1=None, stats1=None):
+    """GroupNorm apply (+SiLU) from block sums produced by the GEMM epilogues (one stats array per source)."""
+    _chk16(x, gamma, beta, x1)
+    lib, ctx, s = _env(x)
+    B, H, W, C0 = x.shape
+    C1 = x1.shape[3] if x1 is not None else 0
+    out = torch.empty((B, H, W, C0 + C1), dtype=torch.float16, device=x.device)
+    _lib.check(lib.dg_op_groupnorm_fused(ctx, _p(x), C0, _pf(stats), _p(x1), C1, _pf(stats1), blk, _p(gamma), _p(beta), _p(out),
+                                         B, H * W, groups, eps, int(silu), s), "dg_op_groupnorm_fused")
+    return out

@@ -121,6 +121,28 @@ int32_t dg_op_gemm(dg_ctx* ctx, const void* A, const void* W, const void* bias, 
 int32_t dg_op_pack_geglu(dg_ctx* ctx, const void* w, const void* b, void* w_out, void* b_out, int32_t inner, int32_t K,
                          void* stream);
 int32_t dg_op_geglu_packed_rows(int32_t inner);
+/* Fused-epilogue variants (the forms the UNet actually launches):
+ * dg_op_gemm_fused: dg_op_gemm plus
+ *    - LayerNorm fold   <- torch.nn.LayerNorm + Linear: W/colsum/bias32 from dg_op_fold_layernorm, ln_stats = per-row
+ *      (sum, sumsq) partials [M][dg_op_gemm_row_parts(ln_c)][2] of A (from a producing GEMM's row_stats_out or
+ *      dg_op_row_stats); out = rstd*(A W^T - mean*colsum) + bias32.
+ *    - row_stats_out    per-row (sum, sumsq) partials of the fp16 result, [M][dg_op_gemm_row_parts(n_out)][2]
+ *    - gn_stats_out     <- torch.nn.GroupNorm statistics of the result: fp32 sums over gn_blk-channel blocks,
+ *      [M/hw][n_out/gn_blk][2], ACCUMULATED (caller zeroes); hw = rows per sample.
+ * dg_op_groupnorm_fused: GroupNorm apply (+SiLU) from such block sums (one array per concatenated source). */
+int32_t dg_op_gemm_row_parts(int32_t n_out);
+int32_t dg_op_gemm_fused(dg_ctx* ctx, const void* A, const void* W, const void* bias, const float* bias32,
+                         const float* colsum, const float* ln_stats, int32_t ln_c, float ln_eps, const void* residual,
+                         void* out, int32_t M, int32_t K, int32_t n_w, int32_t n_out, int32_t geglu, float* row_stats_out,
+                         float* gn_stats_out, int32_t gn_blk, int32_t hw, void* stream);
+int32_t dg_op_fold_layernorm(dg_ctx* ctx, const void* W, const void* bias, const void* gamma, const void* beta, void* Wf,
+                             float* colsum, float* b32, int32_t N, int32_t K, void* stream);
+int32_t dg_op_row_stats(dg_ctx* ctx, const void* x, float* stats, int32_t rows, int32_t C, int32_t parts, void* stream);
+int32_t dg_op_conv3x3_stats(dg_ctx* ctx, const void* x0, int32_t C0, const void* Wp, const void* bias, void* out, int32_t B,
+                            int32_t H, int32_t Wd, int32_t N, float* gn_stats_out, int32_t gn_blk, void* stream);
+int32_t dg_op_groupnorm_fused(dg_ctx* ctx, const void* x0, int32_t C0, const float* stats0, const void* x1, int32_t C1,
+                              const float* stats1, int32_t blk, const void* gamma, const void* beta, void* out, int32_t B,
+                              int32_t HW, int32_t groups, float eps, int32_t silu, void* stream);
 int32_t dg_op_pack_conv3x3(dg_ctx* ctx, const void* w_oihw, void* w_out, int32_t O, int32_t I, void* stream);
 int32_t dg_op_conv3x3(dg_ctx* ctx, const void* x0, int32_t C0, const void* x1, int32_t C1, const void* Wp,
                       const void* bias, const void* rowvec, int32_t ld_rowvec, const void* residual, void* out,

@@ -139,6 +139,63 @@ def test_gemm_geglu(ops, M, K, inner):
     _report("geglu", got, ref, 5e-3, 5e-3)
 
 
+@pytest.mark.parametrize("M,K,N", [(256, 320, 320), (1000, 640, 960), (4096, 320, 320), (77, 1280, 1280), (512, 1280, 3840)])
+def test_gemm_layernorm_fold(ops, M, K, N):
+    """LayerNorm folded into the GEMM epilogue (rstd*(x Wf^T - mean*colsum) + b32) vs F.layer_norm + matmul in fp32."""
+    x = _rand(M, K, seed=50) * 2 + 0.7
+    gamma, beta = _rand(K, seed=51) * 0.2 + 1, _rand(K, seed=52) * 0.1
+    w, b = _rand(N, K, scale=1 / math.sqrt(K), seed=53), _rand(N, scale=0.1, seed=54)
+    got = ops.layernorm_linear(x, gamma, beta, w, b)
+    ref = F.layer_norm(x.float(), (K,), gamma.float(), beta.float(), 1e-5) @ w.float().T + b.float()
+    _report(f"ln-fold gemm {M}x{K}x{N}", got, ref, 6e-3, 5e-3)
+
+
+def test_gemm_layernorm_fold_geglu(ops):
+    M, K, inner = 1000, 320, 1280
+    x = _rand(M, K, seed=55) * 1.5 - 0.3
+    gamma, beta = _rand(K, seed=56) * 0.2 + 1, _rand(K, seed=57) * 0.1
+    w, b = _rand(2 * inner, K, scale=1 / math.sqrt(K), seed=58), _rand(2 * inner, scale=0.1, seed=59)
+    got = ops.layernorm_linear(x, gamma, beta, w, b, geglu=True)
+    y = F.layer_norm(x.float(), (K,), gamma.float(), beta.float(), 1e-5) @ w.float().T + b.float()
+    h, g = y.chunk(2, -1)
+    _report("ln-fold geglu", got, h * F.gelu(g), 6e-3, 6e-3)
+
+
+@pytest.mark.parametrize("M,K,N,hw,blk", [(2048, 320, 320, 1024, 10), (512, 640, 1280, 64, 40), (8192, 64, 320, 4096, 10),
+                                          (96, 128, 128, 32, 4), (48, 64, 64, 16, 2)])
+def test_gemm_fused_statistics(ops, M, K, N, hw, blk):
+    """Row (LayerNorm) and block (GroupNorm) sums produced by the GEMM epilogue equal the sums of its fp16 output."""
+    x, w = _rand(M, K, seed=60), _rand(N, K, scale=1 / math.sqrt(K), seed=61)
+    b, r = _rand(N, seed=62), _rand(M, N, seed=63)
+    out, rs, gs = ops.linear_stats(x, w, b, r, gn_blk=blk, hw=hw)
+    ref = x.float() @ w.float().T + b.float() + r.float()
+    _report("gemm(stats) value", out, ref, 5e-3, 4e-3)
+    o = out.float()
+    want_rs = torch.stack([o.sum(1), (o * o).sum(1)], 1)
+    assert torch.allclose(rs, want_rs, rtol=1e-4, atol=1e-2), (rs - want_rs).abs().max().item()
+    ob = o.view(M // hw, hw, N // blk, blk)
+    want_gs = torch.stack([ob.sum((1, 3)), (ob * ob).sum((1, 3))], -1)
+    assert torch.allclose(gs, want_gs, rtol=2e-4, atol=5e-2), (gs - want_gs).abs().max().item()
+    # the producer's row partials feed the LayerNorm-folded consumer directly
+    if K == N:
+        pass
+
+
+@pytest.mark.parametrize("B,H,W,C,N,blk", [(2, 32, 32, 320, 320, 10), (3, 8, 8, 128, 640, 20), (2, 4, 4, 64, 64, 2)])
+def test_conv3x3_groupnorm_fused(ops, B, H, W, C, N, blk):
+    """conv3x3 epilogue block sums -> GroupNorm apply from those sums == GroupNorm(SiLU) of the conv output."""
+    x = _rand(B, H, W, C, seed=64)
+    w, bias = _rand(N, C, 3, 3, scale=1 / math.sqrt(9 * C), seed=65), _rand(N, scale=0.1, seed=66)
+    out, gs = ops.conv3x3_stats(x, w, bias, blk)
+    ob = out.float().view(B, H * W, N // blk, blk)
+    want = torch.stack([ob.sum((1, 3)), (ob * ob).sum((1, 3))], -1)
+    assert torch.allclose(gs, want, rtol=2e-4, atol=5e-2), (gs - want).abs().max().item()
+    gamma, beta = _rand(N, seed=67) * 0.2 + 1, _rand(N, seed=68) * 0.1
+    got = ops.groupnorm_fused_nhwc(out, gs, gamma, beta, 32, 1e-5, True, blk)
+    ref = F.silu(F.group_norm(out.float().permute(0, 3, 1, 2), 32, gamma.float(), beta.float(), 1e-5)).permute(0, 2, 3, 1)
+    _report("groupnorm from fused sums", got, ref, 4e-3, 4e-3)
+
+
 @pytest.mark.parametrize("B,H,W,C0,C1,N", [(1, 64, 64, 64, 0, 160), (2, 64, 64, 320, 0, 320), (2, 32, 32, 640, 320, 640),
                                            (2, 16, 16, 1280, 0, 1280), (2, 8, 8, 1280, 1280, 1280), (3, 8, 8, 64, 0, 64),
                                            (2, 64, 64, 320, 0, 4), (1, 24, 24, 128, 0, 128), (2, 4, 4, 128, 0, 128)])

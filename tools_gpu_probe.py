@@ -8,7 +8,8 @@ import time
 GROUPS = {
     "elem": ["tests/test_gpu_ops.py", "-k", "groupnorm or layernorm or time_embedding or cfg_ddim"],
     "gemm": ["tests/test_gpu_ops.py", "-k", "gemm_plain"],
-    "gemm_epi": ["tests/test_gpu_ops.py", "-k", "gemm_bias or geglu"],
+    "gemm_epi": ["tests/test_gpu_ops.py", "-k", "gemm_bias or gemm_geglu"],
+    "gemm_fused": ["tests/test_gpu_ops.py", "-k", "layernorm_fold or fused"],
     "conv": ["tests/test_gpu_ops.py", "-k", "conv3x3"],
     "attn64": ["tests/test_gpu_ops.py", "-k", "attention and (64 or 32)"],
     "attn": ["tests/test_gpu_ops.py", "-k", "attention and not (64 or 32)"],
