@@ -680,6 +680,7 @@ int32_t dg_ctx_create(int32_t device, dg_ctx** out) {
   c->gemm.num_sms = c->num_sms;
   DG_TRY(query_max_pairs(&c->gemm.max_pairs));
   DG_CUDA(cudaMalloc(&c->gemm.ws, kSplitWsFloats * sizeof(float)));
+  DG_CUDA(cudaMemset(c->gemm.ws, 0, kSplitWsFloats * sizeof(float)));
   DG_CUDA(cudaMalloc(&c->gemm.tickets, kSplitTickets * sizeof(int)));
   DG_CUDA(cudaMemset(c->gemm.tickets, 0, kSplitTickets * sizeof(int)));
   auto env_int = [](const char* name, int dflt) { const char* e = getenv(name); return e && e[0] ? atoi(e) : dflt; };

@@ -24,8 +24,9 @@
 //   one chunk ahead with 16-byte loads) [GEGLU: value * gelu(gate)] -> fp16 -> 64-byte-swizzled staging ring -> TMA store.
 //   Fused statistics on the rounded outputs: per-row (sum, sum of squares) partials for the LayerNorm that consumes this
 //   tensor, and per-(sample, channel-block) sums for the next GroupNorm (warp shuffle reduce + fp32 atomics).
-// Split-K (small-M layers at the bottom of the U): each split writes its fp32 partial tile to an L2-resident workspace;
-//   the last arriver (atomic ticket) sums the partials in split order (deterministic) and runs the epilogue.
+// Split-K (small-M layers at the bottom of the U): each split adds its fp32 partial tile into an L2-resident accumulator
+//   with 16-byte vector reductions; the last arriver (atomic ticket) reads the sum, re-zeroes it and runs the epilogue.
+//   (fp32 addition order varies run to run: results are reproducible to fp32 rounding, not bit for bit.)
 //
 // Replaces (reference side): torch.nn.Conv2d / Linear / LayerNorm / GroupNorm statistics inside diffusers ResnetBlock2D,
 // Attention, FeedForward, Transformer2DModel, reached from DiverGen/generation/txt2img_diffusers_stages_from_txt.py:255-259.
@@ -61,7 +62,7 @@ struct Gemm2Params {
   int row_parts;
   float* gn_stats_out;     // [B][gn_nblk][2] fp32 atomics: sums over gn_blk-channel blocks
   int gn_blk, gn_nblk;
-  float* ws;               // split-K workspace: [m_tile*tiles_n + nt][split][128][320] fp32
+  float* ws;               // split-K accumulators: [m_tile*tiles_n + nt][128][320] fp32, zero on entry, zero on exit
   int* tickets;            // [m_tile*tiles_n + nt], zero on entry, zero on exit
 };
 
@@ -122,7 +123,8 @@ __device__ __forceinline__ uint32_t mapa_rank(uint32_t local_smem_addr, uint32_t
   return r;
 }
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  // default semantics (no .release.cluster: that form costs a MEMBAR.ALL.GPU + ERRBAR per arrive -- profiles/r01_ncu_pair_v1.txt)
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // The barrier of the even (leader) CTA of the pair at the same offset, as a shared::cluster address.
 __device__ __forceinline__ uint32_t leader_bar_addr(const uint64_t* bar) { return mapa_rank(smem_u32(bar), 0); }
@@ -264,8 +266,9 @@ gemm2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
   const int num_kb = p.taps * kb_per_tap;
 
   if (warp == 0) {
-    // ===================== TMA producer (one lane) =====================
-    if (lane == 0) {
+    // ===================== TMA producer (one elected lane; elect.sync lets the compiler keep TMA operands in uniform
+    // registers -- a `lane == 0` test costs an ELECT / R2UR.BROADCAST waterfall loop per UTMALDG, profiles/r01_ncu_pair_v2.txt)
+    if (elect_one()) {
       int stage = 0; uint32_t phase = 0;
       const uint32_t full0_leader = mapa_rank(smem_u32(&full[0]), 0);
       for (int u = pair_id; u < total_units; u += num_pairs) {
@@ -292,8 +295,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer (one lane of the leader CTA) =====================
-    if (leader && lane == 0) {
+    // ===================== MMA issuer (leader CTA; warp-uniform loop, one elected lane issues) =====================
+    if (leader) {
       constexpr uint32_t idesc = make_idesc_f16(S::kNI, false, 128 * kCta);
       const uint64_t descA0 = make_smem_desc_sw128(smem_u32(smem), 16, 1024);
       const uint64_t descB0 = make_smem_desc_sw128(smem_u32(smem) + S::kABytes, 16, 1024);
@@ -310,14 +313,17 @@ gemm2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
           const uint64_t da = descA0 + (uint64_t)(stage * (S::kStageBytes >> 4));
           const uint64_t db0 = descB0 + (uint64_t)(stage * (S::kStageBytes >> 4));
           const uint64_t db1 = db0 + (uint64_t)(S::kBHalfBytes >> 4);
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const uint32_t acc = (kbi > kb_begin || k > 0) ? 1u : 0u;
-            umma_ss_pair<kCta>(tmem_base, da + 2 * k, db0 + 2 * k, idesc, acc);
-            umma_ss_pair<kCta>(tmem_base + S::kNI, da + 2 * k, db1 + 2 * k, idesc, acc);
+            for (int k = 0; k < 4; ++k) {
+              const uint32_t acc = (kbi > kb_begin || k > 0) ? 1u : 0u;
+              umma_ss_pair<kCta>(tmem_base, da + 2 * k, db0 + 2 * k, idesc, acc);
+              umma_ss_pair<kCta>(tmem_base + S::kNI, da + 2 * k, db1 + 2 * k, idesc, acc);
+            }
+            umma_commit_pair<kCta>(&empty[stage]);
+            if (kbi == kb_end - 1) umma_commit_pair<kCta>(acc_full);
           }
-          umma_commit_pair<kCta>(&empty[stage]);
-          if (kbi == kb_end - 1) umma_commit_pair<kCta>(acc_full);
+          __syncwarp();
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
         acc_phase ^= 1;
@@ -336,7 +342,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
     const uint32_t acc_empty_leader = mapa_rank(smem_u32(acc_empty), 0);
     uint32_t acc_phase = 0;
     uint32_t chunk_ctr = 0;             // staging-ring chunk counter (final epilogues only)
-    if (et == 0) mbar_arrive(&buf_free[0]);   // buffer 0 starts free; buffer 1 is freed after the first store is issued
+    if (ew == 0 && elect_one()) mbar_arrive(&buf_free[0]);   // buffer 0 starts free; buffer 1 is freed after the first store is issued
 
     for (int u = pair_id; u < total_units; u += num_pairs) {
       const Unit t = unit_coord<kCta>(p, u, cta_rank, m_tiles, num_kb);
@@ -401,8 +407,9 @@ gemm2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
 
       bool do_final = true;
       if (p.splits > 1) {
-        // ---- split-K: park this split's fp32 partial in the workspace; the last arriver finishes the tile
-        float* wrow = p.ws + (((size_t)t.ctile * p.splits + t.split) * 128 + r) * S::kBN + hf * S::kNI;
+        // ---- split-K: add this split's fp32 partial into the tile's L2-resident accumulator (16-byte vector reductions);
+        // the last arriver (ticket) reads the sum back, re-zeroes it for the next launch and finishes the tile
+        float* wrow = p.ws + ((size_t)t.ctile * 128 + r) * S::kBN + hf * S::kNI;
 #pragma unroll
         for (int j = 0; j < kChunks; ++j) {
           uint32_t v[32];
@@ -410,19 +417,21 @@ gemm2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
           tmem_ld_wait();
 #pragma unroll
           for (int i = 0; i < 32; i += 4)
-            __stcg(reinterpret_cast<uint4*>(wrow + j * 32 + i), make_uint4(v[i], v[i + 1], v[i + 2], v[i + 3]));
+            asm volatile("red.relaxed.gpu.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(wrow + j * 32 + i), "r"(v[i]), "r"(v[i + 1]),
+                         "r"(v[i + 2]), "r"(v[i + 3])
+                         : "memory");
         }
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive_cluster(acc_empty_leader);
         __threadfence();
         asm volatile("bar.sync 1, 256;" ::: "memory");
-        if (et == 0) *ticket_slot = (uint32_t)atomicAdd(p.tickets + t.ctile, 1);
+        if (ew == 0 && elect_one()) *ticket_slot = (uint32_t)atomicAdd(p.tickets + t.ctile, 1);
         asm volatile("bar.sync 1, 256;" ::: "memory");
         do_final = (*ticket_slot == (uint32_t)(p.splits - 1));
         if (do_final) {
           __threadfence();
-          if (et == 0) p.tickets[t.ctile] = 0;   // ready for the next launch
+          if (ew == 0 && elect_one()) p.tickets[t.ctile] = 0;   // ready for the next launch
         }
       }
 
@@ -434,7 +443,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
         const bool warp_uniform = __all_sync(0xffffffffu, bbc == __shfl_sync(0xffffffffu, bbc, 0)) != 0;
         if (gn_on) gblk = (nt * S::kBN + hf * S::kNI) / p.gn_blk;
         float rs = 0.f, rss = 0.f;     // LayerNorm row statistics of this thread's 160 output columns
-        const float* wsrow = p.ws + ((size_t)t.ctile * p.splits * 128 + r) * S::kBN;
+        float* wsrow = p.ws + ((size_t)t.ctile * 128 + r) * S::kBN;
 
 #pragma unroll 1
         for (int j = 0; j < kChunks; ++j) {
@@ -458,16 +467,14 @@ gemm2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
               for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
             } else {
               if (p.residual && j + 1 < kChunks) load_res(j + 1, res_nxt);
+              float* src = wsrow + c;
 #pragma unroll
-              for (int i = 0; i < 32; ++i) f[i] = 0.f;
-              for (int s = 0; s < p.splits; ++s) {
-                const float* src = wsrow + (size_t)s * 128 * S::kBN + c;
-#pragma unroll
-                for (int i = 0; i < 32; i += 4) {
-                  const float4 v4 = __ldcg(reinterpret_cast<const float4*>(src + i));
-                  f[i] += v4.x; f[i + 1] += v4.y; f[i + 2] += v4.z; f[i + 3] += v4.w;
-                }
+              for (int i = 0; i < 32; i += 4) {
+                const float4 v4 = __ldcg(reinterpret_cast<const float4*>(src + i));
+                f[i] = v4.x; f[i + 1] = v4.y; f[i + 2] = v4.z; f[i + 3] = v4.w;
               }
+#pragma unroll
+              for (int i = 0; i < 32; i += 4) __stcg(reinterpret_cast<float4*>(src + i), make_float4(0.f, 0.f, 0.f, 0.f));
             }
 #pragma unroll
             for (int i = 0; i < 32; i += 4) {
@@ -522,17 +529,18 @@ gemm2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
 #pragma unroll
               for (int i = 0; i < 16; ++i) { a[i] = __uint_as_float(va[i]); g[i] = __uint_as_float(vg[i]); }
             } else {
+              float* src = wsrow + ocol;
 #pragma unroll
-              for (int i = 0; i < 16; ++i) { a[i] = 0.f; g[i] = 0.f; }
-              for (int s = 0; s < p.splits; ++s) {
-                const float* src = wsrow + (size_t)s * 128 * S::kBN + ocol;
+              for (int i = 0; i < 16; i += 4) {
+                const float4 v4 = __ldcg(reinterpret_cast<const float4*>(src + i));
+                const float4 g4 = __ldcg(reinterpret_cast<const float4*>(src + S::kNI + i));
+                a[i] = v4.x; a[i + 1] = v4.y; a[i + 2] = v4.z; a[i + 3] = v4.w;
+                g[i] = g4.x; g[i + 1] = g4.y; g[i + 2] = g4.z; g[i + 3] = g4.w;
+              }
 #pragma unroll
-                for (int i = 0; i < 16; i += 4) {
-                  const float4 v4 = __ldcg(reinterpret_cast<const float4*>(src + i));
-                  const float4 g4 = __ldcg(reinterpret_cast<const float4*>(src + S::kNI + i));
-                  a[i] += v4.x; a[i + 1] += v4.y; a[i + 2] += v4.z; a[i + 3] += v4.w;
-                  g[i] += g4.x; g[i + 1] += g4.y; g[i + 2] += g4.z; g[i + 3] += g4.w;
-                }
+              for (int i = 0; i < 16; i += 4) {
+                __stcg(reinterpret_cast<float4*>(src + i), make_float4(0.f, 0.f, 0.f, 0.f));
+                __stcg(reinterpret_cast<float4*>(src + S::kNI + i), make_float4(0.f, 0.f, 0.f, 0.f));
               }
             }
 #pragma unroll
@@ -596,7 +604,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
           }
           fence_proxy_async();                              // generic-proxy smem writes -> visible to the TMA store
           asm volatile("bar.sync 1, 256;" ::: "memory");
-          if (et == 0) {
+          if (ew == 0 && elect_one()) {
             if (t.valid_m) {
               if constexpr (!kGeglu) {
 #pragma unroll
@@ -619,7 +627,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
           reinterpret_cast<float2*>(p.row_stats_out)[grow * p.row_parts + nt * 2 + hf] = make_float2(rs, rss);
       }
     }
-    if (et == 0) tma_store_wait_all();
+    if (ew == 0 && elect_one()) tma_store_wait_all();
   }
 
   __syncwarp();

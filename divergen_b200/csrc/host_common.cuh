@@ -140,7 +140,7 @@ inline int make_map_2d(CUtensorMap* m, const void* ptr, uint64_t inner, uint64_t
 constexpr int kGemmTileN = 320;     // output columns per tile (two 160-wide accumulators)
 constexpr int kGemmStages1 = 3;     // single-CTA variant: 3 x 56 KB
 constexpr int kGemmStages2 = 5;     // CTA-pair variant:   5 x 36 KB per CTA
-constexpr size_t kSplitWsFloats = (size_t)24 << 20;   // 96 MB fp32 split-K workspace (L2-resident slices in practice)
+constexpr size_t kSplitWsFloats = (size_t)8 << 20;    // 32 MB of fp32 split-K tile accumulators (zero between launches)
 constexpr int kSplitTickets = 1 << 16;
 
 // Device resources shared by every GEMM launch of a context.
@@ -182,12 +182,11 @@ inline int largest_pow2_divisor(int x, int cap) {
 }
 
 // K-split factor: minimise waves x k-blocks-per-split (+ a fixed fix-up cost per extra split).
-inline int choose_splits(int units, int num_kb, int slots, size_t ws_floats_per_unit_split, size_t ws_cap) {
-  if (units >= slots || num_kb < 16) return 1;
+inline int choose_splits(int units, int num_kb, int slots, size_t ws_floats_per_unit, size_t ws_cap) {
+  if (units >= slots || num_kb < 16 || (size_t)units * ws_floats_per_unit > ws_cap) return 1;
   int best = 1;
   double best_cost = 1e30;
   for (int s = 1; s <= 16 && s * 4 <= num_kb; ++s) {
-    if (s > 1 && (size_t)units * s * ws_floats_per_unit_split > ws_cap) break;
     const int waves = (units * s + slots - 1) / slots;
     const double cost = (double)waves * ((num_kb + s - 1) / s + 3) + (s > 1 ? 4.0 + 1.5 * s : 0.0);
     if (cost < best_cost - 1e-9) { best_cost = cost; best = s; }
