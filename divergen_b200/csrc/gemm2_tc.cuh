@@ -64,23 +64,33 @@ struct Gemm2Params {
   int gn_blk, gn_nblk;
   float* ws;               // split-K accumulators: [m_tile*tiles_n + nt][128][320] fp32, zero on entry, zero on exit
   int* tickets;            // [m_tile*tiles_n + nt], zero on entry, zero on exit
+  long long* dbg;          // optional (DG_GEMM_DBG=1): clock64() stamps of CTA 0's first unit, see DG_STAMP sites
 };
+#define DG_STAMP(slot) do { if (p.dbg && blockIdx.x == 0) p.dbg[slot] = clock64(); } while (0)
+#define DG_STAMP_C1(slot) do { if (p.dbg && blockIdx.x == 0 && u == pair_id && j == 1 && et == 0) p.dbg[slot] = clock64(); } while (0)
 
-template <int kCta, int kStages>
+template <int kCta, int kBN, int kStages>
 struct Gemm2Cfg {
+  static_assert(kBN == 320 || kBN == 160, "tile N is one or two 160-wide accumulators");
   static constexpr int kNI = 160;                       // N of one MMA instruction
-  static constexpr int kBN = 320;                       // tile N = two accumulators
+  static constexpr int kNumAcc = kBN / kNI;             // accumulators per tile
+  static constexpr int kAccStages = kNumAcc == 1 ? 2 : 1;   // a 160-wide tile double-buffers in TMEM: epilogue(i) overlaps mainloop(i+1)
+  static constexpr int kAccStride = 256;                // TMEM columns between accumulator stages
   static constexpr int kABytes = 128 * 64 * 2;          // 16 KB: 128 pixels x 64 channels
   static constexpr int kBRows = kNI / kCta;             // weight rows this CTA loads per accumulator
   static constexpr int kBHalfBytes = kBRows * 128;
-  static constexpr int kBBytes = 2 * kBHalfBytes;
+  static constexpr int kBBytes = kNumAcc * kBHalfBytes;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kSubBytes = 128 * 64;            // staging sub-tile [128 rows][32 cols fp16], 64-byte swizzle
-  static constexpr int kRingBytes = 2 * 2 * kSubBytes;  // two buffers x two sub-tiles (one per column half)
-  static constexpr int kVecBytes = 2 * kBN * 4;         // bias + colsum, fp32
-  static constexpr int kBarBytes = 256;
+  // output staging ring, drained by the store warp.  320-wide tiles: 4 slots of one 32-column chunk per column half;
+  // 160-wide tiles: 2 slots of a WHOLE tile (5 sub-tiles) -- one wait / fence / hand-off per tile instead of per chunk
+  static constexpr int kRing = kNumAcc == 1 ? 2 : 4;
+  static constexpr int kSlotSubs = kNumAcc == 1 ? 5 : 2;
+  static constexpr int kRingBytes = kRing * kSlotSubs * kSubBytes;
+  static constexpr int kVecBytes = 2 * 320 * 4;         // bias + colsum, fp32
+  static constexpr int kBarBytes = 512;
   static constexpr int kTotal = kStages * kStageBytes + kRingBytes + kVecBytes + kBarBytes + 1024 /*align slack*/;
-  static_assert(kBHalfBytes % 1024 == 0, "B halves must keep 1024-byte alignment");
+  static_assert(kBHalfBytes % 1024 == 0 && kStageBytes % 1024 == 0, "operand tiles must keep 1024-byte alignment");
   static_assert(kTotal <= 232448, "shared memory budget");
 };
 
@@ -103,8 +113,8 @@ __device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, const void* s
                : "memory");
 }
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void tma_store_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
-__device__ __forceinline__ void tma_store_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+template <int kPending>
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(kPending) : "memory"); }
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
 // ---- CTA-pair primitives ------------------------------------------------------------------------------------------
@@ -213,28 +223,39 @@ __device__ __forceinline__ Unit unit_coord(const Gemm2Params& p, int u, int cta_
   return t;
 }
 
-template <int kCta, int kStages, bool kGeglu>
+template <int kCta, int kBN, int kStages, bool kGeglu>
 __global__ void __launch_bounds__(384, 1)
 gemm2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
-             const __grid_constant__ CUtensorMap mapW, const __grid_constant__ CUtensorMap mapO, const Gemm2Params p) {
-  using S = Gemm2Cfg<kCta, kStages>;
+             const __grid_constant__ CUtensorMap mapW, const __grid_constant__ CUtensorMap mapO,
+             const __grid_constant__ CUtensorMap mapO64, const Gemm2Params p) {
+  // mapO: output boxes of 32 columns (64-byte rows, 64-byte swizzle); mapO64: 64 columns (128-byte rows, 128-byte swizzle) --
+  // the TMA store engine's cost is per row, so the wide (320-column) tiles stage and store 128-byte rows
+  using S = Gemm2Cfg<kCta, kBN, kStages>;
+  static_assert(!kGeglu || kBN == 320, "GEGLU tiles are [160 value | 160 gate]");
   constexpr uint32_t kTmemCols = 512;
   constexpr int kEpiThreads = 256;
-  constexpr int kChunks = 5;   // 32-column chunks per column half (plain) / 32-output chunks (GEGLU)
+  constexpr int kChunks = 5;
+  // columns one epilogue thread converts per chunk: 320-wide tiles give each column-half warp 32 consecutive columns,
+  // 160-wide tiles (and GEGLU outputs) give the two warps of a TMEM quadrant the two 16-column halves of a 32-column chunk
+  constexpr int kCW = (kBN == 320 && !kGeglu) ? 32 : 16;
+  constexpr int kOutW = kGeglu ? S::kNI : kBN;          // output columns per tile
 
+  if (threadIdx.x == 0) DG_STAMP(0);
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sRing = smem + kStages * S::kStageBytes;                       // 1024-aligned
   float* sBias = reinterpret_cast<float*>(sRing + S::kRingBytes);          // [320]
-  float* sCs = sBias + S::kBN;                                             // [320]
+  float* sCs = sBias + 320;                                                // [320]
   uint64_t* bars = reinterpret_cast<uint64_t*>(sRing + S::kRingBytes + S::kVecBytes);
   uint64_t* full = bars;                    // [kStages]  (leader's are the live ones)
   uint64_t* empty = bars + kStages;         // [kStages]
-  uint64_t* acc_full = bars + 2 * kStages;  // [1]
-  uint64_t* acc_empty = acc_full + 1;       // [1]  (leader's is the live one)
-  uint64_t* buf_free = acc_empty + 1;       // [2]  staging ring buffer reusable
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(buf_free + 2);
+  uint64_t* acc_full = bars + 2 * kStages;  // [2]
+  uint64_t* acc_empty = acc_full + 2;       // [2]  (leader's are the live ones)
+  uint64_t* buf_free = acc_empty + 2;       // [kRing]  staging buffer reusable (store warp -> epilogue warps)
+  uint64_t* chunk_ready = buf_free + S::kRing;   // [kRing]  staging buffer written by all 8 epilogue warps (-> store warp)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(chunk_ready + S::kRing);
   volatile uint32_t* ticket_slot = tmem_slot + 1;
+  volatile int* chunk_info = reinterpret_cast<volatile int*>(tmem_slot + 2);   // [kRing][5]: col, x0, y0, b0, flags (1 store, 2 stop)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -244,13 +265,12 @@ gemm2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
   const int num_pairs = gridDim.x / kCta;
 
   if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&mapA0); tma_prefetch_desc(&mapA1); tma_prefetch_desc(&mapW); tma_prefetch_desc(&mapO);
+    tma_prefetch_desc(&mapA0); tma_prefetch_desc(&mapA1); tma_prefetch_desc(&mapW); tma_prefetch_desc(&mapO); tma_prefetch_desc(&mapO64);
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < kStages; ++i) { mbar_init(&full[i], kCta); mbar_init(&empty[i], 1); }
-    mbar_init(acc_full, 1);
-    mbar_init(acc_empty, kCta * 8);
-    mbar_init(&buf_free[0], 1); mbar_init(&buf_free[1], 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], kCta * 8); }
+    for (int i = 0; i < S::kRing; ++i) { mbar_init(&buf_free[i], 1); mbar_init(&chunk_ready[i], 8); }
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc_pair<kCta, kTmemCols>(tmem_slot);
@@ -258,6 +278,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
   if constexpr (kCta == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) DG_STAMP(1);   // prologue done (0 = kernel entry)
 
   const int m_tiles = p.tiles_x * p.tiles_y * p.tiles_b;
   const int m_pairs = (m_tiles + kCta - 1) / kCta;
@@ -275,7 +296,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
         const Unit t = unit_coord<kCta>(p, u, cta_rank, m_tiles, num_kb);
         int tap = t.kb_begin / kb_per_tap;
         int kb = t.kb_begin - tap * kb_per_tap;
-        const int wrow = t.nt * S::kBN + cta_rank * S::kBRows;
+        const int wrow = t.nt * kBN + cta_rank * S::kBRows;
         for (int kbi = t.kb_begin; kbi < t.kb_end; ++kbi) {
           const int dx = (p.taps == 9) ? (tap % 3 - 1) : 0;
           const int dy = (p.taps == 9) ? (tap / 3 - 1) : 0;
@@ -287,8 +308,9 @@ gemm2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
           if (kb < p.kb0) tma_load_4d_pair<kCta>(sa, &mapA0, &full[stage], kb * 64, t.x0 + dx, t.y0 + dy, t.b0);
           else            tma_load_4d_pair<kCta>(sa, &mapA1, &full[stage], (kb - p.kb0) * 64, t.x0 + dx, t.y0 + dy, t.b0);
           const int kcol = kbi * 64;
-          tma_load_2d_pair<kCta>(sb, &mapW, &full[stage], kcol, wrow);
-          tma_load_2d_pair<kCta>(sb + S::kBHalfBytes, &mapW, &full[stage], kcol, wrow + S::kNI);
+#pragma unroll
+          for (int g = 0; g < S::kNumAcc; ++g)
+            tma_load_2d_pair<kCta>(sb + g * S::kBHalfBytes, &mapW, &full[stage], kcol, wrow + g * S::kNI);
           if (++kb == kb_per_tap) { kb = 0; ++tap; }
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
@@ -300,53 +322,92 @@ gemm2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
       constexpr uint32_t idesc = make_idesc_f16(S::kNI, false, 128 * kCta);
       const uint64_t descA0 = make_smem_desc_sw128(smem_u32(smem), 16, 1024);
       const uint64_t descB0 = make_smem_desc_sw128(smem_u32(smem) + S::kABytes, 16, 1024);
-      int stage = 0; uint32_t phase = 0, acc_phase = 0;
+      int stage = 0; uint32_t phase = 0;
+      int as = 0; uint32_t acc_phase = 0;
       for (int u = pair_id; u < total_units; u += num_pairs) {
         const int split = u % p.splits;
         const int kb_begin = (int)(((long long)split * num_kb) / p.splits);
         const int kb_end = (int)(((long long)(split + 1) * num_kb) / p.splits);
-        mbar_wait(acc_empty, acc_phase ^ 1);
+        mbar_wait(&acc_empty[as], acc_phase ^ 1);
         tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * S::kAccStride;
         for (int kbi = kb_begin; kbi < kb_end; ++kbi) {
           mbar_wait(&full[stage], phase);
           tc_fence_after();
+          if (u == pair_id && kbi == kb_begin && lane == 0) DG_STAMP(2);   // first operands landed
           const uint64_t da = descA0 + (uint64_t)(stage * (S::kStageBytes >> 4));
-          const uint64_t db0 = descB0 + (uint64_t)(stage * (S::kStageBytes >> 4));
-          const uint64_t db1 = db0 + (uint64_t)(S::kBHalfBytes >> 4);
+          const uint64_t db = descB0 + (uint64_t)(stage * (S::kStageBytes >> 4));
           if (elect_one()) {
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
               const uint32_t acc = (kbi > kb_begin || k > 0) ? 1u : 0u;
-              umma_ss_pair<kCta>(tmem_base, da + 2 * k, db0 + 2 * k, idesc, acc);
-              umma_ss_pair<kCta>(tmem_base + S::kNI, da + 2 * k, db1 + 2 * k, idesc, acc);
+#pragma unroll
+              for (int g = 0; g < S::kNumAcc; ++g)
+                umma_ss_pair<kCta>(d_tmem + g * S::kNI, da + 2 * k, db + (uint64_t)(g * (S::kBHalfBytes >> 4)) + 2 * k, idesc, acc);
             }
             umma_commit_pair<kCta>(&empty[stage]);
-            if (kbi == kb_end - 1) umma_commit_pair<kCta>(acc_full);
+            if (kbi == kb_end - 1) umma_commit_pair<kCta>(&acc_full[as]);
           }
           __syncwarp();
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
-        acc_phase ^= 1;
+        if (++as == S::kAccStages) { as = 0; acc_phase ^= 1; }
       }
+    }
+  } else if (warp == 3) {
+    // ===================== store warp: drains the staging ring with TMA stores, data-driven by chunk_ready =====================
+    // (the epilogue warps never wait on each other or on a store: they only see ring back-pressure through buf_free)
+    if (elect_one()) {
+      mbar_arrive(&buf_free[0]);        // buffer 0 starts free; buffer c+1 is freed after store c is issued
+      for (uint32_t c = 0;; ++c) {
+        const uint32_t buf = c % S::kRing;
+        mbar_wait(&chunk_ready[buf], (c / S::kRing) & 1);
+        const int col = chunk_info[buf * 5 + 0], x0 = chunk_info[buf * 5 + 1], y0 = chunk_info[buf * 5 + 2];
+        const int b0 = chunk_info[buf * 5 + 3], flags = chunk_info[buf * 5 + 4];
+        if (flags & 2) break;
+        if (flags & 1) {
+          if constexpr (kBN == 160) {
+#pragma unroll
+            for (int k = 0; k < 5; ++k)
+              if (col + k * 32 < p.n_out) tma_store_4d(&mapO, sRing + (buf * 5 + k) * S::kSubBytes, col + k * 32, x0, y0, b0);
+          } else if constexpr (kCW == 32) {
+            if (col < p.n_out) tma_store_4d(&mapO64, sRing + (buf * 2) * S::kSubBytes, col, x0, y0, b0);   // [128][64 cols], clipped at n_out
+          } else {
+            if (col < p.n_out) tma_store_4d(&mapO, sRing + (buf * 2) * S::kSubBytes, col, x0, y0, b0);
+          }
+        }
+        tma_store_commit();
+        tma_store_wait_read<S::kRing - 1>();              // the store issued kRing-1 chunks ago has drained its buffer ...
+        mbar_arrive(&buf_free[(buf + 1) % S::kRing]);     // ... which is the one chunk c + 1 writes next
+      }
+      DG_STAMP(10);                     // stop seen by the store warp
+      tma_store_wait_all();
+      DG_STAMP(11);                     // all stores complete
     }
   } else if (warp >= 4) {
     // ===================== epilogue (8 warps) =====================
     const int ew = warp - 4;
     const int q = ew & 3;               // TMEM lane quadrant (== warp index % 4)
-    const int hf = ew >> 2;             // column half owned by this warp
+    const int hf = ew >> 2;             // which column half (320-wide) / chunk half (160-wide, GEGLU) this warp owns
     const int r = q * 32 + lane;        // accumulator row within this CTA's tile
     const int et = threadIdx.x - 128;   // 0..255
     const int box_xy = p.bw * p.bh;
     const uint32_t row_sw = (uint32_t)((r >> 1) & 3);   // 64-byte swizzle phase of this row
-    const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16);
-    const uint32_t acc_empty_leader = mapa_rank(smem_u32(acc_empty), 0);
-    uint32_t acc_phase = 0;
+    const uint32_t acc_empty_leader = mapa_rank(smem_u32(&acc_empty[0]), 0);
+    const uint32_t sBias_a = smem_u32(sBias), sCs_a = smem_u32(sCs), sRing_a = smem_u32(sRing);
+    const bool has_ln = p.colsum != nullptr;
+    int as = 0; uint32_t acc_phase = 0;
     uint32_t chunk_ctr = 0;             // staging-ring chunk counter (final epilogues only)
-    if (ew == 0 && elect_one()) mbar_arrive(&buf_free[0]);   // buffer 0 starts free; buffer 1 is freed after the first store is issued
+
+    // first tile column of this thread's piece of chunk j (accumulator columns == output columns for plain tiles)
+    // 320 plain: chunk j = tile columns [64j, 64j+64), this warp's half = 32 of them; 160: contiguous 80-column halves;
+    // GEGLU: chunk j = outputs [32j, 32j+32), 16 per warp half
+    auto chunk_col = [&](int j) { return kCW == 32 ? j * 64 + hf * 32 : (kBN == 160 ? hf * 80 + j * 16 : j * 32 + hf * 16); };
 
     for (int u = pair_id; u < total_units; u += num_pairs) {
       const Unit t = unit_coord<kCta>(p, u, cta_rank, m_tiles, num_kb);
       const int nt = t.nt;
+      const uint32_t t_row = tmem_base + as * S::kAccStride + ((uint32_t)(q * 32) << 16);
       // ---- this thread's output row
       int bb, yy = 0, xx = 0;
       size_t grow;                      // global row index (pixel index in [B*H*W))
@@ -364,8 +425,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
       const int bbc = row_ok ? bb : 0;
 
       // ---- per-unit vectors -> smem (previous unit's readers are past that unit's last bar.sync)
-      for (int i = et; i < S::kBN; i += kEpiThreads) {
-        const int n = nt * S::kBN + i;
+      for (int i = et; i < kBN; i += kEpiThreads) {
+        const int n = nt * kBN + i;
         float bv = 0.f, cv = 0.f;
         if (n < p.n_gemm) {
           if (p.bias32) bv = __ldg(p.bias32 + n);
@@ -388,42 +449,58 @@ gemm2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
         ln_b = -mean * ln_a;
       }
       // residual prefetch registers (one chunk ahead)
-      uint4 res_cur[4], res_nxt[4];
-      const __half* res_row = p.residual ? p.residual + grow * p.ld_res + (size_t)nt * (kGeglu ? S::kNI : S::kBN) : nullptr;
+      constexpr int kRV = kCW / 8;      // 16-byte vectors per chunk piece
+      uint4 res_cur[kRV], res_nxt[kRV];
+      const __half* res_row = p.residual ? p.residual + grow * p.ld_res + (size_t)nt * kOutW : nullptr;
       auto load_res = [&](int j, uint4* dst) {
-        const int c = hf * S::kNI + j * 32;   // plain layout only (GEGLU has no residual)
+        const int c = chunk_col(j);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int col = nt * S::kBN + c + i * 8;
+        for (int i = 0; i < kRV; ++i) {
+          const int col = nt * kOutW + c + i * 8;
           dst[i] = (row_ok && col + 8 <= p.n_out) ? __ldg(reinterpret_cast<const uint4*>(res_row + c + i * 8)) : make_uint4(0, 0, 0, 0);
         }
       };
       if (p.residual) load_res(0, res_cur);
 
-      mbar_wait(acc_full, acc_phase);
-      acc_phase ^= 1;
+      mbar_wait(&acc_full[as], acc_phase);
       tc_fence_after();
+      if (u == pair_id && et == 0) DG_STAMP(3);        // first accumulator complete
       asm volatile("bar.sync 1, 256;" ::: "memory");   // sBias / sCs visible
+      auto release_acc = [&]() {        // every TMEM read of this unit has completed: hand the accumulator back
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(acc_empty_leader + as * 8);
+      };
 
       bool do_final = true;
       if (p.splits > 1) {
         // ---- split-K: add this split's fp32 partial into the tile's L2-resident accumulator (16-byte vector reductions);
         // the last arriver (ticket) reads the sum back, re-zeroes it for the next launch and finishes the tile
-        float* wrow = p.ws + ((size_t)t.ctile * 128 + r) * S::kBN + hf * S::kNI;
+        float* wrow = p.ws + ((size_t)t.ctile * 128 + r) * kBN;
 #pragma unroll
-        for (int j = 0; j < kChunks; ++j) {
+        for (int j = 0; j < kBN / 64; ++j) {
+          const int c = hf * (kBN / 2) + j * 32;
           uint32_t v[32];
-          tmem_ld32(t_row + hf * S::kNI + j * 32, v);
+          tmem_ld32(t_row + c, v);
           tmem_ld_wait();
 #pragma unroll
           for (int i = 0; i < 32; i += 4)
-            asm volatile("red.relaxed.gpu.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(wrow + j * 32 + i), "r"(v[i]), "r"(v[i + 1]),
+            asm volatile("red.relaxed.gpu.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(wrow + c + i), "r"(v[i]), "r"(v[i + 1]),
                          "r"(v[i + 2]), "r"(v[i + 3])
                          : "memory");
         }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive_cluster(acc_empty_leader);
+        if constexpr (kBN == 160) {       // 80 columns per half: 2 x 32 above, the last 16 here
+          const int c = hf * 80 + 64;
+          uint32_t v[16];
+          tmem_ld16(t_row + c, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 16; i += 4)
+            asm volatile("red.relaxed.gpu.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(wrow + c + i), "r"(v[i]), "r"(v[i + 1]),
+                         "r"(v[i + 2]), "r"(v[i + 3])
+                         : "memory");
+        }
+        release_acc();
         __threadfence();
         asm volatile("bar.sync 1, 256;" ::: "memory");
         if (ew == 0 && elect_one()) *ticket_slot = (uint32_t)atomicAdd(p.tickets + t.ctile, 1);
@@ -436,60 +513,88 @@ gemm2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
       }
 
       if (do_final) {
-        // GroupNorm block statistics carried across chunks (this thread's columns are contiguous: hf*160 + [0,160))
-        float gs = 0.f, gss = 0.f;
-        int gcnt = 0, gblk = 0;
+        // GroupNorm block statistics: running (sum, sumsq) of the current gn_blk-channel block, flushed when the block changes
         const bool gn_on = p.gn_stats_out != nullptr;
         const bool warp_uniform = __all_sync(0xffffffffu, bbc == __shfl_sync(0xffffffffu, bbc, 0)) != 0;
-        if (gn_on) gblk = (nt * S::kBN + hf * S::kNI) / p.gn_blk;
-        float rs = 0.f, rss = 0.f;     // LayerNorm row statistics of this thread's 160 output columns
-        float* wsrow = p.ws + ((size_t)t.ctile * 128 + r) * S::kBN;
+        float gs = 0.f, gss = 0.f;
+        int gcur = -1;
+        auto gn_flush = [&]() {
+          if (gcur < 0) return;
+          float a0 = gs, a1 = gss;
+          if (warp_uniform) {
+#pragma unroll
+            for (int o = 16; o; o >>= 1) { a0 += __shfl_xor_sync(0xffffffffu, a0, o); a1 += __shfl_xor_sync(0xffffffffu, a1, o); }
+            if (lane == 0 && gcur < p.gn_nblk) {
+              atomicAdd(p.gn_stats_out + ((size_t)bbc * p.gn_nblk + gcur) * 2, a0);
+              atomicAdd(p.gn_stats_out + ((size_t)bbc * p.gn_nblk + gcur) * 2 + 1, a1);
+            }
+          } else if (row_ok && gcur < p.gn_nblk) {
+            atomicAdd(p.gn_stats_out + ((size_t)bbc * p.gn_nblk + gcur) * 2, a0);
+            atomicAdd(p.gn_stats_out + ((size_t)bbc * p.gn_nblk + gcur) * 2 + 1, a1);
+          }
+          gs = 0.f; gss = 0.f;
+        };
+        float rs = 0.f, rss = 0.f;     // LayerNorm row statistics of this thread's output columns
+        float* wsrow = p.ws + ((size_t)t.ctile * 128 + r) * kBN;
 
+        // 160-wide tiles: one staging slot holds the whole tile (one ring wait / fence / hand-off per tile, not per chunk)
+        constexpr bool kWhole = (kBN == 160);
+        uint32_t slot = 0;
+        if constexpr (kWhole) {
+          slot = chunk_ctr % S::kRing;
+          mbar_wait(&buf_free[slot], (chunk_ctr / S::kRing) & 1);
+        }
 #pragma unroll 1
         for (int j = 0; j < kChunks; ++j) {
-          float f[32];
-          int ncols;          // outputs produced by this thread in this chunk
-          int ocol;           // first output column within the tile's output range
+          float f[kCW];
+          const int ocol = chunk_col(j);   // first output column (within the tile) of this thread's piece
+          DG_STAMP_C1(16);
           if constexpr (!kGeglu) {
-            ncols = 32; ocol = hf * S::kNI + j * 32;
             const int c = ocol;
             if (p.splits == 1) {
-              uint32_t v[32];
-              tmem_ld32(t_row + c, v);
-              if (p.residual && j + 1 < kChunks) load_res(j + 1, res_nxt);
-              tmem_ld_wait();
-              if (j == kChunks - 1) {
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive_cluster(acc_empty_leader);
-              }
+              {
+                uint32_t v[kCW];
+                if constexpr (kCW == 32) tmem_ld32(t_row + c, v); else tmem_ld16(t_row + c, v);
+                if (p.residual && j + 1 < kChunks) load_res(j + 1, res_nxt);
+                tmem_ld_wait();
+                DG_STAMP_C1(17);
+                if (j == kChunks - 1) release_acc();
 #pragma unroll
-              for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
+                for (int i = 0; i < kCW; ++i) f[i] = __uint_as_float(v[i]);
+              }
             } else {
               if (p.residual && j + 1 < kChunks) load_res(j + 1, res_nxt);
               float* src = wsrow + c;
 #pragma unroll
-              for (int i = 0; i < 32; i += 4) {
+              for (int i = 0; i < kCW; i += 4) {
                 const float4 v4 = __ldcg(reinterpret_cast<const float4*>(src + i));
                 f[i] = v4.x; f[i + 1] = v4.y; f[i + 2] = v4.z; f[i + 3] = v4.w;
               }
 #pragma unroll
-              for (int i = 0; i < 32; i += 4) __stcg(reinterpret_cast<float4*>(src + i), make_float4(0.f, 0.f, 0.f, 0.f));
+              for (int i = 0; i < kCW; i += 4) __stcg(reinterpret_cast<float4*>(src + i), make_float4(0.f, 0.f, 0.f, 0.f));
             }
+            if (has_ln) {
 #pragma unroll
-            for (int i = 0; i < 32; i += 4) {
-              const float4 b4 = *reinterpret_cast<const float4*>(sBias + c + i);
-              const float4 c4 = *reinterpret_cast<const float4*>(sCs + c + i);
-              f[i] = fmaf(ln_a, f[i], fmaf(ln_b, c4.x, b4.x));
-              f[i + 1] = fmaf(ln_a, f[i + 1], fmaf(ln_b, c4.y, b4.y));
-              f[i + 2] = fmaf(ln_a, f[i + 2], fmaf(ln_b, c4.z, b4.z));
-              f[i + 3] = fmaf(ln_a, f[i + 3], fmaf(ln_b, c4.w, b4.w));
+              for (int i = 0; i < kCW; i += 4) {
+                const float4 b4 = lds_f4(sBias_a + (c + i) * 4);
+                const float4 c4 = lds_f4(sCs_a + (c + i) * 4);
+                f[i] = fmaf(ln_a, f[i], fmaf(ln_b, c4.x, b4.x));
+                f[i + 1] = fmaf(ln_a, f[i + 1], fmaf(ln_b, c4.y, b4.y));
+                f[i + 2] = fmaf(ln_a, f[i + 2], fmaf(ln_b, c4.z, b4.z));
+                f[i + 3] = fmaf(ln_a, f[i + 3], fmaf(ln_b, c4.w, b4.w));
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < kCW; i += 4) {
+                const float4 b4 = lds_f4(sBias_a + (c + i) * 4);
+                f[i] += b4.x; f[i + 1] += b4.y; f[i + 2] += b4.z; f[i + 3] += b4.w;
+              }
             }
             if (p.rowvec) {
-              const int col = nt * S::kBN + c;
+              const int col = nt * kBN + c;
               const __half* rv = p.rowvec + (size_t)bbc * p.ld_rowvec + col;
 #pragma unroll
-              for (int i = 0; i < 32; i += 8) {
+              for (int i = 0; i < kCW; i += 8) {
                 if (col + i + 8 <= p.n_out) {
                   const uint4 b0 = __ldg(reinterpret_cast<const uint4*>(rv + i));
                   float2 tt;
@@ -502,7 +607,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
             }
             if (p.residual) {
 #pragma unroll
-              for (int i = 0; i < 4; ++i) {
+              for (int i = 0; i < kRV; ++i) {
                 float2 tt;
                 tt = unpack_half2(res_cur[i].x); f[i * 8] += tt.x; f[i * 8 + 1] += tt.y;
                 tt = unpack_half2(res_cur[i].y); f[i * 8 + 2] += tt.x; f[i * 8 + 3] += tt.y;
@@ -510,22 +615,17 @@ gemm2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
                 tt = unpack_half2(res_cur[i].w); f[i * 8 + 6] += tt.x; f[i * 8 + 7] += tt.y;
               }
 #pragma unroll
-              for (int i = 0; i < 4; ++i) res_cur[i] = res_nxt[i];
+              for (int i = 0; i < kRV; ++i) res_cur[i] = res_nxt[i];
             }
           } else {
             // GEGLU: accumulator 0 = value columns, accumulator 1 = gate columns of the same 160 outputs
-            ncols = 16; ocol = j * 32 + hf * 16;
             float a[16], g[16];
             if (p.splits == 1) {
               uint32_t va[16], vg[16];
               tmem_ld16(t_row + ocol, va);
               tmem_ld16(t_row + S::kNI + ocol, vg);
               tmem_ld_wait();
-              if (j == kChunks - 1) {
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive_cluster(acc_empty_leader);
-              }
+              if (j == kChunks - 1) release_acc();
 #pragma unroll
               for (int i = 0; i < 16; ++i) { a[i] = __uint_as_float(va[i]); g[i] = __uint_as_float(vg[i]); }
             } else {
@@ -544,96 +644,108 @@ gemm2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
               }
             }
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              const float av = fmaf(ln_a, a[i], fmaf(ln_b, sCs[ocol + i], sBias[ocol + i]));
-              const float gv = fmaf(ln_a, g[i], fmaf(ln_b, sCs[S::kNI + ocol + i], sBias[S::kNI + ocol + i]));
-              f[i] = av * gelu_erf_fast(gv);
+            for (int i = 0; i < 16; i += 4) {
+              const float4 ba = lds_f4(sBias_a + (ocol + i) * 4), ca = lds_f4(sCs_a + (ocol + i) * 4);
+              const float4 bg = lds_f4(sBias_a + (S::kNI + ocol + i) * 4), cg = lds_f4(sCs_a + (S::kNI + ocol + i) * 4);
+              f[i] = fmaf(ln_a, a[i], fmaf(ln_b, ca.x, ba.x)) * gelu_erf_fast(fmaf(ln_a, g[i], fmaf(ln_b, cg.x, bg.x)));
+              f[i + 1] = fmaf(ln_a, a[i + 1], fmaf(ln_b, ca.y, ba.y)) * gelu_erf_fast(fmaf(ln_a, g[i + 1], fmaf(ln_b, cg.y, bg.y)));
+              f[i + 2] = fmaf(ln_a, a[i + 2], fmaf(ln_b, ca.z, ba.z)) * gelu_erf_fast(fmaf(ln_a, g[i + 2], fmaf(ln_b, cg.z, bg.z)));
+              f[i + 3] = fmaf(ln_a, a[i + 3], fmaf(ln_b, ca.w, ba.w)) * gelu_erf_fast(fmaf(ln_a, g[i + 3], fmaf(ln_b, cg.w, bg.w)));
             }
-#pragma unroll
-            for (int i = 16; i < 32; ++i) f[i] = 0.f;
           }
 
           // ---- round to fp16, statistics on the rounded values, write the staging row
-          uint32_t pk[16];
+          uint32_t pk[kCW / 2];
 #pragma unroll
-          for (int i = 0; i < 16; ++i) pk[i] = cvt_pack_half2(f[2 * i], f[2 * i + 1]);
+          for (int i = 0; i < kCW / 2; ++i) pk[i] = cvt_pack_half2(f[2 * i], f[2 * i + 1]);
           if (p.row_stats_out || gn_on) {
-            const int out_w = kGeglu ? S::kNI : S::kBN;
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              if (2 * i < ncols) {
-                const float2 v = unpack_half2(pk[i]);
-                const int col = nt * out_w + ocol + 2 * i;
-                const bool ok0 = row_ok && col < p.n_out, ok1 = row_ok && col + 1 < p.n_out;
-                const float v0 = ok0 ? v.x : 0.f, v1 = ok1 ? v.y : 0.f;
-                rs += v0 + v1; rss = fmaf(v0, v0, fmaf(v1, v1, rss));
-                if (gn_on) {
-                  // two columns per step; gn_blk is even for every supported config (checked on the host)
-                  gs += v0 + v1; gss = fmaf(v0, v0, fmaf(v1, v1, gss));
-                  gcnt += 2;
-                  if (gcnt == p.gn_blk) {
-                    float a0 = gs, a1 = gss;
-                    if (warp_uniform) {
-#pragma unroll
-                      for (int o = 16; o; o >>= 1) { a0 += __shfl_xor_sync(0xffffffffu, a0, o); a1 += __shfl_xor_sync(0xffffffffu, a1, o); }
-                      if (lane == 0 && gblk < p.gn_nblk) {
-                        atomicAdd(p.gn_stats_out + ((size_t)bbc * p.gn_nblk + gblk) * 2, a0);
-                        atomicAdd(p.gn_stats_out + ((size_t)bbc * p.gn_nblk + gblk) * 2 + 1, a1);
-                      }
-                    } else if (row_ok && gblk < p.gn_nblk) {
-                      atomicAdd(p.gn_stats_out + ((size_t)bbc * p.gn_nblk + gblk) * 2, a0);
-                      atomicAdd(p.gn_stats_out + ((size_t)bbc * p.gn_nblk + gblk) * 2 + 1, a1);
-                    }
-                    gs = 0.f; gss = 0.f; gcnt = 0; ++gblk;
-                  }
-                }
+            for (int i = 0; i < kCW / 2; ++i) {
+              const float2 v = unpack_half2(pk[i]);
+              const int col = nt * kOutW + ocol + 2 * i;
+              const bool ok0 = row_ok && col < p.n_out, ok1 = row_ok && col + 1 < p.n_out;
+              const float v0 = ok0 ? v.x : 0.f, v1 = ok1 ? v.y : 0.f;
+              rs += v0 + v1; rss = fmaf(v0, v0, fmaf(v1, v1, rss));
+              if (gn_on) {
+                const int blk = col / p.gn_blk;      // gn_blk is even: both columns of the pair share a block
+                if (blk != gcur) { gn_flush(); gcur = blk; }
+                gs += v0 + v1; gss = fmaf(v0, v0, fmaf(v1, v1, gss));
               }
             }
+            if (gn_on && kCW == 32) { gn_flush(); gcur = -1; }   // 320-wide tiles: this thread's next piece is 64 columns further on
           }
-          const uint32_t buf = chunk_ctr & 1;
-          mbar_wait(&buf_free[buf], (chunk_ctr >> 1) & 1);
-          uint8_t* sub = sRing + (buf * 2 + (kGeglu ? 0 : hf)) * S::kSubBytes + r * 64;
-          if constexpr (!kGeglu) {
+          if constexpr (kWhole) {
+            const uint32_t sub = sRing_a + (slot * 5 + (ocol >> 5)) * S::kSubBytes + r * 64;
+            const uint32_t k0 = (uint32_t)((ocol & 31) >> 3);
+#pragma unroll
+            for (int i = 0; i < 2; ++i) sts_u4(sub + (((k0 + i) ^ row_sw) << 4), pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
+            continue;   // one hand-off per tile, after the loop
+          }
+          const uint32_t buf = chunk_ctr % S::kRing;
+          DG_STAMP_C1(18);
+          mbar_wait(&buf_free[buf], (chunk_ctr / S::kRing) & 1);
+          DG_STAMP_C1(19);
+          if constexpr (kCW == 32) {
+            const uint32_t sub = sRing_a + (buf * 2) * S::kSubBytes + r * 128;   // 128-byte rows, 128-byte swizzle
 #pragma unroll
             for (int i = 0; i < 4; ++i)
-              *reinterpret_cast<uint4*>(sub + (((uint32_t)i ^ row_sw) << 4)) = make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
+              sts_u4(sub + ((((uint32_t)(hf * 4 + i)) ^ (uint32_t)(r & 7)) << 4), pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
           } else {
+            const uint32_t sub = sRing_a + (buf * 2) * S::kSubBytes + r * 64;
 #pragma unroll
             for (int i = 0; i < 2; ++i)
-              *reinterpret_cast<uint4*>(sub + (((uint32_t)(hf * 2 + i) ^ row_sw) << 4)) = make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
+              sts_u4(sub + (((uint32_t)(hf * 2 + i) ^ row_sw) << 4), pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
           }
+          DG_STAMP_C1(20);
           fence_proxy_async();                              // generic-proxy smem writes -> visible to the TMA store
-          asm volatile("bar.sync 1, 256;" ::: "memory");
-          if (ew == 0 && elect_one()) {
-            if (t.valid_m) {
-              if constexpr (!kGeglu) {
-#pragma unroll
-                for (int h2 = 0; h2 < 2; ++h2) {
-                  const int col = nt * S::kBN + h2 * S::kNI + j * 32;
-                  if (col < p.n_out) tma_store_4d(&mapO, sRing + (buf * 2 + h2) * S::kSubBytes, col, t.x0, t.y0, t.b0);
-                }
-              } else {
-                const int col = nt * S::kNI + j * 32;
-                if (col < p.n_out) tma_store_4d(&mapO, sRing + (buf * 2) * S::kSubBytes, col, t.x0, t.y0, t.b0);
-              }
+          DG_STAMP_C1(21);
+          __syncwarp();
+          if (lane == 0) {
+            if (ew == 0) {
+              chunk_info[buf * 5 + 0] = nt * kOutW + j * (kCW == 32 ? 64 : 32); chunk_info[buf * 5 + 1] = t.x0; chunk_info[buf * 5 + 2] = t.y0;
+              chunk_info[buf * 5 + 3] = t.b0; chunk_info[buf * 5 + 4] = t.valid_m ? 1 : 0;
             }
-            tma_store_commit();
-            tma_store_wait_read1();          // the store issued one chunk ago has drained its buffer ...
-            mbar_arrive(&buf_free[buf ^ 1]); // ... so the OTHER buffer is reusable by chunk_ctr + 1
+            mbar_arrive(&chunk_ready[buf]);                 // release: this warp's rows (and the chunk descriptor) are in place
+            if (u == pair_id && ew == 0) DG_STAMP(4 + j);   // chunk j of the first unit staged (4..8)
           }
           ++chunk_ctr;
         }
+        if constexpr (kWhole) {
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) {
+            if (ew == 0) {
+              chunk_info[slot * 5 + 0] = nt * kOutW; chunk_info[slot * 5 + 1] = t.x0; chunk_info[slot * 5 + 2] = t.y0;
+              chunk_info[slot * 5 + 3] = t.b0; chunk_info[slot * 5 + 4] = t.valid_m ? 1 : 0;
+            }
+            mbar_arrive(&chunk_ready[slot]);
+            if (u == pair_id && ew == 0) DG_STAMP(8);
+          }
+          ++chunk_ctr;
+        }
+        if (gn_on) gn_flush();
         if (p.row_stats_out && row_ok)
           reinterpret_cast<float2*>(p.row_stats_out)[grow * p.row_parts + nt * 2 + hf] = make_float2(rs, rss);
       }
+      if (++as == S::kAccStages) { as = 0; acc_phase ^= 1; }
     }
-    if (ew == 0 && elect_one()) tma_store_wait_all();
+    {   // tell the store warp to stop
+      const uint32_t buf = chunk_ctr % S::kRing;
+      mbar_wait(&buf_free[buf], (chunk_ctr / S::kRing) & 1);
+      if (lane == 0) {
+        if (ew == 0) chunk_info[buf * 5 + 4] = 2;
+        mbar_arrive(&chunk_ready[buf]);
+      }
+    }
   }
 
   __syncwarp();
+  if (threadIdx.x == 0) DG_STAMP(12);   // producer warp at the teardown barrier
   tc_fence_before();
   if constexpr (kCta == 2) cluster_sync_all(); else __syncthreads();
+  if (threadIdx.x == 0) DG_STAMP(13);   // teardown barrier passed
   if (warp == 2) { tc_fence_after(); tmem_dealloc_pair<kCta, kTmemCols>(tmem_base); }
+  if (threadIdx.x == 64) DG_STAMP(14);  // TMEM released
 }
 
 }  // namespace dg

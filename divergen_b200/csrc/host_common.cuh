@@ -98,6 +98,7 @@ inline PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
 // rank-4 fp16 map, 128-byte swizzle, zero OOB fill.  dims/box innermost first; strides (bytes) for dims 1..3.
 inline int make_map_4d(CUtensorMap* m, const void* ptr, const uint64_t dims[4], const uint64_t strides[3],
                        const uint32_t box[4], bool weights = false, bool swizzle64 = false) {
+  (void)weights;
   auto fn = get_encode_fn();
   if (!fn) return fail(DG_E_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
   cuuint64_t gd[4] = {dims[0], dims[1], dims[2], dims[3]};
@@ -137,9 +138,12 @@ inline int make_map_2d(CUtensorMap* m, const void* ptr, uint64_t inner, uint64_t
 }
 
 // ------------------------------------------------------------------ GEMM / conv launcher
-constexpr int kGemmTileN = 320;     // output columns per tile (two 160-wide accumulators)
-constexpr int kGemmStages1 = 3;     // single-CTA variant: 3 x 56 KB
-constexpr int kGemmStages2 = 5;     // CTA-pair variant:   5 x 36 KB per CTA
+constexpr int kGemmTileN = 320;     // widest tile: two 160-wide accumulators (GEGLU packing granularity)
+// smem ring depths per (CTAs per tile, tile N): stage bytes are 16 KB of A + 10/20/40 KB of B; + 64 KB output staging ring
+constexpr int kStages_2_320 = 4;    // 4 x 36 KB
+constexpr int kStages_2_160 = 5;    // 5 x 26 KB (+ 80 KB: two whole-tile staging slots)
+constexpr int kStages_1_320 = 2;    // 2 x 56 KB (single-CTA variants: bring-up / A-B runs only, DG_GEMM_CTA=1)
+constexpr int kStages_1_160 = 3;    // 3 x 36 KB
 constexpr size_t kSplitWsFloats = (size_t)8 << 20;    // 32 MB of fp32 split-K tile accumulators (zero between launches)
 constexpr int kSplitTickets = 1 << 16;
 
@@ -173,7 +177,8 @@ struct GemmArgs {
   __half* out = nullptr; int ldo = 0;
 };
 
-inline int gemm_row_parts(int n_out) { return 2 * ((n_out + kGemmTileN - 1) / kGemmTileN); }
+// LayerNorm row partials are always produced by 160-wide tiles: two column halves per tile.
+inline int gemm_row_parts(int n_out) { return 2 * ((n_out + 159) / 160); }
 
 inline int largest_pow2_divisor(int x, int cap) {
   int p = 1;
@@ -181,32 +186,39 @@ inline int largest_pow2_divisor(int x, int cap) {
   return p;
 }
 
-// K-split factor: minimise waves x k-blocks-per-split (+ a fixed fix-up cost per extra split).
+// K-split factor.  Cost model in units of one k-block of MMA time (~0.33 us): a tile costs kb + epilogue, a split adds the
+// partial-tile reduction through L2 (measured ~1.6 us per MB of fp32 vector reductions -- profiles/r01_splitk.txt), so
+// splitting only pays for long-K, few-tile layers (the bottom of the U).  Every split gets >= 16 k-blocks and the whole
+// launch stays within one wave of the persistent grid.  DG_SPLITS=n forces a factor (experiments).
 inline int choose_splits(int units, int num_kb, int slots, size_t ws_floats_per_unit, size_t ws_cap) {
-  if (units >= slots || num_kb < 16 || (size_t)units * ws_floats_per_unit > ws_cap) return 1;
+  static int forced = -1;
+  if (forced < 0) { const char* e = getenv("DG_SPLITS"); forced = e && e[0] ? atoi(e) : 0; }
+  if ((size_t)units * ws_floats_per_unit > ws_cap) return 1;
+  if (forced > 0) return (forced * 4 <= num_kb) ? forced : 1;
+  if (units >= slots || num_kb < 32) return 1;
   int best = 1;
   double best_cost = 1e30;
-  for (int s = 1; s <= 16 && s * 4 <= num_kb; ++s) {
-    const int waves = (units * s + slots - 1) / slots;
-    const double cost = (double)waves * ((num_kb + s - 1) / s + 3) + (s > 1 ? 4.0 + 1.5 * s : 0.0);
+  const double mb_per_unit = (double)ws_floats_per_unit * 4.0 / 1e6;
+  for (int s = 1; s <= 16 && s * 16 <= num_kb && units * s <= slots; ++s) {
+    const double cost = (double)((num_kb + s - 1) / s) + 9.0 + (s > 1 ? 10.0 + 4.8 * mb_per_unit * units * s : 0.0);
     if (cost < best_cost - 1e-9) { best_cost = cost; best = s; }
   }
   return best;
 }
 
-template <int kCta, int kStages, bool kGeglu>
+template <int kCta, int kBN, int kStages, bool kGeglu>
 inline cudaError_t launch_gemm2_t(cudaStream_t stream, int grid_ctas, const CUtensorMap& mA0, const CUtensorMap& mA1,
-                                  const CUtensorMap& mW, const CUtensorMap& mO, const Gemm2Params& p) {
+                                  const CUtensorMap& mW, const CUtensorMap& mO, const CUtensorMap& mO64, const Gemm2Params& p) {
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)grid_ctas);
   cfg.blockDim = dim3(384);
-  cfg.dynamicSmemBytes = Gemm2Cfg<kCta, kStages>::kTotal;
+  cfg.dynamicSmemBytes = Gemm2Cfg<kCta, kBN, kStages>::kTotal;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = kCta; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, gemm2_kernel<kCta, kStages, kGeglu>, mA0, mA1, mW, mO, p);
+  return cudaLaunchKernelEx(&cfg, gemm2_kernel<kCta, kBN, kStages, kGeglu>, mA0, mA1, mW, mO, mO64, p);
 }
 
 inline int launch_gemm(cudaStream_t stream, const GemmRes& res, const GemmArgs& a) {
@@ -220,8 +232,8 @@ inline int launch_gemm(cudaStream_t stream, const GemmRes& res, const GemmArgs& 
   if (a.geglu && (a.residual || a.rowvec || a.row_stats_out || a.gn_stats_out)) return fail(DG_E_ARG, "gemm: geglu epilogue takes bias / LayerNorm fold only");
   if (a.colsum && (!a.ln_stats || !a.bias32 || a.ln_c <= 0)) return fail(DG_E_ARG, "gemm: LayerNorm fold needs ln_stats, bias32 and ln_c");
   if (a.row_stats_out && a.taps != 1) return fail(DG_E_ARG, "gemm: row statistics are produced by plain GEMMs only");
-  if (a.gn_stats_out && (a.gn_blk <= 0 || a.gn_blk % 2 || 160 % a.gn_blk || a.n_out % a.gn_blk))
-    return fail(DG_E_SHAPE, "gemm: fused GroupNorm statistics need an even channel block dividing 160 and n_out (blk %d, n_out %d)", a.gn_blk, a.n_out);
+  if (a.gn_stats_out && (a.gn_blk <= 0 || a.gn_blk % 2 || a.n_out % a.gn_blk))
+    return fail(DG_E_SHAPE, "gemm: fused GroupNorm statistics need an even channel block dividing n_out (blk %d, n_out %d)", a.gn_blk, a.n_out);
   const int kcta = res.cta_mode == 1 ? 1 : 2;
   Gemm2Params p{};
   int W = a.W, H = a.H, B = a.B;
@@ -236,7 +248,15 @@ inline int launch_gemm(cudaStream_t stream, const GemmRes& res, const GemmArgs& 
   p.tiles_b = (B + p.bn - 1) / p.bn;
   p.hw = a.taps == 1 ? (a.hw > 0 ? a.hw : a.H * a.W) : 0;
   p.n_gemm = a.n_w;
-  p.tiles_n = (a.n_w + kGemmTileN - 1) / kGemmTileN;
+  const int num_kb = a.taps * (a.c0 / 64 + a.c1 / 64);
+  // tile width: 320 (two accumulators, single TMEM stage: best operand reuse) for long-K layers; 160 (double-buffered TMEM:
+  // the epilogue overlaps the next main loop, twice the tiles for wave balance) for short-K / epilogue-bound layers
+  static int forced_bn = -1;
+  if (forced_bn < 0) { const char* e = getenv("DG_GEMM_BN"); forced_bn = e && e[0] ? atoi(e) : 0; }
+  int kbn = (a.geglu || (num_kb > 24 && a.n_w > 160)) ? 320 : 160;
+  if (forced_bn == 160 || forced_bn == 320) kbn = a.geglu ? 320 : forced_bn;
+  if (a.row_stats_out) kbn = 160;
+  p.tiles_n = (a.n_w + kbn - 1) / kbn;
   p.n_out = a.n_out;
   p.taps = a.taps;
   p.kb0 = a.c0 / 64; p.kb1 = a.c1 / 64;
@@ -253,12 +273,11 @@ inline int launch_gemm(cudaStream_t stream, const GemmRes& res, const GemmArgs& 
   const int m_units = (m_tiles + kcta - 1) / kcta;
   const int units = m_units * p.tiles_n;
   const int slots = kcta == 2 ? res.max_pairs : res.num_sms;
-  const int num_kb = a.taps * (p.kb0 + p.kb1);
   p.splits = 1;
-  if (res.ws && res.tickets && m_tiles * p.tiles_n <= kSplitTickets)
-    p.splits = choose_splits(units, num_kb, slots, (size_t)kcta * 128 * kGemmTileN, kSplitWsFloats);
+  if (res.ws && res.tickets && !a.row_stats_out && m_tiles * p.tiles_n <= kSplitTickets)
+    p.splits = choose_splits(units, num_kb, slots, (size_t)kcta * 128 * kbn, kSplitWsFloats);
 
-  CUtensorMap mA0, mA1, mW, mO;
+  CUtensorMap mA0, mA1, mW, mO, mO64;
   {
     uint64_t dims[4] = {(uint64_t)a.c0, (uint64_t)W, (uint64_t)H, (uint64_t)B};
     uint64_t st[3] = {(uint64_t)a.c0 * 2, (uint64_t)W * a.c0 * 2, (uint64_t)H * W * a.c0 * 2};
@@ -272,31 +291,54 @@ inline int launch_gemm(cudaStream_t stream, const GemmRes& res, const GemmArgs& 
       mA1 = mA0;
     }
     const uint64_t ktot = (uint64_t)a.taps * (a.c0 + a.c1);
-    DG_TRY(make_map_2d(&mW, a.w, ktot, (uint64_t)a.n_w, ktot * 2, 64, 160 / kcta));
+    DG_TRY(make_map_2d(&mW, a.w, ktot, (uint64_t)a.n_w, ktot * 2, 64, 160 / kcta));   // one accumulator's rows per CTA
     // output tiles: {n_out, W, H, B} boxes of 32 columns x 128 pixels, 64-byte swizzle in smem
     uint64_t od[4] = {(uint64_t)a.n_out, (uint64_t)W, (uint64_t)H, (uint64_t)B};
     uint64_t os[3] = {(uint64_t)a.ldo * 2, (uint64_t)W * a.ldo * 2, (uint64_t)H * W * a.ldo * 2};
     uint32_t obox[4] = {32, (uint32_t)p.bw, (uint32_t)p.bh, (uint32_t)p.bn};
     DG_TRY(make_map_4d(&mO, a.out, od, os, obox, false, true));
+    if (kbn == 320 && !a.geglu) {
+      uint32_t obox64[4] = {64, (uint32_t)p.bw, (uint32_t)p.bh, (uint32_t)p.bn};
+      DG_TRY(make_map_4d(&mO64, a.out, od, os, obox64, false, false));
+    } else {
+      mO64 = mO;
+    }
   }
   const int total_units = units * p.splits;
   const int grid_units = total_units < slots ? total_units : slots;
   if (trace_on())
-    fprintf(stderr, "DG_TRACE gemm M=%d N=%d K=%d taps=%d c0=%d c1=%d units=%d splits=%d grid=%dx%d geglu=%d ln=%d res=%d gn=%d rs=%d\n",
-            a.B * a.H * a.W, a.n_w, a.taps * (a.c0 + a.c1), a.taps, a.c0, a.c1, units, p.splits, grid_units, kcta, a.geglu,
+    fprintf(stderr, "DG_TRACE gemm M=%d N=%d K=%d taps=%d c0=%d c1=%d bn=%d units=%d splits=%d grid=%dx%d geglu=%d ln=%d res=%d gn=%d rs=%d\n",
+            a.B * a.H * a.W, a.n_w, a.taps * (a.c0 + a.c1), a.taps, a.c0, a.c1, kbn, units, p.splits, grid_units, kcta, a.geglu,
             a.colsum != nullptr, a.residual != nullptr, a.gn_stats_out != nullptr, a.row_stats_out != nullptr);
   const double rows_ = (double)a.B * a.H * a.W, ktot_ = (double)a.taps * (a.c0 + a.c1);
   ProfScope prof_(FAM_GEMM, stream, 2.0 * rows_ * ktot_ * (double)a.n_w,
                   2.0 * (rows_ * (a.c0 + a.c1) + ktot_ * a.n_w + rows_ * a.n_out));
+  static int dbg_on = -1;
+  static long long* dbg_dev = nullptr;
+  if (dbg_on < 0) { const char* ev = getenv("DG_GEMM_DBG"); dbg_on = ev && ev[0] == '1'; if (dbg_on) { cudaMalloc(&dbg_dev, 32 * 8); } }
+  if (dbg_on) { cudaMemsetAsync(dbg_dev, 0, 32 * 8, stream); p.dbg = dbg_dev; }
   cudaError_t e;
   if (kcta == 2) {
-    e = a.geglu ? launch_gemm2_t<2, kGemmStages2, true>(stream, grid_units * 2, mA0, mA1, mW, mO, p)
-                : launch_gemm2_t<2, kGemmStages2, false>(stream, grid_units * 2, mA0, mA1, mW, mO, p);
+    if (a.geglu) e = launch_gemm2_t<2, 320, kStages_2_320, true>(stream, grid_units * 2, mA0, mA1, mW, mO, mO64, p);
+    else if (kbn == 320) e = launch_gemm2_t<2, 320, kStages_2_320, false>(stream, grid_units * 2, mA0, mA1, mW, mO, mO64, p);
+    else e = launch_gemm2_t<2, 160, kStages_2_160, false>(stream, grid_units * 2, mA0, mA1, mW, mO, mO64, p);
   } else {
-    e = a.geglu ? launch_gemm2_t<1, kGemmStages1, true>(stream, grid_units, mA0, mA1, mW, mO, p)
-                : launch_gemm2_t<1, kGemmStages1, false>(stream, grid_units, mA0, mA1, mW, mO, p);
+    if (a.geglu) e = launch_gemm2_t<1, 320, kStages_1_320, true>(stream, grid_units, mA0, mA1, mW, mO, mO64, p);
+    else if (kbn == 320) e = launch_gemm2_t<1, 320, kStages_1_320, false>(stream, grid_units, mA0, mA1, mW, mO, mO64, p);
+    else e = launch_gemm2_t<1, 160, kStages_1_160, false>(stream, grid_units, mA0, mA1, mW, mO, mO64, p);
   }
   ++g_launch_counter;
+  if (dbg_on && e == cudaSuccess) {
+    long long h[32];
+    cudaStreamSynchronize(stream);
+    cudaMemcpy(h, dbg_dev, sizeof(h), cudaMemcpyDeviceToHost);
+    fprintf(stderr, "DG_GEMM_DBG bn=%d units=%d splits=%d: prologue %lld | operands +%lld | acc +%lld | chunks", kbn, units, p.splits,
+            h[1] - h[0], h[2] - h[0], h[3] - h[0]);
+    for (int i = 4; i < 9; ++i) fprintf(stderr, " +%lld", h[i] - h[0]);
+    fprintf(stderr, " | chunk1: ld %lld math %lld bufwait %lld st %lld fence %lld", h[17] - h[16], h[18] - h[17], h[19] - h[18], h[20] - h[19], h[21] - h[20]);
+    fprintf(stderr, " | stop +%lld | stores done +%lld | at teardown +%lld | passed +%lld | tmem freed +%lld\n", h[10] - h[0],
+            h[11] - h[0], h[12] - h[0], h[13] - h[0], h[14] - h[0]);
+  }
   if (e != cudaSuccess) return fail(DG_E_CUDA, "gemm2 launch failed: %s", cudaGetErrorString(e));
   return DG_OK;
 }
@@ -349,32 +391,34 @@ inline int init_attn_attr() {
                                AttnCfg<kD, kKV, kStages>::kSmem));
   return DG_OK;
 }
-template <int kCta, int kStages, bool kGeglu>
+template <int kCta, int kBN, int kStages, bool kGeglu>
 inline int init_gemm_attr() {
-  DG_CUDA(cudaFuncSetAttribute(gemm2_kernel<kCta, kStages, kGeglu>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               Gemm2Cfg<kCta, kStages>::kTotal));
+  DG_CUDA(cudaFuncSetAttribute(gemm2_kernel<kCta, kBN, kStages, kGeglu>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               Gemm2Cfg<kCta, kBN, kStages>::kTotal));
   return DG_OK;
 }
-// Co-resident CTA pairs of the pair kernel (persistent grid size).
+// Co-resident CTA pairs of the pair kernels (persistent grid size; every variant is one CTA per SM).
 inline int query_max_pairs(int* out) {
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(2 * 148); cfg.blockDim = dim3(384);
-  cfg.dynamicSmemBytes = Gemm2Cfg<2, kGemmStages2>::kTotal;
+  cfg.dynamicSmemBytes = Gemm2Cfg<2, 160, kStages_2_160>::kTotal;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
   int n = 0;
-  DG_CUDA(cudaOccupancyMaxActiveClusters(&n, gemm2_kernel<2, kGemmStages2, false>, &cfg));
+  DG_CUDA(cudaOccupancyMaxActiveClusters(&n, gemm2_kernel<2, 160, kStages_2_160, false>, &cfg));
   if (n <= 0) return fail(DG_E_CUDA, "no co-resident CTA pair fits (cudaOccupancyMaxActiveClusters = %d)", n);
   *out = n;
   return DG_OK;
 }
 inline int init_kernel_attributes() {
-  DG_TRY((init_gemm_attr<1, kGemmStages1, false>()));
-  DG_TRY((init_gemm_attr<1, kGemmStages1, true>()));
-  DG_TRY((init_gemm_attr<2, kGemmStages2, false>()));
-  DG_TRY((init_gemm_attr<2, kGemmStages2, true>()));
+  DG_TRY((init_gemm_attr<1, 320, kStages_1_320, false>()));
+  DG_TRY((init_gemm_attr<1, 320, kStages_1_320, true>()));
+  DG_TRY((init_gemm_attr<1, 160, kStages_1_160, false>()));
+  DG_TRY((init_gemm_attr<2, 320, kStages_2_320, false>()));
+  DG_TRY((init_gemm_attr<2, 320, kStages_2_320, true>()));
+  DG_TRY((init_gemm_attr<2, 160, kStages_2_160, false>()));
   DG_TRY((init_attn_attr<32, 128, 4>()));
   DG_TRY((init_attn_attr<40, 128, 4>()));
   DG_TRY((init_attn_attr<64, 128, 3>()));
