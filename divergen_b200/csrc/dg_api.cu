@@ -124,7 +124,7 @@ struct dg_unet {
   __half* loop_out = nullptr; // [2B,4,h,w] noise prediction
   int coef_cap = 0;
   // fused-statistics scratch: bump-allocated per forward in launch order (graph-stable addresses)
-  float* gn_arena = nullptr; size_t gn_cap = 0, gn_off = 0;   // GroupNorm block sums (zeroed at the top of a forward)
+  float* gn_arena = nullptr; size_t gn_cap = 0, gn_off = 0;   // GroupNorm slab/block sums (fully overwritten, never zeroed)
   float* ln_arena = nullptr; size_t ln_cap = 0, ln_off = 0;   // LayerNorm row partials (fully overwritten, never zeroed)
   int gn_blk = 0;             // channel-block width of the fused GroupNorm sums (block_out_channels[0] / groups), 0 = off
   // step-invariant work hoisted out of the denoising loop (dg_denoise_loop): cross-attention K/V of the text embedding
@@ -325,10 +325,12 @@ struct Fwd {
 
   bool fuse_gn() const { return u->gn_blk > 0; }
   bool fuse_ln() const { return u->ctx->fuse_ln != 0; }
-  // fused GroupNorm block sums for a [B_, *, *, C] tensor about to be produced (zeroed by the memset at the top of the forward)
-  float* gn_alloc(int B_, int C) {
-    if (!fuse_gn()) return nullptr;
-    const size_t n = (size_t)B_ * (C / u->gn_blk) * 2;
+  // fused GroupNorm block sums [B_][H*W/32][C/blk] float2 for a tensor about to be produced by a 3x3 conv (conv = true:
+  // pixel-box tiles) or a plain GEMM over its B_*H*W rows; nullptr when the shape cannot carry them (the consumer then
+  // runs the stand-alone statistics kernel)
+  float* gn_alloc(int B_, int H, int W, int C, bool conv) {
+    if (!fuse_gn() || !gn_stats_supported(H * W, conv ? W : 0, conv ? H : 0, u->gn_blk, C)) return nullptr;
+    const size_t n = (size_t)B_ * (H * W / 32) * (C / u->gn_blk) * 2;
     if (u->gn_off + n > u->gn_cap) { if (err == DG_OK) err = fail(DG_E_NOMEM, "GroupNorm statistics arena exhausted"); return nullptr; }
     float* p = u->gn_arena + u->gn_off;
     u->gn_off += (n + 3) & ~size_t(3);
@@ -387,14 +389,14 @@ struct Fwd {
     T4 hn = talloc(B_, H, W, r.cin);
     gn(x0, x1, r.n1, u->cfg.norm_eps, 1, hn);
     T4 h1 = talloc(B_, H, W, r.cout);
-    h1.gst = gn_alloc(B_, r.cout);
+    h1.gst = gn_alloc(B_, H, W, r.cout, true);
     conv3(hn, r.c1, temb_all + r.temb_off, nullptr, h1);
     free_(hn);
     T4 h2n = talloc(B_, H, W, r.cout);
     gn(h1, nullptr, r.n2, u->cfg.norm_eps, 1, h2n);
     free_(h1);
     T4 out = talloc(B_, H, W, r.cout);
-    out.gst = gn_alloc(B_, r.cout);
+    out.gst = gn_alloc(B_, H, W, r.cout, true);
     const __half* resid = x0.p;
     T4 sc{};
     if (r.has_sc) {
@@ -459,7 +461,7 @@ struct Fwd {
     free_(g);
     // proj_out + residual with the block input
     T4 out = talloc(B_, in.H, in.W, C);
-    out.gst = gn_alloc(B_, C);
+    out.gst = gn_alloc(B_, in.H, in.W, C, false);
     { LinOpt o; o.residual = in.p; o.gn_out = out.gst; o.hw = S; linear(h.p, C, nullptr, 0, rows, x.proj_out, out.p, o); }
     free_(xn); free_(h);
     return out;
@@ -472,7 +474,6 @@ int run_forward(dg_unet* u, cudaStream_t s, const __half* sample, const __half* 
   u->arena.reset();
   u->gn_off = 0; u->ln_off = 0;
   Fwd f{u, s, sms, B, tokens, ehs, nullptr};
-  if (u->gn_blk > 0) DG_CUDA(cudaMemsetAsync(u->gn_arena, 0, u->gn_cap * sizeof(float), s));
 
   // ---- time embedding: sinusoid -> MLP -> all time_emb_proj(SiLU(emb)) in one GEMV
   const int c0 = cf.block_out_channels[0];
@@ -503,7 +504,7 @@ int run_forward(dg_unet* u, cudaStream_t s, const __half* sample, const __half* 
     const size_t items = (size_t)B * h * w * 64;
     im2col_conv_in_kernel<<<grid_for(items, 256, sms), 256, 0, s>>>(sample, col, B, cf.in_channels, h, w, 64);
     DG_LAUNCH_CHECK();
-    x.gst = f.gn_alloc(B, c0);
+    x.gst = f.gn_alloc(B, h, w, c0, false);
     { Fwd::LinOpt o; o.gn_out = x.gst; o.hw = h * w; f.linear(col, 64, nullptr, 0, B * h * w, u->conv_in, x.p, o); }
     f.free_(col);
   }
@@ -525,7 +526,7 @@ int run_forward(dg_unet* u, cudaStream_t s, const __half* sample, const __half* 
       const size_t items = (size_t)x.B * Ho * Wo * 9 * (x.C / 8);
       im2col3x3_nhwc_kernel<<<grid_for(items, 256, sms), 256, 0, s>>>(x.p, c2, x.B, x.H, x.W, x.C, 2, Ho, Wo);
       DG_LAUNCH_CHECK();
-      y.gst = f.gn_alloc(x.B, x.C);
+      y.gst = f.gn_alloc(x.B, Ho, Wo, x.C, false);
       { Fwd::LinOpt o; o.gn_out = y.gst; o.hw = Ho * Wo; f.linear(c2, 9 * x.C, nullptr, 0, x.B * Ho * Wo, d.down, y.p, o); }
       f.free_(c2);
       x = y; skips.push_back(x);
@@ -555,7 +556,7 @@ int run_forward(dg_unet* u, cudaStream_t s, const __half* sample, const __half* 
       const size_t items = (size_t)x.B * 4 * x.H * x.W * (x.C / 8);
       upsample2x_nhwc_kernel<<<grid_for(items, 256, sms), 256, 0, s>>>(x.p, upx.p, x.B, x.H, x.W, x.C);
       DG_LAUNCH_CHECK();
-      y.gst = f.gn_alloc(x.B, x.C);
+      y.gst = f.gn_alloc(x.B, x.H * 2, x.W * 2, x.C, true);
       f.conv3(upx, b.up, nullptr, nullptr, y);
       f.free_(upx); f.free_(x);
       x = y;
@@ -900,7 +901,7 @@ int32_t dg_unet_prepare(dg_unet* u, int32_t max_batch, int32_t h, int32_t w, int
   {
     // ~70 GroupNorm inputs of at most 4*c0 channels; 48 LayerNorm inputs of at most pix rows x 8 partials
     const int blk = u->gn_blk > 0 ? u->gn_blk : 2;
-    u->gn_cap = (size_t)96 * max_batch * (4 * c0 / blk + 4) * 2;
+    u->gn_cap = (size_t)96 * max_batch * ((size_t)h * w / 32 + 1) * (c0 / blk + 1) * 2;   // level 0 dominates: slabs shrink 4x per level, channels grow <= 2x
     u->ln_cap = (size_t)pix * 64 * (2 + c0 / 80) + ((size_t)1 << 20);   // >= 3x the sum over blocks of rows*parts*2
     DG_CUDA(cudaMalloc((void**)&u->gn_arena, u->gn_cap * sizeof(float)));
     DG_CUDA(cudaMalloc((void**)&u->ln_arena, u->ln_cap * sizeof(float)));

@@ -143,28 +143,43 @@ __global__ void gn_apply_kernel(const __half* __restrict__ x0, int C0, const __h
   }
 }
 
-// Same apply pass, statistics taken from the producers' fused epilogue sums: stats{0,1}[b][C{0,1}/blk][2] hold
-// (sum, sum of squares) over blk-channel blocks of each source (gemm2_tc.cuh); a group of the concatenated tensor is a
-// union of whole blocks, so each CTA first folds them into 32 (mean, rstd) pairs in shared memory.
+// Same apply pass, statistics taken from the producers' fused epilogue sums: stats{0,1}[b][slots][C{0,1}/blk] float2 hold
+// (sum, sum of squares) over blk-channel blocks of each 32-pixel slab of each source (gemm2_tc.cuh).  A group of the
+// concatenated tensor is a union of whole blocks; each CTA first folds slabs x blocks into 32 (mean, rstd) pairs in shared
+// memory, in a fixed order (deterministic).
 __global__ void gn_apply_blk_kernel(const __half* __restrict__ x0, int C0, const __half* __restrict__ x1, int C1, int HW,
                                     int groups, float eps, int pix_per_block, const float* __restrict__ stats0,
-                                    const float* __restrict__ stats1, int blk, const __half* __restrict__ gamma,
+                                    const float* __restrict__ stats1, int blk, int slots, const __half* __restrict__ gamma,
                                     const __half* __restrict__ beta, int do_silu, __half* __restrict__ out) {
+  __shared__ float s_part[4][64][2];
   __shared__ float s_mean[64], s_rstd[64];
   const int C = C0 + C1, cpg = C / groups, nvec = C / 8;
   const int b = blockIdx.y;
   const int p0 = blockIdx.x * pix_per_block;
   const int p1 = min(HW, p0 + pix_per_block);
   const float inv_n = 1.0f / ((float)cpg * (float)HW);
+  {
+    // thread (sub, g): group g, slabs sub, sub+4, ...
+    const int g = threadIdx.x & 63, sub = threadIdx.x >> 6;
+    float a = 0.f, q = 0.f;
+    if (g < groups) {
+      const int nb0 = C0 / blk, nb1 = C1 / blk, bpg = cpg / blk;
+      for (int sl = sub; sl < slots; sl += 4) {
+        for (int i = 0; i < bpg; ++i) {
+          const int cb = g * bpg + i;
+          const float2 v = (cb < nb0) ? reinterpret_cast<const float2*>(stats0)[((size_t)b * slots + sl) * nb0 + cb]
+                                      : reinterpret_cast<const float2*>(stats1)[((size_t)b * slots + sl) * nb1 + (cb - nb0)];
+          a += v.x; q += v.y;
+        }
+      }
+    }
+    s_part[sub][g][0] = a; s_part[sub][g][1] = q;
+  }
+  __syncthreads();
   if ((int)threadIdx.x < groups) {
     const int g = threadIdx.x;
-    const int nb0 = C0 / blk, nb1 = C1 / blk, bpg = cpg / blk;
-    float a = 0.f, q = 0.f;
-    for (int i = 0; i < bpg; ++i) {
-      const int cb = g * bpg + i;
-      const float* sp = (cb < nb0) ? stats0 + ((size_t)b * nb0 + cb) * 2 : stats1 + ((size_t)b * nb1 + (cb - nb0)) * 2;
-      a += sp[0]; q += sp[1];
-    }
+    const float a = (s_part[0][g][0] + s_part[1][g][0]) + (s_part[2][g][0] + s_part[3][g][0]);
+    const float q = (s_part[0][g][1] + s_part[1][g][1]) + (s_part[2][g][1] + s_part[3][g][1]);
     const float mean = a * inv_n;
     const float var = fmaxf(q * inv_n - mean * mean, 0.f);
     s_mean[g] = mean; s_rstd[g] = rsqrtf(var + eps);

@@ -60,8 +60,9 @@ struct Gemm2Params {
   int ld_res;
   float* row_stats_out;    // [rows][row_parts][2]; this launch writes part nt*2 + hf   (plain GEMM only)
   int row_parts;
-  float* gn_stats_out;     // [B][gn_nblk][2] fp32 atomics: sums over gn_blk-channel blocks
-  int gn_blk, gn_nblk;
+  float* gn_stats_out;     // [B][gn_slots][gn_nblk][2]: (sum, sumsq) over gn_blk-channel blocks of each 32-pixel slab,
+  int gn_blk, gn_nblk;     //   every entry written exactly once by one epilogue warp (plain stores: no atomics, no memset)
+  int gn_slots;            // HW / 32
   float* ws;               // split-K accumulators: [m_tile*tiles_n + nt][128][320] fp32, zero on entry, zero on exit
   int* tickets;            // [m_tile*tiles_n + nt], zero on entry, zero on exit
   long long* dbg;          // optional (DG_GEMM_DBG=1): clock64() stamps of CTA 0's first unit, see DG_STAMP sites
@@ -226,10 +227,7 @@ __device__ __forceinline__ Unit unit_coord(const Gemm2Params& p, int u, int cta_
 template <int kCta, int kBN, int kStages, bool kGeglu>
 __global__ void __launch_bounds__(384, 1)
 gemm2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
-             const __grid_constant__ CUtensorMap mapW, const __grid_constant__ CUtensorMap mapO,
-             const __grid_constant__ CUtensorMap mapO64, const Gemm2Params p) {
-  // mapO: output boxes of 32 columns (64-byte rows, 64-byte swizzle); mapO64: 64 columns (128-byte rows, 128-byte swizzle) --
-  // the TMA store engine's cost is per row, so the wide (320-column) tiles stage and store 128-byte rows
+             const __grid_constant__ CUtensorMap mapW, const __grid_constant__ CUtensorMap mapO, const Gemm2Params p) {
   using S = Gemm2Cfg<kCta, kBN, kStages>;
   static_assert(!kGeglu || kBN == 320, "GEGLU tiles are [160 value | 160 gate]");
   constexpr uint32_t kTmemCols = 512;
@@ -265,7 +263,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
   const int num_pairs = gridDim.x / kCta;
 
   if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&mapA0); tma_prefetch_desc(&mapA1); tma_prefetch_desc(&mapW); tma_prefetch_desc(&mapO); tma_prefetch_desc(&mapO64);
+    tma_prefetch_desc(&mapA0); tma_prefetch_desc(&mapA1); tma_prefetch_desc(&mapW); tma_prefetch_desc(&mapO);
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < kStages; ++i) { mbar_init(&full[i], kCta); mbar_init(&empty[i], 1); }
@@ -371,7 +369,9 @@ gemm2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
             for (int k = 0; k < 5; ++k)
               if (col + k * 32 < p.n_out) tma_store_4d(&mapO, sRing + (buf * 5 + k) * S::kSubBytes, col + k * 32, x0, y0, b0);
           } else if constexpr (kCW == 32) {
-            if (col < p.n_out) tma_store_4d(&mapO64, sRing + (buf * 2) * S::kSubBytes, col, x0, y0, b0);   // [128][64 cols], clipped at n_out
+#pragma unroll
+            for (int h2 = 0; h2 < 2; ++h2)
+              if (col + h2 * S::kNI < p.n_out) tma_store_4d(&mapO, sRing + (buf * 2 + h2) * S::kSubBytes, col + h2 * S::kNI, x0, y0, b0);
           } else {
             if (col < p.n_out) tma_store_4d(&mapO, sRing + (buf * 2) * S::kSubBytes, col, x0, y0, b0);
           }
@@ -400,9 +400,9 @@ gemm2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
     uint32_t chunk_ctr = 0;             // staging-ring chunk counter (final epilogues only)
 
     // first tile column of this thread's piece of chunk j (accumulator columns == output columns for plain tiles)
-    // 320 plain: chunk j = tile columns [64j, 64j+64), this warp's half = 32 of them; 160: contiguous 80-column halves;
-    // GEGLU: chunk j = outputs [32j, 32j+32), 16 per warp half
-    auto chunk_col = [&](int j) { return kCW == 32 ? j * 64 + hf * 32 : (kBN == 160 ? hf * 80 + j * 16 : j * 32 + hf * 16); };
+    // plain tiles: each warp owns a contiguous column half (160 or 80 columns) in 5 pieces; GEGLU: chunk j = outputs
+    // [32j, 32j+32), 16 per warp half
+    auto chunk_col = [&](int j) { return kCW == 32 ? hf * S::kNI + j * 32 : (kBN == 160 ? hf * 80 + j * 16 : j * 32 + hf * 16); };
 
     for (int u = pair_id; u < total_units; u += num_pairs) {
       const Unit t = unit_coord<kCta>(p, u, cta_rank, m_tiles, num_kb);
@@ -514,24 +514,26 @@ gemm2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
 
       if (do_final) {
         // GroupNorm block statistics: running (sum, sumsq) of the current gn_blk-channel block, flushed when the block changes
+        // The host enables this only when every warp's 32 rows are one 32-pixel slab of a single sample (HW % 32 == 0).
         const bool gn_on = p.gn_stats_out != nullptr;
-        const bool warp_uniform = __all_sync(0xffffffffu, bbc == __shfl_sync(0xffffffffu, bbc, 0)) != 0;
         float gs = 0.f, gss = 0.f;
-        int gcur = -1;
+        int gcur = 0, gcnt = 0;         // current block index / columns accumulated in it (this thread's columns are contiguous)
+        float2* gn_dst = nullptr;       // this warp's slab: [gn_nblk] (sum, sumsq) pairs
+        if (gn_on) {
+          const int r0 = q * 32;        // first row of this warp within the tile
+          int slab;
+          if (p.taps == 1 && p.H == 1 && p.B == 1) slab = (int)(((size_t)t.x0 + r0) % p.hw) >> 5;
+          else slab = (((t.y0 / p.bh) * p.tiles_x + t.x0 / p.bw) * box_xy + r0 % box_xy) >> 5;
+          const int b_w = __shfl_sync(0xffffffffu, bb, 0);
+          const bool ok_w = __shfl_sync(0xffffffffu, row_ok ? 1 : 0, 0) != 0;
+          if (ok_w) gn_dst = reinterpret_cast<float2*>(p.gn_stats_out) + ((size_t)b_w * p.gn_slots + slab) * p.gn_nblk;
+          gcur = (nt * kOutW + hf * (kOutW / 2)) / p.gn_blk;
+        }
         auto gn_flush = [&]() {
-          if (gcur < 0) return;
           float a0 = gs, a1 = gss;
-          if (warp_uniform) {
 #pragma unroll
-            for (int o = 16; o; o >>= 1) { a0 += __shfl_xor_sync(0xffffffffu, a0, o); a1 += __shfl_xor_sync(0xffffffffu, a1, o); }
-            if (lane == 0 && gcur < p.gn_nblk) {
-              atomicAdd(p.gn_stats_out + ((size_t)bbc * p.gn_nblk + gcur) * 2, a0);
-              atomicAdd(p.gn_stats_out + ((size_t)bbc * p.gn_nblk + gcur) * 2 + 1, a1);
-            }
-          } else if (row_ok && gcur < p.gn_nblk) {
-            atomicAdd(p.gn_stats_out + ((size_t)bbc * p.gn_nblk + gcur) * 2, a0);
-            atomicAdd(p.gn_stats_out + ((size_t)bbc * p.gn_nblk + gcur) * 2 + 1, a1);
-          }
+          for (int o = 16; o; o >>= 1) { a0 += __shfl_xor_sync(0xffffffffu, a0, o); a1 += __shfl_xor_sync(0xffffffffu, a1, o); }
+          if (lane == 0 && gn_dst && gcur < p.gn_nblk) gn_dst[gcur] = make_float2(a0, a1);
           gs = 0.f; gss = 0.f;
         };
         float rs = 0.f, rss = 0.f;     // LayerNorm row statistics of this thread's output columns
@@ -654,26 +656,28 @@ gemm2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
             }
           }
 
-          // ---- round to fp16, statistics on the rounded values, write the staging row
+          // ---- statistics for the consuming normalisation, taken on the fp32 values just before rounding (the fp16
+          // rounding noise is zero-mean and ~2^-11 relative: invisible in sums over >= 320 elements), then round and stage
+          if (p.row_stats_out || gn_on) {
+            const bool all_ok = row_ok && nt * kOutW + ocol + kCW <= p.n_out;
+#pragma unroll
+            for (int i = 0; i < kCW / 2; ++i) {
+              float v0 = f[2 * i], v1 = f[2 * i + 1];
+              if (!all_ok) {
+                const int col = nt * kOutW + ocol + 2 * i;
+                v0 = (row_ok && col < p.n_out) ? v0 : 0.f; v1 = (row_ok && col + 1 < p.n_out) ? v1 : 0.f;
+              }
+              if (gn_on) {                           // gn_blk is even: both columns of the pair share a block
+                gs += v0 + v1; gss = fmaf(v0, v0, fmaf(v1, v1, gss));
+                gcnt += 2;
+                if (gcnt == p.gn_blk) { gn_flush(); ++gcur; gcnt = 0; }
+              }
+              if (p.row_stats_out) { rs += v0 + v1; rss = fmaf(v0, v0, fmaf(v1, v1, rss)); }
+            }
+          }
           uint32_t pk[kCW / 2];
 #pragma unroll
           for (int i = 0; i < kCW / 2; ++i) pk[i] = cvt_pack_half2(f[2 * i], f[2 * i + 1]);
-          if (p.row_stats_out || gn_on) {
-#pragma unroll
-            for (int i = 0; i < kCW / 2; ++i) {
-              const float2 v = unpack_half2(pk[i]);
-              const int col = nt * kOutW + ocol + 2 * i;
-              const bool ok0 = row_ok && col < p.n_out, ok1 = row_ok && col + 1 < p.n_out;
-              const float v0 = ok0 ? v.x : 0.f, v1 = ok1 ? v.y : 0.f;
-              rs += v0 + v1; rss = fmaf(v0, v0, fmaf(v1, v1, rss));
-              if (gn_on) {
-                const int blk = col / p.gn_blk;      // gn_blk is even: both columns of the pair share a block
-                if (blk != gcur) { gn_flush(); gcur = blk; }
-                gs += v0 + v1; gss = fmaf(v0, v0, fmaf(v1, v1, gss));
-              }
-            }
-            if (gn_on && kCW == 32) { gn_flush(); gcur = -1; }   // 320-wide tiles: this thread's next piece is 64 columns further on
-          }
           if constexpr (kWhole) {
             const uint32_t sub = sRing_a + (slot * 5 + (ocol >> 5)) * S::kSubBytes + r * 64;
             const uint32_t k0 = (uint32_t)((ocol & 31) >> 3);
@@ -686,10 +690,9 @@ gemm2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
           mbar_wait(&buf_free[buf], (chunk_ctr / S::kRing) & 1);
           DG_STAMP_C1(19);
           if constexpr (kCW == 32) {
-            const uint32_t sub = sRing_a + (buf * 2) * S::kSubBytes + r * 128;   // 128-byte rows, 128-byte swizzle
+            const uint32_t sub = sRing_a + (buf * 2 + hf) * S::kSubBytes + r * 64;
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
-              sts_u4(sub + ((((uint32_t)(hf * 4 + i)) ^ (uint32_t)(r & 7)) << 4), pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
+            for (int i = 0; i < 4; ++i) sts_u4(sub + (((uint32_t)i ^ row_sw) << 4), pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
           } else {
             const uint32_t sub = sRing_a + (buf * 2) * S::kSubBytes + r * 64;
 #pragma unroll
@@ -702,7 +705,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
           __syncwarp();
           if (lane == 0) {
             if (ew == 0) {
-              chunk_info[buf * 5 + 0] = nt * kOutW + j * (kCW == 32 ? 64 : 32); chunk_info[buf * 5 + 1] = t.x0; chunk_info[buf * 5 + 2] = t.y0;
+              chunk_info[buf * 5 + 0] = nt * kOutW + j * 32; chunk_info[buf * 5 + 1] = t.x0; chunk_info[buf * 5 + 2] = t.y0;
               chunk_info[buf * 5 + 3] = t.b0; chunk_info[buf * 5 + 4] = t.valid_m ? 1 : 0;
             }
             mbar_arrive(&chunk_ready[buf]);                 // release: this warp's rows (and the chunk descriptor) are in place
@@ -723,7 +726,6 @@ gemm2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
           }
           ++chunk_ctr;
         }
-        if (gn_on) gn_flush();
         if (p.row_stats_out && row_ok)
           reinterpret_cast<float2*>(p.row_stats_out)[grow * p.row_parts + nt * 2 + hf] = make_float2(rs, rss);
       }

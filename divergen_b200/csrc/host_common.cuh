@@ -173,7 +173,7 @@ struct GemmArgs {
   const __half* residual = nullptr; int ld_res = 0;
   int geglu = 0;
   float* row_stats_out = nullptr;          // [rows][2*tiles_n][2]
-  float* gn_stats_out = nullptr; int gn_blk = 0;   // [B][n_out/gn_blk][2]
+  float* gn_stats_out = nullptr; int gn_blk = 0;   // [B][HW/32][n_out/gn_blk][2] (see gn_stats_supported)
   __half* out = nullptr; int ldo = 0;
 };
 
@@ -184,6 +184,17 @@ inline int largest_pow2_divisor(int x, int cap) {
   int p = 1;
   while (p * 2 <= cap && x % (p * 2) == 0) p *= 2;
   return p;
+}
+
+// Fused GroupNorm statistics: every epilogue warp (32 accumulator rows) must cover one 32-pixel slab of one sample, and a
+// warp's 80/160-column half must hold whole gn_blk-channel blocks.  W = H = 0 for plain (row-major) GEMMs.
+inline bool gn_stats_supported(int hw, int W, int H, int blk, int n_out) {
+  if (blk <= 0 || blk % 2 || 80 % blk || n_out % blk || hw % 32) return false;
+  if (W > 0) {
+    const int bw = largest_pow2_divisor(W, 128), bh = largest_pow2_divisor(H, 128 / bw);
+    if ((bw * bh) % 32) return false;
+  }
+  return true;
 }
 
 // K-split factor.  Cost model in units of one k-block of MMA time (~0.33 us): a tile costs kb + epilogue, a split adds the
@@ -208,7 +219,7 @@ inline int choose_splits(int units, int num_kb, int slots, size_t ws_floats_per_
 
 template <int kCta, int kBN, int kStages, bool kGeglu>
 inline cudaError_t launch_gemm2_t(cudaStream_t stream, int grid_ctas, const CUtensorMap& mA0, const CUtensorMap& mA1,
-                                  const CUtensorMap& mW, const CUtensorMap& mO, const CUtensorMap& mO64, const Gemm2Params& p) {
+                                  const CUtensorMap& mW, const CUtensorMap& mO, const Gemm2Params& p) {
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)grid_ctas);
   cfg.blockDim = dim3(384);
@@ -218,7 +229,7 @@ inline cudaError_t launch_gemm2_t(cudaStream_t stream, int grid_ctas, const CUte
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = kCta; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, gemm2_kernel<kCta, kBN, kStages, kGeglu>, mA0, mA1, mW, mO, mO64, p);
+  return cudaLaunchKernelEx(&cfg, gemm2_kernel<kCta, kBN, kStages, kGeglu>, mA0, mA1, mW, mO, p);
 }
 
 inline int launch_gemm(cudaStream_t stream, const GemmRes& res, const GemmArgs& a) {
@@ -232,8 +243,9 @@ inline int launch_gemm(cudaStream_t stream, const GemmRes& res, const GemmArgs& 
   if (a.geglu && (a.residual || a.rowvec || a.row_stats_out || a.gn_stats_out)) return fail(DG_E_ARG, "gemm: geglu epilogue takes bias / LayerNorm fold only");
   if (a.colsum && (!a.ln_stats || !a.bias32 || a.ln_c <= 0)) return fail(DG_E_ARG, "gemm: LayerNorm fold needs ln_stats, bias32 and ln_c");
   if (a.row_stats_out && a.taps != 1) return fail(DG_E_ARG, "gemm: row statistics are produced by plain GEMMs only");
-  if (a.gn_stats_out && (a.gn_blk <= 0 || a.gn_blk % 2 || a.n_out % a.gn_blk))
-    return fail(DG_E_SHAPE, "gemm: fused GroupNorm statistics need an even channel block dividing n_out (blk %d, n_out %d)", a.gn_blk, a.n_out);
+  if (a.gn_stats_out && !gn_stats_supported(a.taps == 1 ? (a.hw > 0 ? a.hw : a.H * a.W) : a.H * a.W, a.taps == 9 ? a.W : 0,
+                                            a.taps == 9 ? a.H : 0, a.gn_blk, a.n_out))
+    return fail(DG_E_SHAPE, "gemm: fused GroupNorm statistics unsupported for this shape (hw %d, blk %d, n_out %d)", a.H * a.W, a.gn_blk, a.n_out);
   const int kcta = res.cta_mode == 1 ? 1 : 2;
   Gemm2Params p{};
   int W = a.W, H = a.H, B = a.B;
@@ -266,6 +278,7 @@ inline int launch_gemm(cudaStream_t stream, const GemmRes& res, const GemmArgs& 
   p.residual = a.residual; p.ld_res = a.ld_res;
   p.row_stats_out = a.row_stats_out; p.row_parts = 2 * p.tiles_n;
   p.gn_stats_out = a.gn_stats_out; p.gn_blk = a.gn_blk; p.gn_nblk = a.gn_blk > 0 ? a.n_out / a.gn_blk : 0;
+  p.gn_slots = (a.taps == 1 ? (a.hw > 0 ? a.hw : a.H * a.W) : a.H * a.W) / 32;
   p.ws = res.ws; p.tickets = res.tickets;
   if (a.geglu && !a.bias && !a.bias32) return fail(DG_E_ARG, "gemm: geglu epilogue needs a packed bias");
 
@@ -277,7 +290,7 @@ inline int launch_gemm(cudaStream_t stream, const GemmRes& res, const GemmArgs& 
   if (res.ws && res.tickets && !a.row_stats_out && m_tiles * p.tiles_n <= kSplitTickets)
     p.splits = choose_splits(units, num_kb, slots, (size_t)kcta * 128 * kbn, kSplitWsFloats);
 
-  CUtensorMap mA0, mA1, mW, mO, mO64;
+  CUtensorMap mA0, mA1, mW, mO;
   {
     uint64_t dims[4] = {(uint64_t)a.c0, (uint64_t)W, (uint64_t)H, (uint64_t)B};
     uint64_t st[3] = {(uint64_t)a.c0 * 2, (uint64_t)W * a.c0 * 2, (uint64_t)H * W * a.c0 * 2};
@@ -297,12 +310,6 @@ inline int launch_gemm(cudaStream_t stream, const GemmRes& res, const GemmArgs& 
     uint64_t os[3] = {(uint64_t)a.ldo * 2, (uint64_t)W * a.ldo * 2, (uint64_t)H * W * a.ldo * 2};
     uint32_t obox[4] = {32, (uint32_t)p.bw, (uint32_t)p.bh, (uint32_t)p.bn};
     DG_TRY(make_map_4d(&mO, a.out, od, os, obox, false, true));
-    if (kbn == 320 && !a.geglu) {
-      uint32_t obox64[4] = {64, (uint32_t)p.bw, (uint32_t)p.bh, (uint32_t)p.bn};
-      DG_TRY(make_map_4d(&mO64, a.out, od, os, obox64, false, false));
-    } else {
-      mO64 = mO;
-    }
   }
   const int total_units = units * p.splits;
   const int grid_units = total_units < slots ? total_units : slots;
@@ -319,13 +326,13 @@ inline int launch_gemm(cudaStream_t stream, const GemmRes& res, const GemmArgs& 
   if (dbg_on) { cudaMemsetAsync(dbg_dev, 0, 32 * 8, stream); p.dbg = dbg_dev; }
   cudaError_t e;
   if (kcta == 2) {
-    if (a.geglu) e = launch_gemm2_t<2, 320, kStages_2_320, true>(stream, grid_units * 2, mA0, mA1, mW, mO, mO64, p);
-    else if (kbn == 320) e = launch_gemm2_t<2, 320, kStages_2_320, false>(stream, grid_units * 2, mA0, mA1, mW, mO, mO64, p);
-    else e = launch_gemm2_t<2, 160, kStages_2_160, false>(stream, grid_units * 2, mA0, mA1, mW, mO, mO64, p);
+    if (a.geglu) e = launch_gemm2_t<2, 320, kStages_2_320, true>(stream, grid_units * 2, mA0, mA1, mW, mO, p);
+    else if (kbn == 320) e = launch_gemm2_t<2, 320, kStages_2_320, false>(stream, grid_units * 2, mA0, mA1, mW, mO, p);
+    else e = launch_gemm2_t<2, 160, kStages_2_160, false>(stream, grid_units * 2, mA0, mA1, mW, mO, p);
   } else {
-    if (a.geglu) e = launch_gemm2_t<1, 320, kStages_1_320, true>(stream, grid_units, mA0, mA1, mW, mO, mO64, p);
-    else if (kbn == 320) e = launch_gemm2_t<1, 320, kStages_1_320, false>(stream, grid_units, mA0, mA1, mW, mO, mO64, p);
-    else e = launch_gemm2_t<1, 160, kStages_1_160, false>(stream, grid_units, mA0, mA1, mW, mO, mO64, p);
+    if (a.geglu) e = launch_gemm2_t<1, 320, kStages_1_320, true>(stream, grid_units, mA0, mA1, mW, mO, p);
+    else if (kbn == 320) e = launch_gemm2_t<1, 320, kStages_1_320, false>(stream, grid_units, mA0, mA1, mW, mO, p);
+    else e = launch_gemm2_t<1, 160, kStages_1_160, false>(stream, grid_units, mA0, mA1, mW, mO, p);
   }
   ++g_launch_counter;
   if (dbg_on && e == cudaSuccess) {
@@ -465,6 +472,7 @@ inline int launch_groupnorm(cudaStream_t s, int num_sms, const __half* x0, int C
 inline int launch_groupnorm_fused(cudaStream_t s, int num_sms, const __half* x0, int C0, const float* st0, const __half* x1,
                                   int C1, const float* st1, int blk, const __half* gamma, const __half* beta, __half* out,
                                   int B, int HW, int groups, float eps, int silu) {
+  if (HW % 32) return fail(DG_E_SHAPE, "groupnorm(fused): HW=%d must be a multiple of 32", HW);
   const int C = C0 + C1;
   if (C % groups || C0 % 8 || C1 % 8 || groups > 64) return fail(DG_E_SHAPE, "groupnorm: C=%d+%d groups=%d", C0, C1, groups);
   if (blk <= 0 || (C / groups) % blk || C0 % blk || C1 % blk) return fail(DG_E_SHAPE, "groupnorm: block %d does not tile C=%d+%d", blk, C0, C1);
@@ -472,7 +480,7 @@ inline int launch_groupnorm_fused(cudaStream_t s, int num_sms, const __half* x0,
   int ppb, pstride;
   gn_launch_geometry(C, B, HW, num_sms, &ppb, &pstride);
   dim3 grid((HW + ppb - 1) / ppb, B);
-  gn_apply_blk_kernel<<<grid, 256, 0, s>>>(x0, C0, x1, C1, HW, groups, eps, ppb, st0, st1, blk, gamma, beta, silu, out);
+  gn_apply_blk_kernel<<<grid, 256, 0, s>>>(x0, C0, x1, C1, HW, groups, eps, ppb, st0, st1, blk, HW / 32, gamma, beta, silu, out);
   DG_LAUNCH_CHECK();
   return DG_OK;
 }

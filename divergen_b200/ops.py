@@ -146,7 +146,7 @@ def row_parts(n_out: int) -> int:
 
 def linear_stats(x, weight, bias=None, residual=None, gn_blk: int = 0, hw: int = 0):
     """linear() that also returns the fused statistics of its fp16 result: per-row (sum, sumsq) [M, 2] (partials already
-    added up) and, when gn_blk > 0, GroupNorm block sums [M // hw, N // gn_blk, 2]."""
+    added up) and, when gn_blk > 0, GroupNorm sums per 32-row slab and gn_blk-channel block [M // hw, hw // 32, N // gn_blk, 2]."""
     _chk16(x, weight, bias, residual)
     lib, ctx, s = _env(x)
     M, K = x.shape
@@ -154,7 +154,7 @@ def linear_stats(x, weight, bias=None, residual=None, gn_blk: int = 0, hw: int =
     out = torch.empty((M, N), dtype=torch.float16, device=x.device)
     parts = row_parts(N)
     rs = torch.full((M, parts, 2), float("nan"), dtype=torch.float32, device=x.device)
-    gs = torch.zeros((M // hw, N // gn_blk, 2), dtype=torch.float32, device=x.device) if gn_blk else None
+    gs = torch.full((M // hw, hw // 32, N // gn_blk, 2), float("nan"), dtype=torch.float32, device=x.device) if gn_blk else None
     _lib.check(lib.dg_op_gemm_fused(ctx, _p(x), _p(weight), _p(bias), _pf(None), _pf(None), _pf(None), 0, 0.0,
                                     _p(residual), _p(out), M, K, N, N, 0, _pf(rs), _pf(gs), gn_blk, hw, s),
                "dg_op_gemm_fused(stats)")
@@ -192,7 +192,7 @@ def layernorm_linear(x, gamma, beta, weight, bias=None, eps: float = 1e-5, geglu
 
 
 def conv3x3_stats(x, weight_oihw, bias, gn_blk: int):
-    """conv3x3_nhwc() that also returns the GroupNorm block sums [B, N // gn_blk, 2] of its fp16 result."""
+    """conv3x3_nhwc() that also returns the GroupNorm slab/block sums [B, H*W // 32, N // gn_blk, 2] of its fp16 result."""
     _chk16(x, weight_oihw, bias)
     lib, ctx, s = _env(x)
     B, H, W, C0 = x.shape
@@ -200,7 +200,7 @@ def conv3x3_stats(x, weight_oihw, bias, gn_blk: int):
     wp = torch.empty((O, 9 * C0), dtype=torch.float16, device=x.device)
     _lib.check(lib.dg_op_pack_conv3x3(ctx, _p(weight_oihw), _p(wp), O, C0, s), "dg_op_pack_conv3x3")
     out = torch.empty((B, H, W, O), dtype=torch.float16, device=x.device)
-    gs = torch.zeros((B, O // gn_blk, 2), dtype=torch.float32, device=x.device)
+    gs = torch.full((B, H * W // 32, O // gn_blk, 2), float("nan"), dtype=torch.float32, device=x.device)
     _lib.check(lib.dg_op_conv3x3_stats(ctx, _p(x), C0, _p(wp), _p(bias), _p(out), B, H, W, O, _pf(gs), gn_blk, s),
                "dg_op_conv3x3_stats")
     return out, gs

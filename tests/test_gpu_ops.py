@@ -162,9 +162,10 @@ def test_gemm_layernorm_fold_geglu(ops):
 
 
 @pytest.mark.parametrize("M,K,N,hw,blk", [(2048, 320, 320, 1024, 10), (512, 640, 1280, 64, 40), (8192, 64, 320, 4096, 10),
-                                          (96, 128, 128, 32, 4), (48, 64, 64, 16, 2)])
+                                          (96, 128, 128, 32, 4), (192, 2560, 640, 64, 20)])
 def test_gemm_fused_statistics(ops, M, K, N, hw, blk):
-    """Row (LayerNorm) and block (GroupNorm) sums produced by the GEMM epilogue equal the sums of its fp16 output."""
+    """Row (LayerNorm) and slab/block (GroupNorm) sums produced by the GEMM epilogue match the sums of its fp16 output
+    (they are taken on the fp32 values just before rounding: tolerance = the fp16 rounding noise of the summed elements)."""
     x, w = _rand(M, K, seed=60), _rand(N, K, scale=1 / math.sqrt(K), seed=61)
     b, r = _rand(N, seed=62), _rand(M, N, seed=63)
     out, rs, gs = ops.linear_stats(x, w, b, r, gn_blk=blk, hw=hw)
@@ -172,24 +173,24 @@ def test_gemm_fused_statistics(ops, M, K, N, hw, blk):
     _report("gemm(stats) value", out, ref, 5e-3, 4e-3)
     o = out.float()
     want_rs = torch.stack([o.sum(1), (o * o).sum(1)], 1)
-    assert torch.allclose(rs, want_rs, rtol=1e-4, atol=1e-2), (rs - want_rs).abs().max().item()
-    ob = o.view(M // hw, hw, N // blk, blk)
-    want_gs = torch.stack([ob.sum((1, 3)), (ob * ob).sum((1, 3))], -1)
-    assert torch.allclose(gs, want_gs, rtol=2e-4, atol=5e-2), (gs - want_gs).abs().max().item()
+    assert torch.allclose(rs, want_rs, rtol=2e-3, atol=5e-2), (rs - want_rs).abs().max().item()
+    ob = o.view(M // hw, hw // 32, 32, N // blk, blk)
+    want_gs = torch.stack([ob.sum((2, 4)), (ob * ob).sum((2, 4))], -1)
+    assert torch.allclose(gs, want_gs, rtol=2e-3, atol=5e-2), (gs - want_gs).abs().max().item()
     # the producer's row partials feed the LayerNorm-folded consumer directly
     if K == N:
         pass
 
 
-@pytest.mark.parametrize("B,H,W,C,N,blk", [(2, 32, 32, 320, 320, 10), (3, 8, 8, 128, 640, 20), (2, 4, 4, 64, 64, 2)])
+@pytest.mark.parametrize("B,H,W,C,N,blk", [(2, 32, 32, 320, 320, 10), (3, 8, 8, 128, 640, 20), (2, 16, 8, 64, 64, 2)])
 def test_conv3x3_groupnorm_fused(ops, B, H, W, C, N, blk):
     """conv3x3 epilogue block sums -> GroupNorm apply from those sums == GroupNorm(SiLU) of the conv output."""
     x = _rand(B, H, W, C, seed=64)
     w, bias = _rand(N, C, 3, 3, scale=1 / math.sqrt(9 * C), seed=65), _rand(N, scale=0.1, seed=66)
     out, gs = ops.conv3x3_stats(x, w, bias, blk)
     ob = out.float().view(B, H * W, N // blk, blk)
-    want = torch.stack([ob.sum((1, 3)), (ob * ob).sum((1, 3))], -1)
-    assert torch.allclose(gs, want, rtol=2e-4, atol=5e-2), (gs - want).abs().max().item()
+    want = torch.stack([ob.sum((1, 3)), (ob * ob).sum((1, 3))], -1)     # slab order inside a sample is the kernel's business
+    assert torch.allclose(gs.sum(1), want, rtol=2e-3, atol=1e-1), (gs.sum(1) - want).abs().max().item()
     gamma, beta = _rand(N, seed=67) * 0.2 + 1, _rand(N, seed=68) * 0.1
     got = ops.groupnorm_fused_nhwc(out, gs, gamma, beta, 32, 1e-5, True, blk)
     ref = F.silu(F.group_norm(out.float().permute(0, 3, 1, 2), 32, gamma.float(), beta.float(), 1e-5)).permute(0, 2, 3, 1)
