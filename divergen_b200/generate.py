@@ -1,0 +1,247 @@
+"""Generation driver: the reference's `DiverGen/generation/txt2img_diffusers_stages_from_txt.py`, re-hosted on the B200 path.
+
+Keeps what `convert_dir_structure.py`, `segmentation/` and `filteration/` depend on:
+  * the CLI flags (`--from_file --outdir --n_samples --max_batch_size --seed --dist --ckpt_dir --stages --offset
+    --disable_overwrite`, reference :27-110) plus model / sampler flags the reference hard-codes inside diffusers;
+  * rank sharding: every rank makes `n_samples // world_size` images of every prompt (:124-125), file indices offset by
+    `total_batch_size * rank` (:262), seed `seed + rank` (:200), skip-if-exists resume (:245-252);
+  * file naming `<outdir>/samples/<stage>/<category_id>_<count:07d>.png` (:262-266).
+Differences, all deliberate: the stage is Stable Diffusion (`sd`, the pool the downstream stages call 'sd') instead of the
+DeepFloyd-IF cascade; text embeddings are encoded ONCE on rank 0 for the whole prompt set and broadcast (the path's only
+data-carrying collective) instead of per micro-batch on every rank; micro-batches default to 4 images per pipeline call.
+
+Host-side only: every tensor operation is a C-ABI call (StableDiffusionPipeline -> dg_denoise_loop).  VAE decode / CLIP
+are "next" rows: without `--vae_decode` latents are written as `<cid>_<count:07d>.latent.pt` next to where
+the PNG would go, under the same index contract.
+"""
+from __future__ import annotations
+
+import argparse
+import os
+from dataclasses import dataclass
+from glob import glob
+from typing import Iterator, List, Optional, Sequence, Tuple
+
+
+# ------------------------------------------------------------------ pure index arithmetic (no torch, unit-tested on CPU)
+@dataclass(frozen=True)
+class BatchPlan:
+    """Reference :124-131.  `batch_size` is the number of pipeline calls per prompt, the first of which carries the
+    remainder (`remainder_batch_size` images) when `total_batch_size` is not a multiple of `max_batch_size`."""
+    total_batch_size: int
+    batch_size: int
+    remainder_batch_size: int
+    max_batch_size: int
+
+
+def plan_batches(n_samples: int, world_size: int, max_batch_size: int) -> BatchPlan:
+    total = n_samples // world_size
+    if total * world_size != n_samples:
+        raise ValueError("n_samples must be divisible by world_size")          # reference :125
+    if max_batch_size <= 0:
+        raise ValueError("max_batch_size must be positive")
+    calls, rem = divmod(total, max_batch_size)
+    if rem > 0:
+        calls += 1
+    return BatchPlan(total, calls, rem, max_batch_size)
+
+
+@dataclass(frozen=True)
+class Call:
+    """One pipeline call: `prompt` -> `num_images` images written at file indices `counts`."""
+    index: int            # position in the sorted, repeated prompt list (reference `i`)
+    prompt: str
+    num_images: int
+    counts: Tuple[int, ...]
+
+
+def iter_calls(prompt_lines: Sequence[str], plan: BatchPlan, rank: int, n_samples: int, offset: int) -> Iterator[Call]:
+    """The reference's per-category loop (:221-327) as a generator of (prompt, images, file indices).
+
+    data = sorted(batch_size * lines); call i belongs to prompt number i // batch_size; the first call of a prompt takes the
+    remainder; count = j + tmp + total_batch_size*rank + offset + (i // batch_size) * n_samples (:262)."""
+    data = sorted(plan.batch_size * [l for l in prompt_lines])
+    tmp = 0
+    for i, prompt in enumerate(data):
+        if i % plan.batch_size == 0:
+            tmp = 0
+            cur = plan.remainder_batch_size if plan.remainder_batch_size != 0 else plan.max_batch_size
+        else:
+            cur = plan.max_batch_size
+        base = tmp + plan.total_batch_size * rank + offset + (i // plan.batch_size) * n_samples
+        yield Call(i, prompt.strip(), cur, tuple(base + j for j in range(cur)))
+        tmp += cur
+
+
+def output_name(category_id: str, count: int, ext: str = "png") -> str:
+    return "{}_{:07d}.{}".format(category_id, count, ext)                     # reference :263
+
+
+def list_prompt_files(from_file: Sequence[str]) -> List[str]:
+    """Reference :207-209: a directory expands to its *.txt files.  (The reference discards the result of `sorted`, so its
+    category order is glob order; sorting here only fixes the order, not the set of files or any file name.)"""
+    if len(from_file) == 1 and os.path.isdir(from_file[0]):
+        return sorted(glob(os.path.join(from_file[0], "*.txt")))
+    return list(from_file)
+
+
+def category_id_of(path: str) -> str:
+    return os.path.basename(path).split(".")[0]                               # reference :219
+
+
+# ------------------------------------------------------------------ distributed plumbing
+def init_distributed(backend: str = "nccl"):
+    """Reference :13-24 (env-var rendezvous, one process per GPU)."""
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", 0))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    world_size = int(os.environ.get("WORLD_SIZE", 1))
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    os.environ.setdefault("MASTER_PORT", "29500")
+    if not dist.is_initialized():
+        dist.init_process_group(backend=backend)
+    device = torch.device("cuda:{}".format(local_rank)) if backend == "nccl" else torch.device("cpu")
+    return rank, local_rank, world_size, device
+
+
+def broadcast_embedding_table(table, src: int = 0):
+    """The path's single data-carrying collective: rank `src` holds the [P, 77, D] text-embedding table
+    (+ the unconditional row), every other rank passes a same-shaped buffer or None and receives it."""
+    import torch
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return table
+    rank = dist.get_rank()
+    dev = table.device if table is not None else torch.device("cpu")
+    meta = torch.zeros(4, dtype=torch.int64, device=dev)
+    if rank == src:
+        meta[:3] = torch.tensor(table.shape, dtype=torch.int64)
+        meta[3] = {torch.float16: 0, torch.float32: 1, torch.bfloat16: 2}[table.dtype]
+    dist.broadcast(meta, src=src)
+    if rank != src:
+        dtype = {0: torch.float16, 1: torch.float32, 2: torch.bfloat16}[int(meta[3])]
+        table = torch.empty(tuple(int(v) for v in meta[:3]), dtype=dtype, device=dev)
+    dist.broadcast(table, src=src)
+    return table
+
+
+def synthetic_text_embeddings(prompts: Sequence[str], dim: int, tokens: int = 77, seed: int = 0):
+    """Stand-in for CLIPTextModel when no text encoder weights are present (there are none offline): a seeded N(0,1)
+    embedding per distinct prompt string.  Row 0 is the unconditional ("") embedding."""
+    import hashlib
+    import torch
+    rows = []
+    for p in [""] + list(prompts):
+        h = int.from_bytes(hashlib.sha256(p.encode()).digest()[:8], "little") ^ seed
+        g = torch.Generator().manual_seed(h % (2 ** 63))
+        rows.append(torch.randn(tokens, dim, generator=g))
+    return torch.stack(rows).half()
+
+
+# ------------------------------------------------------------------ CLI
+def build_parser() -> argparse.ArgumentParser:
+    p = argparse.ArgumentParser(description="DiverGen generation driver on the B200-native Stable-Diffusion path")
+    p.add_argument("--prompt", type=str, nargs="?", default="a painting of a virus monster playing guitar")
+    p.add_argument("--from_file", type=str, action="append", help="prompt file(s) or a directory of <category_id>.txt")
+    p.add_argument("--outdir", type=str, nargs="?", default="output/txt2img-samples")
+    p.add_argument("--n_samples", type=int, default=1, help="images per prompt over ALL ranks")
+    p.add_argument("--max_batch_size", type=int, default=4, help="images per pipeline call")
+    p.add_argument("--seed", type=int, default=42)
+    p.add_argument("--dist", action="store_true", default=False, help="one process per GPU (torchrun / torch.distributed.launch)")
+    p.add_argument("--ckpt_dir", type=str, default="models/ldm/stable-diffusion-v1/")
+    p.add_argument("--dataset_json_path", type=str, default="/data/datasets/lvis/lvis_v1_val.json")   # parsed, unused (as upstream)
+    p.add_argument("--stages", type=str, nargs="+", default=["sd"])
+    p.add_argument("--offset", type=int, default=1024)
+    p.add_argument("--disable_overwrite", action="store_true", default=False)
+    # additions (fixed inside diffusers / the checkpoint in the reference)
+    p.add_argument("--model", choices=["sd15", "sd21"], default="sd15")
+    p.add_argument("--num_inference_steps", type=int, default=50)
+    p.add_argument("--guidance_scale", type=float, default=7.5)
+    p.add_argument("--random_init", action="store_true", help="random-init UNet weights (benchmarks; no checkpoint offline)")
+    p.add_argument("--max_prompt_files", type=int, default=0, help="process only the first N category files (0 = all)")
+    return p
+
+
+def main(argv: Optional[Sequence[str]] = None) -> int:
+    import torch
+    from . import DDIMScheduler, SD15_CONFIG, SD21_CONFIG, StableDiffusionPipeline, UNet2DConditionModel
+
+    args = build_parser().parse_args(argv)
+    if args.dist:
+        rank, local_rank, world, device = init_distributed()
+    else:
+        rank, local_rank, world, device = 0, 0, 1, torch.device("cuda:0")
+    print("local rank: {}, global rank: {}, world size: {}, device: {}".format(local_rank, rank, world, device))
+    torch.cuda.set_device(device)
+    plan = plan_batches(args.n_samples, world, args.max_batch_size)
+    stage = args.stages[0]
+    sample_dir = os.path.join(args.outdir, "samples", stage)
+    if rank == 0:
+        os.makedirs(sample_dir, exist_ok=True)
+    if args.dist:
+        torch.distributed.barrier()                                               # reference :152-153
+
+    cfg = SD15_CONFIG if args.model == "sd15" else SD21_CONFIG
+    unet = UNet2DConditionModel(device=device, **{k: v for k, v in cfg.items() if k != "time_cond_proj_dim"})
+    unet_dir = os.path.join(args.ckpt_dir, "unet")
+    st_path = os.path.join(unet_dir, "diffusion_pytorch_model.fp16.safetensors")
+    if os.path.exists(st_path) and not args.random_init:
+        from safetensors.torch import load_file
+        unet.load_state_dict(load_file(st_path))
+    elif args.random_init:
+        g = torch.Generator(device=device).manual_seed(0)
+        sd = {}
+        for k, shp in unet.expected_state_dict_shapes().items():
+            fan_in = 1
+            for d in shp[1:]:
+                fan_in *= d
+            if "norm" in k and k.endswith("weight"):
+                sd[k] = torch.ones(shp, device=device).half()
+            elif k.endswith("bias"):
+                sd[k] = torch.zeros(shp, device=device).half()
+            else:
+                sd[k] = (torch.randn(shp, generator=g, device=device) / max(1.0, fan_in) ** 0.5).half()
+        unet.load_state_dict(sd)
+    else:
+        raise FileNotFoundError("{} not found (use --random_init for benchmarks)".format(st_path))
+    sched = DDIMScheduler(prediction_type="v_prediction" if args.model == "sd21" else "epsilon")
+    pipe = StableDiffusionPipeline(unet, sched)
+    pipe.enable_model_cpu_offload(local_rank)                                    # no-ops kept for call parity (:143,186)
+
+    generator = torch.manual_seed(args.seed + rank)                             # reference :200 (global CPU generator)
+    files = list_prompt_files(args.from_file) if args.from_file else []
+    if args.max_prompt_files > 0:
+        files = files[:args.max_prompt_files]
+    per_file = [(f, open(f).read().splitlines()) for f in files] if files else [("prompt.txt", [args.prompt])]
+    # ---- text embeddings: once, on rank 0, for every distinct prompt; one broadcast
+    prompts = sorted({l.strip() for _, lines in per_file for l in lines})
+    table = synthetic_text_embeddings(prompts, cfg["cross_attention_dim"]).to(device) if rank == 0 else None
+    table = broadcast_embedding_table(table if table is not None else torch.empty(0, device=device))
+    row = {p: i + 1 for i, p in enumerate(prompts)}
+
+    n_done = 0
+    for fi, (path, lines) in enumerate(per_file):
+        cid = category_id_of(path)
+        print("==> Reading prompts from {}, {}/{}".format(path, fi + 1, len(per_file)))
+        for call in iter_calls(lines, plan, rank, args.n_samples, args.offset):
+            last = os.path.join(sample_dir, output_name(cid, call.counts[-1], "latent.pt"))
+            if args.disable_overwrite and os.path.exists(last):
+                print("==> Skipping stage {} for {}...".format(stage, os.path.basename(last)))
+                continue
+            pos = table[row[call.prompt]][None]
+            neg = table[0][None]
+            out = pipe(prompt_embeds=pos, negative_prompt_embeds=neg, generator=generator, output_type="latent",
+                       num_images_per_prompt=call.num_images, num_inference_steps=args.num_inference_steps,
+                       guidance_scale=args.guidance_scale).images
+            for j, count in enumerate(call.counts):
+                torch.save(out[j].cpu(), os.path.join(sample_dir, output_name(cid, count, "latent.pt")))
+            n_done += call.num_images
+    if args.dist:
+        torch.distributed.barrier()
+    print("rank {} wrote {} latents under {}".format(rank, n_done, sample_dir))
+    return 0
+
+
+if __name__ == "__main__":
+    raise SystemExit(main())

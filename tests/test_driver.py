@@ -1,0 +1,75 @@
+"""Host logic of the generation driver (divergen_b200/generate.py) against the reference's index arithmetic
+(DiverGen/generation/txt2img_diffusers_stages_from_txt.py:124-131, :221-238, :262-263) -- pure Python, no GPU."""
+import itertools
+import os
+
+import pytest
+
+from divergen_b200.generate import (build_parser, category_id_of, iter_calls, list_prompt_files, output_name, plan_batches)
+
+
+def _reference_counts(lines, n_samples, world_size, max_batch_size, rank, offset):
+    """Line-by-line restatement of the reference loop (returns [(prompt, [counts...]), ...])."""
+    total_batch_size = n_samples // world_size
+    assert total_batch_size * world_size == n_samples
+    batch_size = total_batch_size // max_batch_size
+    remainder_batch_size = total_batch_size % max_batch_size
+    if remainder_batch_size > 0:
+        batch_size += 1
+    data = sorted(batch_size * list(lines))
+    out, tmp = [], 0
+    for i, prompt in enumerate(data):
+        prompt = prompt.strip()
+        if i % batch_size == 0:
+            tmp = 0
+            cur = remainder_batch_size if remainder_batch_size != 0 else max_batch_size
+        else:
+            cur = max_batch_size
+        out.append((prompt, [j + tmp + total_batch_size * rank + offset + (i // batch_size) * n_samples for j in range(cur)]))
+        tmp += cur
+    return out
+
+
+@pytest.mark.parametrize("n_samples,world,mbs", [(1024, 8, 1), (1024, 8, 4), (8, 8, 1), (24, 2, 5), (7, 1, 3), (32, 4, 8)])
+def test_calls_match_reference_loop(n_samples, world, mbs):
+    lines = ["a photo of a single cat, in a white background", "a photo of a single aerosol can "]
+    plan = plan_batches(n_samples, world, mbs)
+    for rank in range(world):
+        got = [(c.prompt, list(c.counts)) for c in iter_calls(lines, plan, rank, n_samples, 1024)]
+        assert got == _reference_counts(lines, n_samples, world, mbs, rank, 1024)
+
+
+@pytest.mark.parametrize("n_samples,world,mbs", [(1024, 8, 4), (24, 2, 5), (16, 4, 3)])
+def test_ranks_tile_the_index_range_exactly_once(n_samples, world, mbs):
+    """convert_dir_structure.py:133-138 checks count == n_samples per category: all ranks together must write every index of
+    [offset + k*n_samples, offset + (k+1)*n_samples) for prompt k exactly once."""
+    lines = ["p%d" % i for i in range(3)]
+    plan = plan_batches(n_samples, world, mbs)
+    per_prompt = {}
+    for rank in range(world):
+        for c in iter_calls(lines, plan, rank, n_samples, 1024):
+            per_prompt.setdefault(c.prompt, []).extend(c.counts)
+            assert 1 <= c.num_images <= mbs
+    for k, p in enumerate(sorted(lines)):
+        assert sorted(per_prompt[p]) == list(range(1024 + k * n_samples, 1024 + (k + 1) * n_samples))
+
+
+def test_plan_rejects_indivisible():
+    with pytest.raises(ValueError):
+        plan_batches(10, 4, 1)
+
+
+def test_names_and_category_ids(tmp_path):
+    assert output_name("17", 1029) == "17_0001029.png"            # parsed back by convert_dir_structure.py:116-121
+    for cid in ("3", "12", "1203"):
+        (tmp_path / (cid + ".txt")).write_text("a photo of a single thing\n")
+    files = list_prompt_files([str(tmp_path)])
+    assert [category_id_of(f) for f in files] == sorted(["3", "12", "1203"])
+    assert list_prompt_files(["a.txt", "b.txt"]) == ["a.txt", "b.txt"]
+
+
+def test_cli_keeps_reference_flags():
+    a = build_parser().parse_args(["--from_file", "input/lvis_prompt/", "--outdir", "o", "--n_samples", "1024", "--max_batch_size", "1",
+                                   "--seed", "7", "--dist", "--ckpt_dir", "c", "--stages", "sd", "--offset", "0", "--disable_overwrite"])
+    assert (a.from_file, a.n_samples, a.max_batch_size, a.seed, a.dist, a.offset, a.disable_overwrite) == (
+        ["input/lvis_prompt/"], 1024, 1, 7, True, 0, True)
