@@ -81,6 +81,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  griddep_launch();
+  griddep_wait();
 
   if (warp == 0) {
     // ===================== TMA producer =====================

@@ -347,7 +347,7 @@ struct Fwd {
   }
 
   void gn(const T4& x0, const T4* x1, const Norm& n, float eps, int silu, T4& out) {
-    if (fuse_gn() && x0.gst && (!x1 || x1->gst))
+    if (fuse_gn() && x0.gst && (!x1 || x1->gst) && (x0.C + (x1 ? x1->C : 0)) / u->gn_blk <= 256)
       FW(launch_groupnorm_fused(s, sms, x0.p, x0.C, x0.gst, x1 ? x1->p : nullptr, x1 ? x1->C : 0, x1 ? x1->gst : nullptr,
                                 u->gn_blk, n.g, n.b, out.p, x0.B, x0.H * x0.W, u->cfg.norm_num_groups, eps, silu));
     else

@@ -151,38 +151,44 @@ __global__ void gn_apply_blk_kernel(const __half* __restrict__ x0, int C0, const
                                     int groups, float eps, int pix_per_block, const float* __restrict__ stats0,
                                     const float* __restrict__ stats1, int blk, int slots, const __half* __restrict__ gamma,
                                     const __half* __restrict__ beta, int do_silu, __half* __restrict__ out) {
-  __shared__ float s_part[4][64][2];
+  __shared__ float2 s_col[8][256];       // [slab stripe][block column] partial sums
   __shared__ float s_mean[64], s_rstd[64];
+  griddep_launch();
+  griddep_wait();
   const int C = C0 + C1, cpg = C / groups, nvec = C / 8;
   const int b = blockIdx.y;
   const int p0 = blockIdx.x * pix_per_block;
   const int p1 = min(HW, p0 + pix_per_block);
   const float inv_n = 1.0f / ((float)cpg * (float)HW);
   {
-    // thread (sub, g): group g, slabs sub, sub+4, ...
-    const int g = threadIdx.x & 63, sub = threadIdx.x >> 6;
-    float a = 0.f, q = 0.f;
-    if (g < groups) {
-      const int nb0 = C0 / blk, nb1 = C1 / blk, bpg = cpg / blk;
-      for (int sl = sub; sl < slots; sl += 4) {
-        for (int i = 0; i < bpg; ++i) {
-          const int cb = g * bpg + i;
-          const float2 v = (cb < nb0) ? reinterpret_cast<const float2*>(stats0)[((size_t)b * slots + sl) * nb0 + cb]
-                                      : reinterpret_cast<const float2*>(stats1)[((size_t)b * slots + sl) * nb1 + (cb - nb0)];
-          a += v.x; q += v.y;
-        }
-      }
+    // thread (stripe, cb): block column cb, slabs stripe, stripe + nstripe, ...  Consecutive threads read consecutive
+    // float2 entries (coalesced); every sum runs in a fixed order (deterministic).
+    const int nb0 = C0 / blk, nb1 = C1 / blk, nb = nb0 + nb1, bpg = cpg / blk;
+    const int ncol = min(nb, 256);
+    const int nstripe = max(1, min(8, 256 / ncol));
+    const int stripe = threadIdx.x / ncol;
+    if (stripe < nstripe) {
+      const int cb = threadIdx.x % ncol;                          // nb <= 256 (checked by the launcher)
+      const float2* src = (cb < nb0) ? reinterpret_cast<const float2*>(stats0) + (size_t)b * slots * nb0 + cb
+                                     : reinterpret_cast<const float2*>(stats1) + (size_t)b * slots * nb1 + (cb - nb0);
+      const int ld = (cb < nb0) ? nb0 : nb1;
+      float a = 0.f, q = 0.f;
+#pragma unroll 4
+      for (int sl = stripe; sl < slots; sl += nstripe) { const float2 v = __ldg(src + (size_t)sl * ld); a += v.x; q += v.y; }
+      s_col[stripe][cb] = make_float2(a, q);
     }
-    s_part[sub][g][0] = a; s_part[sub][g][1] = q;
-  }
-  __syncthreads();
-  if ((int)threadIdx.x < groups) {
-    const int g = threadIdx.x;
-    const float a = (s_part[0][g][0] + s_part[1][g][0]) + (s_part[2][g][0] + s_part[3][g][0]);
-    const float q = (s_part[0][g][1] + s_part[1][g][1]) + (s_part[2][g][1] + s_part[3][g][1]);
-    const float mean = a * inv_n;
-    const float var = fmaxf(q * inv_n - mean * mean, 0.f);
-    s_mean[g] = mean; s_rstd[g] = rsqrtf(var + eps);
+    __syncthreads();
+    if ((int)threadIdx.x < groups) {
+      const int g = threadIdx.x;
+      float a = 0.f, q = 0.f;
+      for (int i = 0; i < bpg; ++i) {
+        const int cb = g * bpg + i;
+        for (int st = 0; st < nstripe; ++st) { a += s_col[st][cb].x; q += s_col[st][cb].y; }
+      }
+      const float mean = a * inv_n;
+      const float var = fmaxf(q * inv_n - mean * mean, 0.f);
+      s_mean[g] = mean; s_rstd[g] = rsqrtf(var + eps);
+    }
   }
   __syncthreads();
   const GnThreadMap tm(nvec);

@@ -276,6 +276,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
   if constexpr (kCta == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  griddep_launch();                    // the next kernel may begin its own prologue
+  griddep_wait();                      // operands / statistics of the previous kernel are complete and visible
   if (threadIdx.x == 0) DG_STAMP(1);   // prologue done (0 = kernel entry)
 
   const int m_tiles = p.tiles_x * p.tiles_y * p.tiles_b;

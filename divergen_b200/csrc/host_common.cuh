@@ -81,6 +81,35 @@ inline bool trace_on() {
   return v == 1;
 }
 
+// ------------------------------------------------------------------ launches
+// DG_PDL=0 disables programmatic dependent launch (A/B runs).
+inline bool pdl_on() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("DG_PDL"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v == 1;
+}
+// Launch a kernel whose first global access is behind griddep_wait() so that its prologue overlaps the predecessor's tail.
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, int cluster_x,
+                              Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+  cudaLaunchAttribute attr[2];
+  int n = 0;
+  if (cluster_x > 1) {
+    attr[n].id = cudaLaunchAttributeClusterDimension;
+    attr[n].val.clusterDim.x = cluster_x; attr[n].val.clusterDim.y = 1; attr[n].val.clusterDim.z = 1;
+    ++n;
+  }
+  if (pdl_on()) {
+    attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
+  cfg.attrs = attr; cfg.numAttrs = n;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // ------------------------------------------------------------------ tensor maps
 inline PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
   static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
@@ -220,16 +249,8 @@ inline int choose_splits(int units, int num_kb, int slots, size_t ws_floats_per_
 template <int kCta, int kBN, int kStages, bool kGeglu>
 inline cudaError_t launch_gemm2_t(cudaStream_t stream, int grid_ctas, const CUtensorMap& mA0, const CUtensorMap& mA1,
                                   const CUtensorMap& mW, const CUtensorMap& mO, const Gemm2Params& p) {
-  cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3((unsigned)grid_ctas);
-  cfg.blockDim = dim3(384);
-  cfg.dynamicSmemBytes = Gemm2Cfg<kCta, kBN, kStages>::kTotal;
-  cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = kCta; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr; cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, gemm2_kernel<kCta, kBN, kStages, kGeglu>, mA0, mA1, mW, mO, p);
+  return launch_pdl(gemm2_kernel<kCta, kBN, kStages, kGeglu>, dim3((unsigned)grid_ctas), dim3(384),
+                    (size_t)Gemm2Cfg<kCta, kBN, kStages>::kTotal, stream, kCta, mA0, mA1, mW, mO, p);
 }
 
 inline int launch_gemm(cudaStream_t stream, const GemmRes& res, const GemmArgs& a) {
@@ -373,8 +394,11 @@ inline int launch_attn_t(cudaStream_t stream, const __half* q, int ldq, const __
   if (trace_on()) fprintf(stderr, "DG_TRACE attn B=%d heads=%d Sq=%d Sk=%d d=%d\n", B, heads, Sq, Sk, kD);
   ProfScope prof_(FAM_ATTN, stream, 4.0 * B * heads * (double)Sq * Sk * kD,
                   2.0 * B * heads * kD * (2.0 * Sq + 2.0 * Sk));
-  kern<<<grid, 384, C::kSmem, stream>>>(mQ, mK, mV, p);
-  DG_LAUNCH_CHECK();
+  {
+    ++g_launch_counter;
+    cudaError_t e = launch_pdl(kern, grid, dim3(384), (size_t)C::kSmem, stream, 1, mQ, mK, mV, p);
+    if (e != cudaSuccess) return fail(DG_E_CUDA, "attention launch failed: %s", cudaGetErrorString(e));
+  }
   return DG_OK;
 }
 
@@ -475,13 +499,18 @@ inline int launch_groupnorm_fused(cudaStream_t s, int num_sms, const __half* x0,
   if (HW % 32) return fail(DG_E_SHAPE, "groupnorm(fused): HW=%d must be a multiple of 32", HW);
   const int C = C0 + C1;
   if (C % groups || C0 % 8 || C1 % 8 || groups > 64) return fail(DG_E_SHAPE, "groupnorm: C=%d+%d groups=%d", C0, C1, groups);
-  if (blk <= 0 || (C / groups) % blk || C0 % blk || C1 % blk) return fail(DG_E_SHAPE, "groupnorm: block %d does not tile C=%d+%d", blk, C0, C1);
+  if (blk <= 0 || (C / groups) % blk || C0 % blk || C1 % blk || C / blk > 256)
+    return fail(DG_E_SHAPE, "groupnorm: block %d does not tile C=%d+%d (at most 256 blocks)", blk, C0, C1);
   ProfScope prof_(FAM_NORM, s, 0.0, 2.0 * 2.0 * B * HW * (double)C);
   int ppb, pstride;
   gn_launch_geometry(C, B, HW, num_sms, &ppb, &pstride);
   dim3 grid((HW + ppb - 1) / ppb, B);
-  gn_apply_blk_kernel<<<grid, 256, 0, s>>>(x0, C0, x1, C1, HW, groups, eps, ppb, st0, st1, blk, HW / 32, gamma, beta, silu, out);
-  DG_LAUNCH_CHECK();
+  {
+    ++g_launch_counter;
+    cudaError_t e = launch_pdl(gn_apply_blk_kernel, grid, dim3(256), (size_t)0, s, 1, x0, C0, x1, C1, HW, groups, eps, ppb, st0, st1, blk,
+                               HW / 32, gamma, beta, silu, out);
+    if (e != cudaSuccess) return fail(DG_E_CUDA, "groupnorm launch failed: %s", cudaGetErrorString(e));
+  }
   return DG_OK;
 }
 

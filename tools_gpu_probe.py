@@ -13,6 +13,7 @@ GROUPS = {
     "conv": ["tests/test_gpu_ops.py", "-k", "conv3x3"],
     "attn64": ["tests/test_gpu_ops.py", "-k", "attention and (64 or 32)"],
     "attn": ["tests/test_gpu_ops.py", "-k", "attention and not (64 or 32)"],
+    "golden": ["tests/test_golden.py"],
     "unet_tiny": ["tests/test_gpu_unet.py", "-k", "not sd15"],
     "unet_sd15": ["tests/test_gpu_unet.py", "-k", "sd15"],
 }
