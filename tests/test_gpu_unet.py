@@ -156,3 +156,60 @@ def test_sd15_forward_full_width():
     got = unet(x.to(DEV), 981, ehs.to(DEV)).sample
     torch.cuda.synchronize()
     _check(got, ref32, ref16, "sd15 full width")
+
+
+def test_sd21_forward_full_width():
+    """SD-2.1 (768-v) at full width, one CFG pair at the 96x96 latent of BASELINE config 4: heads 5/10/20/20 (d = 64),
+    linear proj_in/out, 1024-wide text context; the 12x12 level (144 pixels, not a multiple of 32) takes the stand-alone
+    GroupNorm statistics path.  fp32 oracle on the GPU as the checker."""
+    _need_gpu()
+    from oracle.unet_oracle import UNetConfig
+    cfg = UNetConfig.sd21()
+    oracle, unet = _models(cfg, seed=0)
+    g = torch.Generator().manual_seed(43)
+    x, ehs = torch.randn(2, 4, 96, 96, generator=g).half(), torch.randn(2, 77, 1024, generator=g).half()
+    with torch.no_grad():
+        o = oracle.to(DEV)
+        ref32 = o(x.to(DEV).float(), torch.tensor([961], device=DEV), ehs.to(DEV).float()).sample.cpu()
+        o = o.half()
+        ref16 = o(x.to(DEV), torch.tensor([961], device=DEV), ehs.to(DEV)).sample.cpu()
+        del o
+    got = unet(x.to(DEV), 961, ehs.to(DEV)).sample
+    torch.cuda.synchronize()
+    _check(got, ref32, ref16, "sd21 full width 96x96")
+
+
+def test_sd15_batch8_sample_independence():
+    """Size-independent property at BASELINE config 2's full shape (UNet batch 8 at 64x64): samples do not interact, so a
+    batch-8 forward of [x0..x3, x0..x3] with permuted contexts equals the batch-2 forwards of each (sample, context) pair.
+    Fused statistics, split-K and tile scheduling all change with the batch; the per-sample result must not (fp32
+    summation order inside split-K reductions may differ: tolerance 2 fp16 ulp of the output range)."""
+    _need_gpu()
+    from divergen_b200 import UNet2DConditionModel
+    unet = UNet2DConditionModel(device=DEV)
+    gen = torch.Generator(device=DEV).manual_seed(0)
+    sd = {}
+    for k, shp in unet.expected_state_dict_shapes().items():
+        fan_in = 1
+        for d in shp[1:]:
+            fan_in *= d
+        if "norm" in k and k.endswith("weight"):
+            sd[k] = (1 + 0.05 * torch.randn(shp, generator=gen, device=DEV)).half()
+        elif k.endswith("bias"):
+            sd[k] = (0.02 * torch.randn(shp, generator=gen, device=DEV)).half()
+        else:
+            sd[k] = (torch.randn(shp, generator=gen, device=DEV) / max(1.0, fan_in) ** 0.5).half()
+    unet.load_state_dict(sd)
+    g = torch.Generator().manual_seed(5)
+    x4 = torch.randn(4, 4, 64, 64, generator=g).half().to(DEV)
+    e4 = torch.randn(4, 77, 768, generator=g).half().to(DEV)
+    big = unet(torch.cat([x4, x4]), 501, torch.cat([e4, e4.flip(0)])).sample.float()
+    torch.cuda.synchronize()
+    scale = big.abs().max().item()
+    for i in (0, 3):
+        small = unet(torch.stack([x4[i], x4[i]]), 501, torch.stack([e4[i], e4[3 - i]])).sample.float()
+        torch.cuda.synchronize()
+        d0 = (small[0] - big[i]).abs().max().item()
+        d1 = (small[1] - big[4 + i]).abs().max().item()
+        print(f"sample {i}: batch-8 vs batch-2 max diff {d0:.3g} / {d1:.3g} (output absmax {scale:.3g})")
+        assert max(d0, d1) <= 2 * scale * 2.0 ** -10 + 1e-4

@@ -14,8 +14,9 @@ GROUPS = {
     "attn64": ["tests/test_gpu_ops.py", "-k", "attention and (64 or 32)"],
     "attn": ["tests/test_gpu_ops.py", "-k", "attention and not (64 or 32)"],
     "golden": ["tests/test_golden.py"],
-    "unet_tiny": ["tests/test_gpu_unet.py", "-k", "not sd15"],
+    "unet_tiny": ["tests/test_gpu_unet.py", "-k", "not sd15 and not sd21"],
     "unet_sd15": ["tests/test_gpu_unet.py", "-k", "sd15"],
+    "unet_sd21": ["tests/test_gpu_unet.py", "-k", "sd21"],
 }
 
 if __name__ == "__main__":
