@@ -389,7 +389,9 @@ inline int launch_attn_t(cudaStream_t stream, const __half* q, int ldq, const __
   AttnParams p{};
   p.Sq = Sq; p.Sk = Sk; p.heads = heads; p.ldo = heads * kD; p.out = out;
   p.scale_log2 = (1.0f / sqrtf((float)kD)) * 1.4426950408889634f;
-  auto kern = attn_tc_kernel<kD, kKV, kStages>;
+  static int poly = -1;
+  if (poly < 0) { const char* e = getenv("DG_ATTN_POLY"); poly = (e && e[0] == '0') ? 0 : 1; }
+  auto kern = poly ? attn_tc_kernel<kD, kKV, kStages, true> : attn_tc_kernel<kD, kKV, kStages, false>;
   dim3 grid((Sq + 255) / 256, heads, B);
   if (trace_on()) fprintf(stderr, "DG_TRACE attn B=%d heads=%d Sq=%d Sk=%d d=%d\n", B, heads, Sq, Sk, kD);
   ProfScope prof_(FAM_ATTN, stream, 4.0 * B * heads * (double)Sq * Sk * kD,
@@ -418,7 +420,9 @@ inline int launch_attention(cudaStream_t stream, const __half* q, int ldq, const
 // Opt every tcgen05 kernel into its dynamic shared-memory size once per device (never during graph capture).
 template <int kD, int kKV, int kStages>
 inline int init_attn_attr() {
-  DG_CUDA(cudaFuncSetAttribute(attn_tc_kernel<kD, kKV, kStages>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  DG_CUDA(cudaFuncSetAttribute(attn_tc_kernel<kD, kKV, kStages, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               AttnCfg<kD, kKV, kStages>::kSmem));
+  DG_CUDA(cudaFuncSetAttribute(attn_tc_kernel<kD, kKV, kStages, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                AttnCfg<kD, kKV, kStages>::kSmem));
   return DG_OK;
 }

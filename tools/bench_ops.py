@@ -38,5 +38,18 @@ def conv():
         print(f"conv B={B} {H}x{H} C={C}->{N} (incl. weight pack): {us:8.1f} us", flush=True)
 
 
+
+
+def attn():
+    for B, heads, S, Sk, d in [(8, 8, 4096, 4096, 40), (8, 8, 1024, 1024, 80), (8, 8, 256, 256, 160), (8, 8, 4096, 77, 40), (4, 5, 9216, 9216, 64)]:
+        C = heads * d
+        q = torch.randn(B, S, C, device="cuda").half()
+        k = torch.randn(B, Sk, C, device="cuda").half()
+        v = torch.randn(B, Sk, C, device="cuda").half()
+        us = timeit(lambda: ops.attention(q, k, v, heads), reps=10)
+        print(f"attn B={B} h={heads} S={S}x{Sk} d={d}: {us:8.1f} us  {4.0 * B * heads * S * Sk * d / us / 1e6:7.1f} TFLOP/s  "
+              f"{B * heads * S * Sk / us / 1e3 / 148:6.2f} exp/ns/SM", flush=True)
+
+
 if __name__ == "__main__":
-    {"gemm": gemm, "conv": conv}[sys.argv[1]]()
+    {"gemm": gemm, "conv": conv, "attn": attn}[sys.argv[1]]()
