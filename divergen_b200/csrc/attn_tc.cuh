@@ -42,7 +42,7 @@ struct AttnCfg {
   static_assert(kO1 + kDPad <= 512, "TMEM budget");
 };
 
-template <int kD, int kKV, int kStages, bool kPoly>
+template <int kD, int kKV, int kStages, int kPoly>   // kPoly: every kPoly-th pair of softmax elements takes the polynomial exp2 (0 = none)
 __global__ void __launch_bounds__(384, 1)
 attn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
                const __grid_constant__ CUtensorMap mapV, const AttnParams p) {
@@ -236,7 +236,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
             float x0, x1;
             unpack_f32x2(x2, x0, x1);
             float p0, p1;
-            if (kPoly && ((i >> 1) % 3) == 2) {
+            if (kPoly > 0 && ((i >> 1) % (kPoly > 0 ? kPoly : 1)) == (kPoly > 0 ? kPoly : 1) - 1) {
               // every third pair: exp2 on the FMA/ALU pipes (the MUFU pipe, 16 results/clk/SM, is this kernel's roofline).
               // 2^x = 2^n * 2^f, n = round(x) via the 1.5*2^23 magic add, 2^f by a degree-3 minimax polynomial on
               // [-0.5, 0.5] (rel. error 7.7e-5, below the fp16 rounding of P), 2^n by adding n to the exponent field.

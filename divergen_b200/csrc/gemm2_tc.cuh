@@ -89,8 +89,9 @@ struct Gemm2Cfg {
   static constexpr int kSlotSubs = kNumAcc == 1 ? 5 : 2;
   static constexpr int kRingBytes = kRing * kSlotSubs * kSubBytes;
   static constexpr int kVecBytes = 2 * 320 * 4;         // bias + colsum, fp32
+  static constexpr int kColBufBytes = 8 * 160 * 8;      // per epilogue warp: (sum, sumsq) of each of its <= 160 columns
   static constexpr int kBarBytes = 512;
-  static constexpr int kTotal = kStages * kStageBytes + kRingBytes + kVecBytes + kBarBytes + 1024 /*align slack*/;
+  static constexpr int kTotal = kStages * kStageBytes + kRingBytes + kVecBytes + kColBufBytes + kBarBytes + 1024 /*align slack*/;
   static_assert(kBHalfBytes % 1024 == 0 && kStageBytes % 1024 == 0, "operand tiles must keep 1024-byte alignment");
   static_assert(kTotal <= 232448, "shared memory budget");
 };
@@ -244,7 +245,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
   uint8_t* sRing = smem + kStages * S::kStageBytes;                       // 1024-aligned
   float* sBias = reinterpret_cast<float*>(sRing + S::kRingBytes);          // [320]
   float* sCs = sBias + 320;                                                // [320]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sRing + S::kRingBytes + S::kVecBytes);
+  float2* sColBuf = reinterpret_cast<float2*>(sRing + S::kRingBytes + S::kVecBytes);   // [8 warps][160]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sRing + S::kRingBytes + S::kVecBytes + S::kColBufBytes);
   uint64_t* full = bars;                    // [kStages]  (leader's are the live ones)
   uint64_t* empty = bars + kStages;         // [kStages]
   uint64_t* acc_full = bars + 2 * kStages;  // [2]
@@ -516,11 +518,13 @@ gemm2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
 
       if (do_final) {
         // GroupNorm block statistics: running (sum, sumsq) of the current gn_blk-channel block, flushed when the block changes
-        // The host enables this only when every warp's 32 rows are one 32-pixel slab of a single sample (HW % 32 == 0).
+        // GroupNorm statistics (host enables them only when every warp's 32 rows are one 32-pixel slab of one sample):
+        // after a chunk is staged, the warp reads its own 32-row slab of the fp16 staging tile back TRANSPOSED (lane =
+        // column, 32 conflict-free 2-byte loads) and keeps per-column (sum, sumsq) in shared memory; at the end of the tile
+        // each lane folds one gn_blk-column block and stores it to the warp's slab entry.  No shuffles, no atomics.
         const bool gn_on = p.gn_stats_out != nullptr;
-        float gs = 0.f, gss = 0.f;
-        int gcur = 0, gcnt = 0;         // current block index / columns accumulated in it (this thread's columns are contiguous)
         float2* gn_dst = nullptr;       // this warp's slab: [gn_nblk] (sum, sumsq) pairs
+        const uint32_t colbuf_a = smem_u32(sColBuf) + (uint32_t)ew * 160 * 8;
         if (gn_on) {
           const int r0 = q * 32;        // first row of this warp within the tile
           int slab;
@@ -529,15 +533,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
           const int b_w = __shfl_sync(0xffffffffu, bb, 0);
           const bool ok_w = __shfl_sync(0xffffffffu, row_ok ? 1 : 0, 0) != 0;
           if (ok_w) gn_dst = reinterpret_cast<float2*>(p.gn_stats_out) + ((size_t)b_w * p.gn_slots + slab) * p.gn_nblk;
-          gcur = (nt * kOutW + hf * (kOutW / 2)) / p.gn_blk;
         }
-        auto gn_flush = [&]() {
-          float a0 = gs, a1 = gss;
-#pragma unroll
-          for (int o = 16; o; o >>= 1) { a0 += __shfl_xor_sync(0xffffffffu, a0, o); a1 += __shfl_xor_sync(0xffffffffu, a1, o); }
-          if (lane == 0 && gn_dst && gcur < p.gn_nblk) gn_dst[gcur] = make_float2(a0, a1);
-          gs = 0.f; gss = 0.f;
-        };
         float rs = 0.f, rss = 0.f;     // LayerNorm row statistics of this thread's output columns
         float* wsrow = p.ws + ((size_t)t.ctile * 128 + r) * kBN;
 
@@ -658,9 +654,9 @@ gemm2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
             }
           }
 
-          // ---- statistics for the consuming normalisation, taken on the fp32 values just before rounding (the fp16
-          // rounding noise is zero-mean and ~2^-11 relative: invisible in sums over >= 320 elements), then round and stage
-          if (p.row_stats_out || gn_on) {
+          // ---- LayerNorm row statistics, on the fp32 values just before rounding (the fp16 rounding noise is zero-mean
+          // and ~2^-11 relative: invisible in sums over >= 320 elements)
+          if (p.row_stats_out) {
             const bool all_ok = row_ok && nt * kOutW + ocol + kCW <= p.n_out;
 #pragma unroll
             for (int i = 0; i < kCW / 2; ++i) {
@@ -669,12 +665,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
                 const int col = nt * kOutW + ocol + 2 * i;
                 v0 = (row_ok && col < p.n_out) ? v0 : 0.f; v1 = (row_ok && col + 1 < p.n_out) ? v1 : 0.f;
               }
-              if (gn_on) {                           // gn_blk is even: both columns of the pair share a block
-                gs += v0 + v1; gss = fmaf(v0, v0, fmaf(v1, v1, gss));
-                gcnt += 2;
-                if (gcnt == p.gn_blk) { gn_flush(); ++gcur; gcnt = 0; }
-              }
-              if (p.row_stats_out) { rs += v0 + v1; rss = fmaf(v0, v0, fmaf(v1, v1, rss)); }
+              rs += v0 + v1; rss = fmaf(v0, v0, fmaf(v1, v1, rss));
             }
           }
           uint32_t pk[kCW / 2];
@@ -685,6 +676,23 @@ gemm2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
             const uint32_t k0 = (uint32_t)((ocol & 31) >> 3);
 #pragma unroll
             for (int i = 0; i < 2; ++i) sts_u4(sub + (((k0 + i) ^ row_sw) << 4), pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
+            if (gn_on) {      // transposed read-back: lane = (row half, column of the 16)
+              __syncwarp();
+              const int col = lane & 15, rh = lane >> 4;
+              const uint32_t slab_a = sRing_a + (slot * 5 + (ocol >> 5)) * S::kSubBytes + (uint32_t)(q * 32 + rh * 16) * 64;
+              const uint32_t kc = k0 + (uint32_t)(col >> 3);
+              float cs = 0.f, css = 0.f;
+#pragma unroll
+              for (int rr = 0; rr < 16; ++rr) {
+                const uint32_t sw = (uint32_t)(((rh * 16 + rr) >> 1) & 3);
+                unsigned short hv;
+                asm volatile("ld.shared.u16 %0, [%1];" : "=h"(hv) : "r"(slab_a + rr * 64 + ((kc ^ sw) << 4) + (col & 7) * 2));
+                const float vv = __half2float(__ushort_as_half(hv));
+                cs += vv; css = fmaf(vv, vv, css);
+              }
+              cs += __shfl_xor_sync(0xffffffffu, cs, 16); css += __shfl_xor_sync(0xffffffffu, css, 16);
+              if (lane < 16) asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(colbuf_a + (uint32_t)(j * 16 + col) * 8), "f"(cs), "f"(css) : "memory");
+            }
             continue;   // one hand-off per tile, after the loop
           }
           const uint32_t buf = chunk_ctr % S::kRing;
@@ -695,6 +703,20 @@ gemm2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
             const uint32_t sub = sRing_a + (buf * 2 + hf) * S::kSubBytes + r * 64;
 #pragma unroll
             for (int i = 0; i < 4; ++i) sts_u4(sub + (((uint32_t)i ^ row_sw) << 4), pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
+            if (gn_on) {      // transposed read-back of this warp's 32 x 32 slab: lane = column
+              __syncwarp();
+              const uint32_t slab_a = sRing_a + (buf * 2 + hf) * S::kSubBytes + (uint32_t)(q * 32) * 64;
+              float cs = 0.f, css = 0.f;
+#pragma unroll
+              for (int rr = 0; rr < 32; ++rr) {
+                const uint32_t sw = (uint32_t)((rr >> 1) & 3);
+                unsigned short hv;
+                asm volatile("ld.shared.u16 %0, [%1];" : "=h"(hv) : "r"(slab_a + rr * 64 + ((((uint32_t)lane >> 3) ^ sw) << 4) + (lane & 7) * 2));
+                const float vv = __half2float(__ushort_as_half(hv));
+                cs += vv; css = fmaf(vv, vv, css);
+              }
+              asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(colbuf_a + (uint32_t)(j * 32 + lane) * 8), "f"(cs), "f"(css) : "memory");
+            }
           } else {
             const uint32_t sub = sRing_a + (buf * 2) * S::kSubBytes + r * 64;
 #pragma unroll
@@ -727,6 +749,21 @@ gemm2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
             if (u == pair_id && ew == 0) DG_STAMP(8);
           }
           ++chunk_ctr;
+        }
+        if (gn_on) {          // fold this warp's columns into gn_blk-channel blocks (fixed order) and store the slab entries
+          __syncwarp();
+          const int half_w = kOutW / 2, nb_half = half_w / p.gn_blk;
+          const int blk0 = (nt * kOutW + hf * half_w) / p.gn_blk;
+          for (int bi = lane; bi < nb_half; bi += 32) {
+            float a0 = 0.f, a1 = 0.f;
+            for (int i = 0; i < p.gn_blk; ++i) {
+              float x, y;
+              asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(x), "=f"(y) : "r"(colbuf_a + (uint32_t)(bi * p.gn_blk + i) * 8));
+              a0 += x; a1 += y;
+            }
+            if (gn_dst && blk0 + bi < p.gn_nblk) gn_dst[blk0 + bi] = make_float2(a0, a1);
+          }
+          __syncwarp();
         }
         if (p.row_stats_out && row_ok)
           reinterpret_cast<float2*>(p.row_stats_out)[grow * p.row_parts + nt * 2 + hf] = make_float2(rs, rss);
