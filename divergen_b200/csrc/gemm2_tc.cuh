@@ -359,8 +359,11 @@ gemm2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
   } else if (warp == 3) {
     // ===================== store warp: drains the staging ring with TMA stores, data-driven by chunk_ready =====================
     // (the epilogue warps never wait on each other or on a store: they only see ring back-pressure through buf_free)
+    // Slots are released kFreeAhead chunks ahead of the chunk being stored, so that the epilogue can stream the NEXT chunk's
+    // residual into its slot while it works on the current one (ring) / prime the next tile's slot (whole-tile slots).
+    constexpr uint32_t kFreeAhead = (kBN == 160) ? 1 : 2;
     if (elect_one()) {
-      mbar_arrive(&buf_free[0]);        // buffer 0 starts free; buffer c+1 is freed after store c is issued
+      for (uint32_t i = 0; i < kFreeAhead; ++i) mbar_arrive(&buf_free[i]);   // the first slots start free
       for (uint32_t c = 0;; ++c) {
         const uint32_t buf = c % S::kRing;
         mbar_wait(&chunk_ready[buf], (c / S::kRing) & 1);
@@ -381,8 +384,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
           }
         }
         tma_store_commit();
-        tma_store_wait_read<S::kRing - 1>();              // the store issued kRing-1 chunks ago has drained its buffer ...
-        mbar_arrive(&buf_free[(buf + 1) % S::kRing]);     // ... which is the one chunk c + 1 writes next
+        tma_store_wait_read<S::kRing - kFreeAhead>();               // store c - (kRing - kFreeAhead) has drained its slot ...
+        mbar_arrive(&buf_free[(buf + kFreeAhead) % S::kRing]);     // ... which chunk c + kFreeAhead uses
       }
       DG_STAMP(10);                     // stop seen by the store warp
       tma_store_wait_all();
@@ -452,19 +455,43 @@ gemm2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
         ln_a = rsqrtf(var + p.ln_eps);
         ln_b = -mean * ln_a;
       }
-      // residual prefetch registers (one chunk ahead)
+      // Residual: each thread copies its own row piece asynchronously (cp.async, no registers) into the very staging
+      // bytes it will later overwrite with the result -- one chunk ahead for the ring (320-wide tiles), the whole tile at
+      // once for whole-tile slots (160-wide) -- and reads it back with one 16-byte shared load per 8 columns.
       constexpr int kRV = kCW / 8;      // 16-byte vectors per chunk piece
-      uint4 res_cur[kRV], res_nxt[kRV];
+      constexpr bool kWhole = (kBN == 160);
       const __half* res_row = p.residual ? p.residual + grow * p.ld_res + (size_t)nt * kOutW : nullptr;
-      auto load_res = [&](int j, uint4* dst) {
+      // shared address of 16-byte vector i of this thread's piece of chunk j in ring slot `sl`
+      auto stage_addr = [&](uint32_t sl, int j, int i) -> uint32_t {
+        if constexpr (kWhole) {
+          const int c = chunk_col(j);
+          return sRing_a + (sl * 5 + (c >> 5)) * S::kSubBytes + r * 64 + (((uint32_t)(((c & 31) >> 3) + i) ^ row_sw) << 4);
+        } else {
+          return sRing_a + (sl * 2 + hf) * S::kSubBytes + r * 64 + (((uint32_t)i ^ row_sw) << 4);
+        }
+      };
+      auto prefetch_res = [&](uint32_t sl, int j) {
         const int c = chunk_col(j);
 #pragma unroll
         for (int i = 0; i < kRV; ++i) {
           const int col = nt * kOutW + c + i * 8;
-          dst[i] = (row_ok && col + 8 <= p.n_out) ? __ldg(reinterpret_cast<const uint4*>(res_row + c + i * 8)) : make_uint4(0, 0, 0, 0);
+          const bool ok = row_ok && col + 8 <= p.n_out;
+          cp_async16(stage_addr(sl, j, i), ok ? (const void*)(res_row + c + i * 8) : (const void*)p.residual, ok ? 16u : 0u);
         }
       };
-      if (p.residual) load_res(0, res_cur);
+      bool res_primed = false;          // chunk 0 (ring) / the whole tile (whole-tile slot) is already in flight
+      if (p.residual && p.splits == 1 && !kGeglu) {
+        const uint32_t sl = chunk_ctr % S::kRing;
+        mbar_wait(&buf_free[sl], (chunk_ctr / S::kRing) & 1);
+        if constexpr (kWhole) {
+#pragma unroll
+          for (int j = 0; j < kChunks; ++j) prefetch_res(sl, j);
+        } else {
+          prefetch_res(sl, 0);
+        }
+        cp_async_commit();
+        res_primed = true;
+      }
 
       mbar_wait(&acc_full[as], acc_phase);
       tc_fence_after();
@@ -538,11 +565,18 @@ gemm2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
         float* wsrow = p.ws + ((size_t)t.ctile * 128 + r) * kBN;
 
         // 160-wide tiles: one staging slot holds the whole tile (one ring wait / fence / hand-off per tile, not per chunk)
-        constexpr bool kWhole = (kBN == 160);
         uint32_t slot = 0;
         if constexpr (kWhole) {
           slot = chunk_ctr % S::kRing;
-          mbar_wait(&buf_free[slot], (chunk_ctr / S::kRing) & 1);
+          if (!res_primed) mbar_wait(&buf_free[slot], (chunk_ctr / S::kRing) & 1);
+          if (p.residual) {
+            if (!res_primed) {
+#pragma unroll
+              for (int jj = 0; jj < kChunks; ++jj) prefetch_res(slot, jj);
+              cp_async_commit();
+            }
+            cp_async_wait<0>();
+          }
         }
 #pragma unroll 1
         for (int j = 0; j < kChunks; ++j) {
@@ -555,7 +589,6 @@ gemm2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
               {
                 uint32_t v[kCW];
                 if constexpr (kCW == 32) tmem_ld32(t_row + c, v); else tmem_ld16(t_row + c, v);
-                if (p.residual && j + 1 < kChunks) load_res(j + 1, res_nxt);
                 tmem_ld_wait();
                 DG_STAMP_C1(17);
                 if (j == kChunks - 1) release_acc();
@@ -563,7 +596,6 @@ gemm2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
                 for (int i = 0; i < kCW; ++i) f[i] = __uint_as_float(v[i]);
               }
             } else {
-              if (p.residual && j + 1 < kChunks) load_res(j + 1, res_nxt);
               float* src = wsrow + c;
 #pragma unroll
               for (int i = 0; i < kCW; i += 4) {
@@ -606,16 +638,33 @@ gemm2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
               }
             }
             if (p.residual) {
-#pragma unroll
-              for (int i = 0; i < kRV; ++i) {
-                float2 tt;
-                tt = unpack_half2(res_cur[i].x); f[i * 8] += tt.x; f[i * 8 + 1] += tt.y;
-                tt = unpack_half2(res_cur[i].y); f[i * 8 + 2] += tt.x; f[i * 8 + 3] += tt.y;
-                tt = unpack_half2(res_cur[i].z); f[i * 8 + 4] += tt.x; f[i * 8 + 5] += tt.y;
-                tt = unpack_half2(res_cur[i].w); f[i * 8 + 6] += tt.x; f[i * 8 + 7] += tt.y;
+              const uint32_t sl = kWhole ? slot : chunk_ctr % S::kRing;
+              if constexpr (!kWhole) {
+                // ring: this chunk's piece was issued one chunk ago (or at unit start); issue the next one, then wait for ours
+                if (j == 0 && !res_primed) {
+                  mbar_wait(&buf_free[sl], (chunk_ctr / S::kRing) & 1);
+                  prefetch_res(sl, 0);
+                  cp_async_commit();
+                }
+                if (j + 1 < kChunks) {
+                  const uint32_t nx = (chunk_ctr + 1) % S::kRing;
+                  mbar_wait(&buf_free[nx], ((chunk_ctr + 1) / S::kRing) & 1);
+                  prefetch_res(nx, j + 1);
+                  cp_async_commit();
+                  cp_async_wait<1>();
+                } else {
+                  cp_async_wait<0>();
+                }
               }
 #pragma unroll
-              for (int i = 0; i < kRV; ++i) res_cur[i] = res_nxt[i];
+              for (int i = 0; i < kRV; ++i) {
+                const uint4 rv = lds_u4(stage_addr(sl, j, i));
+                float2 tt;
+                tt = unpack_half2(rv.x); f[i * 8] += tt.x; f[i * 8 + 1] += tt.y;
+                tt = unpack_half2(rv.y); f[i * 8 + 2] += tt.x; f[i * 8 + 3] += tt.y;
+                tt = unpack_half2(rv.z); f[i * 8 + 4] += tt.x; f[i * 8 + 5] += tt.y;
+                tt = unpack_half2(rv.w); f[i * 8 + 6] += tt.x; f[i * 8 + 7] += tt.y;
+              }
             }
           } else {
             // GEGLU: accumulator 0 = value columns, accumulator 1 = gate columns of the same 160 outputs
