@@ -582,6 +582,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
         for (int j = 0; j < kChunks; ++j) {
           float f[kCW];
           const int ocol = chunk_col(j);   // first output column (within the tile) of this thread's piece
+          // probe the staging slot early: the answer is needed only after the math below
+          const bool slot_ok = kWhole ? true : mbar_test_wait(&buf_free[chunk_ctr % S::kRing], (chunk_ctr / S::kRing) & 1);
           DG_STAMP_C1(16);
           if constexpr (!kGeglu) {
             const int c = ocol;
@@ -746,7 +748,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
           }
           const uint32_t buf = chunk_ctr % S::kRing;
           DG_STAMP_C1(18);
-          mbar_wait(&buf_free[buf], (chunk_ctr / S::kRing) & 1);
+          if (!slot_ok) mbar_wait(&buf_free[buf], (chunk_ctr / S::kRing) & 1);
           DG_STAMP_C1(19);
           if constexpr (kCW == 32) {
             const uint32_t sub = sRing_a + (buf * 2 + hf) * S::kSubBytes + r * 64;

@@ -287,6 +287,14 @@ inline int launch_gemm(cudaStream_t stream, const GemmRes& res, const GemmArgs& 
   static int forced_bn = -1;
   if (forced_bn < 0) { const char* e = getenv("DG_GEMM_BN"); forced_bn = e && e[0] ? atoi(e) : 0; }
   int kbn = (a.geglu || (num_kb > 24 && a.n_w > 160)) ? 320 : 160;
+  {
+    // few-tile layers (the 8x8 / 16x16 levels): 320-wide tiles would leave most SMs idle -- measured on 512x11520x1280:
+    // 58 us (320, 4 splits) vs 43 us (160, 4 splits); 2048x11520x1280: 84 vs 62 us (profiles/r01_ncu_summary.md)
+    const int m_tiles_ = p.tiles_x * p.tiles_y * p.tiles_b;
+    const int units320 = ((m_tiles_ + kcta - 1) / kcta) * ((a.n_w + 319) / 320);
+    const int slots_ = kcta == 2 ? res.max_pairs : res.num_sms;
+    if (!a.geglu && kbn == 320 && units320 * 2 <= slots_) kbn = 160;
+  }
   if (forced_bn == 160 || forced_bn == 320) kbn = a.geglu ? 320 : forced_bn;
   if (a.row_stats_out) kbn = 160;
   p.tiles_n = (a.n_w + kbn - 1) / kbn;
@@ -471,8 +479,10 @@ inline void gn_launch_geometry(int C, int B, int HW, int num_sms, int* ppb_out, 
   const int nvec = C / 8;
   const int pstride = nvec <= 256 ? 256 / nvec : 1;
   // strip length: enough blocks to fill the chip (>= 4 per SM when the tensor allows), >= 8 pixel iterations per thread
-  int ppb = 8 * pstride;
-  while (ppb * 2 <= HW && (size_t)B * ((HW + ppb - 1) / ppb) > (size_t)8 * num_sms) ppb *= 2;
+  static int it0 = -1, waves = -1;
+  if (it0 < 0) { const char* e = getenv("DG_GN_ITERS"); it0 = e && e[0] ? atoi(e) : 8; const char* w = getenv("DG_GN_WAVES"); waves = w && w[0] ? atoi(w) : 8; }
+  int ppb = it0 * pstride;
+  while (ppb * 2 <= HW && (size_t)B * ((HW + ppb - 1) / ppb) > (size_t)waves * num_sms) ppb *= 2;
   *ppb_out = ppb; *pstride_out = pstride;
 }
 
