@@ -26,6 +26,10 @@ sys.path.insert(0, ROOT)
 METRIC = "512x512 images/sec @50 DDIM steps"
 FLOP_PER_SAMPLE_FORWARD = 0.8033e12  # SD-1.5 @64x64 latent (SURVEY.md 8d / BASELINE.md 3)
 IMAGES_PER_GPU = 4
+# DRAM traffic of the GEMM family: mean of dram__bytes_read.sum + dram__bytes_write.sum over the 210 gemm2 launches of one
+# batch-8 forward (one ncu pass, cold caches), see the file named here.  None until that capture exists.
+GEMM_DRAM_BYTES_PER_LAUNCH = None
+GEMM_DRAM_SOURCE = "profiles/r01_gemm2_dram.csv"
 DDIM_STEPS = 50
 GUIDANCE = 7.5
 
@@ -99,6 +103,9 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
     rank, local_rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+    # stdout carries exactly one JSON line: libraries that print there (NCCL's version banner) are pointed at stderr
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
@@ -199,17 +206,19 @@ def run_ours(args):
             cur = dict(ms=list(arrs[0]), flops=list(arrs[1]), bytes=list(arrs[2]), launches=list(launches_f), total_ms=total_ms.value)
             if best is None or cur["total_ms"] < best["total_ms"]:
                 best = cur
-        fam = ["gemm_tc_kernel(linear+conv)", "attn_tc_kernel", "group/layer-norm", "other"]
+        fam = ["gemm2_kernel(linear+conv)", "attn_tc_kernel", "groupnorm-apply", "other"]
         gemm_tf = best["flops"][0] / (best["ms"][0] * 1e-3) / 1e12
         attn_tf = best["flops"][1] / (best["ms"][1] * 1e-3) / 1e12 if best["ms"][1] else 0.0
         norm_gbs = best["bytes"][2] / (best["ms"][2] * 1e-3) / 1e9 if best["ms"][2] else 0.0
         fwd_ms_graph = ms_dev / args.steps / DDIM_STEPS
         whole_tf = FLOP_PER_SAMPLE_FORWARD * 2 * n / (fwd_ms_graph * 1e-3) / 1e12
         roofline = {
-            "bound": "tensor", "kernel": "gemm_tc_kernel<160,6> (all Linear / conv1x1 / conv3x3 launches of one UNet forward)",
+            "bound": "tensor", "kernel": "gemm2_kernel<cta_group 2, tile N 160|320> (all 210 Linear / conv1x1 / conv3x3 launches of one UNet forward)",
             "achieved": round(gemm_tf, 1), "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": round(gemm_tf / pk["tf_sustained"], 4),
             "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({pk['src']}; kernel timed inside a long step)",
-            "traffic": None,
+            "traffic": GEMM_DRAM_BYTES_PER_LAUNCH, "traffic_source": GEMM_DRAM_SOURCE,
+            "algorithmic_flops_per_launch": round(best["flops"][0] / max(1, best["launches"][0]) / 1e9, 2),
+            "algorithmic_bytes_per_launch": round(best["bytes"][0] / max(1, best["launches"][0]) / 1e6, 2),
             "launches_per_forward": best["launches"][0], "avg_launch_us": round(best["ms"][0] * 1e3 / max(1, best["launches"][0]), 2),
             "share_of_forward": round(best["ms"][0] / best["total_ms"], 4),
             "families": {fam[i]: {"ms": round(best["ms"][i], 4), "launches": best["launches"][i],
@@ -219,7 +228,8 @@ def run_ours(args):
             "eager_forward_ms": round(best["total_ms"], 3), "graph_forward_ms": round(fwd_ms_graph, 3),
             "whole_unet_tflops": round(whole_tf, 1), "whole_unet_frac": round(whole_tf / pk["tf_sustained"], 4),
         }
-        cpu = cpu_baseline_sample(max_seconds=30.0)
+        # CPU baseline on rank 0 at N = 1 only (under torchrun OMP_NUM_THREADS=1 would cripple it; the reference arm reports it)
+        cpu = cpu_baseline_sample(max_seconds=30.0) if world == 1 else None
         result = {
             "metric": METRIC, "value": round(value, 4), "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": round(ms_dev / args.steps, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -239,6 +249,8 @@ def run_ours(args):
         dist.barrier()
         dist.destroy_process_group()
     if rank == 0:
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
         print(json.dumps(result), flush=True)
 
 
@@ -315,6 +327,9 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", 0))
     if rank != 0:
         return
+    # torchrun exports OMP_NUM_THREADS=1; this arm is the CPU implementation and uses every host core (before torch loads)
+    os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
+    os.environ["MKL_NUM_THREADS"] = str(os.cpu_count() or 1)
     m = _oracle_sd15()
     t0 = time.perf_counter()
     cpu = cpu_baseline_sample(model=m, reps=max(1, args.steps))
