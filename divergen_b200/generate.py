@@ -239,6 +239,7 @@ def main(argv: Optional[Sequence[str]] = None) -> int:
             n_done += call.num_images
     if args.dist:
         torch.distributed.barrier()
+        torch.distributed.destroy_process_group()
     print("rank {} wrote {} latents under {}".format(rank, n_done, sample_dir))
     return 0
 

@@ -1,0 +1,27 @@
+"""End-to-end run of the generation driver on the GPU (random-init SD-1.5 weights, 2 DDIM steps): the files it writes follow
+the reference's naming / index contract (txt2img_diffusers_stages_from_txt.py:262-263) and resume skips finished work."""
+import os
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def test_driver_writes_reference_index_layout(tmp_path):
+    if not torch.cuda.is_available():
+        pytest.skip("no GPU")
+    from divergen_b200.generate import main
+    argv = ["--from_file", os.path.join(HERE, "fixtures", "prompts"), "--outdir", str(tmp_path), "--n_samples", "3",
+            "--max_batch_size", "2", "--random_init", "--num_inference_steps", "2", "--offset", "10", "--disable_overwrite"]
+    assert main(argv) == 0
+    got = sorted(os.listdir(tmp_path / "samples" / "sd"))
+    want = sorted([f"1_{10 + j:07d}.latent.pt" for j in range(3)] +
+                  [f"7_{10 + k * 3 + j:07d}.latent.pt" for k in range(2) for j in range(3)])
+    assert got == want
+    lat = torch.load(tmp_path / "samples" / "sd" / got[0])
+    assert lat.shape == (4, 64, 64) and lat.dtype == torch.float16 and torch.isfinite(lat.float()).all()
+    mtimes = {f: os.path.getmtime(tmp_path / "samples" / "sd" / f) for f in got}
+    assert main(argv) == 0                                            # second run: everything exists -> skipped
+    assert mtimes == {f: os.path.getmtime(tmp_path / "samples" / "sd" / f) for f in got}

@@ -14,6 +14,7 @@ GROUPS = {
     "attn64": ["tests/test_gpu_ops.py", "-k", "attention and (64 or 32)"],
     "attn": ["tests/test_gpu_ops.py", "-k", "attention and not (64 or 32)"],
     "golden": ["tests/test_golden.py"],
+    "driver": ["tests/test_gpu_driver.py"],
     "unet_tiny": ["tests/test_gpu_unet.py", "-k", "not sd15 and not sd21"],
     "unet_sd15": ["tests/test_gpu_unet.py", "-k", "sd15"],
     "unet_sd21": ["tests/test_gpu_unet.py", "-k", "sd21"],
