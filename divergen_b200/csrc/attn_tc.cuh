@@ -174,12 +174,16 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
       const int kv_valid = min(kKV, p.Sk - j * kKV);
       const bool full_tile = kv_valid == kKV;
       // pass 1: row max (FMNMX3: two columns per instruction, two independent chains)
+      // (TMEM loads are software-pipelined one 32-column chunk ahead of the math in both passes: the single warp that owns
+      // these rows would otherwise expose the tcgen05.ld latency eight times per tile)
       float mx = -INFINITY, mx_b = -INFINITY;
+      uint32_t vv[2][32];
+      tmem_ld32(tS, vv[0]);
+      tmem_ld_wait();
 #pragma unroll
       for (int c = 0; c < kKV; c += 32) {
-        uint32_t v[32];
-        tmem_ld32(tS + c, v);
-        tmem_ld_wait();
+        uint32_t* v = vv[(c >> 5) & 1];
+        if (c + 32 < kKV) tmem_ld32(tS + c + 32, vv[((c >> 5) + 1) & 1]);
         if (full_tile) {
 #pragma unroll
           for (int i = 0; i < 32; i += 4) {
@@ -194,6 +198,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
             mx = fmaxf(mx, s);
           }
         }
+        if (c + 32 < kKV) tmem_ld_wait();
       }
       mx = fmaxf(mx, mx_b);
       const float m_tile = mx * p.scale_log2;
@@ -224,11 +229,14 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
         const uint64_t sc2 = pack_f32x2(p.scale_log2, p.scale_log2);
         const uint64_t nm2 = pack_f32x2(-m_run, -m_run);
         uint64_t sum2 = pack_f32x2(0.f, 0.f);
+        tmem_ld32(tS, vv[0]);
+        tmem_ld_wait();
 #pragma unroll
         for (int c = 0; c < kKV; c += 32) {
-          uint32_t v[32];
-          tmem_ld32(tS + c, v);
-          tmem_ld_wait();
+          uint32_t* v = vv[(c >> 5) & 1];
+          // the next chunk's load must not overtake this chunk's store into the same TMEM columns: P (fp16 pairs) of chunk c
+          // lands in columns [c/2, c/2+16), which chunk c+32 (columns [c+32, c+64)) never overlaps for c >= 0
+          if (c + 32 < kKV) tmem_ld32(tS + c + 32, vv[((c >> 5) + 1) & 1]);
           uint32_t pk[16];
 #pragma unroll
           for (int i = 0; i < 32; i += 2) {
@@ -259,6 +267,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
             pk[i >> 1] = cvt_pack_half2(p0, p1);
             sum2 = add_f32x2(sum2, pack_f32x2(p0, p1));
           }
+          if (c + 32 < kKV) tmem_ld_wait();     // chunk c+32 is in registers before P(c) overwrites columns it might share
           tmem_st16(tS + (c >> 1), pk);
         }
         float s0, s1;
