@@ -15,6 +15,7 @@ GROUPS = {
     "attn": ["tests/test_gpu_ops.py", "-k", "attention and not (64 or 32)"],
     "golden": ["tests/test_golden.py"],
     "driver": ["tests/test_gpu_driver.py"],
+    "edges": ["tests/test_gpu_edges.py"],
     "unet_tiny": ["tests/test_gpu_unet.py", "-k", "not sd15 and not sd21"],
     "unet_sd15": ["tests/test_gpu_unet.py", "-k", "sd15"],
     "unet_sd21": ["tests/test_gpu_unet.py", "-k", "sd21"],
