@@ -99,12 +99,16 @@ struct GraphKey {
   }
 };
 
-struct dg_unet {
+// Packed-weight registry shared by the model handles (UNet, VAE decoder): state-dict key -> destination + packing rule.
+struct WeightStore {
   dg_ctx* ctx = nullptr;
-  dg_unet_config cfg{};
   std::vector<Slot> slots;
   std::map<std::string, int> slot_index;
   std::vector<void*> owned;  // cudaMalloc'd weight buffers
+};
+
+struct dg_unet : WeightStore {
+  dg_unet_config cfg{};
   // modules
   Lin conv_in, conv_out, time1, time2;
   Norm norm_out;
@@ -145,7 +149,7 @@ struct dg_unet {
 
 namespace {
 
-int dev_alloc(dg_unet* u, void** p, size_t bytes) {
+int dev_alloc(WeightStore* u, void** p, size_t bytes) {
   cudaError_t e = cudaMalloc(p, bytes);
   if (e != cudaSuccess) return fail(DG_E_NOMEM, "cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
   cudaMemset(*p, 0, bytes);
@@ -153,7 +157,7 @@ int dev_alloc(dg_unet* u, void** p, size_t bytes) {
   return DG_OK;
 }
 
-int add_slot(dg_unet* u, const std::string& key, std::vector<int64_t> shape, PackKind kind, __half* dst,
+int add_slot(WeightStore* u, const std::string& key, std::vector<int64_t> shape, PackKind kind, __half* dst,
              int64_t row_off = 0, int a = 0, int b = 0) {
   Slot s; s.key = key; s.shape = std::move(shape); s.kind = kind; s.dst = dst; s.row_off = row_off; s.a = a; s.b = b;
   u->slot_index[key] = (int)u->slots.size();
@@ -161,7 +165,7 @@ int add_slot(dg_unet* u, const std::string& key, std::vector<int64_t> shape, Pac
   return DG_OK;
 }
 
-int make_norm(dg_unet* u, const std::string& pfx, int c, Norm* n) {
+int make_norm(WeightStore* u, const std::string& pfx, int c, Norm* n) {
   n->c = c;
   DG_TRY(dev_alloc(u, (void**)&n->g, c * 2));
   DG_TRY(dev_alloc(u, (void**)&n->b, c * 2));
@@ -169,7 +173,7 @@ int make_norm(dg_unet* u, const std::string& pfx, int c, Norm* n) {
   add_slot(u, pfx + ".bias", {c}, PK_COPY, n->b);
   return DG_OK;
 }
-int make_linear(dg_unet* u, const std::string& pfx, int in, int out, bool bias, Lin* l, bool conv1x1 = false) {
+int make_linear(WeightStore* u, const std::string& pfx, int in, int out, bool bias, Lin* l, bool conv1x1 = false) {
   l->in = in; l->out = out; l->rows = out;
   DG_TRY(dev_alloc(u, (void**)&l->w, (size_t)in * out * 2));
   if (conv1x1) add_slot(u, pfx + ".weight", {out, in, 1, 1}, PK_COPY, l->w);
@@ -180,7 +184,7 @@ int make_linear(dg_unet* u, const std::string& pfx, int in, int out, bool bias, 
   }
   return DG_OK;
 }
-int make_conv3(dg_unet* u, const std::string& pfx, int in, int out, Lin* l) {
+int make_conv3(WeightStore* u, const std::string& pfx, int in, int out, Lin* l) {
   l->in = in; l->out = out; l->rows = out;
   DG_TRY(dev_alloc(u, (void**)&l->w, (size_t)in * 9 * out * 2));
   DG_TRY(dev_alloc(u, (void**)&l->b, out * 2));
@@ -727,6 +731,159 @@ int check_prepared(dg_unet* u, int batch, int h, int w, int tokens) {
   return finalize_weights(u);
 }
 
+// ================================================================== VAE decoder
+// AutoencoderKL.decode of StableDiffusionPipeline.__call__ step 8: post_quant_conv -> conv_in -> mid (resnet, single-head
+// attention, resnet) -> 4 up blocks of 3 resnets (+ nearest-x2 upsample conv) -> GroupNorm + SiLU -> conv_out.  Same kernels as
+// the UNet: tcgen05 implicit-GEMM convs / linears (gemm2_kernel), GroupNorm (+SiLU) kernels; the 512-wide single-head
+// attention runs as two tcgen05 GEMMs (Q K^T, P V) around a row-softmax kernel.  Eager launches, no graph (3 % of the image).
+struct VRes { Norm n1, n2; Lin c1, c2, sc; bool has_sc = false; int cin = 0, cout = 0; };
+struct VUp { std::vector<VRes> res; bool has_up = false; Lin up; };
+}  // namespace
+
+struct dg_vae : WeightStore {
+  int ch[4] = {128, 256, 512, 512};
+  int layers = 2, groups = 32, latent_ch = 4, out_ch = 3;
+  float eps = 1e-6f;
+  __half* pq_w = nullptr; __half* pq_b = nullptr;   // post_quant_conv
+  Lin conv_in, conv_out, aq, ak, av, ao;
+  Norm attn_gn, norm_out;
+  VRes mid0, mid1;
+  std::vector<VUp> up;
+  Arena arena;
+  float* gn_stats = nullptr;
+  int max_batch = 0, ws_h = 0, ws_w = 0;
+};
+
+namespace {
+
+int make_vres(dg_vae* v, const std::string& pfx, int cin, int cout, VRes* r) {
+  r->cin = cin; r->cout = cout;
+  DG_TRY(make_norm(v, pfx + ".norm1", cin, &r->n1));
+  DG_TRY(make_conv3(v, pfx + ".conv1", cin, cout, &r->c1));
+  DG_TRY(make_norm(v, pfx + ".norm2", cout, &r->n2));
+  DG_TRY(make_conv3(v, pfx + ".conv2", cout, cout, &r->c2));
+  r->has_sc = cin != cout;
+  if (r->has_sc) DG_TRY(make_linear(v, pfx + ".conv_shortcut", cin, cout, true, &r->sc, true));
+  return DG_OK;
+}
+
+int build_vae(dg_vae* v) {
+  const int* ch = v->ch;
+  const int cm = ch[3];
+  DG_TRY(dev_alloc(v, (void**)&v->pq_w, (size_t)v->latent_ch * v->latent_ch * 2));
+  DG_TRY(dev_alloc(v, (void**)&v->pq_b, (size_t)v->latent_ch * 2));
+  add_slot(v, "post_quant_conv.weight", {v->latent_ch, v->latent_ch, 1, 1}, PK_COPY, v->pq_w);
+  add_slot(v, "post_quant_conv.bias", {v->latent_ch}, PK_COPY, v->pq_b);
+  v->conv_in.in = 64; v->conv_in.out = cm; v->conv_in.rows = cm;
+  DG_TRY(dev_alloc(v, (void**)&v->conv_in.w, (size_t)64 * cm * 2));
+  DG_TRY(dev_alloc(v, (void**)&v->conv_in.b, cm * 2));
+  add_slot(v, "decoder.conv_in.weight", {cm, v->latent_ch, 3, 3}, PK_CONV_IN, v->conv_in.w, 0, cm, v->latent_ch);
+  add_slot(v, "decoder.conv_in.bias", {cm}, PK_COPY, v->conv_in.b);
+  DG_TRY(make_vres(v, "decoder.mid_block.resnets.0", cm, cm, &v->mid0));
+  DG_TRY(make_norm(v, "decoder.mid_block.attentions.0.group_norm", cm, &v->attn_gn));
+  DG_TRY(make_linear(v, "decoder.mid_block.attentions.0.to_q", cm, cm, true, &v->aq));
+  DG_TRY(make_linear(v, "decoder.mid_block.attentions.0.to_k", cm, cm, true, &v->ak));
+  DG_TRY(make_linear(v, "decoder.mid_block.attentions.0.to_v", cm, cm, true, &v->av));
+  DG_TRY(make_linear(v, "decoder.mid_block.attentions.0.to_out.0", cm, cm, true, &v->ao));
+  DG_TRY(make_vres(v, "decoder.mid_block.resnets.1", cm, cm, &v->mid1));
+  v->up.resize(4);
+  int cin = cm;
+  for (int i = 0; i < 4; ++i) {
+    const int cout = ch[3 - i];
+    VUp& u = v->up[i];
+    u.res.resize(v->layers + 1);
+    const std::string pfx = "decoder.up_blocks." + std::to_string(i);
+    for (int j = 0; j <= v->layers; ++j) DG_TRY(make_vres(v, pfx + ".resnets." + std::to_string(j), j == 0 ? cin : cout, cout, &u.res[j]));
+    u.has_up = i != 3;
+    if (u.has_up) DG_TRY(make_conv3(v, pfx + ".upsamplers.0.conv", cout, cout, &u.up));
+    cin = cout;
+  }
+  DG_TRY(make_norm(v, "decoder.conv_norm_out", ch[0], &v->norm_out));
+  DG_TRY(make_conv3(v, "decoder.conv_out", ch[0], v->out_ch, &v->conv_out));
+  return DG_OK;
+}
+
+struct VFwd {
+  dg_vae* v; cudaStream_t s; int err = DG_OK;
+  __half* alloc(size_t bytes) {
+    void* p = v->arena.alloc(bytes);
+    if (!p && err == DG_OK) err = fail(DG_E_NOMEM, "VAE arena exhausted (%zu bytes requested); call dg_vae_prepare with a larger batch", bytes);
+    return (__half*)p;
+  }
+  T4 talloc(int B, int H, int W, int C) { T4 t; t.B = B; t.H = H; t.W = W; t.C = C; t.p = alloc(t.bytes()); return t; }
+  void free_(T4& t) { v->arena.release(t.p); t.p = nullptr; }
+  void gn(const T4& x, const Norm& n, int silu, T4& out) {
+    FW(launch_groupnorm(s, v->ctx->num_sms, x.p, x.C, nullptr, 0, n.g, n.b, out.p, v->gn_stats, x.B, x.H * x.W, v->groups, v->eps, silu));
+  }
+  void conv3(const T4& x, const Lin& w, const __half* residual, T4& out, int ldo = 0) {
+    GemmArgs a; a.a0 = x.p; a.c0 = x.C; a.B = x.B; a.H = x.H; a.W = x.W; a.taps = 9; a.w = w.w; a.n_w = w.rows; a.n_out = w.out;
+    a.bias = w.b; a.residual = residual; a.ld_res = w.out; a.out = out.p; a.ldo = ldo ? ldo : w.out;
+    FW(launch_gemm(s, v->ctx->gemm, a));
+  }
+  void linear(const __half* x, int K, int rows, const __half* w, int n_w, const __half* bias, const __half* residual, __half* out, int ldo) {
+    GemmArgs a; a.a0 = x; a.c0 = K; a.B = 1; a.H = 1; a.W = rows; a.taps = 1; a.w = w; a.n_w = n_w; a.n_out = n_w; a.bias = bias;
+    a.residual = residual; a.ld_res = ldo; a.out = out; a.ldo = ldo;
+    FW(launch_gemm(s, v->ctx->gemm, a));
+  }
+  T4 resnet(const VRes& r, T4& x) {       // consumes x
+    T4 hn = talloc(x.B, x.H, x.W, r.cin);
+    gn(x, r.n1, 1, hn);
+    T4 h1 = talloc(x.B, x.H, x.W, r.cout);
+    conv3(hn, r.c1, nullptr, h1);
+    free_(hn);
+    T4 h2n = talloc(x.B, x.H, x.W, r.cout);
+    gn(h1, r.n2, 1, h2n);
+    free_(h1);
+    T4 out = talloc(x.B, x.H, x.W, r.cout);
+    const __half* resid = x.p;
+    T4 sc{};
+    if (r.has_sc) {
+      sc = talloc(x.B, x.H, x.W, r.cout);
+      linear(x.p, x.C, x.B * x.H * x.W, r.sc.w, r.sc.rows, r.sc.b, nullptr, sc.p, r.cout);
+      resid = sc.p;
+    }
+    conv3(h2n, r.c2, resid, out);
+    free_(h2n);
+    if (r.has_sc) free_(sc);
+    free_(x);
+    return out;
+  }
+  T4 attention(T4& x) {                    // consumes x
+    const int C = x.C, S = x.H * x.W, rows = x.B * S;
+    T4 xn = talloc(x.B, x.H, x.W, C);
+    gn(x, v->attn_gn, 0, xn);
+    __half* q = alloc((size_t)rows * C * 2);
+    __half* k = alloc((size_t)rows * C * 2);
+    __half* vv = alloc((size_t)rows * C * 2);
+    linear(xn.p, C, rows, v->aq.w, C, v->aq.b, nullptr, q, C);
+    linear(xn.p, C, rows, v->ak.w, C, v->ak.b, nullptr, k, C);
+    linear(xn.p, C, rows, v->av.w, C, v->av.b, nullptr, vv, C);
+    // S = h*w is a multiple of 64 (latent sides are multiples of 8): K of the P*V GEMM is whole 64-wide k-blocks
+    __half* sc = alloc((size_t)S * S * 2);
+    __half* vt = alloc((size_t)C * S * 2);
+    if (err) return x;
+    const float scale_log2 = (1.0f / sqrtf((float)C)) * 1.4426950408889634f;
+    for (int b = 0; b < x.B && !err; ++b) {
+      // S = Q_b K_b^T   (K_b as the K-major "weight": [S keys, C])
+      linear(q + (size_t)b * S * C, C, S, k + (size_t)b * S * C, S, nullptr, nullptr, sc, S);
+      softmax_rows_kernel<<<S, 256, 0, s>>>(sc, S, scale_log2);
+      ++g_launch_counter;
+      dim3 tb(32, 8), tg((C + 31) / 32, (S + 31) / 32);
+      transpose_rows_kernel<<<tg, tb, 0, s>>>(vv + (size_t)b * S * C, vt, S, C);
+      ++g_launch_counter;
+      // O_b = P V_b   (V_b^T as the K-major weight: [C, S])
+      linear(sc, S, S, vt, C, nullptr, nullptr, xn.p + (size_t)b * S * C, C);
+    }
+    v->arena.release(sc); v->arena.release(vt); v->arena.release(q); v->arena.release(k); v->arena.release(vv);
+    T4 out = talloc(x.B, x.H, x.W, C);
+    linear(xn.p, C, rows, v->ao.w, C, v->ao.b, x.p, out.p, C);
+    free_(xn); free_(x);
+    return out;
+  }
+};
+
+int vae_missing(dg_vae* v) { int m = 0; for (auto& s : v->slots) m += s.set ? 0 : 1; return m; }
+
 }  // namespace
 
 // ================================================================== C ABI
@@ -824,7 +981,7 @@ int32_t dg_unet_missing_weights(dg_unet* u) {
   return m;
 }
 
-int32_t dg_unet_set_weight(dg_unet* u, const char* key, const void* src, int32_t ndim, const int64_t* shape) {
+static int store_set_weight(WeightStore* u, const char* key, const void* src, int32_t ndim, const int64_t* shape) {
   if (!u || !key || !src || !shape) return fail(DG_E_ARG, "null argument");
   auto it = u->slot_index.find(key);
   if (it == u->slot_index.end()) return fail(DG_E_ARG, "unexpected state-dict key '%s'", key);
@@ -858,6 +1015,10 @@ int32_t dg_unet_set_weight(dg_unet* u, const char* key, const void* src, int32_t
   }
   DG_CUDA(cudaDeviceSynchronize());
   s.set = true;
+  return DG_OK;
+}
+int32_t dg_unet_set_weight(dg_unet* u, const char* key, const void* src, int32_t ndim, const int64_t* shape) {
+  DG_TRY(store_set_weight(u, key, src, ndim, shape));
   u->finalized = false;
   return DG_OK;
 }
@@ -1147,6 +1308,113 @@ int32_t dg_op_time_embedding(dg_ctx* ctx, const float* t_host, int32_t B, int32_
   cudaStreamSynchronize(s);
   cudaFree(d_t); cudaFree(tsin); cudaFree(t1);
   return r;
+}
+
+
+// ---- AutoencoderKL decoder -------------------------------------------------------------------------------------------
+int32_t dg_vae_create(dg_ctx* ctx, const int32_t* block_out_channels, int32_t layers_per_block, dg_vae** out) {
+  if (!ctx || !out) return fail(DG_E_ARG, "null argument");
+  std::unique_ptr<dg_vae> v(new dg_vae());
+  v->ctx = ctx;
+  if (block_out_channels) for (int i = 0; i < 4; ++i) v->ch[i] = block_out_channels[i];
+  if (layers_per_block > 0) v->layers = layers_per_block;
+  for (int i = 0; i < 4; ++i)
+    if (v->ch[i] % 64 || v->ch[i] % v->groups) return fail(DG_E_UNSUPPORTED, "vae block_out_channels[%d]=%d must be a multiple of 64", i, v->ch[i]);
+  DG_CUDA(cudaSetDevice(ctx->device));
+  int r = build_vae(v.get());
+  if (r != DG_OK) { for (void* p : v->owned) cudaFree(p); return r; }
+  *out = v.release();
+  return DG_OK;
+}
+void dg_vae_destroy(dg_vae* v) {
+  if (!v) return;
+  for (void* p : v->owned) cudaFree(p);
+  cudaFree(v->arena.base); cudaFree(v->gn_stats);
+  delete v;
+}
+int32_t dg_vae_num_weights(dg_vae* v) { return v ? (int32_t)v->slots.size() : 0; }
+const char* dg_vae_weight_name(dg_vae* v, int32_t i) {
+  if (!v || i < 0 || i >= (int)v->slots.size()) return nullptr;
+  return v->slots[i].key.c_str();
+}
+int32_t dg_vae_weight_shape(dg_vae* v, int32_t i, int64_t* shape4, int32_t* ndim) {
+  if (!v || i < 0 || i >= (int)v->slots.size() || !shape4 || !ndim) return fail(DG_E_ARG, "bad argument");
+  *ndim = (int32_t)v->slots[i].shape.size();
+  for (int k = 0; k < *ndim; ++k) shape4[k] = v->slots[i].shape[k];
+  return DG_OK;
+}
+int32_t dg_vae_set_weight(dg_vae* v, const char* key, const void* src, int32_t ndim, const int64_t* shape) {
+  return store_set_weight(v, key, src, ndim, shape);
+}
+int32_t dg_vae_prepare(dg_vae* v, int32_t max_batch, int32_t h, int32_t w) {
+  if (!v || max_batch <= 0 || h <= 0 || w <= 0) return fail(DG_E_ARG, "bad argument");
+  DG_CUDA(cudaSetDevice(v->ctx->device));
+  cudaFree(v->arena.base); cudaFree(v->gn_stats);
+  v->arena.base = nullptr; v->gn_stats = nullptr;
+  // peak live set: ~6 full-resolution tensors of ch[0] channels at 8h x 8w (+ the S x S score matrix of one image)
+  const size_t pix = (size_t)max_batch * (8 * h) * (8 * w);
+  const size_t S = (size_t)h * w;
+  size_t bytes = pix * v->ch[0] * 2 * 8 + S * S * 2 + ((size_t)64 << 20);
+  v->arena.size = bytes;
+  cudaError_t e = cudaMalloc((void**)&v->arena.base, bytes);
+  if (e != cudaSuccess) return fail(DG_E_NOMEM, "VAE workspace cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
+  DG_CUDA(cudaMalloc((void**)&v->gn_stats, sizeof(float) * 2 * v->groups * max_batch));
+  v->max_batch = max_batch; v->ws_h = h; v->ws_w = w;
+  return DG_OK;
+}
+int32_t dg_vae_decode(dg_vae* v, const void* latents, float scale, void* out, int32_t B, int32_t h, int32_t w, void* stream) {
+  if (!v || !latents || !out) return fail(DG_E_ARG, "null argument");
+  if (!v->arena.base) return fail(DG_E_STATE, "dg_vae_prepare has not been called");
+  if (B > v->max_batch || h * w > v->ws_h * v->ws_w) return fail(DG_E_SHAPE, "decode (batch %d, %dx%d) exceeds prepared workspace", B, h, w);
+  if (h % 8 || w % 8) return fail(DG_E_SHAPE, "latent size %dx%d must be a multiple of 8", h, w);
+  if (vae_missing(v)) return fail(DG_E_STATE, "%d VAE weights have not been set", vae_missing(v));
+  DG_CUDA(cudaSetDevice(v->ctx->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  const int sms = v->ctx->num_sms;
+  v->arena.reset();
+  VFwd f{v, s};
+  // post_quant_conv (+ 1/scaling_factor) -> conv_in (4-channel NCHW gather -> K = 64 GEMM)
+  __half* z = f.alloc((size_t)B * v->latent_ch * h * w * 2);
+  __half* col = f.alloc((size_t)B * h * w * 64 * 2);
+  T4 x = f.talloc(B, h, w, v->ch[3]);
+  if (f.err) return f.err;
+  latent_pointwise_kernel<<<(unsigned)(((size_t)B * h * w + 255) / 256), 256, 0, s>>>((const __half*)latents, v->pq_w, v->pq_b, z, B, v->latent_ch, h * w, scale);
+  DG_LAUNCH_CHECK();
+  im2col_conv_in_kernel<<<grid_for((size_t)B * h * w * 64, 256, sms), 256, 0, s>>>(z, col, B, v->latent_ch, h, w, 64);
+  DG_LAUNCH_CHECK();
+  f.linear(col, 64, B * h * w, v->conv_in.w, v->conv_in.rows, v->conv_in.b, nullptr, x.p, v->ch[3]);
+  v->arena.release(z); v->arena.release(col);
+  // mid block
+  x = f.resnet(v->mid0, x);
+  if (!f.err) x = f.attention(x);
+  if (!f.err) x = f.resnet(v->mid1, x);
+  // up blocks
+  for (int i = 0; i < 4 && !f.err; ++i) {
+    VUp& u = v->up[i];
+    for (size_t j = 0; j < u.res.size() && !f.err; ++j) x = f.resnet(u.res[j], x);
+    if (u.has_up && !f.err) {
+      T4 upx = f.talloc(x.B, x.H * 2, x.W * 2, x.C);
+      T4 y = f.talloc(x.B, x.H * 2, x.W * 2, x.C);
+      if (f.err) break;
+      upsample2x_nhwc_kernel<<<grid_for((size_t)x.B * 4 * x.H * x.W * (x.C / 8), 256, sms), 256, 0, s>>>(x.p, upx.p, x.B, x.H, x.W, x.C);
+      DG_LAUNCH_CHECK();
+      f.conv3(upx, u.up, nullptr, y);
+      f.free_(upx); f.free_(x);
+      x = y;
+    }
+  }
+  if (f.err) return f.err;
+  T4 xn = f.talloc(x.B, x.H, x.W, x.C);
+  f.gn(x, v->norm_out, 1, xn);
+  const int opitch = (v->out_ch + 7) / 8 * 8;
+  T4 o = f.talloc(x.B, x.H, x.W, opitch);
+  if (f.err) return f.err;
+  f.conv3(xn, v->conv_out, nullptr, o, opitch);
+  if (f.err) return f.err;
+  const size_t n = (size_t)B * v->out_ch * x.H * x.W;
+  nhwc_to_nchw_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(o.p, (__half*)out, B, v->out_ch, x.H * x.W, opitch);
+  DG_LAUNCH_CHECK();
+  return DG_OK;
 }
 
 }  // extern "C"

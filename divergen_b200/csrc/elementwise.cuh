@@ -485,4 +485,77 @@ __global__ void pack_geglu_kernel(const __half* __restrict__ w, __half* __restri
   }
 }
 
+// ------------------------------------------------------------------ VAE decoder helpers
+// post_quant_conv: 1x1 conv over the latent channels (C <= 8) on NCHW fp16, with the 1/scaling_factor of
+// `vae.decode(latents / scaling_factor)` folded in.  out[b,co,p] = bias[co] + sum_ci W[co,ci] * (z[b,ci,p] * scale).
+__global__ void latent_pointwise_kernel(const __half* __restrict__ z, const __half* __restrict__ W, const __half* __restrict__ bias,
+                                        __half* __restrict__ out, int B, int C, int HW, float scale) {
+  const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= (size_t)B * HW) return;
+  const int b = i / HW, p = i % HW;
+  float v[8];
+  for (int c = 0; c < C; ++c) v[c] = __half2float(z[((size_t)b * C + c) * HW + p]) * scale;
+  for (int co = 0; co < C; ++co) {
+    float a = __half2float(bias[co]);
+    for (int ci = 0; ci < C; ++ci) a = fmaf(__half2float(W[co * C + ci]), v[ci], a);
+    out[((size_t)b * C + co) * HW + p] = __float2half_rn(a);
+  }
+}
+
+// Row softmax of an fp16 score matrix in place: P[r, :] = softmax(S[r, :] * scale), fp32 math, one CTA per row
+// (the single-head, full-width attention of the VAE mid block; rows of 4096 scores at 512 x 512 output).
+__global__ void softmax_rows_kernel(__half* __restrict__ S, int n, float scale_log2) {
+  __shared__ float red[32];
+  __half* row = S + (size_t)blockIdx.x * n;
+  float mx = -INFINITY;
+  for (int i = threadIdx.x * 8; i < n; i += blockDim.x * 8) {
+    float f[8];
+    load8(row + i, f);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) mx = fmaxf(mx, f[k]);
+  }
+  for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+  __syncthreads();
+  mx = red[0];
+  for (int w = 1; w < (int)(blockDim.x >> 5); ++w) mx = fmaxf(mx, red[w]);
+  __syncthreads();
+  const float m = mx * scale_log2;
+  float sum = 0.f;
+  for (int i = threadIdx.x * 8; i < n; i += blockDim.x * 8) {
+    float f[8];
+    load8(row + i, f);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) sum += exp2f(fmaf(f[k], scale_log2, -m));
+  }
+  for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = sum;
+  __syncthreads();
+  sum = 0.f;
+  for (int w = 0; w < (int)(blockDim.x >> 5); ++w) sum += red[w];
+  const float inv = 1.0f / sum;
+  for (int i = threadIdx.x * 8; i < n; i += blockDim.x * 8) {
+    float f[8];
+    load8(row + i, f);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) f[k] = exp2f(fmaf(f[k], scale_log2, -m)) * inv;
+    store8(row + i, f);
+  }
+}
+
+// [rows, C] -> [C, rows] fp16 (V^T as the K-major "weight" operand of the P*V GEMM), 32x32 tiles through shared memory.
+__global__ void transpose_rows_kernel(const __half* __restrict__ in, __half* __restrict__ out, int rows, int C) {
+  __shared__ __half tile[32][33];
+  const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int r = r0 + i, c = c0 + threadIdx.x;
+    tile[i][threadIdx.x] = (r < rows && c < C) ? in[(size_t)r * C + c] : __float2half_rn(0.f);
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i, r = r0 + threadIdx.x;
+    if (c < C && r < rows) out[(size_t)c * rows + r] = tile[threadIdx.x][i];
+  }
+}
+
 }  // namespace dg

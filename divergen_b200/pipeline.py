@@ -3,8 +3,8 @@ num_images_per_prompt=, num_inference_steps=, guidance_scale=).images` as called
 (DiverGen/generation/txt2img_diffusers_stages_from_txt.py:242,255-259), semantics per SURVEY.md 3.2.
 
 In scope: latent preparation, the 50-step UNet + CFG + DDIM loop (one C-ABI call, CUDA-graph replayed).
-Out of scope this round ("next" rows f1/f2): VAE decode and the CLIP text encoder -- `output_type='latent'` is the
-native output; other output types need a `vae_decode` callable supplied by the caller and otherwise raise.
+Row f1 (VAE decode): pass `vae=AutoencoderKL(...)` (divergen_b200.vae, `dg_vae_decode`) or any `vae_decode` callable;
+without either only `output_type='latent'` is available.  The CLIP text encoder (row f2) stays a caller-supplied callable.
 """
 from __future__ import annotations
 
@@ -34,9 +34,10 @@ def pt_to_pil(images: torch.Tensor):
 class StableDiffusionPipeline:
     def __init__(self, unet: UNet2DConditionModel, scheduler: DDIMScheduler,
                  text_encoder: Optional[Callable] = None, vae_decode: Optional[Callable] = None,
-                 vae_scale_factor: int = 8):
+                 vae_scale_factor: int = 8, vae=None):
         self.unet, self.scheduler = unet, scheduler
         self.text_encoder, self.vae_decode = text_encoder, vae_decode
+        self.vae = vae
         self.vae_scale_factor = vae_scale_factor
         self.device = unet.device
         self.feature_extractor = None
@@ -108,9 +109,13 @@ class StableDiffusionPipeline:
         if output_type == "latent":
             images = latents
         else:
-            if self.vae_decode is None:
-                raise ValueError("output_type != 'latent' needs a vae_decode callable (VAE decode is row f1, next)")
-            images = self.vae_decode(latents / 0.18215)
+            if self.vae is not None:
+                # image = vae.decode(latents / vae.config.scaling_factor).sample, the division folded into the first kernel
+                images = self.vae.decode(latents, scale=1.0 / self.vae.config.scaling_factor).sample
+            elif self.vae_decode is not None:
+                images = self.vae_decode(latents / 0.18215)
+            else:
+                raise ValueError("output_type != 'latent' needs `vae=` (divergen_b200.AutoencoderKL) or a vae_decode callable")
             if output_type == "pt":
                 images = (images / 2 + 0.5).clamp(0, 1)
             elif output_type == "pil":

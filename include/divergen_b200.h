@@ -107,6 +107,23 @@ int32_t dg_denoise_loop(dg_unet* unet, void* latents, const void* ehs, int32_t c
                         int32_t w, const float* timesteps_host, const float* alpha_t_host, const float* alpha_prev_host,
                         int32_t n_steps, float guidance_scale, int32_t prediction_type, void* stream);
 
+/* ---- AutoencoderKL.decode (StableDiffusionPipeline.__call__ step 8: `vae.decode(latents / scaling_factor).sample`) ----
+ * The step between the denoising loop and `pt_to_pil(image)[j].save(...)` (txt2img_...py:267).  Weights by diffusers
+ * state-dict key (`post_quant_conv.*`, `decoder.*`; 140 tensors for the SD VAE).  block_out_channels: 4 ints or NULL for
+ * the SD config (128, 256, 512, 512); layers_per_block <= 0 -> 2.
+ * dg_vae_decode: latents [B, 4, h, w] fp16 NCHW are multiplied by `scale` (pass 1 / scaling_factor, or 1 if the caller has
+ * already divided); out [B, 3, 8h, 8w] fp16 NCHW in roughly [-1, 1]. */
+typedef struct dg_vae dg_vae;
+int32_t dg_vae_create(dg_ctx* ctx, const int32_t* block_out_channels, int32_t layers_per_block, dg_vae** out);
+void dg_vae_destroy(dg_vae* vae);
+int32_t dg_vae_num_weights(dg_vae* vae);
+const char* dg_vae_weight_name(dg_vae* vae, int32_t index);
+int32_t dg_vae_weight_shape(dg_vae* vae, int32_t index, int64_t* shape4, int32_t* ndim);
+int32_t dg_vae_set_weight(dg_vae* vae, const char* key, const void* src, int32_t ndim, const int64_t* shape);
+int32_t dg_vae_prepare(dg_vae* vae, int32_t max_batch, int32_t h, int32_t w);
+int32_t dg_vae_decode(dg_vae* vae, const void* latents, float scale, void* out, int32_t batch, int32_t h, int32_t w,
+                      void* stream);
+
 /* ---- single operators (exported for the parity tests; the same launchers the UNet uses) ---------------------------
  * dg_op_gemm: out[M, n_out] = epi(A[M, K] * W[n_w, K]^T)      <- torch.nn.Linear / Conv2d 1x1
  *    bias [n_w] / residual [M, n_out] optional; geglu: W is GEGLU-packed (see dg_op_pack_geglu), n_out = inner dim.

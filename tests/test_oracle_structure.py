@@ -55,3 +55,31 @@ def test_config1_plumbing_cpu():
     out = denoise_loop(m, DDIMOracle(), lat, pos, neg, num_inference_steps=50, guidance_scale=7.5, max_steps=1)
     assert out.shape == lat.shape and torch.isfinite(out).all()
     assert not torch.allclose(out, lat)
+
+
+def test_vae_decoder_param_count_and_keys():
+    """SD-1.x/2.x `vae/` checkpoint, decoder side (post_quant_conv + decoder): 49 490 199 parameters in 140 tensors."""
+    from oracle.vae_oracle import VAEConfig, VAEDecoderOracle
+    with torch.device("meta"):
+        m = VAEDecoderOracle(VAEConfig.sd())
+    assert sum(p.numel() for p in m.parameters()) == 49_490_199
+    sd = m.state_dict()
+    assert len(sd) == 140
+    for k in ("post_quant_conv.weight", "decoder.conv_in.weight", "decoder.mid_block.attentions.0.to_q.weight",
+              "decoder.mid_block.attentions.0.to_out.0.bias", "decoder.mid_block.resnets.1.conv2.weight",
+              "decoder.up_blocks.0.upsamplers.0.conv.weight", "decoder.up_blocks.2.resnets.0.conv_shortcut.weight",
+              "decoder.up_blocks.3.resnets.2.norm2.bias", "decoder.conv_norm_out.weight", "decoder.conv_out.bias"):
+        assert k in sd, k
+    assert tuple(sd["decoder.up_blocks.2.resnets.0.conv1.weight"].shape) == (256, 512, 3, 3)
+    assert tuple(sd["decoder.up_blocks.3.resnets.0.conv1.weight"].shape) == (128, 256, 3, 3)
+    assert "decoder.up_blocks.3.upsamplers.0.conv.weight" not in sd
+
+
+def test_vae_decoder_tiny_cpu():
+    from oracle.vae_oracle import VAEConfig, VAEDecoderOracle, seeded_vae_state_dict
+    cfg = VAEConfig.tiny()
+    m = VAEDecoderOracle(cfg).eval()
+    m.load_state_dict(seeded_vae_state_dict(cfg, 0))
+    with torch.no_grad():
+        y = m(torch.randn(2, 4, 8, 8, generator=torch.Generator().manual_seed(1)))
+    assert y.shape == (2, 3, 64, 64) and torch.isfinite(y).all()
