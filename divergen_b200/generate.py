@@ -10,9 +10,10 @@ Differences, all deliberate: the stage is Stable Diffusion (`sd`, the pool the d
 DeepFloyd-IF cascade; text embeddings are encoded ONCE on rank 0 for the whole prompt set and broadcast (the path's only
 data-carrying collective) instead of per micro-batch on every rank; micro-batches default to 4 images per pipeline call.
 
-Host-side only: every tensor operation is a C-ABI call (StableDiffusionPipeline -> dg_denoise_loop).  VAE decode / CLIP
-are "next" rows: without `--vae_decode` latents are written as `<cid>_<count:07d>.latent.pt` next to where
-the PNG would go, under the same index contract.
+Host-side only: every tensor operation is a C-ABI call (StableDiffusionPipeline -> dg_denoise_loop, AutoencoderKL ->
+dg_vae_decode).  With a VAE (`<ckpt_dir>/vae/*.safetensors`, or `--random_init --decode`) PNGs are written exactly where
+the reference writes them; without one, latents go to `<cid>_<count:07d>.latent.pt` under the same index contract.  The
+CLIP text encoder is the remaining "next" row: embeddings are synthetic unless supplied.
 """
 from __future__ import annotations
 
@@ -159,13 +160,40 @@ def build_parser() -> argparse.ArgumentParser:
     p.add_argument("--num_inference_steps", type=int, default=50)
     p.add_argument("--guidance_scale", type=float, default=7.5)
     p.add_argument("--random_init", action="store_true", help="random-init UNet weights (benchmarks; no checkpoint offline)")
+    p.add_argument("--decode", action="store_true", help="with --random_init: also build a random-init VAE and write PNGs")
     p.add_argument("--max_prompt_files", type=int, default=0, help="process only the first N category files (0 = all)")
     return p
 
 
+def random_state_dict(model, device, seed: int = 0):
+    """Random-init weights with the checkpoint's shapes and sane scales (no checkpoint is reachable offline)."""
+    import torch
+    g = torch.Generator(device=device).manual_seed(seed)
+    sd = {}
+    for k, shp in model.expected_state_dict_shapes().items():
+        fan_in = 1
+        for d in shp[1:]:
+            fan_in *= d
+        if "norm" in k and k.endswith("weight"):
+            sd[k] = torch.ones(shp, device=device).half()
+        elif k.endswith("bias"):
+            sd[k] = torch.zeros(shp, device=device).half()
+        else:
+            sd[k] = (torch.randn(shp, generator=g, device=device) / max(1.0, fan_in) ** 0.5).half()
+    return sd
+
+
+def _first_existing(directory: str, names: Sequence[str]) -> Optional[str]:
+    for n in names:
+        if os.path.exists(os.path.join(directory, n)):
+            return os.path.join(directory, n)
+    return None
+
+
 def main(argv: Optional[Sequence[str]] = None) -> int:
     import torch
-    from . import DDIMScheduler, SD15_CONFIG, SD21_CONFIG, StableDiffusionPipeline, UNet2DConditionModel
+    from . import (AutoencoderKL, DDIMScheduler, SD15_CONFIG, SD21_CONFIG, StableDiffusionPipeline,
+                   UNet2DConditionModel, pt_to_pil)
 
     args = build_parser().parse_args(argv)
     if args.dist:
@@ -190,23 +218,22 @@ def main(argv: Optional[Sequence[str]] = None) -> int:
         from safetensors.torch import load_file
         unet.load_state_dict(load_file(st_path))
     elif args.random_init:
-        g = torch.Generator(device=device).manual_seed(0)
-        sd = {}
-        for k, shp in unet.expected_state_dict_shapes().items():
-            fan_in = 1
-            for d in shp[1:]:
-                fan_in *= d
-            if "norm" in k and k.endswith("weight"):
-                sd[k] = torch.ones(shp, device=device).half()
-            elif k.endswith("bias"):
-                sd[k] = torch.zeros(shp, device=device).half()
-            else:
-                sd[k] = (torch.randn(shp, generator=g, device=device) / max(1.0, fan_in) ** 0.5).half()
-        unet.load_state_dict(sd)
+        unet.load_state_dict(random_state_dict(unet, device))
     else:
         raise FileNotFoundError("{} not found (use --random_init for benchmarks)".format(st_path))
     sched = DDIMScheduler(prediction_type="v_prediction" if args.model == "sd21" else "epsilon")
-    pipe = StableDiffusionPipeline(unet, sched)
+    vae = None
+    vae_path = _first_existing(os.path.join(args.ckpt_dir, "vae"), ("diffusion_pytorch_model.fp16.safetensors",
+                                                                     "diffusion_pytorch_model.safetensors"))
+    if vae_path and not args.random_init:
+        from safetensors.torch import load_file
+        vae = AutoencoderKL(device=device)
+        vae.load_state_dict(load_file(vae_path))
+    elif args.random_init and args.decode:
+        vae = AutoencoderKL(device=device)
+        vae.load_state_dict(random_state_dict(vae, device, seed=1))
+    ext = "png" if vae is not None else "latent.pt"
+    pipe = StableDiffusionPipeline(unet, sched, vae=vae)
     pipe.enable_model_cpu_offload(local_rank)                                    # no-ops kept for call parity (:143,186)
 
     generator = torch.manual_seed(args.seed + rank)                             # reference :200 (global CPU generator)
@@ -225,22 +252,29 @@ def main(argv: Optional[Sequence[str]] = None) -> int:
         cid = category_id_of(path)
         print("==> Reading prompts from {}, {}/{}".format(path, fi + 1, len(per_file)))
         for call in iter_calls(lines, plan, rank, args.n_samples, args.offset):
-            last = os.path.join(sample_dir, output_name(cid, call.counts[-1], "latent.pt"))
+            last = os.path.join(sample_dir, output_name(cid, call.counts[-1], ext))
             if args.disable_overwrite and os.path.exists(last):
                 print("==> Skipping stage {} for {}...".format(stage, os.path.basename(last)))
                 continue
             pos = table[row[call.prompt]][None]
             neg = table[0][None]
-            out = pipe(prompt_embeds=pos, negative_prompt_embeds=neg, generator=generator, output_type="latent",
+            out = pipe(prompt_embeds=pos, negative_prompt_embeds=neg, generator=generator,
+                       output_type="pt" if vae is not None else "latent",
                        num_images_per_prompt=call.num_images, num_inference_steps=args.num_inference_steps,
                        guidance_scale=args.guidance_scale).images
+            if vae is not None:
+                out = pt_to_pil(out * 2 - 1)                                      # reference :267 (pt -> PIL -> .save)
             for j, count in enumerate(call.counts):
-                torch.save(out[j].cpu(), os.path.join(sample_dir, output_name(cid, count, "latent.pt")))
+                dst = os.path.join(sample_dir, output_name(cid, count, ext))
+                if vae is not None:
+                    out[j].save(dst)
+                else:
+                    torch.save(out[j].cpu(), dst)
             n_done += call.num_images
     if args.dist:
         torch.distributed.barrier()
         torch.distributed.destroy_process_group()
-    print("rank {} wrote {} latents under {}".format(rank, n_done, sample_dir))
+    print("rank {} wrote {} outputs under {}".format(rank, n_done, sample_dir))
     return 0
 
 

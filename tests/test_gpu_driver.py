@@ -25,3 +25,18 @@ def test_driver_writes_reference_index_layout(tmp_path):
     mtimes = {f: os.path.getmtime(tmp_path / "samples" / "sd" / f) for f in got}
     assert main(argv) == 0                                            # second run: everything exists -> skipped
     assert mtimes == {f: os.path.getmtime(tmp_path / "samples" / "sd" / f) for f in got}
+
+
+def test_driver_writes_pngs_with_vae(tmp_path):
+    """With a VAE attached the driver writes `<category_id>_<index:07d>.png`, 512x512 RGB (reference :262-267)."""
+    if not torch.cuda.is_available():
+        pytest.skip("no GPU")
+    from PIL import Image
+    from divergen_b200.generate import main
+    argv = ["--from_file", os.path.join(HERE, "fixtures", "prompts", "1.txt"), "--outdir", str(tmp_path), "--n_samples", "2",
+            "--max_batch_size", "2", "--random_init", "--decode", "--num_inference_steps", "2", "--offset", "0"]
+    assert main(argv) == 0
+    got = sorted(os.listdir(tmp_path / "samples" / "sd"))
+    assert got == ["1_0000000.png", "1_0000001.png"]
+    im = Image.open(tmp_path / "samples" / "sd" / got[0])
+    assert im.size == (512, 512) and im.mode == "RGB"
