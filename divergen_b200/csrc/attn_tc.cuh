@@ -5,6 +5,9 @@
 //   S_q   = Q_q K_j^T           tcgen05.mma SS (both operands K-major, 128-byte swizzle)      -> TMEM fp32
 //   P_q   = exp2(S_q*c - m)     softmax warps: tcgen05.ld -> registers -> fp16 pairs -> tcgen05.st (P aliases S)
 //   O_q  += P_q V_j             tcgen05.mma TS (A = P from TMEM, B = V tile, MN-major)        -> TMEM fp32
+// With kSBuf = 2 every query tile owns TWO score buffers: S_q(j+2) is issued right after P_q(j) V_j, so the scores of the
+// next key tile are already in TMEM when the softmax group finishes the current one -- the softmax groups (MUFU / issue
+// bound) run back to back and the tensor pipe works in their shadow instead of in series with them.
 // Online softmax keeps a (lazily updated) running max; O is rescaled in TMEM only when the max grows by > 2^8.
 // The S x S score matrix never exists in HBM.  Head dims that are not multiples of 64 (SD-1.5: 40/80/160) are
 // zero-padded by TMA out-of-bounds fill, keys beyond Sk (cross-attention: 77) are masked to -inf.
@@ -17,6 +20,26 @@
 
 namespace dg {
 
+// fp32 -> fp16 conversion of the softmax weights WITHOUT the conversion instruction: F2FP shares the 16-lane XU pipe with
+// MUFU.EX2, and together they are this kernel's roofline (measured: XU 77 % busy, 149 XU instructions per 128 keys per
+// row-warp, 64 of them conversions).  The weights are produced pre-scaled by 2^-kPShift = 2^-(112 - 9):
+//   v = 2^(x - m - kPShift)  has the fp32 exponent field of an fp16 number  =>  fp16 bits of P' = 2^9 * P are bits(v) >> 13.
+// P' <= 2^9 * 2^6 (lazy-max slack) = 2^15 stays finite in fp16; v < 2^-126 (P < 2^-23, the fp16 subnormal floor of the
+// unscaled weights) is flushed to zero by ex2.ftz.  Truncation instead of round-to-nearest biases every weight by
+// E[-2^-11 / mantissa] = -3.52e-4 relative; the row sum l is taken over the unrounded v, so 1/l is corrected by that factor.
+// Measured (round 1): 8 % SLOWER than F2FP with 8 softmax warps per SM (the three extra ALU instructions per pair cost
+// more issue slots than the XU time they free), so it is off; kept for the 16-softmax-warp variant's A/B.
+#ifndef DG_ATTN_BITPACK
+#define DG_ATTN_BITPACK 0
+#endif
+constexpr bool kBitPackP = DG_ATTN_BITPACK != 0;
+constexpr float kPShift = kBitPackP ? 103.0f : 0.0f;
+constexpr float kLazyMax = kBitPackP ? 6.0f : 8.0f;
+__device__ __forceinline__ uint32_t pack_p_bits(float v0, float v1) {
+  if constexpr (kBitPackP) return (__float_as_uint(v0) >> 13) | ((__float_as_uint(v1) << 3) & 0xFFFF0000u);
+  else return cvt_pack_half2(v0, v1);
+}
+
 struct AttnParams {
   int Sq, Sk;        // query / key tokens per sample
   int heads;
@@ -25,7 +48,7 @@ struct AttnParams {
   __half* out;       // [B, Sq, heads*d]
 };
 
-template <int kD, int kKV, int kStages>
+template <int kD, int kKV, int kStages, int kSBuf = 1, int kQ = 2>
 struct AttnCfg {
   static constexpr int kChunks = (kD + 63) / 64;        // 64-wide (128 B) head-dim chunks
   static constexpr int kDPad = (kD + 15) / 16 * 16;     // MMA-K of QK^T and MMA-N of PV
@@ -33,36 +56,38 @@ struct AttnCfg {
   static constexpr int kKVChunkBytes = kKV * 128;
   static constexpr int kKTileBytes = kChunks * kKVChunkBytes;
   static constexpr int kStageBytes = 2 * kKTileBytes;   // K then V
-  static constexpr int kSmem = 2 * kQTileBytes + kStages * kStageBytes + 1024 + 256;
+  static constexpr int kSmem = kQ * kQTileBytes + kStages * kStageBytes + 1024 + 512;
+  static constexpr int kThreads = 128 + kQ * 128;       // producer / MMA / TMEM / spare warp + one 4-warp softmax group per query tile
   // TMEM columns
-  static constexpr int kS0 = 0, kS1 = kKV;
-  static constexpr int kO0 = 2 * kKV;
-  static constexpr int kOStride = (kDPad <= 128) ? 128 : 192;
-  static constexpr int kO1 = kO0 + kOStride;
-  static_assert(kO1 + kDPad <= 512, "TMEM budget");
+  static constexpr int kSStride = kSBuf * kKV;          // score buffer b of query tile q: q * kSStride + b * kKV
+  static constexpr int kO0 = kQ * kSStride;
+  static constexpr int kOStride = (kQ > 2 && kDPad <= 64) ? 64 : (kDPad <= 128) ? 128 : 192;
+  static_assert(kO0 + (kQ - 1) * kOStride + kDPad <= 512, "TMEM budget");
+  static_assert(kStages > kSBuf, "the K tile of S(j + kSBuf) and the V tile of PV(j) are live together");
 };
 
-template <int kD, int kKV, int kStages, int kPoly>   // kPoly: every kPoly-th pair of softmax elements takes the polynomial exp2 (0 = none)
-__global__ void __launch_bounds__(384, 1)
+template <int kD, int kKV, int kStages, int kPoly, int kSBuf, int kQ>   // kPoly: every kPoly-th pair of softmax elements takes the polynomial exp2 (0 = none)
+__global__ void __launch_bounds__(128 + kQ * 128, 1)
 attn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
                const __grid_constant__ CUtensorMap mapV, const AttnParams p) {
-  using C = AttnCfg<kD, kKV, kStages>;
+  using C = AttnCfg<kD, kKV, kStages, kSBuf, kQ>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem;
-  uint8_t* sKV = smem + 2 * C::kQTileBytes;
+  uint8_t* sKV = smem + kQ * C::kQTileBytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sKV + kStages * C::kStageBytes);
   uint64_t* q_full = bars;                 // [1]
   uint64_t* kv_full = bars + 1;            // [kStages]
   uint64_t* kv_empty = kv_full + kStages;  // [kStages]
-  uint64_t* s_full = kv_empty + kStages;   // [2]
-  uint64_t* p_full = s_full + 2;           // [2]
-  uint64_t* o_done = p_full + 2;           // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_done + 2);
+  uint64_t* s_full = kv_empty + kStages;   // [kQ][kSBuf]
+  uint64_t* p_full = s_full + kQ * kSBuf;  // [kQ][kSBuf]  (a softmax warp may run one key tile ahead of its group: per-buffer barriers)
+  uint64_t* o_done = p_full + kQ * kSBuf;  // [kQ]  last PV of the tile
+  uint64_t* pv_done = o_done + kQ;         // [kQ]  every PV (the rare O rescale must not race the accumulate in flight)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + kQ);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int q_row0 = blockIdx.x * 256;
+  const int q_row0 = blockIdx.x * (kQ * 128);
   const int head = blockIdx.y;
   const int batch = blockIdx.z;
   const int nkv = (p.Sk + kKV - 1) / kKV;
@@ -73,7 +98,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
   if (warp == 1 && lane == 0) {
     mbar_init(q_full, 1);
     for (int i = 0; i < kStages; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 128); mbar_init(&o_done[i], 1); }
+    for (int i = 0; i < kQ * kSBuf; ++i) { mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 128); }
+    for (int i = 0; i < kQ; ++i) { mbar_init(&o_done[i], 1); mbar_init(&pv_done[i], 1); }
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc<512>(tmem_slot);
@@ -87,13 +113,13 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (elect_one()) {
-      mbar_arrive_expect_tx(q_full, 2 * C::kQTileBytes);
-      for (int q = 0; q < 2; ++q)
+      mbar_arrive_expect_tx(q_full, kQ * C::kQTileBytes);
+      for (int q = 0; q < kQ; ++q)
         for (int c = 0; c < C::kChunks; ++c)
           tma_load_4d(sQ + q * C::kQTileBytes + c * (128 * 128), &mapQ, q_full, c * 64, head, q_row0 + q * 128, batch);
       int stage = 0; uint32_t phase = 0;
       for (int j = 0; j < nkv; ++j) {
-        mbar_wait(&kv_empty[stage], phase ^ 1);
+        mbar_wait_parked(&kv_empty[stage], phase ^ 1);
         uint8_t* sk = sKV + stage * C::kStageBytes;
         uint8_t* sv = sk + C::kKTileBytes;
         mbar_arrive_expect_tx(&kv_full[stage], C::kStageBytes);
@@ -108,55 +134,61 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
     // ===================== MMA issuer =====================
     constexpr uint32_t idesc_s = make_idesc_f16(kKV, false);
     constexpr uint32_t idesc_o = make_idesc_f16(C::kDPad, true);
-    const uint32_t tS[2] = {tmem_base + C::kS0, tmem_base + C::kS1};
-    const uint32_t tO[2] = {tmem_base + C::kO0, tmem_base + C::kO1};
     const uint32_t sq_addr = smem_u32(sQ);
 
-    auto issue_S = [&](int q, uint32_t sk_addr) {
+    auto issue_S = [&](int q, int b, uint32_t sk_addr) {
 #pragma unroll
       for (int s = 0; s < C::kDPad / 16; ++s) {
         const int c = s >> 2, k = s & 3;
         const uint64_t da = make_smem_desc_sw128(sq_addr + q * C::kQTileBytes + c * (128 * 128) + k * 32, 16, 1024);
         const uint64_t db = make_smem_desc_sw128(sk_addr + c * C::kKVChunkBytes + k * 32, 16, 1024);
-        umma_ss(tS[q], da, db, idesc_s, s ? 1u : 0u);
+        umma_ss(tmem_base + q * C::kSStride + b * kKV, da, db, idesc_s, s ? 1u : 0u);
       }
-      umma_commit(&s_full[q]);
+      umma_commit(&s_full[q * kSBuf + b]);
     };
-    auto issue_PV = [&](int q, uint32_t sv_addr, bool accum) {
+    auto issue_PV = [&](int q, int b, uint32_t sv_addr, bool accum) {
 #pragma unroll
       for (int s = 0; s < kKV / 16; ++s) {
         // V tile: [keys][64-wide d chunk] rows of 128 B => MN-major; 16 keys = 2048 B along K.
         const uint64_t db = make_smem_desc_sw128(sv_addr + s * 2048, C::kKVChunkBytes, 1024);
-        umma_ts(tO[q], tS[q] + s * 8, db, idesc_o, (accum || s) ? 1u : 0u);
+        umma_ts(tmem_base + C::kO0 + q * C::kOStride, tmem_base + q * C::kSStride + b * kKV + s * 8, db, idesc_o, (accum || s) ? 1u : 0u);
       }
     };
 
-    mbar_wait(q_full, 0);
-    int stage = 0; uint32_t phase = 0;
-    // prologue: S_0(0), S_1(0)
-    mbar_wait(&kv_full[0], 0);
-    tc_fence_after();
-    if (elect_one()) { issue_S(0, smem_u32(sKV)); issue_S(1, smem_u32(sKV)); }
-    __syncwarp();
+    mbar_wait_parked(q_full, 0);
+    // prologue: S_q(t) for the first kSBuf key tiles
+    int kstage = 0; uint32_t kphase = 0;     // ring position of key tile `kt`, the next one whose scores get issued
+    int kt = 0;
+    for (; kt < kSBuf && kt < nkv; ++kt) {
+      mbar_wait_parked(&kv_full[kstage], kphase);
+      tc_fence_after();
+      if (elect_one()) {
+        for (int q = 0; q < kQ; ++q) issue_S(q, kt, smem_u32(sKV + kstage * C::kStageBytes));
+      }
+      __syncwarp();
+      if (++kstage == kStages) { kstage = 0; kphase ^= 1; }
+    }
+    int stage = 0;                           // ring position of key tile j (its V half)
     for (int j = 0; j < nkv; ++j) {
       const uint32_t sv_addr = smem_u32(sKV + stage * C::kStageBytes + C::kKTileBytes);
-      int nstage = stage + 1; uint32_t nphase = phase;
-      if (nstage == kStages) { nstage = 0; nphase ^= 1; }
-      const bool has_next = (j + 1 < nkv);
-      if (has_next) mbar_wait(&kv_full[nstage], nphase);
-      const uint32_t sk_next = smem_u32(sKV + nstage * C::kStageBytes);
-      for (int q = 0; q < 2; ++q) {
-        mbar_wait(&p_full[q], j & 1);
+      const bool has_next = (kt < nkv);      // key tile j + kSBuf exists
+      if (has_next) { mbar_wait_parked(&kv_full[kstage], kphase); }
+      const uint32_t sk_next = smem_u32(sKV + kstage * C::kStageBytes);
+      const int b = j % kSBuf;
+      const bool last = (j + 1 == nkv);
+      for (int q = 0; q < kQ; ++q) {
+        mbar_wait_parked(&p_full[q * kSBuf + b], (j / kSBuf) & 1);
         tc_fence_after();
         if (elect_one()) {
-          issue_PV(q, sv_addr, j > 0);
-          if (!has_next) umma_commit(&o_done[q]);
-          if (has_next) issue_S(q, sk_next);
-          if (q == 1) umma_commit(&kv_empty[stage]);
+          issue_PV(q, b, sv_addr, j > 0);
+          umma_commit(last ? &o_done[q] : &pv_done[q]);
+          if (has_next) issue_S(q, b, sk_next);
+          if (q == kQ - 1) umma_commit(&kv_empty[stage]);
         }
         __syncwarp();
       }
-      stage = nstage; phase = nphase;
+      if (has_next) { ++kt; if (++kstage == kStages) { kstage = 0; kphase ^= 1; } }
+      if (++stage == kStages) stage = 0;
     }
   } else if (warp >= 4) {
     // ===================== softmax / correction / epilogue =====================
@@ -164,12 +196,16 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
     const int quad = warp & 3;           // TMEM lane quadrant
     const int row = quad * 32 + lane;    // row within the 128-row tile
     const uint32_t lane_off = (uint32_t)(quad * 32) << 16;
-    const uint32_t tS = tmem_base + (q ? C::kS1 : C::kS0) + lane_off;
-    const uint32_t tO = tmem_base + (q ? C::kO1 : C::kO0) + lane_off;
+    const uint32_t tS_q = tmem_base + (uint32_t)(q * C::kSStride) + lane_off;
+    const uint32_t tO = tmem_base + (uint32_t)(C::kO0 + q * C::kOStride) + lane_off;
+    // with 2 softmax groups per SM the TMEM loads are software-pipelined one 32-column chunk ahead of the math; with 4
+    // groups (16 warps, <= 96 registers) the other warps of the scheduler hide that latency instead
+    constexpr bool kPre = kQ <= 2;
     float m_run = -INFINITY;  // running max (log2 domain, already scaled)
     float l_run = 0.f;
     for (int j = 0; j < nkv; ++j) {
-      mbar_wait(&s_full[q], j & 1);
+      const uint32_t tS = tS_q + (uint32_t)((j % kSBuf) * kKV);
+      mbar_wait(&s_full[q * kSBuf + j % kSBuf], (j / kSBuf) & 1);
       tc_fence_after();
       const int kv_valid = min(kKV, p.Sk - j * kKV);
       const bool full_tile = kv_valid == kKV;
@@ -177,13 +213,13 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
       // (TMEM loads are software-pipelined one 32-column chunk ahead of the math in both passes: the single warp that owns
       // these rows would otherwise expose the tcgen05.ld latency eight times per tile)
       float mx = -INFINITY, mx_b = -INFINITY;
-      uint32_t vv[2][32];
-      tmem_ld32(tS, vv[0]);
-      tmem_ld_wait();
+      uint32_t vv[kPre ? 2 : 1][32];
+      if (kPre) { tmem_ld32(tS, vv[0]); tmem_ld_wait(); }
 #pragma unroll
       for (int c = 0; c < kKV; c += 32) {
-        uint32_t* v = vv[(c >> 5) & 1];
-        if (c + 32 < kKV) tmem_ld32(tS + c + 32, vv[((c >> 5) + 1) & 1]);
+        uint32_t* v = vv[kPre ? (c >> 5) & 1 : 0];
+        if (!kPre) { tmem_ld32(tS + c, v); tmem_ld_wait(); }
+        if (kPre && c + 32 < kKV) tmem_ld32(tS + c + 32, vv[kPre ? ((c >> 5) + 1) & 1 : 0]);
         if (full_tile) {
 #pragma unroll
           for (int i = 0; i < 32; i += 4) {
@@ -198,7 +234,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
             mx = fmaxf(mx, s);
           }
         }
-        if (c + 32 < kKV) tmem_ld_wait();
+        if (kPre && c + 32 < kKV) tmem_ld_wait();
       }
       mx = fmaxf(mx, mx_b);
       const float m_tile = mx * p.scale_log2;
@@ -207,8 +243,10 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
       } else {
         // lazy rescale: only when the max grew enough to threaten the fp16 range of P.  tcgen05.ld/st are warp-wide
         // (.sync.aligned), so the decision is made per warp and rows that do not need it scale by exactly 1.
-        const bool need = m_tile > m_run + 8.0f;
+        const bool need = m_tile > m_run + kLazyMax;
         if (__any_sync(0xffffffffu, need)) {
+          // S(j) was issued before PV(j-1): wait for that accumulate to land before touching O
+          if (kSBuf > 1) { mbar_wait(&pv_done[q], (j - 1) & 1); tc_fence_after(); }
           const float alpha = need ? exp2f(m_run - m_tile) : 1.0f;
           if (need) { m_run = m_tile; l_run *= alpha; }
 #pragma unroll
@@ -227,16 +265,16 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
       float lsum = 0.f;
       if (full_tile) {
         const uint64_t sc2 = pack_f32x2(p.scale_log2, p.scale_log2);
-        const uint64_t nm2 = pack_f32x2(-m_run, -m_run);
+        const uint64_t nm2 = pack_f32x2(-(m_run + kPShift), -(m_run + kPShift));
         uint64_t sum2 = pack_f32x2(0.f, 0.f);
-        tmem_ld32(tS, vv[0]);
-        tmem_ld_wait();
+        if (kPre) { tmem_ld32(tS, vv[0]); tmem_ld_wait(); }
 #pragma unroll
         for (int c = 0; c < kKV; c += 32) {
-          uint32_t* v = vv[(c >> 5) & 1];
+          uint32_t* v = vv[kPre ? (c >> 5) & 1 : 0];
+          if (!kPre) { tmem_ld32(tS + c, v); tmem_ld_wait(); }
           // the next chunk's load must not overtake this chunk's store into the same TMEM columns: P (fp16 pairs) of chunk c
           // lands in columns [c/2, c/2+16), which chunk c+32 (columns [c+32, c+64)) never overlaps for c >= 0
-          if (c + 32 < kKV) tmem_ld32(tS + c + 32, vv[((c >> 5) + 1) & 1]);
+          if (kPre && c + 32 < kKV) tmem_ld32(tS + c + 32, vv[kPre ? ((c >> 5) + 1) & 1 : 0]);
           uint32_t pk[16];
 #pragma unroll
           for (int i = 0; i < 32; i += 2) {
@@ -264,10 +302,10 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
             } else {
               p0 = fast_exp2(x0); p1 = fast_exp2(x1);
             }
-            pk[i >> 1] = cvt_pack_half2(p0, p1);
+            pk[i >> 1] = pack_p_bits(p0, p1);
             sum2 = add_f32x2(sum2, pack_f32x2(p0, p1));
           }
-          if (c + 32 < kKV) tmem_ld_wait();     // chunk c+32 is in registers before P(c) overwrites columns it might share
+          if (kPre && c + 32 < kKV) tmem_ld_wait();     // chunk c+32 is in registers before P(c) overwrites columns it might share
           tmem_st16(tS + (c >> 1), pk);
         }
         float s0, s1;
@@ -282,9 +320,9 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
           uint32_t pk[16];
 #pragma unroll
           for (int i = 0; i < 32; i += 2) {
-            const float p0 = (c + i < kv_valid) ? fast_exp2(__uint_as_float(v[i]) * p.scale_log2 - m_run) : 0.f;
-            const float p1 = (c + i + 1 < kv_valid) ? fast_exp2(__uint_as_float(v[i + 1]) * p.scale_log2 - m_run) : 0.f;
-            pk[i >> 1] = cvt_pack_half2(p0, p1);
+            const float p0 = (c + i < kv_valid) ? fast_exp2(__uint_as_float(v[i]) * p.scale_log2 - (m_run + kPShift)) : 0.f;
+            const float p1 = (c + i + 1 < kv_valid) ? fast_exp2(__uint_as_float(v[i + 1]) * p.scale_log2 - (m_run + kPShift)) : 0.f;
+            pk[i >> 1] = pack_p_bits(p0, p1);
             lsum += p0 + p1;
           }
           tmem_st16(tS + (c >> 1), pk);
@@ -293,13 +331,14 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
       l_run += lsum;
       tmem_st_wait();
       tc_fence_before();
-      mbar_arrive(&p_full[q]);
+      mbar_arrive(&p_full[q * kSBuf + j % kSBuf]);
     }
     // epilogue: O / l -> fp16 global
     mbar_wait(&o_done[q], 0);
     tc_fence_after();
     const int qrow = q_row0 + q * 128 + row;
-    const float inv_l = 1.0f / l_run;
+    // O = sum(P' V) with P' = 2^112 v (truncated), l = sum(v):  out = O * 2^-112 / l, corrected for the truncation bias
+    const float inv_l = kBitPackP ? __fdividef(1.9259299e-34f * 1.000352f, l_run) : 1.0f / l_run;
     __half* orow = p.out + ((size_t)batch * p.Sq + qrow) * p.ldo + head * kD;
 #pragma unroll
     for (int c = 0; c < C::kDPad; c += 16) {

@@ -380,10 +380,10 @@ inline int launch_gemm(cudaStream_t stream, const GemmRes& res, const GemmArgs& 
 }
 
 // ------------------------------------------------------------------ attention launcher
-template <int kD, int kKV, int kStages>
+template <int kD, int kKV, int kStages, int kSBuf, int kQ = 2>
 inline int launch_attn_t(cudaStream_t stream, const __half* q, int ldq, const __half* k, int ldk, const __half* v,
                          int ldv, __half* out, int B, int heads, int Sq, int Sk) {
-  using C = AttnCfg<kD, kKV, kStages>;
+  using C = AttnCfg<kD, kKV, kStages, kSBuf, kQ>;
   CUtensorMap mQ, mK, mV;
   auto mk = [&](CUtensorMap* m, const __half* ptr, int ld, int S, int rows) -> int {
     uint64_t dims[4] = {(uint64_t)kD, (uint64_t)heads, (uint64_t)S, (uint64_t)B};
@@ -398,15 +398,16 @@ inline int launch_attn_t(cudaStream_t stream, const __half* q, int ldq, const __
   p.Sq = Sq; p.Sk = Sk; p.heads = heads; p.ldo = heads * kD; p.out = out;
   p.scale_log2 = (1.0f / sqrtf((float)kD)) * 1.4426950408889634f;
   static int poly = -1;
-  if (poly < 0) { const char* e = getenv("DG_ATTN_POLY"); poly = (e && e[0] == '0') ? 0 : 3; }   // measured: 2, 3, 4 within 3 %
-  auto kern = poly == 0 ? attn_tc_kernel<kD, kKV, kStages, 0> : attn_tc_kernel<kD, kKV, kStages, 3>;
-  dim3 grid((Sq + 255) / 256, heads, B);
+  if (poly < 0) { const char* e = getenv("DG_ATTN_POLY"); poly = e ? atoi(e) : 3; }
+  auto kern = poly == 0 ? attn_tc_kernel<kD, kKV, kStages, 0, kSBuf, kQ>
+              : poly == 2 ? attn_tc_kernel<kD, kKV, kStages, 2, kSBuf, kQ> : attn_tc_kernel<kD, kKV, kStages, 3, kSBuf, kQ>;
+  dim3 grid((Sq + kQ * 128 - 1) / (kQ * 128), heads, B);
   if (trace_on()) fprintf(stderr, "DG_TRACE attn B=%d heads=%d Sq=%d Sk=%d d=%d\n", B, heads, Sq, Sk, kD);
   ProfScope prof_(FAM_ATTN, stream, 4.0 * B * heads * (double)Sq * Sk * kD,
                   2.0 * B * heads * kD * (2.0 * Sq + 2.0 * Sk));
   {
     ++g_launch_counter;
-    cudaError_t e = launch_pdl(kern, grid, dim3(384), (size_t)C::kSmem, stream, 1, mQ, mK, mV, p);
+    cudaError_t e = launch_pdl(kern, grid, dim3(C::kThreads), (size_t)C::kSmem, stream, 1, mQ, mK, mV, p);
     if (e != cudaSuccess) return fail(DG_E_CUDA, "attention launch failed: %s", cudaGetErrorString(e));
   }
   return DG_OK;
@@ -416,20 +417,27 @@ inline int launch_attention(cudaStream_t stream, const __half* q, int ldq, const
                             int ldv, __half* out, int B, int heads, int Sq, int Sk, int d) {
   if ((ldq | ldk | ldv) % 8) return fail(DG_E_SHAPE, "attention: row strides must be multiples of 8 elements");
   switch (d) {
-    case 32: return launch_attn_t<32, 128, 4>(stream, q, ldq, k, ldk, v, ldv, out, B, heads, Sq, Sk);
-    case 40: return launch_attn_t<40, 128, 4>(stream, q, ldq, k, ldk, v, ldv, out, B, heads, Sq, Sk);
-    case 64: return launch_attn_t<64, 128, 3>(stream, q, ldq, k, ldk, v, ldv, out, B, heads, Sq, Sk);
-    case 80: return launch_attn_t<80, 128, 2>(stream, q, ldq, k, ldk, v, ldv, out, B, heads, Sq, Sk);
-    case 160: return launch_attn_t<160, 64, 2>(stream, q, ldq, k, ldk, v, ldv, out, B, heads, Sq, Sk);
+    case 32: return launch_attn_t<32, 128, 4, 1>(stream, q, ldq, k, ldk, v, ldv, out, B, heads, Sq, Sk);
+    case 40: {
+      static int var = -1;     // DG_ATTN_VAR: 0 = 2 query tiles x 128 keys, 1 = 2 x 64 keys double-buffered scores, 2 = 4 query tiles x 64 keys
+      if (var < 0) { const char* e = getenv("DG_ATTN_VAR"); var = e ? atoi(e) : 2; }
+      if (var == 0) return launch_attn_t<40, 128, 4, 1>(stream, q, ldq, k, ldk, v, ldv, out, B, heads, Sq, Sk);
+      if (var == 1) return launch_attn_t<40, 64, 6, 2>(stream, q, ldq, k, ldk, v, ldv, out, B, heads, Sq, Sk);
+      return launch_attn_t<40, 64, 6, 1, 4>(stream, q, ldq, k, ldk, v, ldv, out, B, heads, Sq, Sk);
+    }
+    case 64: return launch_attn_t<64, 128, 3, 1>(stream, q, ldq, k, ldk, v, ldv, out, B, heads, Sq, Sk);
+    case 80: return launch_attn_t<80, 128, 2, 1>(stream, q, ldq, k, ldk, v, ldv, out, B, heads, Sq, Sk);
+    case 160: return launch_attn_t<160, 64, 2, 1>(stream, q, ldq, k, ldk, v, ldv, out, B, heads, Sq, Sk);
     default: return fail(DG_E_UNSUPPORTED, "attention: head dim %d not built (32/40/64/80/160)", d);
   }
 }
 
 // Opt every tcgen05 kernel into its dynamic shared-memory size once per device (never during graph capture).
-template <int kD, int kKV, int kStages>
+template <int kD, int kKV, int kStages, int kSBuf = 1, int kQ = 2>
 inline int init_attn_attr() {
-  DG_CUDA(cudaFuncSetAttribute(attn_tc_kernel<kD, kKV, kStages, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnCfg<kD, kKV, kStages>::kSmem));
-  DG_CUDA(cudaFuncSetAttribute(attn_tc_kernel<kD, kKV, kStages, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnCfg<kD, kKV, kStages>::kSmem));
+  DG_CUDA(cudaFuncSetAttribute(attn_tc_kernel<kD, kKV, kStages, 0, kSBuf, kQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnCfg<kD, kKV, kStages, kSBuf, kQ>::kSmem));
+  DG_CUDA(cudaFuncSetAttribute(attn_tc_kernel<kD, kKV, kStages, 3, kSBuf, kQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnCfg<kD, kKV, kStages, kSBuf, kQ>::kSmem));
+  DG_CUDA(cudaFuncSetAttribute(attn_tc_kernel<kD, kKV, kStages, 2, kSBuf, kQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnCfg<kD, kKV, kStages, kSBuf, kQ>::kSmem));
   return DG_OK;
 }
 template <int kCta, int kBN, int kStages, bool kGeglu>
@@ -462,6 +470,8 @@ inline int init_kernel_attributes() {
   DG_TRY((init_gemm_attr<2, 160, kStages_2_160, false>()));
   DG_TRY((init_attn_attr<32, 128, 4>()));
   DG_TRY((init_attn_attr<40, 128, 4>()));
+  DG_TRY((init_attn_attr<40, 64, 6, 2>()));
+  DG_TRY((init_attn_attr<40, 64, 6, 1, 4>()));
   DG_TRY((init_attn_attr<64, 128, 3>()));
   DG_TRY((init_attn_attr<80, 128, 2>()));
   DG_TRY((init_attn_attr<160, 64, 2>()));
