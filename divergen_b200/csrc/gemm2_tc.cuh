@@ -65,6 +65,7 @@ struct Gemm2Params {
   int gn_slots;            // HW / 32
   float* ws;               // split-K accumulators: [m_tile*tiles_n + nt][128][320] fp32, zero on entry, zero on exit
   int* tickets;            // [m_tile*tiles_n + nt], zero on entry, zero on exit
+  float inv_splits, inv_tiles_n, inv_tiles_x, inv_tiles_y;   // host-computed 1/d for the unit decomposition (fast_div)
   long long* dbg;          // optional (DG_GEMM_DBG=1): clock64() stamps of CTA 0's first unit, see DG_STAMP sites
 };
 #define DG_STAMP(slot) do { if (p.dbg && blockIdx.x == 0) p.dbg[slot] = clock64(); } while (0)
@@ -88,7 +89,7 @@ struct Gemm2Cfg {
   static constexpr int kRing = kNumAcc == 1 ? 2 : 4;
   static constexpr int kSlotSubs = kNumAcc == 1 ? 5 : 2;
   static constexpr int kRingBytes = kRing * kSlotSubs * kSubBytes;
-  static constexpr int kVecBytes = 2 * 320 * 4;         // bias + colsum, fp32
+  static constexpr int kVecBytes = 2 * 2 * 320 * 4;     // 2 generations of (bias, colsum), fp32
   static constexpr int kColBufBytes = 8 * 160 * 8;      // per epilogue warp: (sum, sumsq) of each of its <= 160 columns
   static constexpr int kBarBytes = 512;
   static constexpr int kTotal = kStages * kStageBytes + kRingBytes + kVecBytes + kColBufBytes + kBarBytes + 1024 /*align slack*/;
@@ -236,18 +237,31 @@ __device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr) {
 // ---- work decomposition ----------------------------------------------------------------------------------------------
 struct Unit { int nt, x0, y0, b0, kb_begin, kb_end, split, ctile; bool valid_m; };
 
+// a / d for 0 <= a < 2^20 with a host-computed reciprocal: ~8 instructions instead of the ~25-instruction dependent chain of
+// a 32-bit integer division (the unit decomposition sits between two tiles on every role's critical path).
+__device__ __forceinline__ int fast_div(int a, int d, float inv) {
+  int q = __float2int_rz((__int2float_rn(a) + 0.5f) * inv);
+  const int rem = a - q * d;
+  if (rem < 0) --q; else if (rem >= d) ++q;
+  return q;
+}
+
 template <int kCta>
 __device__ __forceinline__ Unit unit_coord(const Gemm2Params& p, int u, int cta_rank, int m_tiles, int num_kb) {
   Unit t;
-  t.split = u % p.splits;
-  int r = u / p.splits;
-  t.nt = r % p.tiles_n;
-  int mt = (r / p.tiles_n) * kCta + cta_rank;
+  int r = u;
+  t.split = 0;
+  if (p.splits > 1) { r = fast_div(u, p.splits, p.inv_splits); t.split = u - r * p.splits; }
+  const int rq = fast_div(r, p.tiles_n, p.inv_tiles_n);
+  t.nt = r - rq * p.tiles_n;
+  int mt = rq * kCta + cta_rank;
   t.valid_m = mt < m_tiles;
   t.ctile = mt * p.tiles_n + t.nt;
-  t.x0 = (mt % p.tiles_x) * p.bw; mt /= p.tiles_x;
-  t.y0 = (mt % p.tiles_y) * p.bh;
-  t.b0 = (mt / p.tiles_y) * p.bn;    // mt >= m_tiles => b0 >= B: every TMA box of this CTA is out of bounds (zeros)
+  const int mx = fast_div(mt, p.tiles_x, p.inv_tiles_x);
+  t.x0 = (mt - mx * p.tiles_x) * p.bw;
+  const int my = fast_div(mx, p.tiles_y, p.inv_tiles_y);
+  t.y0 = (mx - my * p.tiles_y) * p.bh;
+  t.b0 = my * p.bn;                  // mt >= m_tiles => b0 >= B: every TMA box of this CTA is out of bounds (zeros)
   t.kb_begin = (int)(((long long)t.split * num_kb) / p.splits);
   t.kb_end = (int)(((long long)(t.split + 1) * num_kb) / p.splits);
   return t;
@@ -256,7 +270,8 @@ __device__ __forceinline__ Unit unit_coord(const Gemm2Params& p, int u, int cta_
 template <int kCta, int kBN, int kStages, bool kGeglu>
 __global__ void __launch_bounds__(384, 1)
 gemm2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
-             const __grid_constant__ CUtensorMap mapW, const __grid_constant__ CUtensorMap mapO, const Gemm2Params p) {
+             const __grid_constant__ CUtensorMap mapW, const __grid_constant__ CUtensorMap mapO,
+             const __grid_constant__ CUtensorMap mapR, const Gemm2Params p) {
   using S = Gemm2Cfg<kCta, kBN, kStages>;
   static_assert(!kGeglu || kBN == 320, "GEGLU tiles are [160 value | 160 gate]");
   constexpr uint32_t kTmemCols = 512;
@@ -271,8 +286,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sRing = smem + kStages * S::kStageBytes;                       // 1024-aligned
-  float* sBias = reinterpret_cast<float*>(sRing + S::kRingBytes);          // [320]
-  float* sCs = sBias + 320;                                                // [320]
+  float* sVec = reinterpret_cast<float*>(sRing + S::kRingBytes);           // [2 generations][bias 320 | colsum 320]
   float2* sColBuf = reinterpret_cast<float2*>(sRing + S::kRingBytes + S::kVecBytes);   // [8 warps][160]
   uint64_t* bars = reinterpret_cast<uint64_t*>(sRing + S::kRingBytes + S::kVecBytes + S::kColBufBytes);
   uint64_t* full = bars;                    // [kStages]  (leader's are the live ones)
@@ -281,7 +295,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
   uint64_t* acc_empty = acc_full + 2;       // [2]  (leader's are the live ones)
   uint64_t* buf_free = acc_empty + 2;       // [kRing]  staging buffer reusable (store warp -> epilogue warps)
   uint64_t* chunk_ready = buf_free + S::kRing;   // [kRing]  staging buffer written by all 8 epilogue warps (-> store warp)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(chunk_ready + S::kRing);
+  uint64_t* res_full = chunk_ready + S::kRing;   // [kRing]  residual tile landed in the staging buffer (TMA -> epilogue warps)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_full + S::kRing);
   volatile uint32_t* ticket_slot = tmem_slot + 1;
   volatile int* chunk_info = reinterpret_cast<volatile int*>(tmem_slot + 2);   // [kRing][5]: col, x0, y0, b0, flags (1 store, 2 stop)
 
@@ -294,11 +309,12 @@ gemm2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&mapA0); tma_prefetch_desc(&mapA1); tma_prefetch_desc(&mapW); tma_prefetch_desc(&mapO);
+    if (p.residual) tma_prefetch_desc(&mapR);
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < kStages; ++i) { mbar_init(&full[i], kCta); mbar_init(&empty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], kCta * 8); }
-    for (int i = 0; i < S::kRing; ++i) { mbar_init(&buf_free[i], 1); mbar_init(&chunk_ready[i], 8); }
+    for (int i = 0; i < S::kRing; ++i) { mbar_init(&buf_free[i], 1); mbar_init(&chunk_ready[i], 8); mbar_init(&res_full[i], 1); }
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc_pair<kCta, kTmemCols>(tmem_slot);
@@ -315,6 +331,25 @@ gemm2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
   const int total_units = m_pairs * p.tiles_n * p.splits;
   const int kb_per_tap = p.kb0 + p.kb1;
   const int num_kb = p.taps * kb_per_tap;
+
+  constexpr bool kWholeT = (kBN == 160);
+  // (one thread) residual of unit `tt` -> slot sl: whole-tile slots take all 5 sub-tiles, ring slots chunk j's two halves
+  auto issue_res = [&](uint32_t sl, int j, const Unit& tt) {
+    constexpr int kSubs = kWholeT ? 5 : 2;
+    const int col0 = tt.nt * kOutW + (kWholeT ? 0 : j * 32);
+    const int cstep = kWholeT ? 32 : S::kNI;
+    int nsub = 0;
+#pragma unroll
+    for (int k = 0; k < kSubs; ++k) nsub += (col0 + k * cstep < p.n_out) ? 1 : 0;
+    mbar_arrive_expect_tx(&res_full[sl], (uint32_t)nsub * S::kSubBytes);
+#pragma unroll
+    for (int k = 0; k < kSubs; ++k)
+      if (col0 + k * cstep < p.n_out)
+        tma_load_4d(sRing + (sl * kSubs + k) * S::kSubBytes, &mapR, &res_full[sl], col0 + k * cstep, tt.x0, tt.y0, tt.b0);
+  };
+  // the residual of every tile is streamed by the otherwise idle warp 2 (split-K launches finish few tiles: there the
+  // epilogue issues it itself)
+  const bool res_loader = p.residual != nullptr && p.splits == 1 && !kGeglu;
 
   if (warp == 0) {
     // ===================== TMA producer (one elected lane; elect.sync lets the compiler keep TMA operands in uniform
@@ -384,12 +419,28 @@ gemm2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
         if (++as == S::kAccStages) { as = 0; acc_phase ^= 1; }
       }
     }
+  } else if (warp == 2) {
+    // ===================== residual loader: runs ahead of the epilogue as far as the staging ring allows =====================
+    // (whole-tile slots: the next tile's residual lands while the current tile is converted; ring: two chunks ahead)
+    if (res_loader && elect_one()) {
+      uint32_t c = 0;
+      for (int u = pair_id; u < total_units; u += num_pairs) {
+        const Unit t = unit_coord<kCta>(p, u, cta_rank, m_tiles, num_kb);
+        for (int j = 0; j < (kWholeT ? 1 : kChunks); ++j, ++c) {
+          mbar_wait_parked(&buf_free[c % S::kRing], (c / S::kRing) & 1);
+          issue_res(c % S::kRing, j, t);
+        }
+      }
+    }
   } else if (warp == 3) {
     // ===================== store warp: drains the staging ring with TMA stores, data-driven by chunk_ready =====================
     // (the epilogue warps never wait on each other or on a store: they only see ring back-pressure through buf_free)
     // Slots are released kFreeAhead chunks ahead of the chunk being stored, so that the epilogue can stream the NEXT chunk's
     // residual into its slot while it works on the current one (ring) / prime the next tile's slot (whole-tile slots).
-    constexpr uint32_t kFreeAhead = (kBN == 160) ? 1 : 2;
+    // Whole-tile slots (160-wide tiles, 2 slots): both start free and a slot is handed back as soon as ITS store has been
+    // read out of shared memory, so the epilogue can prime the next tile's residual while it converts the current tile.
+    constexpr bool kWholeSlots = (kBN == 160);
+    constexpr uint32_t kFreeAhead = kWholeSlots ? S::kRing : 2;
     if (elect_one()) {
       for (uint32_t i = 0; i < kFreeAhead; ++i) mbar_arrive(&buf_free[i]);   // the first slots start free
       for (uint32_t c = 0;; ++c) {
@@ -413,7 +464,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
         }
         tma_store_commit();
         tma_store_wait_read<S::kRing - kFreeAhead>();               // store c - (kRing - kFreeAhead) has drained its slot ...
-        mbar_arrive(&buf_free[(buf + kFreeAhead) % S::kRing]);     // ... which chunk c + kFreeAhead uses
+        mbar_arrive(&buf_free[(buf + kFreeAhead) % S::kRing]);     // ... which chunk c + kFreeAhead uses (whole-tile: its own)
       }
       DG_STAMP(10);                     // stop seen by the store warp
       tma_store_wait_all();
@@ -429,7 +480,11 @@ gemm2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
     const int box_xy = p.bw * p.bh;
     const uint32_t row_sw = (uint32_t)((r >> 1) & 3);   // 64-byte swizzle phase of this row
     const uint32_t acc_empty_leader = mapa_rank(smem_u32(&acc_empty[0]), 0);
-    const uint32_t sBias_a = smem_u32(sBias), sCs_a = smem_u32(sCs), sRing_a = smem_u32(sRing);
+    const uint32_t sRing_a = smem_u32(sRing);
+    uint32_t sBias_a = 0, sCs_a = 0;    // current generation of the per-column vectors
+    // this thread's row inside a pixel box (unit-independent)
+    const int row_rb = r / box_xy, row_ry = (r - row_rb * box_xy) / p.bw, row_rx = (r - row_rb * box_xy) % p.bw;
+    int vec_nt = -1, vec_gen = 1;       // column tile they hold; reloaded (into the other generation) only when it changes
     const bool has_ln = p.colsum != nullptr;
     int as = 0; uint32_t acc_phase = 0;
     uint32_t chunk_ctr = 0;             // staging-ring chunk counter (final epilogues only)
@@ -444,31 +499,42 @@ gemm2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
       const int nt = t.nt;
       const uint32_t t_row = tmem_base + as * S::kAccStride + ((uint32_t)(q * 32) << 16);
       // ---- this thread's output row
-      int bb, yy = 0, xx = 0;
+      int bb;
       size_t grow;                      // global row index (pixel index in [B*H*W))
       bool row_ok;
-      if (p.taps == 1 && p.H == 1 && p.B == 1) {
-        grow = (size_t)t.x0 + r;
-        row_ok = t.valid_m && grow < (size_t)p.W;
-        bb = p.hw > 0 ? (int)(grow / p.hw) : 0;
-      } else {
-        const int rb = r / box_xy, rin = r - rb * box_xy;
-        bb = t.b0 + rb; yy = t.y0 + rin / p.bw; xx = t.x0 + rin % p.bw;
-        row_ok = t.valid_m && bb < p.B && yy < p.H && xx < p.W;
-        grow = ((size_t)bb * p.H + yy) * p.W + xx;
-      }
+      auto row_map = [&](const Unit& tt, int& o_bb, size_t& o_grow, bool& o_ok) {
+        if (p.taps == 1 && p.H == 1 && p.B == 1) {
+          o_grow = (size_t)tt.x0 + r;
+          o_ok = tt.valid_m && o_grow < (size_t)p.W;
+          o_bb = p.hw > 0 ? (int)((uint32_t)o_grow / (uint32_t)p.hw) : 0;
+        } else {
+          const int yy = tt.y0 + row_ry, xx = tt.x0 + row_rx;
+          o_bb = tt.b0 + row_rb;
+          o_ok = tt.valid_m && o_bb < p.B && yy < p.H && xx < p.W;
+          o_grow = ((size_t)o_bb * p.H + yy) * p.W + xx;
+        }
+      };
+      row_map(t, bb, grow, row_ok);
       const int bbc = row_ok ? bb : 0;
 
       // ---- per-unit vectors -> smem (previous unit's readers are past that unit's last bar.sync)
-      for (int i = et; i < kBN; i += kEpiThreads) {
-        const int n = nt * kBN + i;
-        float bv = 0.f, cv = 0.f;
-        if (n < p.n_gemm) {
-          if (p.bias32) bv = __ldg(p.bias32 + n);
-          else if (p.bias) bv = __half2float(__ldg(p.bias + n));
-          if (p.colsum) cv = __ldg(p.colsum + n);
+      // (two generations: a warp that runs ahead fills the OTHER generation while slower warps still read this one; the
+      // bar.sync after each fill keeps the skew below one reload)
+      const bool vec_reload = nt != vec_nt;
+      if (vec_reload) {
+        vec_nt = nt; vec_gen ^= 1;
+        float* dstv = sVec + vec_gen * 640;
+        for (int i = et; i < kBN; i += kEpiThreads) {
+          const int n = nt * kBN + i;
+          float bv = 0.f, cv = 0.f;
+          if (n < p.n_gemm) {
+            if (p.bias32) bv = __ldg(p.bias32 + n);
+            else if (p.bias) bv = __half2float(__ldg(p.bias + n));
+            if (p.colsum) cv = __ldg(p.colsum + n);
+          }
+          dstv[i] = bv; dstv[320 + i] = cv;
         }
-        sBias[i] = bv; sCs[i] = cv;
+        sBias_a = smem_u32(dstv); sCs_a = sBias_a + 320 * 4;
       }
       // ---- LayerNorm fold: this row's mean / rstd from the producer's partials
       float ln_a = 1.f, ln_b = 0.f;     // value = ln_a * acc + ln_b * colsum[n] + bias[n]
@@ -483,12 +549,13 @@ gemm2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
         ln_a = rsqrtf(var + p.ln_eps);
         ln_b = -mean * ln_a;
       }
-      // Residual: each thread copies its own row piece asynchronously (cp.async, no registers) into the very staging
-      // bytes it will later overwrite with the result -- one chunk ahead for the ring (320-wide tiles), the whole tile at
-      // once for whole-tile slots (160-wide) -- and reads it back with one 16-byte shared load per 8 columns.
+      // Residual: ONE thread streams the residual tile with TMA (same boxes / 64-byte swizzle as the output store, so it
+      // lands in the very staging bytes the result will overwrite) -- one chunk ahead for the ring (320-wide tiles), the whole
+      // NEXT tile during the current one for whole-tile slots (160-wide); every thread reads its own row piece back with
+      // one 16-byte shared load per 8 columns.  (Per-thread 16-byte cp.async copies of 640-byte-strided rows cost ~4k
+      // cycles per 40 KB tile: 32 half-used sectors per instruction.)
       constexpr int kRV = kCW / 8;      // 16-byte vectors per chunk piece
       constexpr bool kWhole = (kBN == 160);
-      const __half* res_row = p.residual ? p.residual + grow * p.ld_res + (size_t)nt * kOutW : nullptr;
       // shared address of 16-byte vector i of this thread's piece of chunk j in ring slot `sl`
       auto stage_addr = [&](uint32_t sl, int j, int i) -> uint32_t {
         if constexpr (kWhole) {
@@ -498,33 +565,13 @@ gemm2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
           return sRing_a + (sl * 2 + hf) * S::kSubBytes + r * 64 + (((uint32_t)i ^ row_sw) << 4);
         }
       };
-      auto prefetch_res = [&](uint32_t sl, int j) {
-        const int c = chunk_col(j);
-#pragma unroll
-        for (int i = 0; i < kRV; ++i) {
-          const int col = nt * kOutW + c + i * 8;
-          const bool ok = row_ok && col + 8 <= p.n_out;
-          cp_async16(stage_addr(sl, j, i), ok ? (const void*)(res_row + c + i * 8) : (const void*)p.residual, ok ? 16u : 0u);
-        }
-      };
-      bool res_primed = false;          // chunk 0 (ring) / the whole tile (whole-tile slot) is already in flight
-      if (p.residual && p.splits == 1 && !kGeglu) {
-        const uint32_t sl = chunk_ctr % S::kRing;
-        mbar_wait(&buf_free[sl], (chunk_ctr / S::kRing) & 1);
-        if constexpr (kWhole) {
-#pragma unroll
-          for (int j = 0; j < kChunks; ++j) prefetch_res(sl, j);
-        } else {
-          prefetch_res(sl, 0);
-        }
-        cp_async_commit();
-        res_primed = true;
-      }
+      const bool res_primed = res_loader;   // the loader warp owns the slot hand-over: res_full implies buf_free
 
       mbar_wait(&acc_full[as], acc_phase);
       tc_fence_after();
       if (u == pair_id && et == 0) DG_STAMP(3);        // first accumulator complete
-      asm volatile("bar.sync 1, 256;" ::: "memory");   // sBias / sCs visible
+      if (et == 0 && (u - pair_id) / num_pairs < 4) DG_STAMP(22 + 2 * ((u - pair_id) / num_pairs));   // unit k: accumulator complete
+      if (vec_reload) asm volatile("bar.sync 1, 256;" ::: "memory");   // the new generation of bias / colsum is visible
       auto release_acc = [&]() {        // every TMEM read of this unit has completed: hand the accumulator back
         tc_fence_before();
         __syncwarp();
@@ -598,12 +645,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
           slot = chunk_ctr % S::kRing;
           if (!res_primed) mbar_wait(&buf_free[slot], (chunk_ctr / S::kRing) & 1);
           if (p.residual) {
-            if (!res_primed) {
-#pragma unroll
-              for (int jj = 0; jj < kChunks; ++jj) prefetch_res(slot, jj);
-              cp_async_commit();
-            }
-            cp_async_wait<0>();
+            if (!res_primed && et == 0) issue_res(slot, 0, t);
+            mbar_wait(&res_full[slot], (chunk_ctr / S::kRing) & 1);
           }
         }
 #pragma unroll 1
@@ -671,20 +714,18 @@ gemm2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
               const uint32_t sl = kWhole ? slot : chunk_ctr % S::kRing;
               if constexpr (!kWhole) {
                 // ring: this chunk's piece was issued one chunk ago (or at unit start); issue the next one, then wait for ours
-                if (j == 0 && !res_primed) {
-                  mbar_wait(&buf_free[sl], (chunk_ctr / S::kRing) & 1);
-                  prefetch_res(sl, 0);
-                  cp_async_commit();
+                if (et == 0 && !res_loader) {
+                  if (j == 0) {
+                    mbar_wait(&buf_free[sl], (chunk_ctr / S::kRing) & 1);
+                    issue_res(sl, 0, t);
+                  }
+                  if (j + 1 < kChunks) {
+                    const uint32_t nx = (chunk_ctr + 1) % S::kRing;
+                    mbar_wait(&buf_free[nx], ((chunk_ctr + 1) / S::kRing) & 1);
+                    issue_res(nx, j + 1, t);
+                  }
                 }
-                if (j + 1 < kChunks) {
-                  const uint32_t nx = (chunk_ctr + 1) % S::kRing;
-                  mbar_wait(&buf_free[nx], ((chunk_ctr + 1) / S::kRing) & 1);
-                  prefetch_res(nx, j + 1);
-                  cp_async_commit();
-                  cp_async_wait<1>();
-                } else {
-                  cp_async_wait<0>();
-                }
+                mbar_wait(&res_full[sl], (chunk_ctr / S::kRing) & 1);
               }
 #pragma unroll
               for (int i = 0; i < kRV; ++i) {
@@ -830,6 +871,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
             }
             mbar_arrive(&chunk_ready[slot]);
             if (u == pair_id && ew == 0) DG_STAMP(8);
+            if (ew == 0 && (u - pair_id) / num_pairs < 4) DG_STAMP(23 + 2 * ((u - pair_id) / num_pairs));   // unit k handed to the store warp
           }
           ++chunk_ctr;
         }

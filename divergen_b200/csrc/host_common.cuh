@@ -248,9 +248,9 @@ inline int choose_splits(int units, int num_kb, int slots, size_t ws_floats_per_
 
 template <int kCta, int kBN, int kStages, bool kGeglu>
 inline cudaError_t launch_gemm2_t(cudaStream_t stream, int grid_ctas, const CUtensorMap& mA0, const CUtensorMap& mA1,
-                                  const CUtensorMap& mW, const CUtensorMap& mO, const Gemm2Params& p) {
+                                  const CUtensorMap& mW, const CUtensorMap& mO, const CUtensorMap& mR, const Gemm2Params& p) {
   return launch_pdl(gemm2_kernel<kCta, kBN, kStages, kGeglu>, dim3((unsigned)grid_ctas), dim3(384),
-                    (size_t)Gemm2Cfg<kCta, kBN, kStages>::kTotal, stream, kCta, mA0, mA1, mW, mO, p);
+                    (size_t)Gemm2Cfg<kCta, kBN, kStages>::kTotal, stream, kCta, mA0, mA1, mW, mO, mR, p);
 }
 
 inline int launch_gemm(cudaStream_t stream, const GemmRes& res, const GemmArgs& a) {
@@ -319,7 +319,9 @@ inline int launch_gemm(cudaStream_t stream, const GemmRes& res, const GemmArgs& 
   if (res.ws && res.tickets && !a.row_stats_out && m_tiles * p.tiles_n <= kSplitTickets)
     p.splits = choose_splits(units, num_kb, slots, (size_t)kcta * 128 * kbn, kSplitWsFloats);
 
-  CUtensorMap mA0, mA1, mW, mO;
+  p.inv_splits = 1.0f / (float)p.splits; p.inv_tiles_n = 1.0f / (float)p.tiles_n;
+  p.inv_tiles_x = 1.0f / (float)p.tiles_x; p.inv_tiles_y = 1.0f / (float)p.tiles_y;
+  CUtensorMap mA0, mA1, mW, mO, mR;
   {
     uint64_t dims[4] = {(uint64_t)a.c0, (uint64_t)W, (uint64_t)H, (uint64_t)B};
     uint64_t st[3] = {(uint64_t)a.c0 * 2, (uint64_t)W * a.c0 * 2, (uint64_t)H * W * a.c0 * 2};
@@ -339,6 +341,12 @@ inline int launch_gemm(cudaStream_t stream, const GemmRes& res, const GemmArgs& 
     uint64_t os[3] = {(uint64_t)a.ldo * 2, (uint64_t)W * a.ldo * 2, (uint64_t)H * W * a.ldo * 2};
     uint32_t obox[4] = {32, (uint32_t)p.bw, (uint32_t)p.bh, (uint32_t)p.bn};
     DG_TRY(make_map_4d(&mO, a.out, od, os, obox, false, true));
+    if (a.residual) {     // same boxes over the residual tensor: the TMA load lands where the TMA store will read
+      uint64_t rs[3] = {(uint64_t)a.ld_res * 2, (uint64_t)W * a.ld_res * 2, (uint64_t)H * W * a.ld_res * 2};
+      DG_TRY(make_map_4d(&mR, a.residual, od, rs, obox, false, true));
+    } else {
+      mR = mO;
+    }
   }
   const int total_units = units * p.splits;
   const int grid_units = total_units < slots ? total_units : slots;
@@ -351,27 +359,29 @@ inline int launch_gemm(cudaStream_t stream, const GemmRes& res, const GemmArgs& 
                   2.0 * (rows_ * (a.c0 + a.c1) + ktot_ * a.n_w + rows_ * a.n_out));
   static int dbg_on = -1;
   static long long* dbg_dev = nullptr;
-  if (dbg_on < 0) { const char* ev = getenv("DG_GEMM_DBG"); dbg_on = ev && ev[0] == '1'; if (dbg_on) { cudaMalloc(&dbg_dev, 32 * 8); } }
-  if (dbg_on) { cudaMemsetAsync(dbg_dev, 0, 32 * 8, stream); p.dbg = dbg_dev; }
+  if (dbg_on < 0) { const char* ev = getenv("DG_GEMM_DBG"); dbg_on = ev && ev[0] == '1'; if (dbg_on) { cudaMalloc(&dbg_dev, 40 * 8); } }
+  if (dbg_on) { cudaMemsetAsync(dbg_dev, 0, 40 * 8, stream); p.dbg = dbg_dev; }
   cudaError_t e;
   if (kcta == 2) {
-    if (a.geglu) e = launch_gemm2_t<2, 320, kStages_2_320, true>(stream, grid_units * 2, mA0, mA1, mW, mO, p);
-    else if (kbn == 320) e = launch_gemm2_t<2, 320, kStages_2_320, false>(stream, grid_units * 2, mA0, mA1, mW, mO, p);
-    else e = launch_gemm2_t<2, 160, kStages_2_160, false>(stream, grid_units * 2, mA0, mA1, mW, mO, p);
+    if (a.geglu) e = launch_gemm2_t<2, 320, kStages_2_320, true>(stream, grid_units * 2, mA0, mA1, mW, mO, mR, p);
+    else if (kbn == 320) e = launch_gemm2_t<2, 320, kStages_2_320, false>(stream, grid_units * 2, mA0, mA1, mW, mO, mR, p);
+    else e = launch_gemm2_t<2, 160, kStages_2_160, false>(stream, grid_units * 2, mA0, mA1, mW, mO, mR, p);
   } else {
-    if (a.geglu) e = launch_gemm2_t<1, 320, kStages_1_320, true>(stream, grid_units, mA0, mA1, mW, mO, p);
-    else if (kbn == 320) e = launch_gemm2_t<1, 320, kStages_1_320, false>(stream, grid_units, mA0, mA1, mW, mO, p);
-    else e = launch_gemm2_t<1, 160, kStages_1_160, false>(stream, grid_units, mA0, mA1, mW, mO, p);
+    if (a.geglu) e = launch_gemm2_t<1, 320, kStages_1_320, true>(stream, grid_units, mA0, mA1, mW, mO, mR, p);
+    else if (kbn == 320) e = launch_gemm2_t<1, 320, kStages_1_320, false>(stream, grid_units, mA0, mA1, mW, mO, mR, p);
+    else e = launch_gemm2_t<1, 160, kStages_1_160, false>(stream, grid_units, mA0, mA1, mW, mO, mR, p);
   }
   ++g_launch_counter;
   if (dbg_on && e == cudaSuccess) {
-    long long h[32];
+    long long h[40];
     cudaStreamSynchronize(stream);
     cudaMemcpy(h, dbg_dev, sizeof(h), cudaMemcpyDeviceToHost);
     fprintf(stderr, "DG_GEMM_DBG bn=%d units=%d splits=%d: prologue %lld | operands +%lld | acc +%lld | chunks", kbn, units, p.splits,
             h[1] - h[0], h[2] - h[0], h[3] - h[0]);
     for (int i = 4; i < 9; ++i) fprintf(stderr, " +%lld", h[i] - h[0]);
     fprintf(stderr, " | chunk1: ld %lld math %lld bufwait %lld st %lld fence %lld", h[17] - h[16], h[18] - h[17], h[19] - h[18], h[20] - h[19], h[21] - h[20]);
+    fprintf(stderr, " | units (acc, handed):");
+    for (int i = 0; i < 4; ++i) if (h[22 + 2 * i]) fprintf(stderr, " (+%lld, +%lld)", h[22 + 2 * i] - h[0], h[23 + 2 * i] - h[0]);
     fprintf(stderr, " | stop +%lld | stores done +%lld | at teardown +%lld | passed +%lld | tmem freed +%lld\n", h[10] - h[0],
             h[11] - h[0], h[12] - h[0], h[13] - h[0], h[14] - h[0]);
   }

@@ -6,8 +6,8 @@ import torch
 sys.path.insert(0, ".")
 from divergen_b200 import _lib, ops
 
-M, K, N = 18944, int(sys.argv[1]) if len(sys.argv) > 1 else 2880, 320
-hw = 18944 // 8
+M, K, N = int(sys.argv[2]) if len(sys.argv) > 2 else 18944, int(sys.argv[1]) if len(sys.argv) > 1 else 2880, 320
+hw = M // 8
 x = torch.randn(M, K, device="cuda").half()
 w = (torch.randn(N, K, device="cuda") / math.sqrt(K)).half()
 b = torch.randn(N, device="cuda").half()
@@ -19,7 +19,7 @@ rs = torch.empty(M, ops.row_parts(N), 2, device="cuda")
 gs = torch.empty(8, hw // 32, N // 10, 2, device="cuda")
 P = lambda t: C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
 for name, res, rso, gso in (("plain", None, None, None), ("+res", r, None, None), ("+gn", None, None, gs), ("+rs", None, rs, None),
-                            ("+res+gn", r, None, gs)):
+                            ("+res+gn", r, None, gs), ("+res+rs", r, rs, None)):
     print("==", name, file=sys.stderr, flush=True)
     for _ in range(2):
         _lib.check(lib.dg_op_gemm_fused(ctx, P(x), P(w), P(b), P(None), P(None), P(None), 0, 0.0, P(res), P(out), M, K, N, N, 0,
