@@ -24,7 +24,8 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
     if not force and os.path.exists(LIB_PATH) and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(s) for s in srcs):
         return LIB_PATH
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc, *NVCC_FLAGS, "-o", LIB_PATH, os.path.join(CSRC, "dg_api.cu")]
+    extra = os.environ.get("DG_NVCC_EXTRA", "").split()      # e.g. -DDG_GEMM_STAMPS for the clock-stamped debug build
+    cmd = [nvcc, *NVCC_FLAGS, *extra, "-o", LIB_PATH, os.path.join(CSRC, "dg_api.cu")]
     if verbose:
         print(" ".join(cmd), file=sys.stderr)
     subprocess.run(cmd, check=True)

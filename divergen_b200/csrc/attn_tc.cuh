@@ -48,34 +48,42 @@ struct AttnParams {
   __half* out;       // [B, Sq, heads*d]
 };
 
-template <int kD, int kKV, int kStages, int kSBuf = 1, int kQ = 2>
+// kQ = softmax streams per CTA (one 4-warp group, one score buffer set and one O accumulator each).  kSplit = 1: every
+// stream is its own 128-row query tile.  kSplit = 2: two streams share a query tile and take the even / odd key tiles
+// (flash-decoding style); their (m, l, O) are merged through shared memory at the end -- 16 softmax warps per SM with
+// 256-row CTAs, so the 64x64-level grid is 1024 CTAs (6.9 waves) instead of 512 (3.46 waves of 512-row CTAs).
+template <int kD, int kKV, int kStages, int kSBuf = 1, int kQ = 2, int kSplit = 1>
 struct AttnCfg {
+  static constexpr int kQTiles = kQ / kSplit;           // 128-row query tiles per CTA
   static constexpr int kChunks = (kD + 63) / 64;        // 64-wide (128 B) head-dim chunks
   static constexpr int kDPad = (kD + 15) / 16 * 16;     // MMA-K of QK^T and MMA-N of PV
   static constexpr int kQTileBytes = kChunks * 128 * 128;
   static constexpr int kKVChunkBytes = kKV * 128;
   static constexpr int kKTileBytes = kChunks * kKVChunkBytes;
   static constexpr int kStageBytes = 2 * kKTileBytes;   // K then V
-  static constexpr int kSmem = kQ * kQTileBytes + kStages * kStageBytes + 1024 + 512;
+  static constexpr int kExFloats = (kSplit > 1) ? kQTiles * (kDPad + 2) * 128 : 0;   // (m, l, O[kDPad]) x 128 rows, column-major
+  static constexpr int kSmem = kQTiles * kQTileBytes + kStages * kStageBytes + kExFloats * 4 + 1024 + 512;
   static constexpr int kThreads = 128 + kQ * 128;       // producer / MMA / TMEM / spare warp + one 4-warp softmax group per query tile
   // TMEM columns
   static constexpr int kSStride = kSBuf * kKV;          // score buffer b of query tile q: q * kSStride + b * kKV
   static constexpr int kO0 = kQ * kSStride;
   static constexpr int kOStride = (kQ > 2 && kDPad <= 64) ? 64 : (kDPad <= 128) ? 128 : 192;
   static_assert(kO0 + (kQ - 1) * kOStride + kDPad <= 512, "TMEM budget");
-  static_assert(kStages > kSBuf, "the K tile of S(j + kSBuf) and the V tile of PV(j) are live together");
+  static_assert(kStages > kSBuf * kSplit, "the K tile of S(j + kSBuf * kSplit) and the V tile of PV(j) are live together");
+  static_assert(kSplit == 1 || kSplit == 2, "one or two key-tile streams per query tile");
 };
 
-template <int kD, int kKV, int kStages, int kPoly, int kSBuf, int kQ>   // kPoly: every kPoly-th pair of softmax elements takes the polynomial exp2 (0 = none)
+template <int kD, int kKV, int kStages, int kPoly, int kSBuf, int kQ, int kSplit>   // kPoly: every kPoly-th pair of softmax elements takes the polynomial exp2 (0 = none)
 __global__ void __launch_bounds__(128 + kQ * 128, 1)
 attn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
                const __grid_constant__ CUtensorMap mapV, const AttnParams p) {
-  using C = AttnCfg<kD, kKV, kStages, kSBuf, kQ>;
+  using C = AttnCfg<kD, kKV, kStages, kSBuf, kQ, kSplit>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem;
-  uint8_t* sKV = smem + kQ * C::kQTileBytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sKV + kStages * C::kStageBytes);
+  uint8_t* sKV = smem + C::kQTiles * C::kQTileBytes;
+  float* sEx = reinterpret_cast<float*>(sKV + kStages * C::kStageBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sKV + kStages * C::kStageBytes + C::kExFloats * 4);
   uint64_t* q_full = bars;                 // [1]
   uint64_t* kv_full = bars + 1;            // [kStages]
   uint64_t* kv_empty = kv_full + kStages;  // [kStages]
@@ -87,7 +95,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int q_row0 = blockIdx.x * (kQ * 128);
+  const int q_row0 = blockIdx.x * (C::kQTiles * 128);
   const int head = blockIdx.y;
   const int batch = blockIdx.z;
   const int nkv = (p.Sk + kKV - 1) / kKV;
@@ -113,8 +121,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (elect_one()) {
-      mbar_arrive_expect_tx(q_full, kQ * C::kQTileBytes);
-      for (int q = 0; q < kQ; ++q)
+      mbar_arrive_expect_tx(q_full, C::kQTiles * C::kQTileBytes);
+      for (int q = 0; q < C::kQTiles; ++q)
         for (int c = 0; c < C::kChunks; ++c)
           tma_load_4d(sQ + q * C::kQTileBytes + c * (128 * 128), &mapQ, q_full, c * 64, head, q_row0 + q * 128, batch);
       int stage = 0; uint32_t phase = 0;
@@ -140,7 +148,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
 #pragma unroll
       for (int s = 0; s < C::kDPad / 16; ++s) {
         const int c = s >> 2, k = s & 3;
-        const uint64_t da = make_smem_desc_sw128(sq_addr + q * C::kQTileBytes + c * (128 * 128) + k * 32, 16, 1024);
+        const uint64_t da = make_smem_desc_sw128(sq_addr + (q / kSplit) * C::kQTileBytes + c * (128 * 128) + k * 32, 16, 1024);
         const uint64_t db = make_smem_desc_sw128(sk_addr + c * C::kKVChunkBytes + k * 32, 16, 1024);
         umma_ss(tmem_base + q * C::kSStride + b * kKV, da, db, idesc_s, s ? 1u : 0u);
       }
@@ -156,43 +164,49 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
     };
 
     mbar_wait_parked(q_full, 0);
-    // prologue: S_q(t) for the first kSBuf key tiles
-    int kstage = 0; uint32_t kphase = 0;     // ring position of key tile `kt`, the next one whose scores get issued
-    int kt = 0;
-    for (; kt < kSBuf && kt < nkv; ++kt) {
-      mbar_wait_parked(&kv_full[kstage], kphase);
+    // stream s = qq * kSplit + h works on the key tiles j with j % kSplit == h; its local iteration is jj = j / kSplit and
+    // its score buffer b = jj % kSBuf.  After P_s(j) V_j the scores of its tile j + kSplit * kSBuf are issued into buffer b.
+    int ready = 0;                           // key tiles whose K/V have landed (kv_full waited)
+    auto ensure = [&](int t) {
+      while (ready <= t) { mbar_wait_parked(&kv_full[ready % kStages], (ready / kStages) & 1); ++ready; }
       tc_fence_after();
+    };
+    constexpr int kAhead = kSplit * kSBuf;
+    for (int t = 0; t < kAhead && t < nkv; ++t) {
+      ensure(t);
       if (elect_one()) {
-        for (int q = 0; q < kQ; ++q) issue_S(q, kt, smem_u32(sKV + kstage * C::kStageBytes));
+        for (int qq = 0; qq < C::kQTiles; ++qq)
+          issue_S(qq * kSplit + t % kSplit, (t / kSplit) % kSBuf, smem_u32(sKV + (t % kStages) * C::kStageBytes));
       }
       __syncwarp();
-      if (++kstage == kStages) { kstage = 0; kphase ^= 1; }
     }
-    int stage = 0;                           // ring position of key tile j (its V half)
     for (int j = 0; j < nkv; ++j) {
+      const int stage = j % kStages;
       const uint32_t sv_addr = smem_u32(sKV + stage * C::kStageBytes + C::kKTileBytes);
-      const bool has_next = (kt < nkv);      // key tile j + kSBuf exists
-      if (has_next) { mbar_wait_parked(&kv_full[kstage], kphase); }
-      const uint32_t sk_next = smem_u32(sKV + kstage * C::kStageBytes);
-      const int b = j % kSBuf;
-      const bool last = (j + 1 == nkv);
-      for (int q = 0; q < kQ; ++q) {
-        mbar_wait_parked(&p_full[q * kSBuf + b], (j / kSBuf) & 1);
+      const int jj = j / kSplit, b = jj % kSBuf;
+      const int tn = j + kAhead;             // the tile whose scores go into the buffer this step frees
+      const bool has_next = tn < nkv;
+      if (has_next) ensure(tn);
+      const uint32_t sk_next = smem_u32(sKV + (tn % kStages) * C::kStageBytes);
+      const bool last = (j + kSplit >= nkv); // the stream's last tile
+      for (int qq = 0; qq < C::kQTiles; ++qq) {
+        const int st = qq * kSplit + j % kSplit;
+        mbar_wait_parked(&p_full[st * kSBuf + b], (jj / kSBuf) & 1);
         tc_fence_after();
         if (elect_one()) {
-          issue_PV(q, b, sv_addr, j > 0);
-          umma_commit(last ? &o_done[q] : &pv_done[q]);
-          if (has_next) issue_S(q, b, sk_next);
-          if (q == kQ - 1) umma_commit(&kv_empty[stage]);
+          issue_PV(st, b, sv_addr, jj > 0);
+          umma_commit(last ? &o_done[st] : &pv_done[st]);
+          if (has_next) issue_S(st, b, sk_next);
+          if (qq == C::kQTiles - 1) umma_commit(&kv_empty[stage]);
         }
         __syncwarp();
       }
-      if (has_next) { ++kt; if (++kstage == kStages) { kstage = 0; kphase ^= 1; } }
-      if (++stage == kStages) stage = 0;
     }
   } else if (warp >= 4) {
     // ===================== softmax / correction / epilogue =====================
-    const int q = (warp - 4) >> 2;       // query tile handled by this warp group
+    const int q = (warp - 4) >> 2;       // stream handled by this warp group
+    const int qt = q / kSplit;           // its query tile
+    const int h = q % kSplit;            // its share of the key tiles: j % kSplit == h
     const int quad = warp & 3;           // TMEM lane quadrant
     const int row = quad * 32 + lane;    // row within the 128-row tile
     const uint32_t lane_off = (uint32_t)(quad * 32) << 16;
@@ -203,9 +217,9 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
     constexpr bool kPre = kQ <= 2;
     float m_run = -INFINITY;  // running max (log2 domain, already scaled)
     float l_run = 0.f;
-    for (int j = 0; j < nkv; ++j) {
-      const uint32_t tS = tS_q + (uint32_t)((j % kSBuf) * kKV);
-      mbar_wait(&s_full[q * kSBuf + j % kSBuf], (j / kSBuf) & 1);
+    for (int jj = 0, j = h; j < nkv; ++jj, j += kSplit) {
+      const uint32_t tS = tS_q + (uint32_t)((jj % kSBuf) * kKV);
+      mbar_wait(&s_full[q * kSBuf + jj % kSBuf], (jj / kSBuf) & 1);
       tc_fence_after();
       const int kv_valid = min(kKV, p.Sk - j * kKV);
       const bool full_tile = kv_valid == kKV;
@@ -238,7 +252,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
       }
       mx = fmaxf(mx, mx_b);
       const float m_tile = mx * p.scale_log2;
-      if (j == 0) {
+      if (jj == 0) {
         m_run = m_tile;
       } else {
         // lazy rescale: only when the max grew enough to threaten the fp16 range of P.  tcgen05.ld/st are warp-wide
@@ -246,7 +260,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
         const bool need = m_tile > m_run + kLazyMax;
         if (__any_sync(0xffffffffu, need)) {
           // S(j) was issued before PV(j-1): wait for that accumulate to land before touching O
-          if (kSBuf > 1) { mbar_wait(&pv_done[q], (j - 1) & 1); tc_fence_after(); }
+          if (kSBuf > 1) { mbar_wait(&pv_done[q], (jj - 1) & 1); tc_fence_after(); }
           const float alpha = need ? exp2f(m_run - m_tile) : 1.0f;
           if (need) { m_run = m_tile; l_run *= alpha; }
 #pragma unroll
@@ -331,20 +345,51 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
       l_run += lsum;
       tmem_st_wait();
       tc_fence_before();
-      mbar_arrive(&p_full[q * kSBuf + j % kSBuf]);
+      mbar_arrive(&p_full[q * kSBuf + jj % kSBuf]);
     }
     // epilogue: O / l -> fp16 global
-    mbar_wait(&o_done[q], 0);
-    tc_fence_after();
-    const int qrow = q_row0 + q * 128 + row;
+    const bool has_tiles = h < nkv;      // (a second stream has nothing to do when there is a single key tile)
+    if (has_tiles) { mbar_wait(&o_done[q], 0); tc_fence_after(); }
+    const int qrow = q_row0 + qt * 128 + row;
     // O = sum(P' V) with P' = 2^112 v (truncated), l = sum(v):  out = O * 2^-112 / l, corrected for the truncation bias
-    const float inv_l = kBitPackP ? __fdividef(1.9259299e-34f * 1.000352f, l_run) : 1.0f / l_run;
+    constexpr float kInvScale = kBitPackP ? 1.9259299e-34f * 1.000352f : 1.0f;
+    float a_own = 1.0f, a_oth = 0.0f;    // merge weights of this stream's and the partner stream's accumulators
+    const float* ex = sEx + qt * (C::kDPad + 2) * 128 + row;   // partner's (m, l, O[..]) of this row, element e at ex[e * 128]
+    if constexpr (kSplit == 2) {
+      if (h == 1) {
+        float* exw = sEx + qt * (C::kDPad + 2) * 128 + row;
+        exw[0] = has_tiles ? m_run : -INFINITY;
+        exw[128] = has_tiles ? l_run : 0.f;
+#pragma unroll
+        for (int c = 0; c < C::kDPad; c += 16) {
+          uint32_t o[16];
+          if (has_tiles) { tmem_ld16(tO + c, o); tmem_ld_wait(); }
+#pragma unroll
+          for (int i = 0; i < 16; ++i) exw[(2 + c + i) * 128] = has_tiles ? __uint_as_float(o[i]) : 0.f;
+        }
+        asm volatile("bar.arrive %0, 256;" ::"r"(1 + qt) : "memory");
+      } else {
+        asm volatile("bar.sync %0, 256;" ::"r"(1 + qt) : "memory");
+        const float m1 = ex[0], l1 = ex[128];
+        const float m = fmaxf(m_run, m1);
+        a_own = exp2f(m_run - m);
+        a_oth = (l1 > 0.f) ? exp2f(m1 - m) : 0.f;
+        l_run = l_run * a_own + l1 * a_oth;
+      }
+    }
+    const float inv_l = (kSplit == 2 && h == 1) ? 0.f : __fdividef(kInvScale, l_run);
     __half* orow = p.out + ((size_t)batch * p.Sq + qrow) * p.ldo + head * kD;
 #pragma unroll
     for (int c = 0; c < C::kDPad; c += 16) {
+      if (kSplit == 2 && h == 1) break;  // the partner stream writes the merged rows
       uint32_t o[16];
       tmem_ld16(tO + c, o);
       tmem_ld_wait();
+      if constexpr (kSplit == 2) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+          o[i] = __float_as_uint(fmaf(__uint_as_float(o[i]), a_own, ex[(2 + c + i) * 128] * a_oth));
+      }
       if (qrow < p.Sq) {
         uint4 w0, w1;
         w0.x = pack_half2(__uint_as_float(o[0]) * inv_l, __uint_as_float(o[1]) * inv_l);

@@ -68,8 +68,15 @@ struct Gemm2Params {
   float inv_splits, inv_tiles_n, inv_tiles_x, inv_tiles_y;   // host-computed 1/d for the unit decomposition (fast_div)
   long long* dbg;          // optional (DG_GEMM_DBG=1): clock64() stamps of CTA 0's first unit, see DG_STAMP sites
 };
+// Clock stamps are compiled in only for instrumented builds (DG_NVCC_EXTRA=-DDG_GEMM_STAMPS): their predicates otherwise
+// sit in the per-chunk epilogue loop of every launch.
+#ifdef DG_GEMM_STAMPS
 #define DG_STAMP(slot) do { if (p.dbg && blockIdx.x == 0) p.dbg[slot] = clock64(); } while (0)
 #define DG_STAMP_C1(slot) do { if (p.dbg && blockIdx.x == 0 && u == pair_id && j == 1 && et == 0) p.dbg[slot] = clock64(); } while (0)
+#else
+#define DG_STAMP(slot) do { } while (0)
+#define DG_STAMP_C1(slot) do { } while (0)
+#endif
 
 template <int kCta, int kBN, int kStages>
 struct Gemm2Cfg {
@@ -782,14 +789,19 @@ gemm2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
           // and ~2^-11 relative: invisible in sums over >= 320 elements)
           if (p.row_stats_out) {
             const bool all_ok = row_ok && nt * kOutW + ocol + kCW <= p.n_out;
+            if (__all_sync(0xffffffffu, all_ok)) {      // interior piece (a real branch: the masked form costs 2 selects per element)
 #pragma unroll
-            for (int i = 0; i < kCW / 2; ++i) {
-              float v0 = f[2 * i], v1 = f[2 * i + 1];
-              if (!all_ok) {
-                const int col = nt * kOutW + ocol + 2 * i;
-                v0 = (row_ok && col < p.n_out) ? v0 : 0.f; v1 = (row_ok && col + 1 < p.n_out) ? v1 : 0.f;
+              for (int i = 0; i < kCW / 2; ++i) {
+                const float v0 = f[2 * i], v1 = f[2 * i + 1];
+                rs += v0 + v1; rss = fmaf(v0, v0, fmaf(v1, v1, rss));
               }
-              rs += v0 + v1; rss = fmaf(v0, v0, fmaf(v1, v1, rss));
+            } else {
+#pragma unroll
+              for (int i = 0; i < kCW / 2; ++i) {
+                const int col = nt * kOutW + ocol + 2 * i;
+                const float v0 = (row_ok && col < p.n_out) ? f[2 * i] : 0.f, v1 = (row_ok && col + 1 < p.n_out) ? f[2 * i + 1] : 0.f;
+                rs += v0 + v1; rss = fmaf(v0, v0, fmaf(v1, v1, rss));
+              }
             }
           }
           uint32_t pk[kCW / 2];

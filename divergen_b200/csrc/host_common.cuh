@@ -359,7 +359,13 @@ inline int launch_gemm(cudaStream_t stream, const GemmRes& res, const GemmArgs& 
                   2.0 * (rows_ * (a.c0 + a.c1) + ktot_ * a.n_w + rows_ * a.n_out));
   static int dbg_on = -1;
   static long long* dbg_dev = nullptr;
-  if (dbg_on < 0) { const char* ev = getenv("DG_GEMM_DBG"); dbg_on = ev && ev[0] == '1'; if (dbg_on) { cudaMalloc(&dbg_dev, 40 * 8); } }
+  if (dbg_on < 0) {
+    const char* ev = getenv("DG_GEMM_DBG"); dbg_on = ev && ev[0] == '1';
+#ifndef DG_GEMM_STAMPS
+    if (dbg_on) { fprintf(stderr, "DG_GEMM_DBG needs a library built with DG_NVCC_EXTRA=-DDG_GEMM_STAMPS\n"); dbg_on = 0; }
+#endif
+    if (dbg_on) { cudaMalloc(&dbg_dev, 40 * 8); }
+  }
   if (dbg_on) { cudaMemsetAsync(dbg_dev, 0, 40 * 8, stream); p.dbg = dbg_dev; }
   cudaError_t e;
   if (kcta == 2) {
@@ -390,10 +396,10 @@ inline int launch_gemm(cudaStream_t stream, const GemmRes& res, const GemmArgs& 
 }
 
 // ------------------------------------------------------------------ attention launcher
-template <int kD, int kKV, int kStages, int kSBuf, int kQ = 2>
+template <int kD, int kKV, int kStages, int kSBuf, int kQ = 2, int kSplit = 1>
 inline int launch_attn_t(cudaStream_t stream, const __half* q, int ldq, const __half* k, int ldk, const __half* v,
                          int ldv, __half* out, int B, int heads, int Sq, int Sk) {
-  using C = AttnCfg<kD, kKV, kStages, kSBuf, kQ>;
+  using C = AttnCfg<kD, kKV, kStages, kSBuf, kQ, kSplit>;
   CUtensorMap mQ, mK, mV;
   auto mk = [&](CUtensorMap* m, const __half* ptr, int ld, int S, int rows) -> int {
     uint64_t dims[4] = {(uint64_t)kD, (uint64_t)heads, (uint64_t)S, (uint64_t)B};
@@ -409,9 +415,9 @@ inline int launch_attn_t(cudaStream_t stream, const __half* q, int ldq, const __
   p.scale_log2 = (1.0f / sqrtf((float)kD)) * 1.4426950408889634f;
   static int poly = -1;
   if (poly < 0) { const char* e = getenv("DG_ATTN_POLY"); poly = e ? atoi(e) : 3; }
-  auto kern = poly == 0 ? attn_tc_kernel<kD, kKV, kStages, 0, kSBuf, kQ>
-              : poly == 2 ? attn_tc_kernel<kD, kKV, kStages, 2, kSBuf, kQ> : attn_tc_kernel<kD, kKV, kStages, 3, kSBuf, kQ>;
-  dim3 grid((Sq + kQ * 128 - 1) / (kQ * 128), heads, B);
+  auto kern = poly == 0 ? attn_tc_kernel<kD, kKV, kStages, 0, kSBuf, kQ, kSplit>
+              : poly == 2 ? attn_tc_kernel<kD, kKV, kStages, 2, kSBuf, kQ, kSplit> : attn_tc_kernel<kD, kKV, kStages, 3, kSBuf, kQ, kSplit>;
+  dim3 grid((Sq + C::kQTiles * 128 - 1) / (C::kQTiles * 128), heads, B);
   if (trace_on()) fprintf(stderr, "DG_TRACE attn B=%d heads=%d Sq=%d Sk=%d d=%d\n", B, heads, Sq, Sk, kD);
   ProfScope prof_(FAM_ATTN, stream, 4.0 * B * heads * (double)Sq * Sk * kD,
                   2.0 * B * heads * kD * (2.0 * Sq + 2.0 * Sk));
@@ -430,10 +436,11 @@ inline int launch_attention(cudaStream_t stream, const __half* q, int ldq, const
     case 32: return launch_attn_t<32, 128, 4, 1>(stream, q, ldq, k, ldk, v, ldv, out, B, heads, Sq, Sk);
     case 40: {
       static int var = -1;     // DG_ATTN_VAR: 0 = 2 query tiles x 128 keys, 1 = 2 x 64 keys double-buffered scores, 2 = 4 query tiles x 64 keys
-      if (var < 0) { const char* e = getenv("DG_ATTN_VAR"); var = e ? atoi(e) : 2; }
+      if (var < 0) { const char* e = getenv("DG_ATTN_VAR"); var = e ? atoi(e) : 2; }   // 3 = 2 query tiles x 2 key-tile streams (measured equal to 2 at batch 8; better wave fit at small batch)
       if (var == 0) return launch_attn_t<40, 128, 4, 1>(stream, q, ldq, k, ldk, v, ldv, out, B, heads, Sq, Sk);
       if (var == 1) return launch_attn_t<40, 64, 6, 2>(stream, q, ldq, k, ldk, v, ldv, out, B, heads, Sq, Sk);
-      return launch_attn_t<40, 64, 6, 1, 4>(stream, q, ldq, k, ldk, v, ldv, out, B, heads, Sq, Sk);
+      if (var == 2) return launch_attn_t<40, 64, 6, 1, 4>(stream, q, ldq, k, ldk, v, ldv, out, B, heads, Sq, Sk);
+      return launch_attn_t<40, 64, 6, 1, 4, 2>(stream, q, ldq, k, ldk, v, ldv, out, B, heads, Sq, Sk);
     }
     case 64: return launch_attn_t<64, 128, 3, 1>(stream, q, ldq, k, ldk, v, ldv, out, B, heads, Sq, Sk);
     case 80: return launch_attn_t<80, 128, 2, 1>(stream, q, ldq, k, ldk, v, ldv, out, B, heads, Sq, Sk);
@@ -443,11 +450,11 @@ inline int launch_attention(cudaStream_t stream, const __half* q, int ldq, const
 }
 
 // Opt every tcgen05 kernel into its dynamic shared-memory size once per device (never during graph capture).
-template <int kD, int kKV, int kStages, int kSBuf = 1, int kQ = 2>
+template <int kD, int kKV, int kStages, int kSBuf = 1, int kQ = 2, int kSplit = 1>
 inline int init_attn_attr() {
-  DG_CUDA(cudaFuncSetAttribute(attn_tc_kernel<kD, kKV, kStages, 0, kSBuf, kQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnCfg<kD, kKV, kStages, kSBuf, kQ>::kSmem));
-  DG_CUDA(cudaFuncSetAttribute(attn_tc_kernel<kD, kKV, kStages, 3, kSBuf, kQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnCfg<kD, kKV, kStages, kSBuf, kQ>::kSmem));
-  DG_CUDA(cudaFuncSetAttribute(attn_tc_kernel<kD, kKV, kStages, 2, kSBuf, kQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnCfg<kD, kKV, kStages, kSBuf, kQ>::kSmem));
+  DG_CUDA(cudaFuncSetAttribute(attn_tc_kernel<kD, kKV, kStages, 0, kSBuf, kQ, kSplit>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnCfg<kD, kKV, kStages, kSBuf, kQ, kSplit>::kSmem));
+  DG_CUDA(cudaFuncSetAttribute(attn_tc_kernel<kD, kKV, kStages, 3, kSBuf, kQ, kSplit>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnCfg<kD, kKV, kStages, kSBuf, kQ, kSplit>::kSmem));
+  DG_CUDA(cudaFuncSetAttribute(attn_tc_kernel<kD, kKV, kStages, 2, kSBuf, kQ, kSplit>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnCfg<kD, kKV, kStages, kSBuf, kQ, kSplit>::kSmem));
   return DG_OK;
 }
 template <int kCta, int kBN, int kStages, bool kGeglu>
@@ -482,6 +489,7 @@ inline int init_kernel_attributes() {
   DG_TRY((init_attn_attr<40, 128, 4>()));
   DG_TRY((init_attn_attr<40, 64, 6, 2>()));
   DG_TRY((init_attn_attr<40, 64, 6, 1, 4>()));
+  DG_TRY((init_attn_attr<40, 64, 6, 1, 4, 2>()));
   DG_TRY((init_attn_attr<64, 128, 3>()));
   DG_TRY((init_attn_attr<80, 128, 2>()));
   DG_TRY((init_attn_attr<160, 64, 2>()));
