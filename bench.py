@@ -28,7 +28,7 @@ FLOP_PER_SAMPLE_FORWARD = 0.8033e12  # SD-1.5 @64x64 latent (SURVEY.md 8d / BASE
 IMAGES_PER_GPU = 4
 # DRAM traffic of the GEMM family: mean of dram__bytes_read.sum + dram__bytes_write.sum over the 210 gemm2 launches of one
 # batch-8 forward (one ncu pass, cold caches), see the file named here.
-GEMM_DRAM_BYTES_PER_LAUNCH = 27967388   # read 27.04 MB + write 0.93 MB (outputs mostly stay in the 126 MB L2)
+GEMM_DRAM_BYTES_PER_LAUNCH = 27955415   # read 27.04 MB + write 0.92 MB (outputs mostly stay in the 126 MB L2)
 GEMM_DRAM_SOURCE = "profiles/r01_gemm2_dram.csv"
 DDIM_STEPS = 50
 GUIDANCE = 7.5
