@@ -375,7 +375,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
         for (int kbi = t.kb_begin; kbi < t.kb_end; ++kbi) {
           const int dx = (p.taps == 9) ? (tap % 3 - 1) : 0;
           const int dy = (p.taps == 9) ? (tap / 3 - 1) : 0;
-          mbar_wait(&empty[stage], phase ^ 1);
+          mbar_wait_parked(&empty[stage], phase ^ 1);
           uint8_t* sa = smem + stage * S::kStageBytes;
           uint8_t* sb = sa + S::kABytes;
           if (leader) mbar_arrive_expect_tx(&full[stage], kCta * S::kStageBytes);
@@ -403,11 +403,11 @@ gemm2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
         const int split = u % p.splits;
         const int kb_begin = (int)(((long long)split * num_kb) / p.splits);
         const int kb_end = (int)(((long long)(split + 1) * num_kb) / p.splits);
-        mbar_wait(&acc_empty[as], acc_phase ^ 1);
+        mbar_wait_parked(&acc_empty[as], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * S::kAccStride;
         for (int kbi = kb_begin; kbi < kb_end; ++kbi) {
-          mbar_wait(&full[stage], phase);
+          mbar_wait_parked(&full[stage], phase);
           tc_fence_after();
           if (u == pair_id && kbi == kb_begin && lane == 0) DG_STAMP(2);   // first operands landed
           const uint64_t da = descA0 + (uint64_t)(stage * (S::kStageBytes >> 4));
@@ -455,7 +455,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
       for (uint32_t i = 0; i < kFreeAhead; ++i) mbar_arrive(&buf_free[i]);   // the first slots start free
       for (uint32_t c = 0;; ++c) {
         const uint32_t buf = c % S::kRing;
-        mbar_wait(&chunk_ready[buf], (c / S::kRing) & 1);
+        mbar_wait_parked(&chunk_ready[buf], (c / S::kRing) & 1);
         const int col = chunk_info[buf * 5 + 0], x0 = chunk_info[buf * 5 + 1], y0 = chunk_info[buf * 5 + 2];
         const int b0 = chunk_info[buf * 5 + 3], flags = chunk_info[buf * 5 + 4];
         if (flags & 2) break;
