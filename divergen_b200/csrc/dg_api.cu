@@ -209,7 +209,7 @@ int make_fused_rows(dg_unet* u, const std::vector<std::string>& keys, int in, in
   for (size_t i = 0; i < keys.size(); ++i) add_slot(u, keys[i], {out_each, in}, PK_ROWS, l->w, (int64_t)i * out_each, out_each, in);
   return DG_OK;
 }
-int geglu_rows(int inner) { return ((inner + kGemmTileN / 2 - 1) / (kGemmTileN / 2)) * kGemmTileN; }
+int geglu_rows(int inner) { return ((inner + kGegluHalf - 1) / kGegluHalf) * kGegluTile; }
 int make_xf(dg_unet* u, const std::string& pfx, int c, int heads, Xf* x) {
   const dg_unet_config& cf = u->cfg;
   x->c = c; x->heads = heads; x->ff_inner = 4 * c;
@@ -1007,8 +1007,8 @@ static int store_set_weight(WeightStore* u, const char* key, const void* src, in
       break;
     case PK_GEGLU_W:
     case PK_GEGLU_B: {
-      const int tiles = geglu_rows(s.a) / kGemmTileN;
-      pack_geglu_kernel<<<grid_for((size_t)tiles * kGemmTileN * s.b, 256, sms), 256>>>(w, s.dst, s.a, s.b, kGemmTileN, tiles);
+      const int tiles = geglu_rows(s.a) / kGegluTile;
+      pack_geglu_kernel<<<grid_for((size_t)tiles * kGegluTile * s.b, 256, sms), 256>>>(w, s.dst, s.a, s.b, kGegluTile, kGegluHalf, tiles);
       DG_LAUNCH_CHECK();
       break;
     }
@@ -1251,11 +1251,11 @@ int32_t dg_op_groupnorm_fused(dg_ctx* ctx, const void* x0, int32_t C0, const flo
 
 int32_t dg_op_pack_geglu(dg_ctx* ctx, const void* w, const void* b, void* w_out, void* b_out, int32_t inner, int32_t K, void* stream) {
   if (!ctx || !w || !b || !w_out || !b_out) return fail(DG_E_ARG, "null argument");
-  const int tiles = geglu_rows(inner) / kGemmTileN;
+  const int tiles = geglu_rows(inner) / kGegluTile;
   cudaStream_t s = (cudaStream_t)stream;
-  pack_geglu_kernel<<<grid_for((size_t)tiles * kGemmTileN * K, 256, ctx->num_sms), 256, 0, s>>>((const __half*)w, (__half*)w_out, inner, K, kGemmTileN, tiles);
+  pack_geglu_kernel<<<grid_for((size_t)tiles * kGegluTile * K, 256, ctx->num_sms), 256, 0, s>>>((const __half*)w, (__half*)w_out, inner, K, kGegluTile, kGegluHalf, tiles);
   DG_LAUNCH_CHECK();
-  pack_geglu_kernel<<<grid_for((size_t)tiles * kGemmTileN, 256, ctx->num_sms), 256, 0, s>>>((const __half*)b, (__half*)b_out, inner, 1, kGemmTileN, tiles);
+  pack_geglu_kernel<<<grid_for((size_t)tiles * kGegluTile, 256, ctx->num_sms), 256, 0, s>>>((const __half*)b, (__half*)b_out, inner, 1, kGegluTile, kGegluHalf, tiles);
   DG_LAUNCH_CHECK();
   return DG_OK;
 }

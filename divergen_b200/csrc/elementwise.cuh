@@ -471,17 +471,16 @@ __global__ void pack_conv_in_kernel(const __half* __restrict__ w, __half* __rest
   }
 }
 // GEGLU interleave: proj [2*inner, K] (rows [0,inner) value, [inner,2 inner) gate) -> tiles of `tile` rows:
-// [value(half rows) | gate(half rows)], zero padded to n_tiles*tile rows.  `vec_k == 1` packs a bias vector.
+// [value(hf rows) | gate(hf rows) | zero rows up to `tile`], zero padded to n_tiles*tile rows.  K == 1 packs a bias vector.
 __global__ void pack_geglu_kernel(const __half* __restrict__ w, __half* __restrict__ out, int inner, int K, int tile,
-                                  int n_tiles) {
-  const int hf = tile / 2;
+                                  int hf, int n_tiles) {
   const size_t total = (size_t)n_tiles * tile * K;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     const int k = i % K; const int r = i / K;
     const int t = r / tile, rr = r % tile;
     const int j = t * hf + (rr % hf);
     const bool gate = rr >= hf;
-    out[i] = (j < inner) ? w[((size_t)(gate ? inner + j : j)) * K + k] : __float2half_rn(0.f);
+    out[i] = (rr < 2 * hf && j < inner) ? w[((size_t)(gate ? inner + j : j)) * K + k] : __float2half_rn(0.f);
   }
 }
 

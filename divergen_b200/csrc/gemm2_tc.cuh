@@ -283,14 +283,17 @@ gemm2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
              const __grid_constant__ CUtensorMap mapW, const __grid_constant__ CUtensorMap mapO,
              const __grid_constant__ CUtensorMap mapR, const Gemm2Params p) {
   using S = Gemm2Cfg<kCta, kBN, kStages>;
-  static_assert(!kGeglu || kBN == 320, "GEGLU tiles are [160 value | 160 gate]");
+  // GEGLU tiles: 320-wide [160 value | 160 gate] (one TMEM stage) or 160-wide [64 value | 64 gate | 32 zero rows] -- the
+  // latter wastes a fifth of the MMA columns but runs on the double-buffered accumulator, so the packed-GELU epilogue
+  // (~3x the MMA time of a K = 320 tile) overlaps the next tile's MMA instead of serialising with it.
+  constexpr int kGateOff = (kBN == 320) ? S::kNI : 64;   // accumulator column of the gate half
   constexpr uint32_t kTmemCols = 512;
   constexpr int kEpiThreads = 256;
-  constexpr int kChunks = 5;
+  constexpr int kChunks = (kGeglu && kBN == 160) ? 2 : 5;
   // columns one epilogue thread converts per chunk: 320-wide tiles give each column-half warp 32 consecutive columns,
   // 160-wide tiles (and GEGLU outputs) give the two warps of a TMEM quadrant the two 16-column halves of a 32-column chunk
   constexpr int kCW = (kBN == 320 && !kGeglu) ? 32 : 16;
-  constexpr int kOutW = kGeglu ? S::kNI : kBN;          // output columns per tile
+  constexpr int kOutW = kGeglu ? kGateOff : kBN;        // output columns per tile
 
   if (threadIdx.x == 0) DG_STAMP(0);
   extern __shared__ uint8_t smem_raw[];
@@ -462,7 +465,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
         if (flags & 1) {
           if constexpr (kBN == 160) {
 #pragma unroll
-            for (int k = 0; k < 5; ++k)
+            for (int k = 0; k < kOutW / 32; ++k)
               if (col + k * 32 < p.n_out) tma_store_4d(&mapO, sRing + (buf * 5 + k) * S::kSubBytes, col + k * 32, x0, y0, b0);
           } else if constexpr (kCW == 32) {
 #pragma unroll
@@ -502,7 +505,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
     // first tile column of this thread's piece of chunk j (accumulator columns == output columns for plain tiles)
     // plain tiles: each warp owns a contiguous column half (160 or 80 columns) in 5 pieces; GEGLU: chunk j = outputs
     // [32j, 32j+32), 16 per warp half
-    auto chunk_col = [&](int j) { return kCW == 32 ? hf * S::kNI + j * 32 : (kBN == 160 ? hf * 80 + j * 16 : j * 32 + hf * 16); };
+    auto chunk_col = [&](int j) { return kCW == 32 ? hf * S::kNI + j * 32 : (kBN == 160 ? (kGeglu ? hf * 32 + j * 16 : hf * 80 + j * 16) : j * 32 + hf * 16); };
 
     for (int u = pair_id; u < total_units; u += num_pairs) {
       const Unit t = unit_coord<kCta>(p, u, cta_rank, m_tiles, num_kb);
@@ -756,7 +759,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
             if (p.splits == 1) {
               uint32_t va[16], vg[16];
               tmem_ld16(t_row + ocol, va);
-              tmem_ld16(t_row + S::kNI + ocol, vg);
+              tmem_ld16(t_row + kGateOff + ocol, vg);
               tmem_ld_wait();
               if (j == kChunks - 1) release_acc();
 #pragma unroll
@@ -766,20 +769,20 @@ gemm2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
 #pragma unroll
               for (int i = 0; i < 16; i += 4) {
                 const float4 v4 = __ldcg(reinterpret_cast<const float4*>(src + i));
-                const float4 g4 = __ldcg(reinterpret_cast<const float4*>(src + S::kNI + i));
+                const float4 g4 = __ldcg(reinterpret_cast<const float4*>(src + kGateOff + i));
                 a[i] = v4.x; a[i + 1] = v4.y; a[i + 2] = v4.z; a[i + 3] = v4.w;
                 g[i] = g4.x; g[i + 1] = g4.y; g[i + 2] = g4.z; g[i + 3] = g4.w;
               }
 #pragma unroll
               for (int i = 0; i < 16; i += 4) {
                 __stcg(reinterpret_cast<float4*>(src + i), make_float4(0.f, 0.f, 0.f, 0.f));
-                __stcg(reinterpret_cast<float4*>(src + S::kNI + i), make_float4(0.f, 0.f, 0.f, 0.f));
+                __stcg(reinterpret_cast<float4*>(src + kGateOff + i), make_float4(0.f, 0.f, 0.f, 0.f));
               }
             }
 #pragma unroll
             for (int i = 0; i < 16; i += 4) {
               const float4 ba = lds_f4(sBias_a + (ocol + i) * 4), ca = lds_f4(sCs_a + (ocol + i) * 4);
-              const float4 bg = lds_f4(sBias_a + (S::kNI + ocol + i) * 4), cg = lds_f4(sCs_a + (S::kNI + ocol + i) * 4);
+              const float4 bg = lds_f4(sBias_a + (kGateOff + ocol + i) * 4), cg = lds_f4(sCs_a + (kGateOff + ocol + i) * 4);
               const uint64_t la2 = pack_f32x2(ln_a, ln_a), lb2 = pack_f32x2(ln_b, ln_b), zero2 = pack_f32x2(0.f, 0.f);
               // value = ln_a*acc + (ln_b*colsum + bias), two columns per FFMA2
               const uint64_t av01 = fma_f32x2(la2, pack_f32x2(a[i], a[i + 1]), fma_f32x2(lb2, pack_f32x2(ca.x, ca.y), pack_f32x2(ba.x, ba.y)));

@@ -167,7 +167,16 @@ inline int make_map_2d(CUtensorMap* m, const void* ptr, uint64_t inner, uint64_t
 }
 
 // ------------------------------------------------------------------ GEMM / conv launcher
-constexpr int kGemmTileN = 320;     // widest tile: two 160-wide accumulators (GEGLU packing granularity)
+constexpr int kGemmTileN = 320;     // widest tile: two 160-wide accumulators
+// GEGLU packing: tiles of kGegluTile weight rows = [kGegluHalf value | kGegluHalf gate | zero rows].  Default 320/160 on
+// the 320-wide kernel.  DG_NVCC_EXTRA=-DDG_GEGLU_NARROW builds 160/64 on the double-buffered 160-wide kernel (epilogue
+// overlaps the next tile's MMA) -- measured SLOWER on the whole forward (10.20 vs 9.95 ms): 2.5x more tiles, each paying
+// the ~1.2 k-cycle gap between tiles, and a fifth of the MMA columns wasted.
+#ifdef DG_GEGLU_NARROW
+constexpr int kGegluTile = 160, kGegluHalf = 64;
+#else
+constexpr int kGegluTile = 320, kGegluHalf = 160;
+#endif
 // smem ring depths per (CTAs per tile, tile N): stage bytes are 16 KB of A + 10/20/40 KB of B; + 64 KB output staging ring
 constexpr int kStages_2_320 = 4;    // 4 x 36 KB
 constexpr int kStages_2_160 = 5;    // 5 x 26 KB (+ 80 KB: two whole-tile staging slots)
@@ -286,7 +295,7 @@ inline int launch_gemm(cudaStream_t stream, const GemmRes& res, const GemmArgs& 
   // the epilogue overlaps the next main loop, twice the tiles for wave balance) for short-K / epilogue-bound layers
   static int forced_bn = -1;
   if (forced_bn < 0) { const char* e = getenv("DG_GEMM_BN"); forced_bn = e && e[0] ? atoi(e) : 0; }
-  int kbn = (a.geglu || (num_kb > 24 && a.n_w > 160)) ? 320 : 160;
+  int kbn = a.geglu ? kGegluTile : (num_kb > 24 && a.n_w > 160) ? 320 : 160;
   {
     // few-tile layers (the 8x8 / 16x16 levels): 320-wide tiles would leave most SMs idle -- measured on 512x11520x1280:
     // 58 us (320, 4 splits) vs 43 us (160, 4 splits); 2048x11520x1280: 84 vs 62 us (profiles/r01_ncu_summary.md)
@@ -295,7 +304,7 @@ inline int launch_gemm(cudaStream_t stream, const GemmRes& res, const GemmArgs& 
     const int slots_ = kcta == 2 ? res.max_pairs : res.num_sms;
     if (!a.geglu && kbn == 320 && units320 * 2 <= slots_) kbn = 160;
   }
-  if (forced_bn == 160 || forced_bn == 320) kbn = a.geglu ? 320 : forced_bn;
+  if (forced_bn == 160 || forced_bn == 320) kbn = a.geglu ? kGegluTile : forced_bn;
   if (a.row_stats_out) kbn = 160;
   p.tiles_n = (a.n_w + kbn - 1) / kbn;
   p.n_out = a.n_out;
@@ -355,8 +364,10 @@ inline int launch_gemm(cudaStream_t stream, const GemmRes& res, const GemmArgs& 
             a.B * a.H * a.W, a.n_w, a.taps * (a.c0 + a.c1), a.taps, a.c0, a.c1, kbn, units, p.splits, grid_units, kcta, a.geglu,
             a.colsum != nullptr, a.residual != nullptr, a.gn_stats_out != nullptr, a.row_stats_out != nullptr);
   const double rows_ = (double)a.B * a.H * a.W, ktot_ = (double)a.taps * (a.c0 + a.c1);
-  ProfScope prof_(FAM_GEMM, stream, 2.0 * rows_ * ktot_ * (double)a.n_w,
-                  2.0 * (rows_ * (a.c0 + a.c1) + ktot_ * a.n_w + rows_ * a.n_out));
+  // algorithmic work: a GEGLU projection has 2 * n_out weight rows (the packing's zero rows are not work)
+  const double n_alg_ = a.geglu ? 2.0 * a.n_out : (double)a.n_w;
+  ProfScope prof_(FAM_GEMM, stream, 2.0 * rows_ * ktot_ * n_alg_,
+                  2.0 * (rows_ * (a.c0 + a.c1) + ktot_ * n_alg_ + rows_ * a.n_out));
   static int dbg_on = -1;
   static long long* dbg_dev = nullptr;
   if (dbg_on < 0) {
@@ -369,11 +380,11 @@ inline int launch_gemm(cudaStream_t stream, const GemmRes& res, const GemmArgs& 
   if (dbg_on) { cudaMemsetAsync(dbg_dev, 0, 40 * 8, stream); p.dbg = dbg_dev; }
   cudaError_t e;
   if (kcta == 2) {
-    if (a.geglu) e = launch_gemm2_t<2, 320, kStages_2_320, true>(stream, grid_units * 2, mA0, mA1, mW, mO, mR, p);
+    if (a.geglu) e = launch_gemm2_t<2, kGegluTile, kGegluTile == 320 ? kStages_2_320 : kStages_2_160, true>(stream, grid_units * 2, mA0, mA1, mW, mO, mR, p);
     else if (kbn == 320) e = launch_gemm2_t<2, 320, kStages_2_320, false>(stream, grid_units * 2, mA0, mA1, mW, mO, mR, p);
     else e = launch_gemm2_t<2, 160, kStages_2_160, false>(stream, grid_units * 2, mA0, mA1, mW, mO, mR, p);
   } else {
-    if (a.geglu) e = launch_gemm2_t<1, 320, kStages_1_320, true>(stream, grid_units, mA0, mA1, mW, mO, mR, p);
+    if (a.geglu) e = launch_gemm2_t<1, kGegluTile, kGegluTile == 320 ? kStages_1_320 : kStages_1_160, true>(stream, grid_units, mA0, mA1, mW, mO, mR, p);
     else if (kbn == 320) e = launch_gemm2_t<1, 320, kStages_1_320, false>(stream, grid_units, mA0, mA1, mW, mO, mR, p);
     else e = launch_gemm2_t<1, 160, kStages_1_160, false>(stream, grid_units, mA0, mA1, mW, mO, mR, p);
   }
@@ -482,6 +493,8 @@ inline int init_kernel_attributes() {
   DG_TRY((init_gemm_attr<1, 320, kStages_1_320, false>()));
   DG_TRY((init_gemm_attr<1, 320, kStages_1_320, true>()));
   DG_TRY((init_gemm_attr<1, 160, kStages_1_160, false>()));
+  DG_TRY((init_gemm_attr<1, 160, kStages_1_160, true>()));
+  DG_TRY((init_gemm_attr<2, 160, kStages_2_160, true>()));
   DG_TRY((init_gemm_attr<2, 320, kStages_2_320, false>()));
   DG_TRY((init_gemm_attr<2, 320, kStages_2_320, true>()));
   DG_TRY((init_gemm_attr<2, 160, kStages_2_160, false>()));
