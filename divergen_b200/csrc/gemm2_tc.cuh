@@ -508,6 +508,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
     auto chunk_col = [&](int j) { return kCW == 32 ? hf * S::kNI + j * 32 : (kBN == 160 ? (kGeglu ? hf * 32 + j * 16 : hf * 80 + j * 16) : j * 32 + hf * 16); };
 
     for (int u = pair_id; u < total_units; u += num_pairs) {
+      if (et == 0 && u == pair_id + num_pairs) DG_STAMP(30);      // second tile: loop top
       const Unit t = unit_coord<kCta>(p, u, cta_rank, m_tiles, num_kb);
       const int nt = t.nt;
       const uint32_t t_row = tmem_base + as * S::kAccStride + ((uint32_t)(q * 32) << 16);
@@ -580,6 +581,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
       };
       const bool res_primed = res_loader;   // the loader warp owns the slot hand-over: res_full implies buf_free
 
+      if (et == 0 && u == pair_id + num_pairs) DG_STAMP(31);      // second tile: setup done, about to wait for the accumulator
       mbar_wait(&acc_full[as], acc_phase);
       tc_fence_after();
       if (u == pair_id && et == 0) DG_STAMP(3);        // first accumulator complete
@@ -817,6 +819,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
 #pragma unroll
           for (int i = 0; i < kCW / 2; ++i) pk[i] = cvt_pack_half2(f[2 * i], f[2 * i + 1]);
           if constexpr (kWhole) {
+            DG_STAMP_C1(18);
             const uint32_t sub = sRing_a + (slot * 5 + (ocol >> 5)) * S::kSubBytes + r * 64;
             const uint32_t k0 = (uint32_t)((ocol & 31) >> 3);
 #pragma unroll
@@ -838,6 +841,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
               cs += __shfl_xor_sync(0xffffffffu, cs, 16); css += __shfl_xor_sync(0xffffffffu, css, 16);
               if (lane < 16) asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(colbuf_a + (uint32_t)(j * 16 + col) * 8), "f"(cs), "f"(css) : "memory");
             }
+            DG_STAMP_C1(19);
             continue;   // one hand-off per tile, after the loop
           }
           const uint32_t buf = chunk_ctr % S::kRing;

@@ -399,6 +399,7 @@ inline int launch_gemm(cudaStream_t stream, const GemmRes& res, const GemmArgs& 
     fprintf(stderr, " | chunk1: ld %lld math %lld bufwait %lld st %lld fence %lld", h[17] - h[16], h[18] - h[17], h[19] - h[18], h[20] - h[19], h[21] - h[20]);
     fprintf(stderr, " | units (acc, handed):");
     for (int i = 0; i < 4; ++i) if (h[22 + 2 * i]) fprintf(stderr, " (+%lld, +%lld)", h[22 + 2 * i] - h[0], h[23 + 2 * i] - h[0]);
+    fprintf(stderr, " | tile 1: loop top +%lld, setup done +%lld", h[30] - h[0], h[31] - h[0]);
     fprintf(stderr, " | stop +%lld | stores done +%lld | at teardown +%lld | passed +%lld | tmem freed +%lld\n", h[10] - h[0],
             h[11] - h[0], h[12] - h[0], h[13] - h[0], h[14] - h[0]);
   }
