@@ -74,6 +74,14 @@ SIGNATURES = {
     "dg_vae_set_weight": (_I, [_P, C.c_char_p, _P, _I, C.POINTER(_L)]),
     "dg_vae_prepare": (_I, [_P, _I, _I, _I]),
     "dg_vae_decode": (_I, [_P, _P, _F, _P, _I, _I, _I, _P]),
+    "dg_clip_create": (_I, [_P, _I, _I, _I, _I, _I, _I, C.POINTER(_P)]),
+    "dg_clip_destroy": (None, [_P]),
+    "dg_clip_num_weights": (_I, [_P]),
+    "dg_clip_weight_name": (C.c_char_p, [_P, _I]),
+    "dg_clip_weight_shape": (_I, [_P, _I, C.POINTER(_L), C.POINTER(_I)]),
+    "dg_clip_set_weight": (_I, [_P, C.c_char_p, _P, _I, C.POINTER(_L)]),
+    "dg_clip_prepare": (_I, [_P, _I]),
+    "dg_clip_encode": (_I, [_P, C.POINTER(_I), _I, _I, _P, _P]),
     "dg_op_gemm": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "dg_op_pack_geglu": (_I, [_P, _P, _P, _P, _P, _I, _I, _P]),
     "dg_op_geglu_packed_rows": (_I, [_I]),

@@ -1,0 +1,116 @@
+"""`CLIPTextModel` -- the transformers class surface over `dg_clip_*` (include/divergen_b200.h), SURVEY.md 8f row f2.
+
+The reference obtains `prompt_embeds, negative_embeds = stage_1.encode_prompt(prompt)`
+(DiverGen/generation/txt2img_diffusers_stages_from_txt.py:242); inside diffusers that is
+`text_encoder(tokenizer(prompt, padding="max_length", max_length=77, truncation=True).input_ids)[0]`.
+Keeps: `.config.{vocab_size, hidden_size, intermediate_size, num_hidden_layers, num_attention_heads,
+max_position_embeddings}`, `.dtype`, `.device`, `.to()`, `.eval()`, `load_state_dict` with transformers key names
+(196 tensors, 123 060 480 parameters for SD-1.x; `position_ids` buffers are accepted and ignored) and
+`forward(input_ids) -> .last_hidden_state` (also `[0]`).  Attention masks other than CLIP's built-in causal mask, pooled
+output and hidden-state lists are not provided: the Stable-Diffusion pipeline uses none of them.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from types import SimpleNamespace
+from typing import Dict, Tuple
+
+import torch
+
+from . import _lib
+
+SD_CLIP_CONFIG = dict(vocab_size=49408, hidden_size=768, intermediate_size=3072, num_hidden_layers=12,
+                      num_attention_heads=12, max_position_embeddings=77)
+
+
+class CLIPTextOutput(tuple):
+    """`BaseModelOutputWithPooling`-like: `out.last_hidden_state` and `out[0]`."""
+    def __new__(cls, last_hidden_state):
+        self = super().__new__(cls, (last_hidden_state,))
+        self.last_hidden_state = last_hidden_state
+        return self
+
+
+class CLIPTextModel:
+    def __init__(self, device="cuda:0", **config):
+        cfg = dict(SD_CLIP_CONFIG)
+        cfg.update(config)
+        if cfg.get("hidden_act", "quick_gelu") != "quick_gelu":
+            raise ValueError("only hidden_act='quick_gelu' (the SD-1.x text encoder) is supported")
+        self.config = SimpleNamespace(**cfg)
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise ValueError("divergen_b200 has no CPU path; device must be a CUDA (sm_100) device")
+        self.dtype = torch.float16
+        self._lib = _lib.load()
+        self._ctx = _lib.context(self.device.index or 0)
+        h = C.c_void_p()
+        _lib.check(self._lib.dg_clip_create(self._ctx, cfg["vocab_size"], cfg["hidden_size"], cfg["intermediate_size"],
+                                            cfg["num_hidden_layers"], cfg["num_attention_heads"],
+                                            cfg["max_position_embeddings"], C.byref(h)), "dg_clip_create")
+        self._h = h
+        self._prepared = 0
+
+    def to(self, *args, **kwargs):
+        return self
+
+    def eval(self):
+        return self
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None):
+                self._lib.dg_clip_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    def expected_state_dict_shapes(self) -> Dict[str, Tuple[int, ...]]:
+        out = {}
+        shp, nd = (C.c_int64 * 4)(), C.c_int32()
+        for i in range(self._lib.dg_clip_num_weights(self._h)):
+            name = self._lib.dg_clip_weight_name(self._h, i).decode()
+            _lib.check(self._lib.dg_clip_weight_shape(self._h, i, shp, C.byref(nd)))
+            out[name] = tuple(shp[k] for k in range(nd.value))
+        return out
+
+    def load_state_dict(self, state_dict, strict: bool = True):
+        expected = self.expected_state_dict_shapes()
+        missing = [k for k in expected if k not in state_dict]
+        unexpected = [k for k in state_dict if k not in expected and not k.endswith("position_ids")]
+        if strict and (missing or unexpected):
+            raise RuntimeError(f"load_state_dict: missing {missing[:5]} (+{max(0, len(missing) - 5)}), "
+                               f"unexpected {unexpected[:5]} (+{max(0, len(unexpected) - 5)})")
+        for k, v in state_dict.items():
+            if k not in expected:
+                continue
+            t = v.detach().to(device=self.device, dtype=torch.float16).contiguous()
+            shp = (C.c_int64 * max(1, t.dim()))(*t.shape)
+            _lib.check(self._lib.dg_clip_set_weight(self._h, k.encode(), C.c_void_p(t.data_ptr()), t.dim(), shp),
+                       f"dg_clip_set_weight({k})")
+        return SimpleNamespace(missing_keys=missing, unexpected_keys=unexpected)
+
+    def forward(self, input_ids, attention_mask=None, position_ids=None, output_attentions=None,
+                output_hidden_states=None, return_dict=None):
+        for name, val in (("attention_mask", attention_mask), ("position_ids", position_ids),
+                          ("output_attentions", output_attentions), ("output_hidden_states", output_hidden_states)):
+            if val is not None and val is not False:
+                raise ValueError(f"CLIPTextModel.forward: `{name}` is not supported by divergen_b200")
+        ids = torch.as_tensor(input_ids)
+        if ids.dim() == 1:
+            ids = ids[None]
+        if ids.dim() != 2 or ids.shape[1] > self.config.max_position_embeddings:
+            raise ValueError(f"input_ids must be [batch, <= {self.config.max_position_embeddings}], got {tuple(ids.shape)}")
+        ids = ids.to("cpu", torch.int32).contiguous()
+        b, s = ids.shape
+        if b > self._prepared:
+            _lib.check(self._lib.dg_clip_prepare(self._h, b), "dg_clip_prepare")
+            self._prepared = b
+        out = torch.empty((b, s, self.config.hidden_size), dtype=torch.float16, device=self.device)
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        _lib.check(self._lib.dg_clip_encode(self._h, C.cast(ids.data_ptr(), C.POINTER(C.c_int32)), b, s,
+                                            C.c_void_p(out.data_ptr()), C.c_void_p(stream)), "dg_clip_encode")
+        torch.cuda.current_stream(self.device).synchronize()      # `ids` is pageable host memory: keep it alive until copied
+        return CLIPTextOutput(out)
+
+    __call__ = forward

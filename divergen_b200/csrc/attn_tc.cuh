@@ -45,6 +45,7 @@ struct AttnParams {
   int heads;
   int ldo;           // output row stride (elements) = heads*d
   float scale_log2;  // d^-1/2 * log2(e)
+  int causal;        // 1: key t is visible to query row r only if t <= r (CLIP text encoder); kSplit == 1 variants only
   __half* out;       // [B, Sq, heads*d]
 };
 
@@ -221,8 +222,11 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
       const uint32_t tS = tS_q + (uint32_t)((jj % kSBuf) * kKV);
       mbar_wait(&s_full[q * kSBuf + jj % kSBuf], (jj / kSBuf) & 1);
       tc_fence_after();
-      const int kv_valid = min(kKV, p.Sk - j * kKV);
-      const bool full_tile = kv_valid == kKV;
+      // keys of this tile visible to this thread's row: the tile's valid keys, cut at the diagonal under a causal mask
+      // (a row always sees key 0, so the first tile never masks a whole row)
+      const int kv_tile = min(kKV, p.Sk - j * kKV);
+      const int kv_valid = p.causal ? min(kv_tile, q_row0 + qt * 128 + row + 1 - j * kKV) : kv_tile;
+      const bool full_tile = kv_tile == kKV && !p.causal;
       // pass 1: row max (FMNMX3: two columns per instruction, two independent chains)
       // (TMEM loads are software-pipelined one 32-column chunk ahead of the math in both passes: the single warp that owns
       // these rows would otherwise expose the tcgen05.ld latency eight times per tile)

@@ -203,7 +203,7 @@ int make_res(dg_unet* u, const std::string& pfx, int cin, int cout, Res* r, int*
   if (r->has_sc) DG_TRY(make_linear(u, pfx + ".conv_shortcut", cin, cout, true, &r->sc, true));
   return DG_OK;
 }
-int make_fused_rows(dg_unet* u, const std::vector<std::string>& keys, int in, int out_each, Lin* l) {
+int make_fused_rows(WeightStore* u, const std::vector<std::string>& keys, int in, int out_each, Lin* l) {
   l->in = in; l->out = out_each * (int)keys.size(); l->rows = l->out;
   DG_TRY(dev_alloc(u, (void**)&l->w, (size_t)in * l->out * 2));
   for (size_t i = 0; i < keys.size(); ++i) add_slot(u, keys[i], {out_each, in}, PK_ROWS, l->w, (int64_t)i * out_each, out_each, in);
@@ -887,6 +887,56 @@ int vae_missing(dg_vae* v) { int m = 0; for (auto& s : v->slots) m += s.set ? 0 
 }  // namespace
 
 // ================================================================== C ABI
+// ====================================================================================================================
+// CLIP text encoder: transformers `CLIPTextModel.forward(input_ids).last_hidden_state`, the
+// `prompt_embeds` the reference obtains through `stage_1.encode_prompt(prompt)` (txt2img_diffusers_stages_from_txt.py:242).
+// Pre-LN transformer, causal self-attention, quick_gelu MLP, final LayerNorm; weights by transformers state-dict key.
+struct ClipLayer { Norm ln1, ln2; Lin qkv, out, fc1, fc2; };
+struct dg_clip : WeightStore {
+  int vocab = 49408, hidden = 768, inter = 3072, layers = 12, heads = 12, max_pos = 77;
+  float eps = 1e-5f;
+  __half* tok = nullptr; __half* pos = nullptr;
+  std::vector<ClipLayer> L;
+  Norm final_ln;
+  __half* ws = nullptr; int* ids_dev = nullptr;
+  int max_batch = 0;
+};
+
+namespace {
+
+int build_clip(dg_clip* c) {
+  const int C = c->hidden;
+  DG_TRY(dev_alloc(c, (void**)&c->tok, (size_t)c->vocab * C * 2));
+  DG_TRY(dev_alloc(c, (void**)&c->pos, (size_t)c->max_pos * C * 2));
+  add_slot(c, "text_model.embeddings.token_embedding.weight", {c->vocab, C}, PK_COPY, c->tok);
+  add_slot(c, "text_model.embeddings.position_embedding.weight", {c->max_pos, C}, PK_COPY, c->pos);
+  c->L.resize(c->layers);
+  for (int i = 0; i < c->layers; ++i) {
+    ClipLayer& l = c->L[i];
+    const std::string pfx = "text_model.encoder.layers." + std::to_string(i);
+    DG_TRY(make_norm(c, pfx + ".layer_norm1", C, &l.ln1));
+    DG_TRY(make_fused_rows(c, {pfx + ".self_attn.q_proj.weight", pfx + ".self_attn.k_proj.weight", pfx + ".self_attn.v_proj.weight"}, C, C, &l.qkv));
+    DG_TRY(dev_alloc(c, (void**)&l.qkv.b, (size_t)3 * C * 2));
+    add_slot(c, pfx + ".self_attn.q_proj.bias", {C}, PK_ROWS, l.qkv.b, 0, C, 1);
+    add_slot(c, pfx + ".self_attn.k_proj.bias", {C}, PK_ROWS, l.qkv.b, C, C, 1);
+    add_slot(c, pfx + ".self_attn.v_proj.bias", {C}, PK_ROWS, l.qkv.b, 2 * C, C, 1);
+    DG_TRY(make_linear(c, pfx + ".self_attn.out_proj", C, C, true, &l.out));
+    DG_TRY(make_norm(c, pfx + ".layer_norm2", C, &l.ln2));
+    DG_TRY(make_linear(c, pfx + ".mlp.fc1", C, c->inter, true, &l.fc1));
+    DG_TRY(make_linear(c, pfx + ".mlp.fc2", c->inter, C, true, &l.fc2));
+  }
+  DG_TRY(make_norm(c, "text_model.final_layer_norm", C, &c->final_ln));
+  return DG_OK;
+}
+
+int clip_linear(dg_clip* c, cudaStream_t s, const __half* x, int K, int rows, const Lin& w, const __half* residual, __half* out) {
+  GemmArgs a; a.a0 = x; a.c0 = K; a.B = 1; a.H = 1; a.W = rows; a.taps = 1; a.w = w.w; a.n_w = w.rows; a.n_out = w.out; a.bias = w.b;
+  a.residual = residual; a.ld_res = w.out; a.out = out; a.ldo = w.out;
+  return launch_gemm(s, c->ctx->gemm, a);
+}
+
+}  // namespace
+
 extern "C" {
 
 int32_t dg_version(void) { return 100; }
@@ -1414,6 +1464,85 @@ int32_t dg_vae_decode(dg_vae* v, const void* latents, float scale, void* out, in
   const size_t n = (size_t)B * v->out_ch * x.H * x.W;
   nhwc_to_nchw_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(o.p, (__half*)out, B, v->out_ch, x.H * x.W, opitch);
   DG_LAUNCH_CHECK();
+  return DG_OK;
+}
+
+
+// ---- CLIP text encoder ------------------------------------------------------------------------------------------------
+int32_t dg_clip_create(dg_ctx* ctx, int32_t vocab, int32_t hidden, int32_t intermediate, int32_t layers, int32_t heads,
+                       int32_t max_positions, dg_clip** out) {
+  if (!ctx || !out) return fail(DG_E_ARG, "null argument");
+  if (hidden <= 0 || heads <= 0 || hidden != heads * 64) return fail(DG_E_UNSUPPORTED, "clip: head dim must be 64 (hidden %d, heads %d)", hidden, heads);
+  if (hidden % 64 || hidden > 1280 || intermediate % 64 || vocab <= 0 || layers <= 0 || max_positions <= 0)
+    return fail(DG_E_UNSUPPORTED, "clip: unsupported configuration");
+  std::unique_ptr<dg_clip> c(new dg_clip());
+  c->ctx = ctx; c->vocab = vocab; c->hidden = hidden; c->inter = intermediate; c->layers = layers; c->heads = heads; c->max_pos = max_positions;
+  DG_CUDA(cudaSetDevice(ctx->device));
+  int r = build_clip(c.get());
+  if (r != DG_OK) { for (void* p : c->owned) cudaFree(p); return r; }
+  *out = c.release();
+  return DG_OK;
+}
+void dg_clip_destroy(dg_clip* c) {
+  if (!c) return;
+  for (void* p : c->owned) cudaFree(p);
+  cudaFree(c->ws); cudaFree(c->ids_dev);
+  delete c;
+}
+int32_t dg_clip_num_weights(dg_clip* c) { return c ? (int32_t)c->slots.size() : 0; }
+const char* dg_clip_weight_name(dg_clip* c, int32_t i) {
+  if (!c || i < 0 || i >= (int)c->slots.size()) return nullptr;
+  return c->slots[i].key.c_str();
+}
+int32_t dg_clip_weight_shape(dg_clip* c, int32_t i, int64_t* shape4, int32_t* ndim) {
+  if (!c || i < 0 || i >= (int)c->slots.size() || !shape4 || !ndim) return fail(DG_E_ARG, "bad argument");
+  *ndim = (int32_t)c->slots[i].shape.size();
+  for (int k = 0; k < *ndim; ++k) shape4[k] = c->slots[i].shape[k];
+  return DG_OK;
+}
+int32_t dg_clip_set_weight(dg_clip* c, const char* key, const void* src, int32_t ndim, const int64_t* shape) {
+  return store_set_weight(c, key, src, ndim, shape);
+}
+int32_t dg_clip_prepare(dg_clip* c, int32_t max_batch) {
+  if (!c || max_batch <= 0) return fail(DG_E_ARG, "bad argument");
+  DG_CUDA(cudaSetDevice(c->ctx->device));
+  cudaFree(c->ws); cudaFree(c->ids_dev);
+  c->ws = nullptr; c->ids_dev = nullptr;
+  const size_t rows = (size_t)max_batch * c->max_pos;
+  // x, x2, h, att [rows, C]; qkv [rows, 3C]; f [rows, inter]
+  const size_t elems = rows * ((size_t)7 * c->hidden + c->inter);
+  cudaError_t e = cudaMalloc((void**)&c->ws, elems * 2);
+  if (e != cudaSuccess) return fail(DG_E_NOMEM, "clip workspace cudaMalloc(%zu) failed: %s", elems * 2, cudaGetErrorString(e));
+  DG_CUDA(cudaMalloc((void**)&c->ids_dev, rows * sizeof(int)));
+  c->max_batch = max_batch;
+  return DG_OK;
+}
+int32_t dg_clip_encode(dg_clip* c, const int32_t* input_ids, int32_t batch, int32_t seq, void* out, void* stream) {
+  if (!c || !input_ids || !out) return fail(DG_E_ARG, "null argument");
+  if (!c->ws) return fail(DG_E_STATE, "dg_clip_prepare has not been called");
+  if (batch <= 0 || batch > c->max_batch || seq <= 0 || seq > c->max_pos) return fail(DG_E_SHAPE, "clip: batch %d x %d tokens exceeds the prepared workspace", batch, seq);
+  for (const Slot& sl : c->slots) if (!sl.set) return fail(DG_E_STATE, "clip weight %s has not been set", sl.key.c_str());
+  DG_CUDA(cudaSetDevice(c->ctx->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  const int C = c->hidden, rows = batch * seq, sms = c->ctx->num_sms;
+  const size_t R = (size_t)c->max_batch * c->max_pos;
+  __half* x = c->ws; __half* x2 = x + R * C; __half* h = x2 + R * C; __half* att = h + R * C;
+  __half* qkv = att + R * C; __half* f = qkv + R * 3 * C;
+  DG_CUDA(cudaMemcpyAsync(c->ids_dev, input_ids, (size_t)rows * sizeof(int), cudaMemcpyHostToDevice, s));
+  clip_embed_kernel<<<(unsigned)(((size_t)rows * (C / 8) + 255) / 256), 256, 0, s>>>(c->ids_dev, c->tok, c->pos, x, rows, seq, C, c->vocab);
+  DG_LAUNCH_CHECK();
+  for (const ClipLayer& l : c->L) {
+    DG_TRY(launch_layernorm(s, x, l.ln1.g, l.ln1.b, h, rows, C, c->eps));
+    DG_TRY(clip_linear(c, s, h, C, rows, l.qkv, nullptr, qkv));
+    DG_TRY(launch_attention(s, qkv, 3 * C, qkv + C, 3 * C, qkv + 2 * C, 3 * C, att, batch, c->heads, seq, seq, 64, /*causal=*/1));
+    DG_TRY(clip_linear(c, s, att, C, rows, l.out, x, x2));
+    DG_TRY(launch_layernorm(s, x2, l.ln2.g, l.ln2.b, h, rows, C, c->eps));
+    DG_TRY(clip_linear(c, s, h, C, rows, l.fc1, nullptr, f));
+    quick_gelu_kernel<<<grid_for((size_t)rows * c->inter / 8, 256, sms), 256, 0, s>>>(f, (size_t)rows * c->inter / 8);
+    DG_LAUNCH_CHECK();
+    DG_TRY(clip_linear(c, s, f, c->inter, rows, l.fc2, x2, x));
+  }
+  DG_TRY(launch_layernorm(s, x, c->final_ln.g, c->final_ln.b, (__half*)out, rows, C, c->eps));
   return DG_OK;
 }
 

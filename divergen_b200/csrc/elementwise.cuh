@@ -484,6 +484,34 @@ __global__ void pack_geglu_kernel(const __half* __restrict__ w, __half* __restri
   }
 }
 
+// ------------------------------------------------------------------ CLIP text encoder helpers
+// CLIPTextEmbeddings: out[b*S + t, :] = token_embedding[ids[b*S + t], :] + position_embedding[t, :].  8 channels / thread.
+__global__ void clip_embed_kernel(const int* __restrict__ ids, const __half* __restrict__ tok, const __half* __restrict__ pos,
+                                  __half* __restrict__ out, int rows, int S, int C, int vocab) {
+  const int nvec = C / 8;
+  const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= (size_t)rows * nvec) return;
+  const int r = (int)(i / nvec), v = (int)(i % nvec);
+  int id = ids[r];
+  id = id < 0 ? 0 : (id >= vocab ? vocab - 1 : id);
+  float a[8], b[8];
+  load8(tok + (size_t)id * C + v * 8, a);
+  load8(pos + (size_t)(r % S) * C + v * 8, b);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) a[k] += b[k];
+  store8(out + (size_t)r * C + v * 8, a);
+}
+// CLIP's `quick_gelu`: x * sigmoid(1.702 x), in place.
+__global__ void quick_gelu_kernel(__half* __restrict__ x, size_t nvec) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < nvec; i += (size_t)gridDim.x * blockDim.x) {
+    float f[8];
+    load8(x + i * 8, f);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) f[k] = __fdividef(f[k], 1.0f + __expf(-1.702f * f[k]));
+    store8(x + i * 8, f);
+  }
+}
+
 // ------------------------------------------------------------------ VAE decoder helpers
 // post_quant_conv: 1x1 conv over the latent channels (C <= 8) on NCHW fp16, with the 1/scaling_factor of
 // `vae.decode(latents / scaling_factor)` folded in.  out[b,co,p] = bias[co] + sum_ci W[co,ci] * (z[b,ci,p] * scale).

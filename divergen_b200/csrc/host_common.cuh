@@ -410,7 +410,7 @@ inline int launch_gemm(cudaStream_t stream, const GemmRes& res, const GemmArgs& 
 // ------------------------------------------------------------------ attention launcher
 template <int kD, int kKV, int kStages, int kSBuf, int kQ = 2, int kSplit = 1>
 inline int launch_attn_t(cudaStream_t stream, const __half* q, int ldq, const __half* k, int ldk, const __half* v,
-                         int ldv, __half* out, int B, int heads, int Sq, int Sk) {
+                         int ldv, __half* out, int B, int heads, int Sq, int Sk, int causal = 0) {
   using C = AttnCfg<kD, kKV, kStages, kSBuf, kQ, kSplit>;
   CUtensorMap mQ, mK, mV;
   auto mk = [&](CUtensorMap* m, const __half* ptr, int ld, int S, int rows) -> int {
@@ -423,7 +423,8 @@ inline int launch_attn_t(cudaStream_t stream, const __half* q, int ldq, const __
   DG_TRY(mk(&mK, k, ldk, Sk, kKV));
   DG_TRY(mk(&mV, v, ldv, Sk, kKV));
   AttnParams p{};
-  p.Sq = Sq; p.Sk = Sk; p.heads = heads; p.ldo = heads * kD; p.out = out;
+  p.Sq = Sq; p.Sk = Sk; p.heads = heads; p.ldo = heads * kD; p.out = out; p.causal = causal;
+  if (causal && kSplit != 1) return fail(DG_E_UNSUPPORTED, "attention: causal mask needs a one-stream-per-query-tile variant");
   p.scale_log2 = (1.0f / sqrtf((float)kD)) * 1.4426950408889634f;
   static int poly = -1;
   if (poly < 0) { const char* e = getenv("DG_ATTN_POLY"); poly = e ? atoi(e) : 3; }
@@ -442,7 +443,8 @@ inline int launch_attn_t(cudaStream_t stream, const __half* q, int ldq, const __
 }
 
 inline int launch_attention(cudaStream_t stream, const __half* q, int ldq, const __half* k, int ldk, const __half* v,
-                            int ldv, __half* out, int B, int heads, int Sq, int Sk, int d) {
+                            int ldv, __half* out, int B, int heads, int Sq, int Sk, int d, int causal = 0) {
+  if (causal && d != 64) return fail(DG_E_UNSUPPORTED, "attention: causal mask is built for head dim 64 only");
   if ((ldq | ldk | ldv) % 8) return fail(DG_E_SHAPE, "attention: row strides must be multiples of 8 elements");
   switch (d) {
     case 32: return launch_attn_t<32, 128, 4, 1>(stream, q, ldq, k, ldk, v, ldv, out, B, heads, Sq, Sk);
@@ -454,7 +456,7 @@ inline int launch_attention(cudaStream_t stream, const __half* q, int ldq, const
       if (var == 2) return launch_attn_t<40, 64, 6, 1, 4>(stream, q, ldq, k, ldk, v, ldv, out, B, heads, Sq, Sk);
       return launch_attn_t<40, 64, 6, 1, 4, 2>(stream, q, ldq, k, ldk, v, ldv, out, B, heads, Sq, Sk);
     }
-    case 64: return launch_attn_t<64, 128, 3, 1>(stream, q, ldq, k, ldk, v, ldv, out, B, heads, Sq, Sk);
+    case 64: return launch_attn_t<64, 128, 3, 1>(stream, q, ldq, k, ldk, v, ldv, out, B, heads, Sq, Sk, causal);
     case 80: return launch_attn_t<80, 128, 2, 1>(stream, q, ldq, k, ldk, v, ldv, out, B, heads, Sq, Sk);
     case 160: return launch_attn_t<160, 64, 2, 1>(stream, q, ldq, k, ldk, v, ldv, out, B, heads, Sq, Sk);
     default: return fail(DG_E_UNSUPPORTED, "attention: head dim %d not built (32/40/64/80/160)", d);

@@ -4,7 +4,9 @@ num_images_per_prompt=, num_inference_steps=, guidance_scale=).images` as called
 
 In scope: latent preparation, the 50-step UNet + CFG + DDIM loop (one C-ABI call, CUDA-graph replayed).
 Row f1 (VAE decode): pass `vae=AutoencoderKL(...)` (divergen_b200.vae, `dg_vae_decode`) or any `vae_decode` callable;
-without either only `output_type='latent'` is available.  The CLIP text encoder (row f2) stays a caller-supplied callable.
+without either only `output_type='latent'` is available.  Row f2 (CLIP text encoder): pass
+`text_encoder=CLIPTextModel(...)` (divergen_b200.clip, `dg_clip_encode`) together with a `tokenizer` (transformers
+`CLIPTokenizer`; its vocabulary files are not shipped here), or any `text_encoder(prompt) -> embeddings` callable.
 """
 from __future__ import annotations
 
@@ -34,8 +36,9 @@ def pt_to_pil(images: torch.Tensor):
 class StableDiffusionPipeline:
     def __init__(self, unet: UNet2DConditionModel, scheduler: DDIMScheduler,
                  text_encoder: Optional[Callable] = None, vae_decode: Optional[Callable] = None,
-                 vae_scale_factor: int = 8, vae=None):
+                 vae_scale_factor: int = 8, vae=None, tokenizer=None):
         self.unet, self.scheduler = unet, scheduler
+        self.tokenizer = tokenizer
         self.text_encoder, self.vae_decode = text_encoder, vae_decode
         self.vae = vae
         self.vae_scale_factor = vae_scale_factor
@@ -56,9 +59,15 @@ class StableDiffusionPipeline:
                       negative_prompt=None):
         if self.text_encoder is None:
             raise ValueError("no text_encoder attached: pass prompt_embeds/negative_prompt_embeds (CLIP is row f2, next)")
-        pos = self.text_encoder(prompt)
-        neg = self.text_encoder(negative_prompt if negative_prompt is not None else "")
-        return pos, neg
+        neg_prompt = negative_prompt if negative_prompt is not None else ""
+        if self.tokenizer is not None:
+            # diffusers: text_encoder(tokenizer(prompt, padding="max_length", max_length=77, truncation=True).input_ids)[0]
+            def enc(text):
+                ids = self.tokenizer(text, padding="max_length", max_length=self.tokenizer.model_max_length, truncation=True,
+                                     return_tensors="pt").input_ids
+                return self.text_encoder(ids)[0]
+            return enc(prompt), enc(neg_prompt)
+        return self.text_encoder(prompt), self.text_encoder(neg_prompt)
 
     @torch.no_grad()
     def __call__(self, prompt=None, height: Optional[int] = None, width: Optional[int] = None,

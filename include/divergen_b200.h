@@ -124,6 +124,23 @@ int32_t dg_vae_prepare(dg_vae* vae, int32_t max_batch, int32_t h, int32_t w);
 int32_t dg_vae_decode(dg_vae* vae, const void* latents, float scale, void* out, int32_t batch, int32_t h, int32_t w,
                       void* stream);
 
+/* ---- CLIPTextModel.forward(input_ids).last_hidden_state (the `prompt_embeds` of `stage_1.encode_prompt(prompt)`,
+ * txt2img_diffusers_stages_from_txt.py:242; transformers `CLIPTextModel`, 123 060 480 parameters in 196 tensors for SD-1.x) ----
+ * Weights by transformers state-dict key (`text_model.embeddings.*`, `text_model.encoder.layers.N.*`,
+ * `text_model.final_layer_norm.*`).  Head dim must be 64 (hidden = 64 * heads).
+ * dg_clip_encode: input_ids = HOST int32 [batch, seq] (tokenizer output, seq <= max_positions); out = device fp16
+ * [batch, seq, hidden]. */
+typedef struct dg_clip dg_clip;
+int32_t dg_clip_create(dg_ctx* ctx, int32_t vocab, int32_t hidden, int32_t intermediate, int32_t layers, int32_t heads,
+                       int32_t max_positions, dg_clip** out);
+void dg_clip_destroy(dg_clip* clip);
+int32_t dg_clip_num_weights(dg_clip* clip);
+const char* dg_clip_weight_name(dg_clip* clip, int32_t index);
+int32_t dg_clip_weight_shape(dg_clip* clip, int32_t index, int64_t* shape4, int32_t* ndim);
+int32_t dg_clip_set_weight(dg_clip* clip, const char* key, const void* src, int32_t ndim, const int64_t* shape);
+int32_t dg_clip_prepare(dg_clip* clip, int32_t max_batch);
+int32_t dg_clip_encode(dg_clip* clip, const int32_t* input_ids, int32_t batch, int32_t seq, void* out, void* stream);
+
 /* ---- single operators (exported for the parity tests; the same launchers the UNet uses) ---------------------------
  * dg_op_gemm: out[M, n_out] = epi(A[M, K] * W[n_w, K]^T)      <- torch.nn.Linear / Conv2d 1x1
  *    bias [n_w] / residual [M, n_out] optional; geglu: W is GEGLU-packed (see dg_op_pack_geglu), n_out = inner dim.

@@ -1,0 +1,94 @@
+"""GPU parity of the CLIP text encoder through the transformers-shaped surface / `dg_clip_encode`
+against `transformers.CLIPTextModel` itself (the library the reference's pipeline calls; transformers is part of the image,
+so this row's parity IS pinned to upstream): random-init weights rounded to fp16, same token ids.
+Same statement as tests/test_gpu_unet.py: max|err| <= 2e-2 * max|ref| + 1e-3, cosine >= 0.999,
+rms(E_new) <= 2 * rms(E_torch) + 1e-4 with E_torch = upstream run in fp16 on the GPU against upstream in fp32 on the CPU.
+"""
+import pytest
+import torch
+
+from tests.test_gpu_unet import DEV, _check, _need_gpu
+
+pytestmark = pytest.mark.gpu
+
+
+def _models(seed=0, **cfg_kw):
+    from transformers import CLIPTextConfig
+    from transformers import CLIPTextModel as HFCLIPTextModel
+    from divergen_b200 import CLIPTextModel
+    cfg = CLIPTextConfig(hidden_act="quick_gelu", layer_norm_eps=1e-5, **cfg_kw)
+    torch.manual_seed(seed)
+    ref = HFCLIPTextModel(cfg).eval()
+    sd = {k: v.half().float() for k, v in ref.state_dict().items() if not k.endswith("position_ids")}
+    ref.load_state_dict(sd, strict=False)
+    ours = CLIPTextModel(device=DEV, **cfg_kw)
+    res = ours.load_state_dict(sd)
+    assert not res.missing_keys and not res.unexpected_keys
+    return ref, ours
+
+
+def _ids(b, s, vocab, seed):
+    g = torch.Generator().manual_seed(seed)
+    ids = torch.randint(1, vocab - 2, (b, s), generator=g)
+    ids[:, 0] = vocab - 2                    # BOS
+    for i in range(b):                       # EOS somewhere, padding (= EOS id, as CLIP's tokenizer pads) after it
+        e = int(torch.randint(2, s, (1,), generator=g))
+        ids[i, e:] = vocab - 1
+    return ids
+
+
+TINY = dict(vocab_size=1000, hidden_size=128, intermediate_size=256, num_hidden_layers=2, num_attention_heads=2,
+            max_position_embeddings=77)
+
+
+@pytest.mark.parametrize("b,s", [(1, 77), (3, 77), (2, 16)])
+def test_tiny_clip_text_encoder(b, s):
+    _need_gpu()
+    ref, ours = _models(0, **TINY)
+    ids = _ids(b, s, TINY["vocab_size"], 1)
+    with torch.no_grad():
+        ref32 = ref(input_ids=ids).last_hidden_state
+        ref16 = ref.half().to(DEV)(input_ids=ids.to(DEV)).last_hidden_state
+    out = ours(ids)
+    got = out.last_hidden_state
+    assert got.shape == (b, s, TINY["hidden_size"]) and out[0] is got
+    _check(got, ref32, ref16, name=f"clip tiny b={b} s={s}")
+
+
+def test_clip_is_causal():
+    """Changing a later token must not change the embeddings of earlier positions (CLIP's causal mask)."""
+    _need_gpu()
+    _, ours = _models(0, **TINY)
+    ids = _ids(1, 77, TINY["vocab_size"], 2)
+    a = ours(ids).last_hidden_state.clone()
+    ids2 = ids.clone()
+    ids2[0, 40] = (ids2[0, 40] + 17) % 900 + 1
+    b = ours(ids2).last_hidden_state
+    assert torch.equal(a[0, :40], b[0, :40])
+    assert not torch.equal(a[0, 40:], b[0, 40:])
+
+
+def test_sd_clip_text_encoder_full_width():
+    """The SD-1.x text encoder (ViT-L/14 text tower: 12 x 768, 123 M parameters), prompt + empty-prompt pair."""
+    _need_gpu()
+    from divergen_b200 import SD_CLIP_CONFIG
+    ref, ours = _models(3, **SD_CLIP_CONFIG)
+    assert len(ours.expected_state_dict_shapes()) == 196
+    ids = _ids(2, 77, SD_CLIP_CONFIG["vocab_size"], 4)
+    with torch.no_grad():
+        ref32 = ref(input_ids=ids).last_hidden_state
+        ref16 = ref.half().to(DEV)(input_ids=ids.to(DEV)).last_hidden_state
+    got = ours(ids).last_hidden_state
+    _check(got, ref32, ref16, name="clip sd 2x77")
+
+
+def test_clip_errors():
+    _need_gpu()
+    from divergen_b200 import CLIPTextModel
+    with pytest.raises((RuntimeError, ValueError)):
+        CLIPTextModel(device=DEV, hidden_size=96, num_attention_heads=2)          # head dim 48
+    m = CLIPTextModel(device=DEV, **TINY)
+    with pytest.raises((RuntimeError, ValueError)):
+        m(torch.zeros(1, 77, dtype=torch.long))                                  # weights not set
+    with pytest.raises(ValueError):
+        m(torch.zeros(1, 78, dtype=torch.long))

@@ -83,3 +83,19 @@ def test_vae_decoder_tiny_cpu():
     with torch.no_grad():
         y = m(torch.randn(2, 4, 8, 8, generator=torch.Generator().manual_seed(1)))
     assert y.shape == (2, 3, 64, 64) and torch.isfinite(y).all()
+
+
+def test_clip_text_model_upstream_structure():
+    """Row f2's checker is transformers.CLIPTextModel itself: pin the SD-1.x text tower's size and key names."""
+    from transformers import CLIPTextConfig, CLIPTextModel
+    cfg = CLIPTextConfig(vocab_size=49408, hidden_size=768, intermediate_size=3072, num_hidden_layers=12,
+                         num_attention_heads=12, max_position_embeddings=77, hidden_act="quick_gelu")
+    with torch.device("meta"):
+        m = CLIPTextModel(cfg)
+    assert sum(p.numel() for p in m.parameters()) == 123_060_480
+    keys = [k for k in m.state_dict() if not k.endswith("position_ids")]
+    assert len(keys) == 196
+    for k in ("text_model.embeddings.token_embedding.weight", "text_model.embeddings.position_embedding.weight",
+              "text_model.encoder.layers.0.self_attn.q_proj.bias", "text_model.encoder.layers.11.mlp.fc2.weight",
+              "text_model.final_layer_norm.weight"):
+        assert k in keys, k

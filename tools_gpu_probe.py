@@ -19,6 +19,7 @@ GROUPS = {
     "unet_tiny": ["tests/test_gpu_unet.py", "-k", "not sd15 and not sd21"],
     "unet_sd15": ["tests/test_gpu_unet.py", "-k", "sd15"],
     "unet_sd21": ["tests/test_gpu_unet.py", "-k", "sd21"],
+    "clip": ["tests/test_gpu_clip.py"],
     "vae_tiny": ["tests/test_gpu_vae.py", "-k", "not sd_vae"],
     "vae_sd": ["tests/test_gpu_vae.py", "-k", "sd_vae"],
 }
