@@ -82,6 +82,7 @@ SIGNATURES = {
     "dg_clip_set_weight": (_I, [_P, C.c_char_p, _P, _I, C.POINTER(_L)]),
     "dg_clip_prepare": (_I, [_P, _I]),
     "dg_clip_encode": (_I, [_P, C.POINTER(_I), _I, _I, _P, _P]),
+    "dg_op_image_to_uint8": (_I, [_P, _P, _P, _I, _I, _I, _I, _P]),
     "dg_op_gemm": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "dg_op_pack_geglu": (_I, [_P, _P, _P, _P, _P, _I, _I, _P]),
     "dg_op_geglu_packed_rows": (_I, [_I]),

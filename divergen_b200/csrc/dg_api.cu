@@ -1546,4 +1546,14 @@ int32_t dg_clip_encode(dg_clip* c, const int32_t* input_ids, int32_t batch, int3
   return DG_OK;
 }
 
+
+int32_t dg_op_image_to_uint8(dg_ctx* ctx, const void* img, void* out_u8, int32_t B, int32_t C, int32_t H, int32_t W, void* stream) {
+  if (!ctx || !img || !out_u8 || B <= 0 || C <= 0 || C > 4 || H <= 0 || W <= 0) return fail(DG_E_ARG, "bad argument");
+  DG_CUDA(cudaSetDevice(ctx->device));
+  const size_t n = (size_t)B * H * W;
+  image_to_uint8_hwc_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const __half*)img, (unsigned char*)out_u8, B, C, H * W);
+  DG_LAUNCH_CHECK();
+  return DG_OK;
+}
+
 }  // extern "C"

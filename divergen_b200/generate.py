@@ -140,6 +140,69 @@ def synthetic_text_embeddings(prompts: Sequence[str], dim: int, tokens: int = 77
     return torch.stack(rows).half()
 
 
+class AsyncImageWriter:
+    """Output path: uint8 images leave the device through pinned memory on a side copy, and PNG
+    encoding (zlib releases the GIL) runs on worker threads while the GPU denoises the next micro-batch.  File names and
+    PNG content are what `pt_to_pil(image)[j].save(out_path)` (reference :267) produces."""
+
+    def __init__(self, workers: int = 4):
+        from concurrent.futures import ThreadPoolExecutor
+        self._pool = ThreadPoolExecutor(max_workers=max(1, workers))
+        self._pending = []
+
+    def submit(self, images_u8, paths: Sequence[str]):
+        import torch
+        host = torch.empty(images_u8.shape, dtype=torch.uint8, pin_memory=True)
+        host.copy_(images_u8, non_blocking=True)
+        done = torch.cuda.Event()
+        done.record()
+        self._pending.append(self._pool.submit(self._save, host, done, list(paths)))
+
+    @staticmethod
+    def _save(host, done, paths):
+        from PIL import Image
+        done.synchronize()
+        arr = host.numpy()
+        for j, path in enumerate(paths):
+            Image.fromarray(arr[j]).save(path)
+        return len(paths)
+
+    def close(self) -> int:
+        n = sum(f.result() for f in self._pending)
+        self._pending = []
+        self._pool.shutdown(wait=True)
+        return n
+
+
+def encode_prompt_table(prompts: Sequence[str], tokenizer, text_encoder, batch: int = 64):
+    """Text embeddings of every distinct prompt, once, on rank 0 (row 0 = the unconditional "" prompt): what the reference
+    recomputes per micro-batch on every rank through `stage_1.encode_prompt(prompt)` (:242).  `tokenizer` is a transformers
+    `CLIPTokenizer`-like callable, `text_encoder` a `CLIPTextModel` (divergen_b200.clip or any `.forward(ids)[0]`)."""
+    import torch
+    texts = [""] + list(prompts)
+    rows = []
+    for i in range(0, len(texts), batch):
+        ids = tokenizer(texts[i:i + batch], padding="max_length", max_length=getattr(tokenizer, "model_max_length", 77),
+                        truncation=True, return_tensors="pt").input_ids
+        rows.append(text_encoder(ids)[0].to(torch.float16))
+    return torch.cat(rows, dim=0)
+
+
+def load_text_encoder(ckpt_dir: str, device):
+    """(tokenizer, text_encoder) from `<ckpt_dir>/tokenizer` + `<ckpt_dir>/text_encoder/model*.safetensors`, or None when
+    either is missing (no checkpoint is reachable offline: the driver then falls back to synthetic embeddings)."""
+    tok_dir = os.path.join(ckpt_dir, "tokenizer")
+    te_path = _first_existing(os.path.join(ckpt_dir, "text_encoder"), ("model.fp16.safetensors", "model.safetensors"))
+    if not (os.path.isdir(tok_dir) and te_path):
+        return None
+    from safetensors.torch import load_file
+    from transformers import CLIPTokenizer
+    from . import CLIPTextModel
+    enc = CLIPTextModel(device=device)
+    enc.load_state_dict(load_file(te_path))
+    return CLIPTokenizer.from_pretrained(tok_dir), enc
+
+
 # ------------------------------------------------------------------ CLI
 def build_parser() -> argparse.ArgumentParser:
     p = argparse.ArgumentParser(description="DiverGen generation driver on the B200-native Stable-Diffusion path")
@@ -160,6 +223,7 @@ def build_parser() -> argparse.ArgumentParser:
     p.add_argument("--num_inference_steps", type=int, default=50)
     p.add_argument("--guidance_scale", type=float, default=7.5)
     p.add_argument("--random_init", action="store_true", help="random-init UNet weights (benchmarks; no checkpoint offline)")
+    p.add_argument("--png_workers", type=int, default=4, help="PNG encoder threads per rank")
     p.add_argument("--decode", action="store_true", help="with --random_init: also build a random-init VAE and write PNGs")
     p.add_argument("--max_prompt_files", type=int, default=0, help="process only the first N category files (0 = all)")
     return p
@@ -192,8 +256,7 @@ def _first_existing(directory: str, names: Sequence[str]) -> Optional[str]:
 
 def main(argv: Optional[Sequence[str]] = None) -> int:
     import torch
-    from . import (AutoencoderKL, DDIMScheduler, SD15_CONFIG, SD21_CONFIG, StableDiffusionPipeline,
-                   UNet2DConditionModel, pt_to_pil)
+    from . import AutoencoderKL, DDIMScheduler, SD15_CONFIG, SD21_CONFIG, StableDiffusionPipeline, UNet2DConditionModel
 
     args = build_parser().parse_args(argv)
     if args.dist:
@@ -243,11 +306,16 @@ def main(argv: Optional[Sequence[str]] = None) -> int:
     per_file = [(f, open(f).read().splitlines()) for f in files] if files else [("prompt.txt", [args.prompt])]
     # ---- text embeddings: once, on rank 0, for every distinct prompt; one broadcast
     prompts = sorted({l.strip() for _, lines in per_file for l in lines})
-    table = synthetic_text_embeddings(prompts, cfg["cross_attention_dim"]).to(device) if rank == 0 else None
+    table = None
+    if rank == 0:
+        te = None if args.random_init else load_text_encoder(args.ckpt_dir, device)
+        table = (encode_prompt_table(prompts, te[0], te[1]) if te is not None
+                 else synthetic_text_embeddings(prompts, cfg["cross_attention_dim"])).to(device)
     table = broadcast_embedding_table(table if table is not None else torch.empty(0, device=device))
     row = {p: i + 1 for i, p in enumerate(prompts)}
 
     n_done = 0
+    writer = AsyncImageWriter(args.png_workers) if vae is not None else None
     for fi, (path, lines) in enumerate(per_file):
         cid = category_id_of(path)
         print("==> Reading prompts from {}, {}/{}".format(path, fi + 1, len(per_file)))
@@ -259,18 +327,18 @@ def main(argv: Optional[Sequence[str]] = None) -> int:
             pos = table[row[call.prompt]][None]
             neg = table[0][None]
             out = pipe(prompt_embeds=pos, negative_prompt_embeds=neg, generator=generator,
-                       output_type="pt" if vae is not None else "latent",
+                       output_type="uint8" if vae is not None else "latent",
                        num_images_per_prompt=call.num_images, num_inference_steps=args.num_inference_steps,
                        guidance_scale=args.guidance_scale).images
+            dsts = [os.path.join(sample_dir, output_name(cid, count, ext)) for count in call.counts]
             if vae is not None:
-                out = pt_to_pil(out * 2 - 1)                                      # reference :267 (pt -> PIL -> .save)
-            for j, count in enumerate(call.counts):
-                dst = os.path.join(sample_dir, output_name(cid, count, ext))
-                if vae is not None:
-                    out[j].save(dst)
-                else:
+                writer.submit(out, dsts)                                          # reference :267 (pt -> PIL -> .save), asynchronously
+            else:
+                for j, dst in enumerate(dsts):
                     torch.save(out[j].cpu(), dst)
             n_done += call.num_images
+    if writer is not None:
+        writer.close()
     if args.dist:
         torch.distributed.barrier()
         torch.distributed.destroy_process_group()

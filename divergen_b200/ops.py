@@ -216,3 +216,14 @@ def groupnorm_fused_nhwc(x, stats, gamma, beta, groups: int, eps: float, silu: b
     _lib.check(lib.dg_op_groupnorm_fused(ctx, _p(x), C0, _pf(stats), _p(x1), C1, _pf(stats1), blk, _p(gamma), _p(beta), _p(out),
                                          B, H * W, groups, eps, int(silu), s), "dg_op_groupnorm_fused")
     return out
+
+
+def image_to_uint8(images):
+    """[B, C, H, W] fp16 in [-1, 1] -> [B, H, W, C] uint8 on the device: diffusers.utils.pt_to_pil's arithmetic
+    (`(x / 2 + 0.5).clamp(0, 1)`, `* 255`, round) without the host round trip of the float image."""
+    _chk16(images)
+    lib, ctx, s = _env(images)
+    B, Cc, H, W = images.shape
+    out = torch.empty((B, H, W, Cc), dtype=torch.uint8, device=images.device)
+    _lib.check(lib.dg_op_image_to_uint8(ctx, _p(images), C.c_void_p(out.data_ptr()), B, Cc, H, W, s), "dg_op_image_to_uint8")
+    return out

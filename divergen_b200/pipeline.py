@@ -127,8 +127,14 @@ class StableDiffusionPipeline:
                 raise ValueError("output_type != 'latent' needs `vae=` (divergen_b200.AutoencoderKL) or a vae_decode callable")
             if output_type == "pt":
                 images = (images / 2 + 0.5).clamp(0, 1)
-            elif output_type == "pil":
-                images = pt_to_pil(images)
+            elif output_type in ("pil", "uint8"):
+                # pt_to_pil's arithmetic on the device (row f4): [B, H, W, 3] uint8; "uint8" hands that tensor to the caller
+                # (the driver copies it to pinned memory asynchronously and PNG-encodes on worker threads)
+                from . import ops
+                from PIL import Image
+                images = ops.image_to_uint8(images.to(torch.float16).contiguous())
+                if output_type == "pil":
+                    images = [Image.fromarray(a) for a in images.cpu().numpy()]
             else:
                 raise ValueError(output_type)
         return StableDiffusionPipelineOutput(images=images) if return_dict else (images, None)

@@ -141,6 +141,10 @@ int32_t dg_clip_set_weight(dg_clip* clip, const char* key, const void* src, int3
 int32_t dg_clip_prepare(dg_clip* clip, int32_t max_batch);
 int32_t dg_clip_encode(dg_clip* clip, const int32_t* input_ids, int32_t batch, int32_t seq, void* out, void* stream);
 
+/* ---- output path: `pt_to_pil(image)` arithmetic on the device (txt2img_diffusers_stages_from_txt.py:267) ----
+ * img [B, C<=4, H, W] fp16 in [-1, 1]  ->  out_u8 [B, H, W, C] uint8 = round(clamp(img / 2 + 0.5, 0, 1) * 255). */
+int32_t dg_op_image_to_uint8(dg_ctx* ctx, const void* img, void* out_u8, int32_t B, int32_t C, int32_t H, int32_t W, void* stream);
+
 /* ---- single operators (exported for the parity tests; the same launchers the UNet uses) ---------------------------
  * dg_op_gemm: out[M, n_out] = epi(A[M, K] * W[n_w, K]^T)      <- torch.nn.Linear / Conv2d 1x1
  *    bias [n_w] / residual [M, n_out] optional; geglu: W is GEGLU-packed (see dg_op_pack_geglu), n_out = inner dim.

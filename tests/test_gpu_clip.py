@@ -92,3 +92,28 @@ def test_clip_errors():
         m(torch.zeros(1, 77, dtype=torch.long))                                  # weights not set
     with pytest.raises(ValueError):
         m(torch.zeros(1, 78, dtype=torch.long))
+
+
+def test_driver_embedding_table_with_device_encoder():
+    """generate.encode_prompt_table: one row per distinct prompt plus the unconditional row 0, through the device encoder."""
+    _need_gpu()
+    from types import SimpleNamespace
+    from divergen_b200.generate import encode_prompt_table
+    ref, ours = _models(0, **TINY)
+
+    class StubTokenizer:                       # CLIPTokenizer's calling convention; its vocabulary files are not shipped
+        model_max_length = 77
+
+        def __call__(self, texts, padding=None, max_length=77, truncation=True, return_tensors="pt"):
+            rows = []
+            for t in texts:
+                toks = [998] + [1 + (ord(c) % 900) for c in t][:max_length - 2] + [999]
+                rows.append(toks + [999] * (max_length - len(toks)))
+            return SimpleNamespace(input_ids=torch.tensor(rows))
+
+    prompts = ["a photo of a cat", "a photo of a single aerosol can", "x"]
+    table = encode_prompt_table(prompts, StubTokenizer(), ours, batch=2)
+    assert table.shape == (4, 77, TINY["hidden_size"]) and table.dtype == torch.float16
+    with torch.no_grad():
+        want = ref(input_ids=StubTokenizer()([""] + prompts).input_ids).last_hidden_state
+    _check(table, want, name="driver embedding table")

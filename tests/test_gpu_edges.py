@@ -112,3 +112,19 @@ def test_pipeline_guidance_off_images_per_prompt_and_seeding():
         pipe(prompt_embeds=pos, negative_prompt_embeds=neg, eta=0.5, num_inference_steps=2, output_type="latent")
     with pytest.raises(ValueError):
         pipe(prompt_embeds=pos, negative_prompt_embeds=neg, num_inference_steps=2, height=100, width=128, output_type="latent")
+
+
+def test_image_to_uint8_matches_pt_to_pil():
+    """Row f4: the device-side uint8 conversion is bit-identical to diffusers' pt_to_pil arithmetic (as restated in
+    divergen_b200.pipeline.pt_to_pil) on values inside, outside and exactly on the clamp / rounding boundaries."""
+    if not torch.cuda.is_available():
+        pytest.skip("no GPU")
+    import numpy as np
+    from divergen_b200 import ops, pt_to_pil
+    g = torch.Generator().manual_seed(0)
+    img = (torch.randn(3, 3, 40, 24, generator=g) * 0.8).half()
+    img[0, 0, 0, :8] = torch.tensor([-1.0, 1.0, 0.0, -1.5, 1.5, 1 / 255, -1 / 255, 0.00392]).half()
+    got = ops.image_to_uint8(img.cuda()).cpu().numpy()
+    want = np.stack([np.asarray(p) for p in pt_to_pil(img.cuda())])
+    assert got.shape == (3, 40, 24, 3) and got.dtype == np.uint8
+    assert np.array_equal(got, want)
