@@ -65,6 +65,7 @@ struct Gemm2Params {
   int gn_slots;            // HW / 32
   float* ws;               // split-K accumulators: [m_tile*tiles_n + nt][128][320] fp32, zero on entry, zero on exit
   int* tickets;            // [m_tile*tiles_n + nt], zero on entry, zero on exit
+  int sk_bulk;             // split-K launch with one tile per CTA (host-checked): partials travel as bulk shared->global reductions
   float inv_splits, inv_tiles_n, inv_tiles_x, inv_tiles_y;   // host-computed 1/d for the unit decomposition (fast_div)
   long long* dbg;          // optional (DG_GEMM_DBG=1): clock64() stamps of CTA 0's first unit, see DG_STAMP sites
 };
@@ -309,7 +310,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
   uint64_t* buf_free = acc_empty + 2;       // [kRing]  staging buffer reusable (store warp -> epilogue warps)
   uint64_t* chunk_ready = buf_free + S::kRing;   // [kRing]  staging buffer written by all 8 epilogue warps (-> store warp)
   uint64_t* res_full = chunk_ready + S::kRing;   // [kRing]  residual tile landed in the staging buffer (TMA -> epilogue warps)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_full + S::kRing);
+  uint64_t* sk_full = res_full + S::kRing;       // [1]      split-K: the summed fp32 tile landed in the (idle) operand stages
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sk_full + 1);
   volatile uint32_t* ticket_slot = tmem_slot + 1;
   volatile int* chunk_info = reinterpret_cast<volatile int*>(tmem_slot + 2);   // [kRing][5]: col, x0, y0, b0, flags (1 store, 2 stop)
 
@@ -328,6 +330,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
     for (int i = 0; i < kStages; ++i) { mbar_init(&full[i], kCta); mbar_init(&empty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], kCta * 8); }
     for (int i = 0; i < S::kRing; ++i) { mbar_init(&buf_free[i], 1); mbar_init(&chunk_ready[i], 8); mbar_init(&res_full[i], 1); }
+    mbar_init(sk_full, 1);
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc_pair<kCta, kTmemCols>(tmem_slot);
@@ -594,7 +597,52 @@ gemm2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
       };
 
       bool do_final = true;
-      if (p.splits > 1) {
+      // 160-wide tiles, one tile per CTA: the partial goes through the (idle) staging ring as ONE bulk reduction per
+      // 32-column chunk -- the L2 adds whole lines instead of 16-byte pieces of 640-byte-strided rows (~1.6 us per MB).
+      // Workspace tile layout (private to this kernel): [5 chunks][128 rows][32 floats], 16-byte pieces XOR-swizzled by row & 7.
+      constexpr bool kSkBulkT = (kBN == 160) && !kGeglu;
+      const bool sk_bulk = kSkBulkT && p.sk_bulk;
+      float* ws_tile = p.ws + (size_t)t.ctile * 128 * kBN;
+      if (p.splits > 1 && sk_bulk) {
+#pragma unroll
+        for (int j = 0; j < 5; ++j) {
+          const int c = hf * 80 + j * 16;
+          const uint32_t dst = sRing_a + (uint32_t)(c >> 5) * 16384u + (uint32_t)r * 128u;
+          const uint32_t pb = (uint32_t)(c & 31) >> 2;
+          uint32_t v[16];
+          tmem_ld16(t_row + c, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 4; ++i) sts_u4(dst + (((pb + i) ^ (uint32_t)(r & 7)) << 4), v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+        }
+        release_acc();
+        fence_proxy_async();
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (et == 0) {
+#pragma unroll
+          for (int cc = 0; cc < 5; ++cc) bulk_reduce_add_f32(ws_tile + cc * 4096, sRing + cc * 16384, 16384u);
+          bulk_commit();
+          bulk_wait_all();                       // the reductions have been performed, not merely read out of shared memory
+          __threadfence();
+          *ticket_slot = (uint32_t)atomicAdd(p.tickets + t.ctile, 1);
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        do_final = (*ticket_slot == (uint32_t)(p.splits - 1));
+        if (do_final) {
+          // last arriver: pull the summed tile into the operand stages (this CTA's only tile is done with them), then zero
+          // the workspace tile for the next launch with coalesced stores
+          __threadfence();
+          if (et == 0) {
+            p.tickets[t.ctile] = 0;
+            fence_proxy_async();
+            mbar_arrive_expect_tx(sk_full, 5u * 16384u);
+#pragma unroll
+            for (int cc = 0; cc < 5; ++cc) bulk_load_g2s(smem + cc * 16384, ws_tile + cc * 4096, 16384u, sk_full);
+          }
+          mbar_wait(sk_full, 0);
+          for (int i = et; i < 128 * kBN / 4; i += kEpiThreads) __stcg(reinterpret_cast<float4*>(ws_tile) + i, make_float4(0.f, 0.f, 0.f, 0.f));
+        }
+      } else if (p.splits > 1) {
         // ---- split-K: add this split's fp32 partial into the tile's L2-resident accumulator (16-byte vector reductions);
         // the last arriver (ticket) reads the sum back, re-zeroes it for the next launch and finishes the tile
         float* wrow = p.ws + ((size_t)t.ctile * 128 + r) * kBN;
@@ -685,6 +733,14 @@ gemm2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
                 if (j == kChunks - 1) release_acc();
 #pragma unroll
                 for (int i = 0; i < kCW; ++i) f[i] = __uint_as_float(v[i]);
+              }
+            } else if (sk_bulk) {
+              const uint32_t srcs = smem_u32(smem) + (uint32_t)(c >> 5) * 16384u + (uint32_t)r * 128u;
+              const uint32_t pb = (uint32_t)(c & 31) >> 2;
+#pragma unroll
+              for (int i = 0; i < kCW; i += 4) {
+                const float4 v4 = lds_f4(srcs + (((pb + (uint32_t)(i >> 2)) ^ (uint32_t)(r & 7)) << 4));
+                f[i] = v4.x; f[i + 1] = v4.y; f[i + 2] = v4.z; f[i + 3] = v4.w;
               }
             } else {
               float* src = wsrow + c;

@@ -244,12 +244,17 @@ inline int choose_splits(int units, int num_kb, int slots, size_t ws_floats_per_
   if (forced < 0) { const char* e = getenv("DG_SPLITS"); forced = e && e[0] ? atoi(e) : 0; }
   if ((size_t)units * ws_floats_per_unit > ws_cap) return 1;
   if (forced > 0) return (forced * 4 <= num_kb) ? forced : 1;
-  if (units >= slots || num_kb < 32) return 1;
+  static int min_total = -1;
+  if (min_total < 0) { const char* e = getenv("DG_SK_MINTOTAL"); min_total = e ? atoi(e) : 32; }
+  if (units >= slots || num_kb < min_total) return 1;
   int best = 1;
   double best_cost = 1e30;
   const double mb_per_unit = (double)ws_floats_per_unit * 4.0 / 1e6;
-  for (int s = 1; s <= 16 && s * 16 <= num_kb && units * s <= slots; ++s) {
-    const double cost = (double)((num_kb + s - 1) / s) + 9.0 + (s > 1 ? 10.0 + 4.8 * mb_per_unit * units * s : 0.0);
+  static double coef = -1.0; static int minkb = -1;
+  if (coef < 0) { const char* e = getenv("DG_SK_COEF"); coef = e ? atof(e) : 4.8; }
+  if (minkb < 0) { const char* e = getenv("DG_SK_MINKB"); minkb = e ? atoi(e) : 16; }
+  for (int s = 1; s <= 16 && s * minkb <= num_kb && units * s <= slots; ++s) {
+    const double cost = (double)((num_kb + s - 1) / s) + 9.0 + (s > 1 ? 10.0 + coef * mb_per_unit * units * s : 0.0);
     if (cost < best_cost - 1e-9) { best_cost = cost; best = s; }
   }
   return best;
@@ -328,6 +333,8 @@ inline int launch_gemm(cudaStream_t stream, const GemmRes& res, const GemmArgs& 
   if (res.ws && res.tickets && !a.row_stats_out && m_tiles * p.tiles_n <= kSplitTickets)
     p.splits = choose_splits(units, num_kb, slots, (size_t)kcta * 128 * kbn, kSplitWsFloats);
 
+  p.sk_bulk = (p.splits > 1 && units * p.splits <= slots) ? 1 : 0;   // one tile per CTA: operand stages are idle for the final sum
+  { static int nb = -1; if (nb < 0) { const char* e = getenv("DG_SK_BULK"); nb = (e && e[0] == '0') ? 0 : 1; } if (!nb) p.sk_bulk = 0; }
   p.inv_splits = 1.0f / (float)p.splits; p.inv_tiles_n = 1.0f / (float)p.tiles_n;
   p.inv_tiles_x = 1.0f / (float)p.tiles_x; p.inv_tiles_y = 1.0f / (float)p.tiles_y;
   CUtensorMap mA0, mA1, mW, mO, mR;
