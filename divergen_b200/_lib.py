@@ -82,6 +82,15 @@ SIGNATURES = {
     "dg_clip_set_weight": (_I, [_P, C.c_char_p, _P, _I, C.POINTER(_L)]),
     "dg_clip_prepare": (_I, [_P, _I]),
     "dg_clip_encode": (_I, [_P, C.POINTER(_I), _I, _I, _P, _P]),
+    "dg_clipscore_create": (_I, [_P, C.POINTER(_I), C.POINTER(_I), _I, C.POINTER(_P)]),
+    "dg_clipscore_destroy": (None, [_P]),
+    "dg_clipscore_num_weights": (_I, [_P]),
+    "dg_clipscore_weight_name": (C.c_char_p, [_P, _I]),
+    "dg_clipscore_weight_shape": (_I, [_P, _I, C.POINTER(_L), C.POINTER(_I)]),
+    "dg_clipscore_set_weight": (_I, [_P, C.c_char_p, _P, _I, C.POINTER(_L)]),
+    "dg_clipscore_set_logit_scale": (_I, [_P, _F]),
+    "dg_clipscore_prepare": (_I, [_P, _I, _I]),
+    "dg_clipscore_score": (_I, [_P, _P, _I, C.POINTER(_I), C.POINTER(_I), _I, _I, C.POINTER(_F), _P]),
     "dg_op_image_to_uint8": (_I, [_P, _P, _P, _I, _I, _I, _I, _P]),
     "dg_op_gemm": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "dg_op_pack_geglu": (_I, [_P, _P, _P, _P, _P, _I, _I, _P]),

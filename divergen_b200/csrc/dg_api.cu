@@ -58,7 +58,7 @@ struct Arena {
 };
 
 // ================================================================== weights
-enum PackKind { PK_COPY, PK_CONV3, PK_CONV_IN, PK_GEGLU_W, PK_GEGLU_B, PK_ROWS };
+enum PackKind { PK_COPY, PK_CONV3, PK_CONV_IN, PK_GEGLU_W, PK_GEGLU_B, PK_ROWS, PK_PAD_ROWS };
 
 struct Slot {
   std::string key;
@@ -904,16 +904,11 @@ struct dg_clip : WeightStore {
 
 namespace {
 
-int build_clip(dg_clip* c) {
-  const int C = c->hidden;
-  DG_TRY(dev_alloc(c, (void**)&c->tok, (size_t)c->vocab * C * 2));
-  DG_TRY(dev_alloc(c, (void**)&c->pos, (size_t)c->max_pos * C * 2));
-  add_slot(c, "text_model.embeddings.token_embedding.weight", {c->vocab, C}, PK_COPY, c->tok);
-  add_slot(c, "text_model.embeddings.position_embedding.weight", {c->max_pos, C}, PK_COPY, c->pos);
-  c->L.resize(c->layers);
-  for (int i = 0; i < c->layers; ++i) {
-    ClipLayer& l = c->L[i];
-    const std::string pfx = "text_model.encoder.layers." + std::to_string(i);
+int build_clip_layers(WeightStore* c, const std::string& tower, int C, int inter, int layers, std::vector<ClipLayer>* L) {
+  L->resize(layers);
+  for (int i = 0; i < layers; ++i) {
+    ClipLayer& l = (*L)[i];
+    const std::string pfx = tower + ".encoder.layers." + std::to_string(i);
     DG_TRY(make_norm(c, pfx + ".layer_norm1", C, &l.ln1));
     DG_TRY(make_fused_rows(c, {pfx + ".self_attn.q_proj.weight", pfx + ".self_attn.k_proj.weight", pfx + ".self_attn.v_proj.weight"}, C, C, &l.qkv));
     DG_TRY(dev_alloc(c, (void**)&l.qkv.b, (size_t)3 * C * 2));
@@ -922,17 +917,87 @@ int build_clip(dg_clip* c) {
     add_slot(c, pfx + ".self_attn.v_proj.bias", {C}, PK_ROWS, l.qkv.b, 2 * C, C, 1);
     DG_TRY(make_linear(c, pfx + ".self_attn.out_proj", C, C, true, &l.out));
     DG_TRY(make_norm(c, pfx + ".layer_norm2", C, &l.ln2));
-    DG_TRY(make_linear(c, pfx + ".mlp.fc1", C, c->inter, true, &l.fc1));
-    DG_TRY(make_linear(c, pfx + ".mlp.fc2", c->inter, C, true, &l.fc2));
+    DG_TRY(make_linear(c, pfx + ".mlp.fc1", C, inter, true, &l.fc1));
+    DG_TRY(make_linear(c, pfx + ".mlp.fc2", inter, C, true, &l.fc2));
   }
+  return DG_OK;
+}
+
+int build_clip(dg_clip* c) {
+  const int C = c->hidden;
+  DG_TRY(dev_alloc(c, (void**)&c->tok, (size_t)c->vocab * C * 2));
+  DG_TRY(dev_alloc(c, (void**)&c->pos, (size_t)c->max_pos * C * 2));
+  add_slot(c, "text_model.embeddings.token_embedding.weight", {c->vocab, C}, PK_COPY, c->tok);
+  add_slot(c, "text_model.embeddings.position_embedding.weight", {c->max_pos, C}, PK_COPY, c->pos);
+  DG_TRY(build_clip_layers(c, "text_model", C, c->inter, c->layers, &c->L));
   DG_TRY(make_norm(c, "text_model.final_layer_norm", C, &c->final_ln));
   return DG_OK;
 }
 
-int clip_linear(dg_clip* c, cudaStream_t s, const __half* x, int K, int rows, const Lin& w, const __half* residual, __half* out) {
+int clip_linear(dg_ctx* ctx, cudaStream_t s, const __half* x, int K, int rows, const Lin& w, const __half* residual, __half* out) {
   GemmArgs a; a.a0 = x; a.c0 = K; a.B = 1; a.H = 1; a.W = rows; a.taps = 1; a.w = w.w; a.n_w = w.rows; a.n_out = w.out; a.bias = w.b;
   a.residual = residual; a.ld_res = w.out; a.out = out; a.ldo = w.out;
-  return launch_gemm(s, c->ctx->gemm, a);
+  return launch_gemm(s, ctx->gemm, a);
+}
+
+// Pre-LN transformer layers (CLIPEncoderLayer x N) over x [batch * seq, C]; buffers: x2, h, att [rows, C], qkv [rows, 3C],
+// f [rows, inter].  The result is back in x.
+int run_clip_layers(dg_ctx* ctx, cudaStream_t s, const std::vector<ClipLayer>& L, __half* x, __half* x2, __half* h, __half* att,
+                    __half* qkv, __half* f, int batch, int seq, int C, int inter, int heads, int causal, float eps) {
+  const int rows = batch * seq;
+  for (const ClipLayer& l : L) {
+    DG_TRY(launch_layernorm(s, x, l.ln1.g, l.ln1.b, h, rows, C, eps));
+    DG_TRY(clip_linear(ctx, s, h, C, rows, l.qkv, nullptr, qkv));
+    DG_TRY(launch_attention(s, qkv, 3 * C, qkv + C, 3 * C, qkv + 2 * C, 3 * C, att, batch, heads, seq, seq, 64, causal));
+    DG_TRY(clip_linear(ctx, s, att, C, rows, l.out, x, x2));
+    DG_TRY(launch_layernorm(s, x2, l.ln2.g, l.ln2.b, h, rows, C, eps));
+    DG_TRY(clip_linear(ctx, s, h, C, rows, l.fc1, nullptr, f));
+    quick_gelu_kernel<<<grid_for((size_t)rows * inter / 8, 256, ctx->num_sms), 256, 0, s>>>(f, (size_t)rows * inter / 8);
+    DG_LAUNCH_CHECK();
+    DG_TRY(clip_linear(ctx, s, f, inter, rows, l.fc2, x2, x));
+  }
+  return DG_OK;
+}
+
+}  // namespace
+
+// CLIP similarity scorer: `clip_model(images, text)` -> logits_per_text of OpenAI CLIP ViT-L/14 as used
+// by DiverGen/filteration/get_clip_score.py:176-180 (weights by transformers `CLIPModel` state-dict key).
+struct dg_clipscore : WeightStore {
+  int vocab = 49408, t_hidden = 768, t_inter = 3072, t_layers = 12, t_heads = 12, max_pos = 77;
+  int image = 224, patch = 14, v_hidden = 1024, v_inter = 4096, v_layers = 24, v_heads = 16, proj = 768;
+  int kpad = 640;
+  float eps = 1e-5f, logit_scale = 4.6052f;
+  __half* tok = nullptr; __half* tpos = nullptr; std::vector<ClipLayer> TL; Norm t_final; Lin t_proj;
+  __half* patch_w = nullptr; __half* cls = nullptr; __half* vpos = nullptr; Norm pre_ln, post_ln; std::vector<ClipLayer> VL; Lin v_proj;
+  __half* ws = nullptr; int* ids_dev = nullptr; int* eos_dev = nullptr;
+  int max_images = 0, max_texts = 0;
+  size_t ws_elems = 0;
+};
+
+namespace {
+
+int build_clipscore(dg_clipscore* c) {
+  const int Ct = c->t_hidden, Cv = c->v_hidden, n = c->image / c->patch, S = n * n + 1, kreal = 3 * c->patch * c->patch;
+  c->kpad = (kreal + 63) / 64 * 64;
+  DG_TRY(dev_alloc(c, (void**)&c->tok, (size_t)c->vocab * Ct * 2));
+  DG_TRY(dev_alloc(c, (void**)&c->tpos, (size_t)c->max_pos * Ct * 2));
+  add_slot(c, "text_model.embeddings.token_embedding.weight", {c->vocab, Ct}, PK_COPY, c->tok);
+  add_slot(c, "text_model.embeddings.position_embedding.weight", {c->max_pos, Ct}, PK_COPY, c->tpos);
+  DG_TRY(build_clip_layers(c, "text_model", Ct, c->t_inter, c->t_layers, &c->TL));
+  DG_TRY(make_norm(c, "text_model.final_layer_norm", Ct, &c->t_final));
+  DG_TRY(make_linear(c, "text_projection", Ct, c->proj, false, &c->t_proj));
+  DG_TRY(dev_alloc(c, (void**)&c->patch_w, (size_t)Cv * c->kpad * 2));
+  DG_TRY(dev_alloc(c, (void**)&c->cls, (size_t)Cv * 2));
+  DG_TRY(dev_alloc(c, (void**)&c->vpos, (size_t)S * Cv * 2));
+  add_slot(c, "vision_model.embeddings.class_embedding", {Cv}, PK_COPY, c->cls);
+  add_slot(c, "vision_model.embeddings.patch_embedding.weight", {Cv, 3, c->patch, c->patch}, PK_PAD_ROWS, c->patch_w, c->kpad, Cv, kreal);
+  add_slot(c, "vision_model.embeddings.position_embedding.weight", {S, Cv}, PK_COPY, c->vpos);
+  DG_TRY(make_norm(c, "vision_model.pre_layrnorm", Cv, &c->pre_ln));      // (sic: the upstream key is misspelt)
+  DG_TRY(build_clip_layers(c, "vision_model", Cv, c->v_inter, c->v_layers, &c->VL));
+  DG_TRY(make_norm(c, "vision_model.post_layernorm", Cv, &c->post_ln));
+  DG_TRY(make_linear(c, "visual_projection", Cv, c->proj, false, &c->v_proj));
+  return DG_OK;
 }
 
 }  // namespace
@@ -1047,6 +1112,10 @@ static int store_set_weight(WeightStore* u, const char* key, const void* src, in
   switch (s.kind) {
     case PK_COPY: DG_CUDA(cudaMemcpy(s.dst, w, n * 2, cudaMemcpyDeviceToDevice)); break;
     case PK_ROWS: DG_CUDA(cudaMemcpy(s.dst + (size_t)s.row_off * s.b, w, n * 2, cudaMemcpyDeviceToDevice)); break;
+    case PK_PAD_ROWS:      // a rows of b elements -> rows of row_off elements, zero padded (patch embedding: K 588 -> 640)
+      DG_CUDA(cudaMemset(s.dst, 0, (size_t)s.a * s.row_off * 2));
+      DG_CUDA(cudaMemcpy2D(s.dst, (size_t)s.row_off * 2, w, (size_t)s.b * 2, (size_t)s.b * 2, s.a, cudaMemcpyDeviceToDevice));
+      break;
     case PK_CONV3:
       pack_conv3x3_kernel<<<grid_for(n, 256, sms), 256>>>(w, s.dst, s.a, s.b, s.b);
       DG_LAUNCH_CHECK();
@@ -1524,24 +1593,14 @@ int32_t dg_clip_encode(dg_clip* c, const int32_t* input_ids, int32_t batch, int3
   for (const Slot& sl : c->slots) if (!sl.set) return fail(DG_E_STATE, "clip weight %s has not been set", sl.key.c_str());
   DG_CUDA(cudaSetDevice(c->ctx->device));
   cudaStream_t s = (cudaStream_t)stream;
-  const int C = c->hidden, rows = batch * seq, sms = c->ctx->num_sms;
+  const int C = c->hidden, rows = batch * seq;
   const size_t R = (size_t)c->max_batch * c->max_pos;
   __half* x = c->ws; __half* x2 = x + R * C; __half* h = x2 + R * C; __half* att = h + R * C;
   __half* qkv = att + R * C; __half* f = qkv + R * 3 * C;
   DG_CUDA(cudaMemcpyAsync(c->ids_dev, input_ids, (size_t)rows * sizeof(int), cudaMemcpyHostToDevice, s));
   clip_embed_kernel<<<(unsigned)(((size_t)rows * (C / 8) + 255) / 256), 256, 0, s>>>(c->ids_dev, c->tok, c->pos, x, rows, seq, C, c->vocab);
   DG_LAUNCH_CHECK();
-  for (const ClipLayer& l : c->L) {
-    DG_TRY(launch_layernorm(s, x, l.ln1.g, l.ln1.b, h, rows, C, c->eps));
-    DG_TRY(clip_linear(c, s, h, C, rows, l.qkv, nullptr, qkv));
-    DG_TRY(launch_attention(s, qkv, 3 * C, qkv + C, 3 * C, qkv + 2 * C, 3 * C, att, batch, c->heads, seq, seq, 64, /*causal=*/1));
-    DG_TRY(clip_linear(c, s, att, C, rows, l.out, x, x2));
-    DG_TRY(launch_layernorm(s, x2, l.ln2.g, l.ln2.b, h, rows, C, c->eps));
-    DG_TRY(clip_linear(c, s, h, C, rows, l.fc1, nullptr, f));
-    quick_gelu_kernel<<<grid_for((size_t)rows * c->inter / 8, 256, sms), 256, 0, s>>>(f, (size_t)rows * c->inter / 8);
-    DG_LAUNCH_CHECK();
-    DG_TRY(clip_linear(c, s, f, c->inter, rows, l.fc2, x2, x));
-  }
+  DG_TRY(run_clip_layers(c->ctx, s, c->L, x, x2, h, att, qkv, f, batch, seq, C, c->inter, c->heads, /*causal=*/1, c->eps));
   DG_TRY(launch_layernorm(s, x, c->final_ln.g, c->final_ln.b, (__half*)out, rows, C, c->eps));
   return DG_OK;
 }
@@ -1552,6 +1611,125 @@ int32_t dg_op_image_to_uint8(dg_ctx* ctx, const void* img, void* out_u8, int32_t
   DG_CUDA(cudaSetDevice(ctx->device));
   const size_t n = (size_t)B * H * W;
   image_to_uint8_hwc_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const __half*)img, (unsigned char*)out_u8, B, C, H * W);
+  DG_LAUNCH_CHECK();
+  return DG_OK;
+}
+
+
+// ---- CLIP similarity scorer -------------------------------------------------------------------------------------------
+int32_t dg_clipscore_create(dg_ctx* ctx, const int32_t* text_cfg6, const int32_t* vision_cfg6, int32_t projection_dim, dg_clipscore** out) {
+  if (!ctx || !out) return fail(DG_E_ARG, "null argument");
+  std::unique_ptr<dg_clipscore> c(new dg_clipscore());
+  c->ctx = ctx;
+  if (text_cfg6) { c->vocab = text_cfg6[0]; c->t_hidden = text_cfg6[1]; c->t_inter = text_cfg6[2]; c->t_layers = text_cfg6[3]; c->t_heads = text_cfg6[4]; c->max_pos = text_cfg6[5]; }
+  if (vision_cfg6) { c->image = vision_cfg6[0]; c->patch = vision_cfg6[1]; c->v_hidden = vision_cfg6[2]; c->v_inter = vision_cfg6[3]; c->v_layers = vision_cfg6[4]; c->v_heads = vision_cfg6[5]; }
+  if (projection_dim > 0) c->proj = projection_dim;
+  if (c->t_hidden != 64 * c->t_heads || c->v_hidden != 64 * c->v_heads) return fail(DG_E_UNSUPPORTED, "clipscore: head dim must be 64 in both towers");
+  if (c->t_hidden % 64 || c->v_hidden % 64 || c->t_hidden > 1280 || c->v_hidden > 1280 || c->t_inter % 64 || c->v_inter % 64 || c->proj % 8 ||
+      c->patch <= 0 || c->image % c->patch || c->vocab <= 0 || c->max_pos <= 0)
+    return fail(DG_E_UNSUPPORTED, "clipscore: unsupported configuration");
+  DG_CUDA(cudaSetDevice(ctx->device));
+  int r = build_clipscore(c.get());
+  if (r != DG_OK) { for (void* p : c->owned) cudaFree(p); return r; }
+  *out = c.release();
+  return DG_OK;
+}
+void dg_clipscore_destroy(dg_clipscore* c) {
+  if (!c) return;
+  for (void* p : c->owned) cudaFree(p);
+  cudaFree(c->ws); cudaFree(c->ids_dev); cudaFree(c->eos_dev);
+  delete c;
+}
+int32_t dg_clipscore_num_weights(dg_clipscore* c) { return c ? (int32_t)c->slots.size() : 0; }
+const char* dg_clipscore_weight_name(dg_clipscore* c, int32_t i) {
+  if (!c || i < 0 || i >= (int)c->slots.size()) return nullptr;
+  return c->slots[i].key.c_str();
+}
+int32_t dg_clipscore_weight_shape(dg_clipscore* c, int32_t i, int64_t* shape4, int32_t* ndim) {
+  if (!c || i < 0 || i >= (int)c->slots.size() || !shape4 || !ndim) return fail(DG_E_ARG, "bad argument");
+  *ndim = (int32_t)c->slots[i].shape.size();
+  for (int k = 0; k < *ndim; ++k) shape4[k] = c->slots[i].shape[k];
+  return DG_OK;
+}
+int32_t dg_clipscore_set_weight(dg_clipscore* c, const char* key, const void* src, int32_t ndim, const int64_t* shape) {
+  return store_set_weight(c, key, src, ndim, shape);
+}
+int32_t dg_clipscore_set_logit_scale(dg_clipscore* c, float logit_scale) {
+  if (!c) return fail(DG_E_ARG, "null argument");
+  c->logit_scale = logit_scale;
+  return DG_OK;
+}
+int32_t dg_clipscore_prepare(dg_clipscore* c, int32_t max_images, int32_t max_texts) {
+  if (!c || max_images <= 0 || max_texts <= 0) return fail(DG_E_ARG, "bad argument");
+  DG_CUDA(cudaSetDevice(c->ctx->device));
+  cudaFree(c->ws); cudaFree(c->ids_dev); cudaFree(c->eos_dev);
+  c->ws = nullptr; c->ids_dev = nullptr; c->eos_dev = nullptr;
+  const int n = c->image / c->patch, S = n * n + 1;
+  const size_t vrows = (size_t)max_images * S, trows = (size_t)max_texts * c->max_pos;
+  const size_t v_elems = vrows * ((size_t)7 * c->v_hidden + c->v_inter) + (size_t)max_images * n * n * (c->kpad + c->v_hidden);
+  const size_t t_elems = trows * ((size_t)7 * c->t_hidden + c->t_inter);
+  const size_t feat = (size_t)(max_images + max_texts) * (c->proj + 2 * (size_t)std::max(c->v_hidden, c->t_hidden));
+  c->ws_elems = std::max(v_elems, t_elems) + feat + 1024;
+  cudaError_t e = cudaMalloc((void**)&c->ws, c->ws_elems * 2);
+  if (e != cudaSuccess) return fail(DG_E_NOMEM, "clipscore workspace cudaMalloc(%zu) failed: %s", c->ws_elems * 2, cudaGetErrorString(e));
+  DG_CUDA(cudaMalloc((void**)&c->ids_dev, trows * sizeof(int)));
+  DG_CUDA(cudaMalloc((void**)&c->eos_dev, (size_t)max_texts * sizeof(int)));
+  c->max_images = max_images; c->max_texts = max_texts;
+  return DG_OK;
+}
+int32_t dg_clipscore_score(dg_clipscore* c, const void* pixel_values, int32_t n_images, const int32_t* input_ids, const int32_t* eos_index,
+                           int32_t n_texts, int32_t seq, float* logits_per_text, void* stream) {
+  if (!c || !pixel_values || !input_ids || !eos_index || !logits_per_text) return fail(DG_E_ARG, "null argument");
+  if (!c->ws) return fail(DG_E_STATE, "dg_clipscore_prepare has not been called");
+  if (n_images <= 0 || n_images > c->max_images || n_texts <= 0 || n_texts > c->max_texts || seq <= 0 || seq > c->max_pos)
+    return fail(DG_E_SHAPE, "clipscore: %d images / %d texts x %d tokens exceed the prepared workspace", n_images, n_texts, seq);
+  for (const Slot& sl : c->slots) if (!sl.set) return fail(DG_E_STATE, "clipscore weight %s has not been set", sl.key.c_str());
+  DG_CUDA(cudaSetDevice(c->ctx->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  const int sms = c->ctx->num_sms;
+  const int n = c->image / c->patch, P = n * n, S = P + 1, Cv = c->v_hidden, Ct = c->t_hidden, D = c->proj;
+  // features live at the top of the workspace, the towers share the rest
+  const int Cmax = std::max(Cv, Ct);
+  __half* feat_img = c->ws; __half* feat_txt = feat_img + (size_t)c->max_images * D;
+  __half* pooled = feat_txt + (size_t)c->max_texts * D; __half* pooled_n = pooled + (size_t)(c->max_images + c->max_texts) * Cmax;
+  __half* base = pooled_n + (size_t)(c->max_images + c->max_texts) * Cmax;
+  base = (__half*)(((uintptr_t)base + 255) & ~(uintptr_t)255);
+  {   // ---- image tower
+    const size_t R = (size_t)c->max_images * S;
+    __half* x = base; __half* x2 = x + R * Cv; __half* h = x2 + R * Cv; __half* att = h + R * Cv; __half* qkv = att + R * Cv;
+    __half* f = qkv + R * 3 * Cv; __half* col = f + R * c->v_inter; __half* pe = col + (size_t)c->max_images * P * c->kpad;
+    const int rows = n_images * S;
+    clip_patch_im2col_kernel<<<grid_for((size_t)n_images * P * c->kpad, 256, sms), 256, 0, s>>>((const __half*)pixel_values, col, n_images, 3, c->image, c->patch, c->kpad);
+    DG_LAUNCH_CHECK();
+    Lin pw; pw.w = c->patch_w; pw.b = nullptr; pw.in = c->kpad; pw.out = Cv; pw.rows = Cv;
+    DG_TRY(clip_linear(c->ctx, s, col, c->kpad, n_images * P, pw, nullptr, pe));
+    clip_vision_embed_kernel<<<(unsigned)(((size_t)rows * (Cv / 8) + 255) / 256), 256, 0, s>>>(pe, c->cls, c->vpos, x2, n_images, S, Cv);
+    DG_LAUNCH_CHECK();
+    DG_TRY(launch_layernorm(s, x2, c->pre_ln.g, c->pre_ln.b, x, rows, Cv, c->eps));
+    DG_TRY(run_clip_layers(c->ctx, s, c->VL, x, x2, h, att, qkv, f, n_images, S, Cv, c->v_inter, c->v_heads, /*causal=*/0, c->eps));
+    gather_rows_kernel<<<(unsigned)(((size_t)n_images * (Cv / 8) + 255) / 256), 256, 0, s>>>(x, nullptr, pooled, n_images, S, Cv);
+    DG_LAUNCH_CHECK();
+    DG_TRY(launch_layernorm(s, pooled, c->post_ln.g, c->post_ln.b, pooled_n, n_images, Cv, c->eps));
+    DG_TRY(clip_linear(c->ctx, s, pooled_n, Cv, n_images, c->v_proj, nullptr, feat_img));
+  }
+  {   // ---- text tower
+    const size_t R = (size_t)c->max_texts * c->max_pos;
+    __half* x = base; __half* x2 = x + R * Ct; __half* h = x2 + R * Ct; __half* att = h + R * Ct; __half* qkv = att + R * Ct;
+    __half* f = qkv + R * 3 * Ct;
+    const int rows = n_texts * seq;
+    DG_CUDA(cudaMemcpyAsync(c->ids_dev, input_ids, (size_t)rows * sizeof(int), cudaMemcpyHostToDevice, s));
+    DG_CUDA(cudaMemcpyAsync(c->eos_dev, eos_index, (size_t)n_texts * sizeof(int), cudaMemcpyHostToDevice, s));
+    clip_embed_kernel<<<(unsigned)(((size_t)rows * (Ct / 8) + 255) / 256), 256, 0, s>>>(c->ids_dev, c->tok, c->tpos, x, rows, seq, Ct, c->vocab);
+    DG_LAUNCH_CHECK();
+    DG_TRY(run_clip_layers(c->ctx, s, c->TL, x, x2, h, att, qkv, f, n_texts, seq, Ct, c->t_inter, c->t_heads, /*causal=*/1, c->eps));
+    DG_TRY(launch_layernorm(s, x, c->t_final.g, c->t_final.b, x2, rows, Ct, c->eps));
+    __half* tp = pooled + (size_t)c->max_images * Cmax;
+    gather_rows_kernel<<<(unsigned)(((size_t)n_texts * (Ct / 8) + 255) / 256), 256, 0, s>>>(x2, c->eos_dev, tp, n_texts, seq, Ct);
+    DG_LAUNCH_CHECK();
+    DG_TRY(clip_linear(c->ctx, s, tp, Ct, n_texts, c->t_proj, nullptr, feat_txt));
+  }
+  const int pairs = n_texts * n_images;
+  clip_logits_kernel<<<(pairs + 7) / 8, 256, 0, s>>>(feat_txt, feat_img, logits_per_text, n_texts, n_images, D, expf(c->logit_scale));
   DG_LAUNCH_CHECK();
   return DG_OK;
 }

@@ -526,6 +526,68 @@ __global__ void quick_gelu_kernel(__half* __restrict__ x, size_t nvec) {
   }
 }
 
+// ---- CLIP image tower helpers
+// Patch embedding as a GEMM: col[b*P + p, (c, ky, kx)] = image[b, c, py*ps + ky, px*ps + kx], K zero-padded to `kpad`.
+__global__ void clip_patch_im2col_kernel(const __half* __restrict__ img, __half* __restrict__ col, int B, int Cin, int size, int ps,
+                                         int kpad) {
+  const int n = size / ps, P = n * n, kreal = Cin * ps * ps;
+  const size_t total = (size_t)B * P * kpad;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int k = (int)(i % kpad); const size_t rp = i / kpad;
+    const int p = (int)(rp % P), b = (int)(rp / P);
+    __half v = __float2half_rn(0.f);
+    if (k < kreal) {
+      const int c = k / (ps * ps), ky = (k / ps) % ps, kx = k % ps;
+      const int y = (p / n) * ps + ky, x = (p % n) * ps + kx;
+      v = img[(((size_t)b * Cin + c) * size + y) * size + x];
+    }
+    col[i] = v;
+  }
+}
+// CLIPVisionEmbeddings: x[b, 0] = class_embedding + pos[0];  x[b, 1 + p] = patch[b, p] + pos[1 + p].
+__global__ void clip_vision_embed_kernel(const __half* __restrict__ patch, const __half* __restrict__ cls, const __half* __restrict__ pos,
+                                         __half* __restrict__ out, int B, int S, int C) {
+  const int nvec = C / 8;
+  const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= (size_t)B * S * nvec) return;
+  const int v = (int)(i % nvec); const size_t r = i / nvec;
+  const int t = (int)(r % S), b = (int)(r / S);
+  float a[8], pe[8];
+  if (t == 0) load8(cls + v * 8, a); else load8(patch + ((size_t)b * (S - 1) + (t - 1)) * C + v * 8, a);
+  load8(pos + (size_t)t * C + v * 8, pe);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) a[k] += pe[k];
+  store8(out + r * C + v * 8, a);
+}
+// out[i, :] = x[i * stride + idx[i], :]  (class token: idx == nullptr -> row i * stride; text pooling: idx = EOS position)
+__global__ void gather_rows_kernel(const __half* __restrict__ x, const int* __restrict__ idx, __half* __restrict__ out, int n, int stride,
+                                   int C) {
+  const int nvec = C / 8;
+  const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= (size_t)n * nvec) return;
+  const int v = (int)(i % nvec), r = (int)(i / nvec);
+  const size_t src = (size_t)r * stride + (idx ? idx[r] : 0);
+  *reinterpret_cast<uint4*>(out + (size_t)r * C + v * 8) = *reinterpret_cast<const uint4*>(x + src * C + v * 8);
+}
+// logits_per_text[t, b] = exp(logit_scale) * <text_t / |text_t|, image_b / |image_b|>   (fp32; one warp per (t, b))
+__global__ void clip_logits_kernel(const __half* __restrict__ txt, const __half* __restrict__ img, float* __restrict__ out, int T, int B,
+                                   int D, float scale) {
+  const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (w >= T * B) return;
+  const int t = w / B, b = w % B;
+  float dot = 0.f, nt = 0.f, ni = 0.f;
+  for (int k = lane; k < D; k += 32) {
+    const float a = __half2float(txt[(size_t)t * D + k]), c = __half2float(img[(size_t)b * D + k]);
+    dot = fmaf(a, c, dot); nt = fmaf(a, a, nt); ni = fmaf(c, c, ni);
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) {
+    dot += __shfl_xor_sync(0xffffffffu, dot, o); nt += __shfl_xor_sync(0xffffffffu, nt, o); ni += __shfl_xor_sync(0xffffffffu, ni, o);
+  }
+  if (lane == 0) out[w] = scale * dot * rsqrtf(nt) * rsqrtf(ni);
+}
+
 // ------------------------------------------------------------------ VAE decoder helpers
 // post_quant_conv: 1x1 conv over the latent channels (C <= 8) on NCHW fp16, with the 1/scaling_factor of
 // `vae.decode(latents / scaling_factor)` folded in.  out[b,co,p] = bias[co] + sum_ci W[co,ci] * (z[b,ci,p] * scale).

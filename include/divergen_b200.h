@@ -141,6 +141,26 @@ int32_t dg_clip_set_weight(dg_clip* clip, const char* key, const void* src, int3
 int32_t dg_clip_prepare(dg_clip* clip, int32_t max_batch);
 int32_t dg_clip_encode(dg_clip* clip, const int32_t* input_ids, int32_t batch, int32_t seq, void* out, void* stream);
 
+/* ---- CLIP similarity scores: `_, logits_per_text = clip_model(images, text)` of OpenAI CLIP ViT-L/14
+ * (DiverGen/filteration/get_clip_score.py:176-180); weights by transformers `CLIPModel` state-dict key (text_model.*,
+ * vision_model.*, visual_projection.weight, text_projection.weight; `logit_scale` through dg_clipscore_set_logit_scale) ----
+ * text_cfg6 = {vocab, hidden, intermediate, layers, heads, max_positions}, vision_cfg6 = {image_size, patch_size, hidden,
+ * intermediate, layers, heads}; NULL = ViT-L/14.  Head dim must be 64 in both towers.
+ * dg_clipscore_score: pixel_values = device fp16 [n_images, 3, image, image] (already resized / cropped / normalised as
+ * clip's `preprocess` does), input_ids = HOST int32 [n_texts, seq], eos_index = HOST int32 [n_texts] (position of the
+ * end-of-text token: `input_ids.argmax(-1)`), logits_per_text = device fp32 [n_texts, n_images]. */
+typedef struct dg_clipscore dg_clipscore;
+int32_t dg_clipscore_create(dg_ctx* ctx, const int32_t* text_cfg6, const int32_t* vision_cfg6, int32_t projection_dim, dg_clipscore** out);
+void dg_clipscore_destroy(dg_clipscore* cs);
+int32_t dg_clipscore_num_weights(dg_clipscore* cs);
+const char* dg_clipscore_weight_name(dg_clipscore* cs, int32_t index);
+int32_t dg_clipscore_weight_shape(dg_clipscore* cs, int32_t index, int64_t* shape4, int32_t* ndim);
+int32_t dg_clipscore_set_weight(dg_clipscore* cs, const char* key, const void* src, int32_t ndim, const int64_t* shape);
+int32_t dg_clipscore_set_logit_scale(dg_clipscore* cs, float logit_scale);
+int32_t dg_clipscore_prepare(dg_clipscore* cs, int32_t max_images, int32_t max_texts);
+int32_t dg_clipscore_score(dg_clipscore* cs, const void* pixel_values, int32_t n_images, const int32_t* input_ids, const int32_t* eos_index,
+                           int32_t n_texts, int32_t seq, float* logits_per_text, void* stream);
+
 /* ---- output path: `pt_to_pil(image)` arithmetic on the device (txt2img_diffusers_stages_from_txt.py:267) ----
  * img [B, C<=4, H, W] fp16 in [-1, 1]  ->  out_u8 [B, H, W, C] uint8 = round(clamp(img / 2 + 0.5, 0, 1) * 255). */
 int32_t dg_op_image_to_uint8(dg_ctx* ctx, const void* img, void* out_u8, int32_t B, int32_t C, int32_t H, int32_t W, void* stream);

@@ -117,3 +117,58 @@ def test_driver_embedding_table_with_device_encoder():
     with torch.no_grad():
         want = ref(input_ids=StubTokenizer()([""] + prompts).input_ids).last_hidden_state
     _check(table, want, name="driver embedding table")
+
+
+# ---------------------------------------------------------------- row f3: CLIP similarity scores (both towers)
+def _clip_models(seed, text_kw, vision_kw, proj):
+    from transformers import CLIPConfig, CLIPModel
+    from divergen_b200 import CLIPScorer
+    v = text_kw["vocab_size"]             # the end-of-text token is the largest id, as in CLIP's vocabulary (49407)
+    cfg = CLIPConfig(text_config=dict(hidden_act="quick_gelu", layer_norm_eps=1e-5, projection_dim=proj, eos_token_id=v - 1,
+                                      bos_token_id=v - 2, pad_token_id=v - 1, **text_kw),
+                     vision_config=dict(hidden_act="quick_gelu", layer_norm_eps=1e-5, projection_dim=proj, **vision_kw),
+                     projection_dim=proj)
+    torch.manual_seed(seed)
+    ref = CLIPModel(cfg).eval()
+    sd = {k: (v if k == "logit_scale" else v.half().float()) for k, v in ref.state_dict().items() if not k.endswith("position_ids")}
+    ref.load_state_dict(sd, strict=False)
+    ours = CLIPScorer(device=DEV, text_config=text_kw, vision_config=vision_kw, projection_dim=proj)
+    res = ours.load_state_dict(sd)
+    assert not res.missing_keys and not res.unexpected_keys
+    return ref, ours
+
+
+TINY_VISION = dict(image_size=56, patch_size=14, hidden_size=128, intermediate_size=256, num_hidden_layers=2, num_attention_heads=2)
+
+
+@pytest.mark.parametrize("b,t", [(3, 1), (2, 2)])
+def test_tiny_clip_scores(b, t):
+    """logits_per_text against transformers.CLIPModel (fp32): |err| <= 1e-2 * max|ref| + 2e-2 (fp16 features, logits O(10))."""
+    _need_gpu()
+    ref, ours = _clip_models(0, TINY, TINY_VISION, 64)
+    g = torch.Generator().manual_seed(5)
+    px = torch.randn(b, 3, 56, 56, generator=g).half()
+    ids = _ids(t, 77, TINY["vocab_size"], 6)
+    with torch.no_grad():
+        want = ref(input_ids=ids, pixel_values=px.float()).logits_per_text
+    got = ours(px.to(DEV), ids).cpu()
+    assert got.shape == (t, b)
+    err = (got - want).abs().max().item()
+    print(f"clip scores tiny b={b} t={t}: max err {err:.4g}, ref {want.flatten().tolist()}")
+    assert err <= 1e-2 * want.abs().max().item() + 2e-2
+
+
+def test_vit_l14_clip_scores_full_width():
+    """ViT-L/14 (24 x 1024 image tower at 257 tokens + 12 x 768 text tower, 427.6 M parameters): 2 images, 1 prompt."""
+    _need_gpu()
+    from divergen_b200.clip import VIT_L14_TEXT, VIT_L14_VISION
+    ref, ours = _clip_models(1, VIT_L14_TEXT, VIT_L14_VISION, 768)
+    g = torch.Generator().manual_seed(7)
+    px = torch.randn(2, 3, 224, 224, generator=g).half()
+    ids = _ids(1, 77, VIT_L14_TEXT["vocab_size"], 8)
+    with torch.no_grad():
+        want = ref(input_ids=ids, pixel_values=px.float()).logits_per_text
+    got = ours(px.to(DEV), ids).cpu()
+    err = (got - want).abs().max().item()
+    print(f"clip scores ViT-L/14: max err {err:.4g}, ref {want.flatten().tolist()}, got {got.flatten().tolist()}")
+    assert err <= 1e-2 * want.abs().max().item() + 5e-3
