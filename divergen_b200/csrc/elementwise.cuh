@@ -168,12 +168,25 @@ __global__ void gn_apply_blk_kernel(const __half* __restrict__ x0, int C0, const
   __shared__ float2 s_col[8][256];       // [slab stripe][block column] partial sums
   __shared__ float s_mean[64], s_rstd[64];
   griddep_launch();
-  griddep_wait();
   const int C = C0 + C1, cpg = C / groups, nvec = C / 8;
   const int b = blockIdx.y;
   const int p0 = blockIdx.x * pix_per_block;
   const int p1 = min(HW, p0 + pix_per_block);
   const float inv_n = 1.0f / ((float)cpg * (float)HW);
+  // Latency chain of a short launch: statistics -> (barrier) -> affine -> activation loads -> stores.  The affine parameters
+  // are weights (no dependence on the producer kernel: loaded before the programmatic-dependency wait) and the first
+  // activation vector does not depend on the statistics: both are in flight while the statistics are folded.
+  const GnThreadMap tm(nvec);
+  const bool have0 = tm.v0 < nvec;
+  float g0[8], be0[8], f0[8];
+  if (have0) { load8(gamma + tm.v0 * 8, g0); load8(beta + tm.v0 * 8, be0); }
+  griddep_wait();
+  const int pf = p0 + tm.pofs;
+  const bool havep = have0 && pf < p1;
+  if (havep) {
+    const int c = tm.v0 * 8;
+    load8(((c < C0) ? x0 + c : x1 + (c - C0)) + ((size_t)b * HW + pf) * ((c < C0) ? C0 : C1), f0);
+  }
   {
     // thread (stripe, cb): block column cb, slabs stripe, stripe + nstripe, ...  Consecutive threads read consecutive
     // float2 entries (coalesced); every sum runs in a fixed order (deterministic).
@@ -205,12 +218,16 @@ __global__ void gn_apply_blk_kernel(const __half* __restrict__ x0, int C0, const
     }
   }
   __syncthreads();
-  const GnThreadMap tm(nvec);
   for (int v = tm.v0; v < nvec; v += tm.vstep) {
     const int c = v * 8;
     float sc[8], sf[8], g[8], be[8];
-    load8(gamma + c, g);
-    load8(beta + c, be);
+    if (v == tm.v0) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { g[k] = g0[k]; be[k] = be0[k]; }
+    } else {
+      load8(gamma + c, g);
+      load8(beta + c, be);
+    }
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
       const int grp = (c + k) / cpg;
@@ -223,7 +240,12 @@ __global__ void gn_apply_blk_kernel(const __half* __restrict__ x0, int C0, const
     for (int p = p0 + tm.pofs; p < p1; p += tm.pstride) {
       const size_t pix = (size_t)b * HW + p;
       float f[8];
-      load8(src + pix * ld, f);
+      if (v == tm.v0 && p == pf) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) f[k] = f0[k];
+      } else {
+        load8(src + pix * ld, f);
+      }
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
         const float y = fmaf(f[k], sc[k], sf[k]);
