@@ -101,8 +101,9 @@ struct Gemm2Cfg {
   static constexpr int kSlotSubs = kNumAcc == 1 ? 5 : 2;
   static constexpr int kRingBytes = kRing * kSlotSubs * kSubBytes;
   static constexpr int kVecBytes = 2 * 2 * 320 * 4;     // 2 generations of (bias, colsum), fp32
-  static constexpr int kColBufBytes = 8 * 160 * 8;      // per epilogue warp: (sum, sumsq) of each of its <= 160 columns
-  static constexpr int kBarBytes = 512;
+  static constexpr int kColBufBytes = 8 * (kBN / 2) * 8;   // per epilogue warp: (sum, sumsq) of each of its kBN / 2 columns
+  static constexpr int kUnitTab = 32;                   // this CTA's first tiles, decomposed once in the prologue
+  static constexpr int kBarBytes = 512 + kUnitTab * 40;
   static constexpr int kTotal = kStages * kStageBytes + kRingBytes + kVecBytes + kColBufBytes + kBarBytes + 1024 /*align slack*/;
   static_assert(kBHalfBytes % 1024 == 0 && kStageBytes % 1024 == 0, "operand tiles must keep 1024-byte alignment");
   static_assert(kTotal <= 232448, "shared memory budget");
@@ -334,6 +335,15 @@ gemm2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc_pair<kCta, kTmemCols>(tmem_slot);
+  // The tile decomposition (a chain of divisions per tile on every role's critical path, ~0.5 k cycles in the gap between two
+  // tiles of the epilogue) is done once, one tile per lane, while the barriers / TMEM are being set up.
+  Unit* sUnits = reinterpret_cast<Unit*>(reinterpret_cast<uint8_t*>(bars) + 512);
+  if (warp == 3) {
+    const int m_tiles_ = p.tiles_x * p.tiles_y * p.tiles_b;
+    const int total_ = ((m_tiles_ + kCta - 1) / kCta) * p.tiles_n * p.splits;
+    const int u = pair_id + lane * num_pairs;
+    if (lane < S::kUnitTab && u < total_) sUnits[lane] = unit_coord<kCta>(p, u, cta_rank, m_tiles_, p.taps * (p.kb0 + p.kb1));
+  }
   tc_fence_before();
   if constexpr (kCta == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
@@ -348,6 +358,10 @@ gemm2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
   const int kb_per_tap = p.kb0 + p.kb1;
   const int num_kb = p.taps * kb_per_tap;
 
+  // k-th tile of this CTA (u = pair_id + k * num_pairs)
+  auto unit_at = [&](int u, int k) -> Unit {
+    return k < S::kUnitTab ? sUnits[k] : unit_coord<kCta>(p, u, cta_rank, m_tiles, num_kb);
+  };
   constexpr bool kWholeT = (kBN == 160);
   // (one thread) residual of unit `tt` -> slot sl: whole-tile slots take all 5 sub-tiles, ring slots chunk j's two halves
   auto issue_res = [&](uint32_t sl, int j, const Unit& tt) {
@@ -373,8 +387,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
     if (elect_one()) {
       int stage = 0; uint32_t phase = 0;
       const uint32_t full0_leader = mapa_rank(smem_u32(&full[0]), 0);
-      for (int u = pair_id; u < total_units; u += num_pairs) {
-        const Unit t = unit_coord<kCta>(p, u, cta_rank, m_tiles, num_kb);
+      for (int u = pair_id, uk = 0; u < total_units; u += num_pairs, ++uk) {
+        const Unit t = unit_at(u, uk);
         int tap = t.kb_begin / kb_per_tap;
         int kb = t.kb_begin - tap * kb_per_tap;
         const int wrow = t.nt * kBN + cta_rank * S::kBRows;
@@ -405,7 +419,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
       const uint64_t descB0 = make_smem_desc_sw128(smem_u32(smem) + S::kABytes, 16, 1024);
       int stage = 0; uint32_t phase = 0;
       int as = 0; uint32_t acc_phase = 0;
-      for (int u = pair_id; u < total_units; u += num_pairs) {
+      for (int u = pair_id, uk = 0; u < total_units; u += num_pairs, ++uk) {
         const int split = u % p.splits;
         const int kb_begin = (int)(((long long)split * num_kb) / p.splits);
         const int kb_end = (int)(((long long)(split + 1) * num_kb) / p.splits);
@@ -440,8 +454,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
     // (whole-tile slots: the next tile's residual lands while the current tile is converted; ring: two chunks ahead)
     if (res_loader && elect_one()) {
       uint32_t c = 0;
-      for (int u = pair_id; u < total_units; u += num_pairs) {
-        const Unit t = unit_coord<kCta>(p, u, cta_rank, m_tiles, num_kb);
+      for (int u = pair_id, uk = 0; u < total_units; u += num_pairs, ++uk) {
+        const Unit t = unit_at(u, uk);
         for (int j = 0; j < (kWholeT ? 1 : kChunks); ++j, ++c) {
           mbar_wait_parked(&buf_free[c % S::kRing], (c / S::kRing) & 1);
           issue_res(c % S::kRing, j, t);
@@ -510,9 +524,9 @@ gemm2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
     // [32j, 32j+32), 16 per warp half
     auto chunk_col = [&](int j) { return kCW == 32 ? hf * S::kNI + j * 32 : (kBN == 160 ? (kGeglu ? hf * 32 + j * 16 : hf * 80 + j * 16) : j * 32 + hf * 16); };
 
-    for (int u = pair_id; u < total_units; u += num_pairs) {
+    for (int u = pair_id, uk = 0; u < total_units; u += num_pairs, ++uk) {
       if (et == 0 && u == pair_id + num_pairs) DG_STAMP(30);      // second tile: loop top
-      const Unit t = unit_coord<kCta>(p, u, cta_rank, m_tiles, num_kb);
+      const Unit t = unit_at(u, uk);
       const int nt = t.nt;
       const uint32_t t_row = tmem_base + as * S::kAccStride + ((uint32_t)(q * 32) << 16);
       // ---- this thread's output row
@@ -689,7 +703,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
         // each lane folds one gn_blk-column block and stores it to the warp's slab entry.  No shuffles, no atomics.
         const bool gn_on = p.gn_stats_out != nullptr;
         float2* gn_dst = nullptr;       // this warp's slab: [gn_nblk] (sum, sumsq) pairs
-        const uint32_t colbuf_a = smem_u32(sColBuf) + (uint32_t)ew * 160 * 8;
+        const uint32_t colbuf_a = smem_u32(sColBuf) + (uint32_t)ew * (kBN / 2) * 8;
         if (gn_on) {
           const int r0 = q * 32;        // first row of this warp within the tile
           int slab;
