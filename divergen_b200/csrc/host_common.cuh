@@ -300,7 +300,9 @@ inline int launch_gemm(cudaStream_t stream, const GemmRes& res, const GemmArgs& 
   // the epilogue overlaps the next main loop, twice the tiles for wave balance) for short-K / epilogue-bound layers
   static int forced_bn = -1;
   if (forced_bn < 0) { const char* e = getenv("DG_GEMM_BN"); forced_bn = e && e[0] ? atoi(e) : 0; }
-  int kbn = a.geglu ? kGegluTile : (num_kb > 24 && a.n_w > 160) ? 320 : 160;
+  static int kb_thresh = -1;
+  if (kb_thresh < 0) { const char* e = getenv("DG_GEMM_KB_THRESH"); kb_thresh = e ? atoi(e) : 24; }
+  int kbn = a.geglu ? kGegluTile : (num_kb > kb_thresh && a.n_w > 160) ? 320 : 160;
   {
     // few-tile layers (the 8x8 / 16x16 levels): 320-wide tiles would leave most SMs idle -- measured on 512x11520x1280:
     // 58 us (320, 4 splits) vs 43 us (160, 4 splits); 2048x11520x1280: 84 vs 62 us (profiles/r01_ncu_summary.md)
