@@ -98,3 +98,18 @@ def test_pipeline_with_vae_pt_output():
                num_inference_steps=4, height=128, width=128).images
     assert img.shape == (2, 3, 128, 128) and torch.isfinite(img).all()
     assert img.min().item() >= 0.0 and img.max().item() <= 1.0
+
+
+def test_sd_vae_decode_full_size_512():
+    """BASELINE's image size: one 64x64 latent -> 512x512 through the SD VAE (the 4096-token mid-block attention and the
+    262144-pixel 128-channel convolutions), against the fp32 oracle on the host."""
+    _need_gpu()
+    from oracle.vae_oracle import VAEConfig
+    oracle, vae = _models(VAEConfig.sd(), seed=2)
+    z = torch.randn(1, 4, 64, 64, generator=torch.Generator().manual_seed(9)).half()
+    with torch.no_grad():
+        ref32 = oracle(z.float())
+        ref16 = oracle.half().to(DEV)(z.to(DEV))
+    got = vae.decode(z.to(DEV)).sample
+    assert got.shape == (1, 3, 512, 512)
+    _check(got, ref32, ref16, name="vae sd 64x64 -> 512x512")
