@@ -78,6 +78,29 @@ def output_name(category_id: str, count: int, ext: str = "png") -> str:
     return "{}_{:07d}.{}".format(category_id, count, ext)                     # reference :263
 
 
+def load_category_names(lvis_json_path: str) -> dict:
+    """`id_to_name = {d['id']: d['name'] for d in data}` of generation/convert_dir_structure.py:88-91 (a JSON list of
+    LVIS category records)."""
+    import json
+    with open(lvis_json_path, "r") as f:
+        data = json.load(f)
+    return {int(d["id"]): d["name"] for d in data}
+
+
+def output_dir_for(outdir: str, stage: str, category_id: str, id_to_name: Optional[dict]) -> str:
+    """Where a category's files go.  Without category names: `<outdir>/samples/<stage>/` (reference generation script
+    :144-146,262-266).  With them: `<outdir>/<stage>/<category_name>/` -- the layout generation/convert_dir_structure.py
+    :113-121 produces by COPYING every PNG (file names unchanged), which segmentation/ and filteration/ read; writing it
+    directly removes that pass over 1.2 M files."""
+    if id_to_name is None:
+        return os.path.join(outdir, "samples", stage)
+    try:
+        name = id_to_name[int(category_id)]
+    except (KeyError, ValueError):
+        raise ValueError("category id '{}' (from the prompt file name) is not in the LVIS category JSON".format(category_id))
+    return os.path.join(outdir, stage, name)
+
+
 def list_prompt_files(from_file: Sequence[str]) -> List[str]:
     """Reference :207-209: a directory expands to its *.txt files.  (The reference discards the result of `sorted`, so its
     category order is glob order; sorting here only fixes the order, not the set of files or any file name.)"""
@@ -224,6 +247,8 @@ def build_parser() -> argparse.ArgumentParser:
     p.add_argument("--guidance_scale", type=float, default=7.5)
     p.add_argument("--random_init", action="store_true", help="random-init UNet weights (benchmarks; no checkpoint offline)")
     p.add_argument("--png_workers", type=int, default=4, help="PNG encoder threads per rank")
+    p.add_argument("--in_lvis_json_path", type=str, default=None,
+                   help="LVIS category JSON (as for convert_dir_structure.py): write <outdir>/<stage>/<category_name>/ directly")
     p.add_argument("--decode", action="store_true", help="with --random_init: also build a random-init VAE and write PNGs")
     p.add_argument("--max_prompt_files", type=int, default=0, help="process only the first N category files (0 = all)")
     return p
@@ -267,7 +292,8 @@ def main(argv: Optional[Sequence[str]] = None) -> int:
     torch.cuda.set_device(device)
     plan = plan_batches(args.n_samples, world, args.max_batch_size)
     stage = args.stages[0]
-    sample_dir = os.path.join(args.outdir, "samples", stage)
+    id_to_name = load_category_names(args.in_lvis_json_path) if args.in_lvis_json_path else None
+    sample_dir = os.path.join(args.outdir, "samples", stage) if id_to_name is None else os.path.join(args.outdir, stage)
     if rank == 0:
         os.makedirs(sample_dir, exist_ok=True)
     if args.dist:
@@ -318,9 +344,12 @@ def main(argv: Optional[Sequence[str]] = None) -> int:
     writer = AsyncImageWriter(args.png_workers) if vae is not None else None
     for fi, (path, lines) in enumerate(per_file):
         cid = category_id_of(path)
+        cat_dir = output_dir_for(args.outdir, stage, cid, id_to_name)
+        if id_to_name is not None:
+            os.makedirs(cat_dir, exist_ok=True)                                   # convert_dir_structure.py:94-99 (every rank: idempotent)
         print("==> Reading prompts from {}, {}/{}".format(path, fi + 1, len(per_file)))
         for call in iter_calls(lines, plan, rank, args.n_samples, args.offset):
-            last = os.path.join(sample_dir, output_name(cid, call.counts[-1], ext))
+            last = os.path.join(cat_dir, output_name(cid, call.counts[-1], ext))
             if args.disable_overwrite and os.path.exists(last):
                 print("==> Skipping stage {} for {}...".format(stage, os.path.basename(last)))
                 continue
@@ -330,7 +359,7 @@ def main(argv: Optional[Sequence[str]] = None) -> int:
                        output_type="uint8" if vae is not None else "latent",
                        num_images_per_prompt=call.num_images, num_inference_steps=args.num_inference_steps,
                        guidance_scale=args.guidance_scale).images
-            dsts = [os.path.join(sample_dir, output_name(cid, count, ext)) for count in call.counts]
+            dsts = [os.path.join(cat_dir, output_name(cid, count, ext)) for count in call.counts]
             if vae is not None:
                 writer.submit(out, dsts)                                          # reference :267 (pt -> PIL -> .save), asynchronously
             else:

@@ -73,3 +73,21 @@ def test_cli_keeps_reference_flags():
                                    "--seed", "7", "--dist", "--ckpt_dir", "c", "--stages", "sd", "--offset", "0", "--disable_overwrite"])
     assert (a.from_file, a.n_samples, a.max_batch_size, a.seed, a.dist, a.offset, a.disable_overwrite) == (
         ["input/lvis_prompt/"], 1024, 1, 7, True, 0, True)
+
+
+def test_category_layout_matches_convert_dir_structure(tmp_path):
+    """Row f4: with the LVIS category JSON the driver's destination is exactly what generation/convert_dir_structure.py
+    :113-121 produces from `samples/<stage>/<id>_<index>.png`: `<outdir>/<stage>/<category_name>/<same file name>`."""
+    import json
+    from divergen_b200.generate import load_category_names, output_dir_for, output_name
+    cats = [{"id": 1, "name": "aerosol_can"}, {"id": 7, "name": "alligator"}]
+    jp = tmp_path / "cats.json"
+    jp.write_text(json.dumps(cats))
+    id_to_name = load_category_names(str(jp))
+    assert id_to_name == {1: "aerosol_can", 7: "alligator"}
+    # the reference's conversion of one generated file
+    filename = output_name("7", 1034, "png")
+    category_id = int(filename.split("_")[0])                                   # convert_dir_structure.py:116
+    want = os.path.join("out", "sd", id_to_name[category_id], filename)         # :118-120
+    assert os.path.join(output_dir_for("out", "sd", "7", id_to_name), filename) == want
+    assert output_dir_for("out", "sd", "7", None) == os.path.join("out", "samples", "sd")

@@ -40,3 +40,23 @@ def test_driver_writes_pngs_with_vae(tmp_path):
     assert got == ["1_0000000.png", "1_0000001.png"]
     im = Image.open(tmp_path / "samples" / "sd" / got[0])
     assert im.size == (512, 512) and im.mode == "RGB"
+
+
+def test_driver_writes_category_layout_directly(tmp_path):
+    """With --in_lvis_json_path the files land in `<outdir>/<stage>/<category_name>/` (what convert_dir_structure.py builds
+    by copying), same file names; resume looks there too."""
+    if not torch.cuda.is_available():
+        pytest.skip("no GPU")
+    import json
+    from divergen_b200.generate import main
+    cats = tmp_path / "cats.json"
+    cats.write_text(json.dumps([{"id": 1, "name": "aerosol_can"}, {"id": 7, "name": "alligator"}]))
+    argv = ["--from_file", os.path.join(HERE, "fixtures", "prompts", "1.txt"), "--outdir", str(tmp_path / "out"), "--n_samples", "2",
+            "--max_batch_size", "2", "--random_init", "--num_inference_steps", "2", "--offset", "0", "--disable_overwrite",
+            "--in_lvis_json_path", str(cats)]
+    assert main(argv) == 0
+    d = tmp_path / "out" / "sd" / "aerosol_can"
+    assert sorted(os.listdir(d)) == ["1_0000000.latent.pt", "1_0000001.latent.pt"]
+    assert not (tmp_path / "out" / "samples").exists()
+    m = os.path.getmtime(d / "1_0000000.latent.pt")
+    assert main(argv) == 0 and os.path.getmtime(d / "1_0000000.latent.pt") == m
