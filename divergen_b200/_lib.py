@@ -92,6 +92,8 @@ SIGNATURES = {
     "dg_clipscore_prepare": (_I, [_P, _I, _I]),
     "dg_clipscore_score": (_I, [_P, _P, _I, C.POINTER(_I), C.POINTER(_I), _I, _I, C.POINTER(_F), _P]),
     "dg_op_image_to_uint8": (_I, [_P, _P, _P, _I, _I, _I, _I, _P]),
+    "dg_op_resample_u8": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, C.POINTER(_I), C.POINTER(_I), _I, _I, _P]),
+    "dg_op_clip_normalize": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, C.POINTER(_F), C.POINTER(_F), _P]),
     "dg_op_gemm": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "dg_op_pack_geglu": (_I, [_P, _P, _P, _P, _P, _I, _I, _P]),
     "dg_op_geglu_packed_rows": (_I, [_I]),

@@ -1734,4 +1734,27 @@ int32_t dg_clipscore_score(dg_clipscore* c, const void* pixel_values, int32_t n_
   return DG_OK;
 }
 
+
+int32_t dg_op_resample_u8(dg_ctx* ctx, const void* in_u8, void* out_u8, int32_t B, int32_t Hin, int32_t Win, int32_t C, int32_t Hout,
+                          int32_t Wout, const int32_t* bounds, const int32_t* coeffs, int32_t ksize, int32_t axis, void* stream) {
+  if (!ctx || !in_u8 || !out_u8 || !bounds || !coeffs || B <= 0 || C <= 0 || ksize <= 0 || (axis != 0 && axis != 1)) return fail(DG_E_ARG, "bad argument");
+  if ((axis == 0 && Hout != Hin) || (axis == 1 && Wout != Win)) return fail(DG_E_SHAPE, "resample: one axis per pass");
+  DG_CUDA(cudaSetDevice(ctx->device));
+  const size_t n = (size_t)B * Hout * Wout * C;
+  resample_u8_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const unsigned char*)in_u8, (unsigned char*)out_u8, B, Hin, Win, C,
+                                                                                   Hout, Wout, bounds, coeffs, ksize, axis);
+  DG_LAUNCH_CHECK();
+  return DG_OK;
+}
+int32_t dg_op_clip_normalize(dg_ctx* ctx, const void* in_u8, void* out, int32_t B, int32_t H, int32_t W, int32_t top, int32_t left, int32_t n,
+                             const float* mean3, const float* std3, void* stream) {
+  if (!ctx || !in_u8 || !out || !mean3 || !std3 || B <= 0 || n <= 0 || top < 0 || left < 0 || top + n > H || left + n > W) return fail(DG_E_ARG, "bad argument");
+  DG_CUDA(cudaSetDevice(ctx->device));
+  const size_t cnt = (size_t)B * 3 * n * n;
+  clip_normalize_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const unsigned char*)in_u8, (__half*)out, B, H, W, top, left, n,
+                                                                                        mean3[0], mean3[1], mean3[2], std3[0], std3[1], std3[2]);
+  DG_LAUNCH_CHECK();
+  return DG_OK;
+}
+
 }  // extern "C"

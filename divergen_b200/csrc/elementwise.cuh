@@ -610,6 +610,47 @@ __global__ void clip_logits_kernel(const __half* __restrict__ txt, const __half*
   if (lane == 0) out[w] = scale * dot * rsqrtf(nt) * rsqrtf(ni);
 }
 
+// ---- clip `preprocess` on the device (rows f3 / f4): PIL's antialiased bicubic resize in its own 8-bit fixed point
+// (Pillow src/libImaging/Resample.c, ImagingResampleHorizontal_8bpc / Vertical_8bpc: coefficients quantised to 22 bits by the
+// host, accumulator seeded with 1 << 21, result = clip8(acc >> 22), one pass per axis with a uint8 intermediate image), so
+// the pixels CLIP sees are the ones `Image.open(png).resize(...)` would produce.
+// One thread per output byte.  axis 0: along x (in [B,H,Win,C] -> out [B,H,Wout,C]); axis 1: along y.
+__global__ void resample_u8_kernel(const unsigned char* __restrict__ in, unsigned char* __restrict__ out, int B, int Hin, int Win,
+                                   int C, int Hout, int Wout, const int* __restrict__ bounds, const int* __restrict__ kk, int ksize,
+                                   int axis) {
+  const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  const size_t total = (size_t)B * Hout * Wout * C;
+  if (i >= total) return;
+  const int c = (int)(i % C); size_t t = i / C;
+  const int x = (int)(t % Wout); t /= Wout;
+  const int y = (int)(t % Hout); const int b = (int)(t / Hout);
+  const int o = axis == 0 ? x : y;
+  const int lo = bounds[2 * o], n = bounds[2 * o + 1];
+  const int* k = kk + (size_t)o * ksize;
+  int acc = 1 << 21;
+  if (axis == 0) {
+    const unsigned char* src = in + (((size_t)b * Hin + y) * Win + lo) * C + c;
+    for (int j = 0; j < n; ++j) acc += (int)src[(size_t)j * C] * k[j];
+  } else {
+    const unsigned char* src = in + (((size_t)b * Hin + lo) * Win + x) * C + c;
+    for (int j = 0; j < n; ++j) acc += (int)src[(size_t)j * Win * C] * k[j];
+  }
+  const int v = acc >> 22;
+  out[i] = (unsigned char)(v < 0 ? 0 : (v > 255 ? 255 : v));
+}
+// CenterCrop + ToTensor + Normalize: u8 [B,H,W,3] -> fp16 [B,3,n,n], ((v / 255) - mean) / std in fp32.
+__global__ void clip_normalize_kernel(const unsigned char* __restrict__ in, __half* __restrict__ out, int B, int H, int W, int top, int left,
+                                      int n, float m0, float m1, float m2, float s0, float s1, float s2) {
+  const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= (size_t)B * 3 * n * n) return;
+  const int x = (int)(i % n); size_t t = i / n;
+  const int y = (int)(t % n); t /= n;
+  const int c = (int)(t % 3); const int b = (int)(t / 3);
+  const float v = (float)in[(((size_t)b * H + top + y) * W + left + x) * 3 + c] / 255.0f;
+  const float m = c == 0 ? m0 : (c == 1 ? m1 : m2), sd = c == 0 ? s0 : (c == 1 ? s1 : s2);
+  out[i] = __float2half_rn((v - m) / sd);
+}
+
 // ------------------------------------------------------------------ VAE decoder helpers
 // post_quant_conv: 1x1 conv over the latent channels (C <= 8) on NCHW fp16, with the 1/scaling_factor of
 // `vae.decode(latents / scaling_factor)` folded in.  out[b,co,p] = bias[co] + sum_ci W[co,ci] * (z[b,ci,p] * scale).

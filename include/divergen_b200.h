@@ -165,6 +165,17 @@ int32_t dg_clipscore_score(dg_clipscore* cs, const void* pixel_values, int32_t n
  * img [B, C<=4, H, W] fp16 in [-1, 1]  ->  out_u8 [B, H, W, C] uint8 = round(clamp(img / 2 + 0.5, 0, 1) * 255). */
 int32_t dg_op_image_to_uint8(dg_ctx* ctx, const void* img, void* out_u8, int32_t B, int32_t C, int32_t H, int32_t W, void* stream);
 
+/* ---- clip `preprocess` on the device (filteration/get_clip_score.py:128-150: Resize(224, BICUBIC) / CenterCrop / ToTensor /
+ * Normalize on the PIL image): Pillow's 8-bit fixed-point antialiased resampling, one axis per pass.
+ * dg_op_resample_u8: in [B, Hin, Win, C] uint8 -> out [B, Hout, Wout, C]; axis 0 resamples x (Hout == Hin), axis 1 y;
+ * bounds = device int32 [n_out][2] (first input index, tap count), coeffs = device int32 [n_out][ksize] (22-bit fixed point,
+ * computed by the host exactly as Pillow's precompute_coeffs / normalize_coeffs_8bpc do).
+ * dg_op_clip_normalize: crop [top, top+n) x [left, left+n), (v / 255 - mean) / std, -> fp16 [B, 3, n, n]. */
+int32_t dg_op_resample_u8(dg_ctx* ctx, const void* in_u8, void* out_u8, int32_t B, int32_t Hin, int32_t Win, int32_t C, int32_t Hout,
+                          int32_t Wout, const int32_t* bounds, const int32_t* coeffs, int32_t ksize, int32_t axis, void* stream);
+int32_t dg_op_clip_normalize(dg_ctx* ctx, const void* in_u8, void* out, int32_t B, int32_t H, int32_t W, int32_t top, int32_t left, int32_t n,
+                             const float* mean3, const float* std3, void* stream);
+
 /* ---- single operators (exported for the parity tests; the same launchers the UNet uses) ---------------------------
  * dg_op_gemm: out[M, n_out] = epi(A[M, K] * W[n_w, K]^T)      <- torch.nn.Linear / Conv2d 1x1
  *    bias [n_w] / residual [M, n_out] optional; geglu: W is GEGLU-packed (see dg_op_pack_geglu), n_out = inner dim.

@@ -20,6 +20,7 @@ GROUPS = {
     "unet_sd15": ["tests/test_gpu_unet.py", "-k", "sd15"],
     "unet_sd21": ["tests/test_gpu_unet.py", "-k", "sd21"],
     "clip": ["tests/test_gpu_clip.py"],
+    "preprocess": ["tests/test_preprocess.py"],
     "vae_tiny": ["tests/test_gpu_vae.py", "-k", "not sd_vae"],
     "vae_sd": ["tests/test_gpu_vae.py", "-k", "sd_vae"],
 }
