@@ -197,6 +197,32 @@ class AsyncImageWriter:
         return n
 
 
+def clip_scores_for(scorer, tokenizer, images_u8, category_name: str):
+    """Row f3 fused into generation: the CLIP score filteration/get_clip_score.py:174-180 would compute after re-reading the
+    PNG -- `text = 'a photo of a single {}'.format(' '.join(category_name.split('_')))`, `logits_per_text` of ViT-L/14 --
+    taken from the uint8 image while it is still on the device (PNG is lossless and the resize is Pillow's, bit for bit, so
+    the pixels are the same).  Returns a list of floats, one per image."""
+    from .preprocess import clip_preprocess
+    text = "a photo of a single {}".format(" ".join(category_name.split("_")))
+    ids = tokenizer([text], padding="max_length", max_length=getattr(tokenizer, "model_max_length", 77), truncation=True,
+                    return_tensors="pt").input_ids
+    return scorer(clip_preprocess(images_u8), ids).view(-1).cpu().tolist()
+
+
+def load_clip_scorer(clip_dir: str, device):
+    """(tokenizer, scorer) from a transformers-format CLIP directory (`openai/clip-vit-large-patch14`: model.safetensors +
+    tokenizer files), or None."""
+    path = _first_existing(clip_dir, ("model.fp16.safetensors", "model.safetensors")) if clip_dir else None
+    if not path:
+        return None
+    from safetensors.torch import load_file
+    from transformers import CLIPTokenizer
+    from . import CLIPScorer
+    sc = CLIPScorer(device=device)
+    sc.load_state_dict(load_file(path))
+    return CLIPTokenizer.from_pretrained(clip_dir), sc
+
+
 def encode_prompt_table(prompts: Sequence[str], tokenizer, text_encoder, batch: int = 64):
     """Text embeddings of every distinct prompt, once, on rank 0 (row 0 = the unconditional "" prompt): what the reference
     recomputes per micro-batch on every rank through `stage_1.encode_prompt(prompt)` (:242).  `tokenizer` is a transformers
@@ -247,6 +273,9 @@ def build_parser() -> argparse.ArgumentParser:
     p.add_argument("--guidance_scale", type=float, default=7.5)
     p.add_argument("--random_init", action="store_true", help="random-init UNet weights (benchmarks; no checkpoint offline)")
     p.add_argument("--png_workers", type=int, default=4, help="PNG encoder threads per rank")
+    p.add_argument("--clip_dir", type=str, default=None,
+                   help="transformers-format CLIP ViT-L/14 directory: score every image on the device (needs --in_lvis_json_path "
+                        "for the category names) and write <outdir>/clip_scores_<stage>_rank<r>.json")
     p.add_argument("--in_lvis_json_path", type=str, default=None,
                    help="LVIS category JSON (as for convert_dir_structure.py): write <outdir>/<stage>/<category_name>/ directly")
     p.add_argument("--decode", action="store_true", help="with --random_init: also build a random-init VAE and write PNGs")
@@ -342,6 +371,8 @@ def main(argv: Optional[Sequence[str]] = None) -> int:
 
     n_done = 0
     writer = AsyncImageWriter(args.png_workers) if vae is not None else None
+    clip = load_clip_scorer(args.clip_dir, device) if (vae is not None and id_to_name is not None) else None
+    scores = {}
     for fi, (path, lines) in enumerate(per_file):
         cid = category_id_of(path)
         cat_dir = output_dir_for(args.outdir, stage, cid, id_to_name)
@@ -362,12 +393,19 @@ def main(argv: Optional[Sequence[str]] = None) -> int:
             dsts = [os.path.join(cat_dir, output_name(cid, count, ext)) for count in call.counts]
             if vae is not None:
                 writer.submit(out, dsts)                                          # reference :267 (pt -> PIL -> .save), asynchronously
+                if clip is not None:
+                    for dst, sc in zip(dsts, clip_scores_for(clip[1], clip[0], out, id_to_name[int(cid)])):
+                        scores.setdefault(cid, {})[os.path.basename(dst)] = sc
             else:
                 for j, dst in enumerate(dsts):
                     torch.save(out[j].cpu(), dst)
             n_done += call.num_images
     if writer is not None:
         writer.close()
+    if clip is not None:
+        import json
+        with open(os.path.join(args.outdir, "clip_scores_{}_rank{}.json".format(stage, rank)), "w") as f:
+            json.dump(scores, f)
     if args.dist:
         torch.distributed.barrier()
         torch.distributed.destroy_process_group()

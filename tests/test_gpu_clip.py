@@ -172,3 +172,36 @@ def test_vit_l14_clip_scores_full_width():
     err = (got - want).abs().max().item()
     print(f"clip scores ViT-L/14: max err {err:.4g}, ref {want.flatten().tolist()}, got {got.flatten().tolist()}")
     assert err <= 1e-2 * want.abs().max().item() + 5e-3
+
+
+def test_scoring_before_writing_equals_scoring_the_png(tmp_path):
+    """Row f3 fused into generation: the score taken from the device uint8 image equals the score the filteration script
+    would get from the written PNG (PIL open -> clip preprocess -> CLIPModel), here with a tiny random-init CLIP whose image
+    size is 56 (so `preprocess` resizes 160x128 -> 70x56 and crops)."""
+    _need_gpu()
+    import numpy as np
+    from types import SimpleNamespace
+    from PIL import Image
+    from divergen_b200.preprocess import CLIP_MEAN, CLIP_STD, clip_preprocess, resize_size
+    ref, ours = _clip_models(0, TINY, TINY_VISION, 64)
+    imgs = np.random.default_rng(3).integers(0, 256, (2, 160, 128, 3), dtype=np.uint8)
+    ids = _ids(1, 77, TINY["vocab_size"], 11)
+    # what the driver does (clip_scores_for, with the tokenizer output given directly)
+    got = ours(clip_preprocess(torch.from_numpy(imgs).cuda(), n_px=56), ids).view(-1).cpu()
+    # what filteration does after the fact
+    mean, std = torch.tensor(CLIP_MEAN).view(3, 1, 1), torch.tensor(CLIP_STD).view(3, 1, 1)
+    px = []
+    for b in range(2):
+        path = tmp_path / f"{b}.png"
+        Image.fromarray(imgs[b]).save(path)
+        im = Image.open(path).convert("RGB")
+        oh, ow = resize_size(im.height, im.width, 56)
+        im = im.resize((ow, oh), Image.BICUBIC)
+        top, left = int(round((oh - 56) / 2.0)), int(round((ow - 56) / 2.0))
+        t = torch.from_numpy(np.asarray(im)[top:top + 56, left:left + 56].copy()).permute(2, 0, 1).float() / 255.0
+        px.append((t - mean) / std)
+    with torch.no_grad():
+        want = ref(input_ids=ids, pixel_values=torch.stack(px)).logits_per_text.view(-1)
+    err = (got - want).abs().max().item()
+    print(f"fused scoring: max err {err:.4g}, ref {want.tolist()}")
+    assert err <= 1e-2 * want.abs().max().item() + 2e-2
