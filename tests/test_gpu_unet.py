@@ -213,3 +213,34 @@ def test_sd15_batch8_sample_independence():
         d1 = (small[1] - big[4 + i]).abs().max().item()
         print(f"sample {i}: batch-8 vs batch-2 max diff {d0:.3g} / {d1:.3g} (output absmax {scale:.3g})")
         assert max(d0, d1) <= 2 * scale * 2.0 ** -10 + 1e-4
+
+
+def test_sd15_full_size_loop_equals_stepwise():
+    """BASELINE config 2's shape (4 images, UNet batch 8, 64x64 latents, SD-1.5 full width), 3 DDIM steps: the fused device loop
+    (`dg_denoise_loop`: hoisted text K/V and time-embedding table, CUDA-graph replay, fused CFG + DDIM kernel) against the
+    same loop driven step by step through `UNet2DConditionModel.forward` + `DDIMScheduler.step` -- the hoisting and the graph
+    must not change the result beyond fp16 rounding of the intermediate noise tensor."""
+    _need_gpu()
+    from divergen_b200 import DDIMScheduler, StableDiffusionPipeline, UNet2DConditionModel
+    from divergen_b200.generate import random_state_dict
+    unet = UNet2DConditionModel(device=DEV)
+    unet.load_state_dict(random_state_dict(unet, torch.device(DEV)))
+    g = torch.Generator().manual_seed(21)
+    lat = torch.randn(4, 4, 64, 64, generator=g).half()
+    pos, neg = torch.randn(4, 77, 768, generator=g).half(), torch.randn(4, 77, 768, generator=g).half()
+    pipe = StableDiffusionPipeline(unet, DDIMScheduler())
+    got = pipe(prompt_embeds=pos, negative_prompt_embeds=neg, latents=lat, num_inference_steps=3, guidance_scale=7.5,
+               output_type="latent").images.float().cpu()
+    sch = DDIMScheduler()
+    sch.set_timesteps(3)
+    x = lat.to(DEV).clone()
+    ehs = torch.cat([neg, pos]).to(DEV)
+    for t in sch.timesteps:
+        n = unet(torch.cat([x, x]), t, ehs).sample
+        u, c = n.chunk(2)
+        x = sch.step((u.float() + 7.5 * (c.float() - u.float())).half(), t, x).prev_sample
+    want = x.float().cpu()
+    d = (got - want).abs().max().item()
+    print(f"sd15 full-size loop vs step-by-step: max diff {d:.4g}, absmax {want.abs().max().item():.4g}")
+    assert torch.isfinite(got).all()
+    assert d <= 2e-2 * want.abs().max().item() + 5e-3
