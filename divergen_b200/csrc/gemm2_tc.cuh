@@ -345,7 +345,12 @@ gemm2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
     if (lane < S::kUnitTab && u < total_) sUnits[lane] = unit_coord<kCta>(p, u, cta_rank, m_tiles_, p.taps * (p.kb0 + p.kb1));
   }
   tc_fence_before();
-  if constexpr (kCta == 2) cluster_sync_all(); else __syncthreads();
+  __syncthreads();                     // TMEM address, tile table and barrier init are visible CTA-wide (shared-memory ordering)
+  if constexpr (kCta == 2) {
+    // the peer only needs to know that this CTA's mbarriers are initialised (fence.mbarrier_init.release.cluster above): a
+    // relaxed arrive is enough -- the release form costs a MEMBAR.ALL.GPU in every launch's prologue
+    asm volatile("barrier.cluster.arrive.relaxed.aligned;\n\tbarrier.cluster.wait.aligned;" ::: "memory");
+  }
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   griddep_launch();                    // the next kernel may begin its own prologue
@@ -1003,7 +1008,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
   __syncwarp();
   if (threadIdx.x == 0) DG_STAMP(12);   // producer warp at the teardown barrier
   tc_fence_before();
-  if constexpr (kCta == 2) cluster_sync_all(); else __syncthreads();
+  if constexpr (kCta == 2) cluster_sync_all(); else __syncthreads();   // (a relaxed arrive here measured within noise: kept strict)
   if (threadIdx.x == 0) DG_STAMP(13);   // teardown barrier passed
   if (warp == 2) { tc_fence_after(); tmem_dealloc_pair<kCta, kTmemCols>(tmem_base); }
   if (threadIdx.x == 64) DG_STAMP(14);  // TMEM released
