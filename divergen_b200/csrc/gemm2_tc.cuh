@@ -13,20 +13,27 @@
 // their own 128 pixels of A and HALF of each 160-row weight block; tcgen05.mma.cta_group::2 (M = 256) reads the other
 // half from the peer's shared memory.  Per CTA: the same 36 KB per k-block now feeds 128 x 320 outputs (57 B/clk/SM).
 //
-// Warp roles (384 threads per CTA): warp 0 = TMA producer (one lane), warp 1 = MMA issuer (one lane, leader CTA only),
-// warp 2 = TMEM allocator, warps 4..11 = epilogue.  Persistent over work units (tile x K-split), kStages-deep smem ring.
-// Barrier protocol for a pair: both producers' TMA bytes complete on the LEADER's full barrier (peer-bit-masked barrier
-// address); the leader's tcgen05.commit multicasts stage-free / accumulator-ready arrivals to both CTAs; every epilogue
-// warp of either CTA arrives remotely on the leader's accumulator-free barrier.
+// Warp roles (384 threads per CTA): warp 0 = TMA producer (elected lane), warp 1 = MMA issuer (elected lane, leader CTA
+// only), warp 2 = TMEM allocator, then residual loader, warp 3 = tile-table builder, then store warp, warps 4..11 = epilogue.
+// Persistent over work units (tile x K-split); the first 32 units of a CTA are decomposed once in the prologue (one per lane)
+// into a shared-memory table.  kStages-deep operand ring.  Barrier protocol for a pair: both producers' TMA bytes complete on
+// the LEADER's full barrier (peer-bit-masked barrier address); the leader's tcgen05.commit multicasts stage-free /
+// accumulator-ready arrivals to both CTAs; every epilogue warp of either CTA arrives remotely on the leader's
+// accumulator-free barrier.  Prologue hand-shake: CTA barrier + relaxed cluster arrive (mbarrier init is published with
+// fence.mbarrier_init.release.cluster); single-thread roles wait with the suspend-time hint.
 //
-// Epilogue (per CTA: its own 128 rows x 320 columns, fp32 in TMEM), in chunks of 32 columns per thread:
-//   tcgen05.ld -> [LayerNorm fold: rstd*(acc - mean*colsum[n])] + bias (+ time-embedding vector) (+ residual, prefetched
-//   one chunk ahead with 16-byte loads) [GEGLU: value * gelu(gate)] -> fp16 -> 64-byte-swizzled staging ring -> TMA store.
-//   Fused statistics on the rounded outputs: per-row (sum, sum of squares) partials for the LayerNorm that consumes this
-//   tensor, and per-(sample, channel-block) sums for the next GroupNorm (warp shuffle reduce + fp32 atomics).
-// Split-K (small-M layers at the bottom of the U): each split adds its fp32 partial tile into an L2-resident accumulator
-//   with 16-byte vector reductions; the last arriver (atomic ticket) reads the sum, re-zeroes it and runs the epilogue.
-//   (fp32 addition order varies run to run: results are reproducible to fp32 rounding, not bit for bit.)
+// Epilogue (per CTA: its own 128 rows x kBN columns, fp32 in TMEM), in chunks of 32 / 16 columns per thread:
+//   tcgen05.ld -> [LayerNorm fold: rstd*(acc - mean*colsum[n])] + bias (+ time-embedding row) (+ residual: streamed by TMA
+//   from the loader warp into the very staging bytes the result will overwrite, a whole tile / two chunks ahead)
+//   [GEGLU: value * gelu(gate), packed fp32x2] -> fp16 -> 64-byte-swizzled staging (whole-tile slots for 160-wide tiles, a
+//   4-slot chunk ring for 320-wide ones) -> TMA store by the store warp (data-driven through mbarriers).
+//   Fused statistics for the consumer: per-row (sum, sum of squares) partials for the next LayerNorm (thread = row, fp32
+//   values before rounding), and per-(32-pixel slab, channel block) sums for the next GroupNorm (the warp reads its staged
+//   fp16 slab back transposed: no shuffles, no atomics, deterministic).
+// Split-K (small-M layers at the bottom of the U; one tile per CTA): each split stages its fp32 partial in the idle output
+//   ring and adds it to an L2-resident tile accumulator with bulk shared->global reductions (cp.reduce.async.bulk.add.f32,
+//   16 KB per 32-column chunk); the last arriver (atomic ticket) bulk-loads the sum into the idle operand stages, re-zeroes
+//   the workspace and runs the epilogue.  (fp32 addition order varies run to run: reproducible to fp32 rounding.)
 //
 // Replaces (reference side): torch.nn.Conv2d / Linear / LayerNorm / GroupNorm statistics inside diffusers ResnetBlock2D,
 // Attention, FeedForward, Transformer2DModel, reached from DiverGen/generation/txt2img_diffusers_stages_from_txt.py:255-259.
