@@ -91,3 +91,19 @@ def test_category_layout_matches_convert_dir_structure(tmp_path):
     want = os.path.join("out", "sd", id_to_name[category_id], filename)         # :118-120
     assert os.path.join(output_dir_for("out", "sd", "7", id_to_name), filename) == want
     assert output_dir_for("out", "sd", "7", None) == os.path.join("out", "samples", "sd")
+
+
+def test_category_layout_rejects_unknown_ids():
+    from divergen_b200.generate import output_dir_for
+    with pytest.raises(ValueError):
+        output_dir_for("out", "sd", "prompt", {1: "aerosol_can"})        # --prompt runs have no category id
+    with pytest.raises(ValueError):
+        output_dir_for("out", "sd", "9", {1: "aerosol_can"})
+
+
+def test_clip_score_text_is_the_filteration_prompt():
+    """clip_scores_for builds `'a photo of a single {}'.format(' '.join(category_name.split('_')))` (get_clip_score.py:175)."""
+    import inspect
+    from divergen_b200 import generate
+    src = inspect.getsource(generate.clip_scores_for)
+    assert "\"a photo of a single {}\".format(\" \".join(category_name.split(\"_\")))" in src
