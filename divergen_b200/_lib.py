@@ -80,6 +80,7 @@ SIGNATURES = {
     "dg_clip_weight_name": (C.c_char_p, [_P, _I]),
     "dg_clip_weight_shape": (_I, [_P, _I, C.POINTER(_L), C.POINTER(_I)]),
     "dg_clip_set_weight": (_I, [_P, C.c_char_p, _P, _I, C.POINTER(_L)]),
+    "dg_clip_set_activation": (_I, [_P, _I]),
     "dg_clip_prepare": (_I, [_P, _I]),
     "dg_clip_encode": (_I, [_P, C.POINTER(_I), _I, _I, _P, _P]),
     "dg_clipscore_create": (_I, [_P, C.POINTER(_I), C.POINTER(_I), _I, C.POINTER(_P)]),
@@ -92,6 +93,7 @@ SIGNATURES = {
     "dg_clipscore_prepare": (_I, [_P, _I, _I]),
     "dg_clipscore_score": (_I, [_P, _P, _I, C.POINTER(_I), C.POINTER(_I), _I, _I, C.POINTER(_F), _P]),
     "dg_op_image_to_uint8": (_I, [_P, _P, _P, _I, _I, _I, _I, _P]),
+    "dg_op_mask_composite_u8": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _P]),
     "dg_op_resample_u8": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, C.POINTER(_I), C.POINTER(_I), _I, _I, _P]),
     "dg_op_clip_normalize": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, C.POINTER(_F), C.POINTER(_F), _P]),
     "dg_op_gemm": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),

@@ -20,7 +20,11 @@ import torch
 from . import _lib
 
 SD_CLIP_CONFIG = dict(vocab_size=49408, hidden_size=768, intermediate_size=3072, num_hidden_layers=12,
-                      num_attention_heads=12, max_position_embeddings=77)
+                      num_attention_heads=12, max_position_embeddings=77, hidden_act="quick_gelu")
+# SD-2.x: OpenCLIP ViT-H/14 text tower as shipped in `stabilityai/stable-diffusion-2-1/text_encoder/config.json` (the
+# penultimate-layer trick is baked in: the checkpoint has 23 layers)
+SD21_CLIP_CONFIG = dict(vocab_size=49408, hidden_size=1024, intermediate_size=4096, num_hidden_layers=23,
+                        num_attention_heads=16, max_position_embeddings=77, hidden_act="gelu")
 
 
 class CLIPTextOutput(tuple):
@@ -35,8 +39,9 @@ class CLIPTextModel:
     def __init__(self, device="cuda:0", **config):
         cfg = dict(SD_CLIP_CONFIG)
         cfg.update(config)
-        if cfg.get("hidden_act", "quick_gelu") != "quick_gelu":
-            raise ValueError("only hidden_act='quick_gelu' (the SD-1.x text encoder) is supported")
+        act = cfg.setdefault("hidden_act", "quick_gelu")
+        if act not in ("quick_gelu", "gelu"):
+            raise ValueError("hidden_act must be 'quick_gelu' (SD-1.x text encoder) or 'gelu' (SD-2.x OpenCLIP text encoder)")
         self.config = SimpleNamespace(**cfg)
         self.device = torch.device(device)
         if self.device.type != "cuda":
@@ -49,6 +54,7 @@ class CLIPTextModel:
                                             cfg["num_hidden_layers"], cfg["num_attention_heads"],
                                             cfg["max_position_embeddings"], C.byref(h)), "dg_clip_create")
         self._h = h
+        _lib.check(self._lib.dg_clip_set_activation(h, {"quick_gelu": 0, "gelu": 1}[act]), "dg_clip_set_activation")
         self._prepared = 0
 
     def to(self, *args, **kwargs):

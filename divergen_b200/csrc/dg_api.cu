@@ -895,6 +895,7 @@ struct ClipLayer { Norm ln1, ln2; Lin qkv, out, fc1, fc2; };
 struct dg_clip : WeightStore {
   int vocab = 49408, hidden = 768, inter = 3072, layers = 12, heads = 12, max_pos = 77;
   float eps = 1e-5f;
+  int act = 0;               // 0 quick_gelu, 1 erf gelu (dg_clip_set_activation)
   __half* tok = nullptr; __half* pos = nullptr;
   std::vector<ClipLayer> L;
   Norm final_ln;
@@ -943,7 +944,7 @@ int clip_linear(dg_ctx* ctx, cudaStream_t s, const __half* x, int K, int rows, c
 // Pre-LN transformer layers (CLIPEncoderLayer x N) over x [batch * seq, C]; buffers: x2, h, att [rows, C], qkv [rows, 3C],
 // f [rows, inter].  The result is back in x.
 int run_clip_layers(dg_ctx* ctx, cudaStream_t s, const std::vector<ClipLayer>& L, __half* x, __half* x2, __half* h, __half* att,
-                    __half* qkv, __half* f, int batch, int seq, int C, int inter, int heads, int causal, float eps) {
+                    __half* qkv, __half* f, int batch, int seq, int C, int inter, int heads, int causal, float eps, int act = 0) {
   const int rows = batch * seq;
   for (const ClipLayer& l : L) {
     DG_TRY(launch_layernorm(s, x, l.ln1.g, l.ln1.b, h, rows, C, eps));
@@ -952,7 +953,7 @@ int run_clip_layers(dg_ctx* ctx, cudaStream_t s, const std::vector<ClipLayer>& L
     DG_TRY(clip_linear(ctx, s, att, C, rows, l.out, x, x2));
     DG_TRY(launch_layernorm(s, x2, l.ln2.g, l.ln2.b, h, rows, C, eps));
     DG_TRY(clip_linear(ctx, s, h, C, rows, l.fc1, nullptr, f));
-    quick_gelu_kernel<<<grid_for((size_t)rows * inter / 8, 256, ctx->num_sms), 256, 0, s>>>(f, (size_t)rows * inter / 8);
+    quick_gelu_kernel<<<grid_for((size_t)rows * inter / 8, 256, ctx->num_sms), 256, 0, s>>>(f, (size_t)rows * inter / 8, act);
     DG_LAUNCH_CHECK();
     DG_TRY(clip_linear(ctx, s, f, inter, rows, l.fc2, x2, x));
   }
@@ -1572,6 +1573,11 @@ int32_t dg_clip_weight_shape(dg_clip* c, int32_t i, int64_t* shape4, int32_t* nd
 int32_t dg_clip_set_weight(dg_clip* c, const char* key, const void* src, int32_t ndim, const int64_t* shape) {
   return store_set_weight(c, key, src, ndim, shape);
 }
+int32_t dg_clip_set_activation(dg_clip* c, int32_t act) {
+  if (!c || (act != 0 && act != 1)) return fail(DG_E_ARG, "clip: activation must be 0 (quick_gelu) or 1 (gelu)");
+  c->act = act;
+  return DG_OK;
+}
 int32_t dg_clip_prepare(dg_clip* c, int32_t max_batch) {
   if (!c || max_batch <= 0) return fail(DG_E_ARG, "bad argument");
   DG_CUDA(cudaSetDevice(c->ctx->device));
@@ -1600,7 +1606,7 @@ int32_t dg_clip_encode(dg_clip* c, const int32_t* input_ids, int32_t batch, int3
   DG_CUDA(cudaMemcpyAsync(c->ids_dev, input_ids, (size_t)rows * sizeof(int), cudaMemcpyHostToDevice, s));
   clip_embed_kernel<<<(unsigned)(((size_t)rows * (C / 8) + 255) / 256), 256, 0, s>>>(c->ids_dev, c->tok, c->pos, x, rows, seq, C, c->vocab);
   DG_LAUNCH_CHECK();
-  DG_TRY(run_clip_layers(c->ctx, s, c->L, x, x2, h, att, qkv, f, batch, seq, C, c->inter, c->heads, /*causal=*/1, c->eps));
+  DG_TRY(run_clip_layers(c->ctx, s, c->L, x, x2, h, att, qkv, f, batch, seq, C, c->inter, c->heads, /*causal=*/1, c->eps, c->act));
   DG_TRY(launch_layernorm(s, x, c->final_ln.g, c->final_ln.b, (__half*)out, rows, C, c->eps));
   return DG_OK;
 }
@@ -1735,6 +1741,18 @@ int32_t dg_clipscore_score(dg_clipscore* c, const void* pixel_values, int32_t n_
 }
 
 
+int32_t dg_op_mask_composite_u8(dg_ctx* ctx, const void* img_u8, const void* mask_u8, void* out_u8, uint32_t* count, int32_t B, int32_t H,
+                                int32_t W, void* stream) {
+  if (!ctx || !img_u8 || !mask_u8 || !out_u8 || !count || B <= 0 || H <= 0 || W <= 0) return fail(DG_E_ARG, "bad argument");
+  DG_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  DG_CUDA(cudaMemsetAsync(count, 0, sizeof(uint32_t) * B, s));
+  const int hw = H * W;
+  dim3 grid((unsigned)std::min((hw + 255) / 256, 4 * ctx->num_sms), (unsigned)B);
+  mask_composite_u8_kernel<<<grid, 256, 0, s>>>((const unsigned char*)img_u8, (const unsigned char*)mask_u8, (unsigned char*)out_u8, count, B, hw);
+  DG_LAUNCH_CHECK();
+  return DG_OK;
+}
 int32_t dg_op_resample_u8(dg_ctx* ctx, const void* in_u8, void* out_u8, int32_t B, int32_t Hin, int32_t Win, int32_t C, int32_t Hout,
                           int32_t Wout, const int32_t* bounds, const int32_t* coeffs, int32_t ksize, int32_t axis, void* stream) {
   if (!ctx || !in_u8 || !out_u8 || !bounds || !coeffs || B <= 0 || C <= 0 || ksize <= 0 || (axis != 0 && axis != 1)) return fail(DG_E_ARG, "bad argument");

@@ -538,12 +538,18 @@ __global__ void clip_embed_kernel(const int* __restrict__ ids, const __half* __r
   store8(out + (size_t)r * C + v * 8, a);
 }
 // CLIP's `quick_gelu`: x * sigmoid(1.702 x), in place.
-__global__ void quick_gelu_kernel(__half* __restrict__ x, size_t nvec) {
+// act: 0 = quick_gelu x*sigmoid(1.702x) (OpenAI CLIP, SD-1.x text encoder), 1 = erf GELU (OpenCLIP ViT-H, SD-2.x text encoder)
+__global__ void quick_gelu_kernel(__half* __restrict__ x, size_t nvec, int act) {
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < nvec; i += (size_t)gridDim.x * blockDim.x) {
     float f[8];
     load8(x + i * 8, f);
+    if (act == 0) {
 #pragma unroll
-    for (int k = 0; k < 8; ++k) f[k] = __fdividef(f[k], 1.0f + __expf(-1.702f * f[k]));
+      for (int k = 0; k < 8; ++k) f[k] = __fdividef(f[k], 1.0f + __expf(-1.702f * f[k]));
+    } else {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) f[k] = 0.5f * f[k] * (1.0f + erff(f[k] * 0.70710678118654752f));
+    }
     store8(x + i * 8, f);
   }
 }
@@ -649,6 +655,26 @@ __global__ void clip_normalize_kernel(const unsigned char* __restrict__ in, __ha
   const float v = (float)in[(((size_t)b * H + top + y) * W + left + x) * 3 + c] / 255.0f;
   const float m = c == 0 ? m0 : (c == 1 ? m1 : m2), sd = c == 0 ? s0 : (c == 1 ? s1 : s2);
   out[i] = __float2half_rn((v - m) / sd);
+}
+
+// ---- filteration mask compositing (DiverGen/filteration/get_clip_score.py:133-146, --use_mask):
+//   mask_im = mask > 128;  image = image * mask_im + ones_like(image) * (1 - mask_im)   (background becomes the value 1, as there)
+//   area    = sum(mask_im) / H / W   -- accumulated as an exact integer count per image (warp-aggregated atomics)
+// img / out [B, HW, 3] uint8, mask [B, HW] uint8, count [B] (zeroed by the caller).
+__global__ void mask_composite_u8_kernel(const unsigned char* __restrict__ img, const unsigned char* __restrict__ mask,
+                                         unsigned char* __restrict__ out, unsigned int* __restrict__ count, int B, int HW) {
+  const int b = blockIdx.y;
+  unsigned int local = 0;
+  for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < HW; p += gridDim.x * blockDim.x) {
+    const size_t i = (size_t)b * HW + p;
+    const bool m = mask[i] > 128;
+    local += m ? 1u : 0u;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) out[i * 3 + c] = m ? img[i * 3 + c] : (unsigned char)1;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
+  if ((threadIdx.x & 31) == 0 && local) atomicAdd(count + b, local);
 }
 
 // ------------------------------------------------------------------ VAE decoder helpers

@@ -33,10 +33,14 @@ def pt_to_pil(images: torch.Tensor):
     return [Image.fromarray(a) for a in arr]
 
 
+_COMPONENTS = ("unet", "scheduler", "vae", "text_encoder", "tokenizer")
+
+
 class StableDiffusionPipeline:
     def __init__(self, unet: UNet2DConditionModel, scheduler: DDIMScheduler,
                  text_encoder: Optional[Callable] = None, vae_decode: Optional[Callable] = None,
                  vae_scale_factor: int = 8, vae=None, tokenizer=None):
+        self._lazy = None
         self.unet, self.scheduler = unet, scheduler
         self.tokenizer = tokenizer
         self.text_encoder, self.vae_decode = text_encoder, vae_decode
@@ -46,11 +50,66 @@ class StableDiffusionPipeline:
         self.feature_extractor = None
         self.safety_checker = None
 
-    def to(self, device):
+    # ---- DiffusionPipeline.from_pretrained (divergen_b200/loading.py): the components are built on the GPU the caller names
+    # with .to(device) / enable_model_cpu_offload(gpu_id) (reference :141-143), or on the current CUDA device at first use.
+    @classmethod
+    def from_pretrained(cls, pretrained_model_name_or_path, **kwargs):
+        from .loading import DiffusionPipeline
+        return DiffusionPipeline.from_pretrained(pretrained_model_name_or_path, **kwargs)
+
+    def _init_lazy(self, spec):
+        self._lazy = spec
+        self.vae_decode = None
+        self.vae_scale_factor = 8
+        self.feature_extractor = None
+        self.safety_checker = None
+
+    def _materialize(self, device=None):
+        if getattr(self, "_lazy", None) is None:
+            return
+        from .loading import materialize
+        spec, self._lazy = self._lazy, None
+        dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        if dev.type != "cuda":
+            raise ValueError("divergen_b200 has no CPU path; move the pipeline to a CUDA (sm_100) device")
+        if dev.index is None:
+            dev = torch.device("cuda", torch.cuda.current_device())
+        for k, v in materialize(spec, dev).items():
+            setattr(self, k, v)
+        self.device = dev
+        if self.vae is not None:
+            self.vae_scale_factor = 2 ** (len(self.vae.config.block_out_channels) - 1)
+
+    def __getattr__(self, name):
+        # only reached when normal lookup fails: a component of a not-yet-materialised from_pretrained pipeline
+        if name in _COMPONENTS + ("device",) and self.__dict__.get("_lazy") is not None:
+            self._materialize()
+            return self.__dict__[name]
+        raise AttributeError(name)
+
+    @property
+    def components(self):
+        return {k: getattr(self, k) for k in _COMPONENTS}
+
+    def to(self, device=None, *args, **kwargs):
+        if isinstance(device, torch.dtype):               # pipe.to(torch.float16): the only dtype there is
+            if device != torch.float16:
+                raise ValueError("divergen_b200 stores fp16 only")
+            return self
+        if device is not None and getattr(self, "_lazy", None) is not None:
+            self._materialize(device)
+        elif device is not None and torch.device(device).type == "cuda":
+            d = torch.device(device)
+            if d.index is not None and d != self.device:
+                raise ValueError("pipeline lives on {}; divergen_b200 components do not migrate between devices".format(self.device))
+        elif device is not None:
+            raise ValueError("divergen_b200 has no CPU path")
         return self
 
-    def enable_model_cpu_offload(self, gpu_id=None):
+    def enable_model_cpu_offload(self, gpu_id=None, device=None):
         """Accepted for call compatibility (txt2img_...py:143); weights stay resident in HBM (1.7 GB of 180 GB)."""
+        if getattr(self, "_lazy", None) is not None:
+            self._materialize(device if device is not None else ("cuda:{}".format(gpu_id) if gpu_id is not None else None))
 
     def enable_xformers_memory_efficient_attention(self):
         """Accepted for call compatibility (txt2img_...py:186); attention is always the fused tcgen05 kernel."""

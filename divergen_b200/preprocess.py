@@ -123,3 +123,21 @@ def clip_preprocess(images: torch.Tensor, n_px: int = 224, mean=CLIP_MEAN, std=C
     _lib.check(lib.dg_op_clip_normalize(ctx, C.c_void_p(x.data_ptr()), C.c_void_p(out.data_ptr()), b, oh, ow, top, left, n_px, m, s,
                                         C.c_void_p(torch.cuda.current_stream(images.device).cuda_stream)), "dg_op_clip_normalize")
     return out
+
+
+def mask_composite(images: torch.Tensor, masks: torch.Tensor):
+    """filteration/get_clip_score.py:133-146 on the device: `mask_im = mask > 128`, background pixels become the value 1,
+    `area = sum(mask_im) / H / W`.  images [B, H, W, 3] uint8, masks [B, H, W] uint8 -> (composited images, areas fp64 [B])."""
+    if images.dtype != torch.uint8 or masks.dtype != torch.uint8 or images.dim() != 4 or images.shape[3] != 3:
+        raise ValueError("mask_composite expects [B, H, W, 3] uint8 images and [B, H, W] uint8 masks")
+    if tuple(masks.shape) != tuple(images.shape[:3]):
+        raise ValueError("mask shape {} does not match images {}".format(tuple(masks.shape), tuple(images.shape)))
+    images, masks = images.contiguous(), masks.contiguous()
+    b, h, w, _ = images.shape
+    out = torch.empty_like(images)
+    count = torch.empty(b, dtype=torch.int32, device=images.device)
+    lib, ctx = _lib.load(), _lib.context(images.device.index or 0)
+    _lib.check(lib.dg_op_mask_composite_u8(ctx, C.c_void_p(images.data_ptr()), C.c_void_p(masks.data_ptr()), C.c_void_p(out.data_ptr()),
+                                           C.c_void_p(count.data_ptr()), b, h, w,
+                                           C.c_void_p(torch.cuda.current_stream(images.device).cuda_stream)), "dg_op_mask_composite_u8")
+    return out, count.cpu().double() / h / w

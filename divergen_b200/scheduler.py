@@ -45,6 +45,21 @@ class DDIMScheduler:
         self.num_inference_steps: Optional[int] = None
         self.timesteps = torch.from_numpy(np.arange(0, num_train_timesteps)[::-1].copy().astype(np.int64))
 
+    @classmethod
+    def from_config(cls, config, **overrides):
+        """`DDIMScheduler.from_config(scheduler_config.json dict | another scheduler's .config)`: the noise-schedule fields
+        are taken, sampler-specific fields of other scheduler classes (PNDM's `skip_prk_steps`, ...) are dropped.
+        `clip_sample` defaults to False here (the Stable-Diffusion DDIM config); a config that asks for clipping raises."""
+        c = dict(vars(config)) if not isinstance(config, dict) else dict(config)
+        c.update(overrides)
+        if c.get("trained_betas") is not None:
+            raise ValueError("trained_betas is not supported")
+        if c.get("thresholding") or c.get("rescale_betas_zero_snr"):
+            raise ValueError("thresholding / rescale_betas_zero_snr are not supported")
+        keys = ("num_train_timesteps", "beta_start", "beta_end", "beta_schedule", "clip_sample", "set_alpha_to_one",
+                "steps_offset", "prediction_type", "timestep_spacing")
+        return cls(**{k: c[k] for k in keys if k in c})
+
     def set_timesteps(self, num_inference_steps: int, device=None):
         if num_inference_steps > self.config.num_train_timesteps:
             raise ValueError("num_inference_steps exceeds num_train_timesteps")

@@ -26,6 +26,18 @@ class DecoderOutput:
 SD_VAE_CONFIG = dict(latent_channels=4, out_channels=3, block_out_channels=(128, 256, 512, 512), layers_per_block=2,
                      norm_num_groups=32, scaling_factor=0.18215)
 _IGNORED_PREFIXES = ("encoder.", "quant_conv.")
+# Published SD-1.x / 2.x `vae/diffusion_pytorch_model*.safetensors` files predate diffusers' Attention refactor: the mid-block
+# attention is stored under the deprecated AttentionBlock names, which diffusers renames at load time
+# (`_convert_deprecated_attention_blocks`).  Same mapping here.
+_DEPRECATED_ATTN = {".query.": ".to_q.", ".key.": ".to_k.", ".value.": ".to_v.", ".proj_attn.": ".to_out.0."}
+
+
+def _rename_deprecated(key: str) -> str:
+    if ".attentions." in key:
+        for old, new in _DEPRECATED_ATTN.items():
+            if old in key:
+                return key.replace(old, new)
+    return key
 
 
 class AutoencoderKL:
@@ -74,6 +86,7 @@ class AutoencoderKL:
 
     def load_state_dict(self, state_dict, strict: bool = True):
         expected = self.expected_state_dict_shapes()
+        state_dict = {_rename_deprecated(k): v for k, v in state_dict.items()}
         missing = [k for k in expected if k not in state_dict]
         unexpected = [k for k in state_dict if k not in expected and not k.startswith(_IGNORED_PREFIXES)]
         if strict and (missing or unexpected):

@@ -138,6 +138,9 @@ int32_t dg_clip_num_weights(dg_clip* clip);
 const char* dg_clip_weight_name(dg_clip* clip, int32_t index);
 int32_t dg_clip_weight_shape(dg_clip* clip, int32_t index, int64_t* shape4, int32_t* ndim);
 int32_t dg_clip_set_weight(dg_clip* clip, const char* key, const void* src, int32_t ndim, const int64_t* shape);
+/* MLP activation: 0 = quick_gelu (OpenAI CLIP ViT-L/14, the SD-1.x text encoder; default), 1 = erf GELU (OpenCLIP ViT-H/14,
+ * the SD-2.x text encoder; transformers `hidden_act: "gelu"`). */
+int32_t dg_clip_set_activation(dg_clip* clip, int32_t act);
 int32_t dg_clip_prepare(dg_clip* clip, int32_t max_batch);
 int32_t dg_clip_encode(dg_clip* clip, const int32_t* input_ids, int32_t batch, int32_t seq, void* out, void* stream);
 
@@ -171,6 +174,10 @@ int32_t dg_op_image_to_uint8(dg_ctx* ctx, const void* img, void* out_u8, int32_t
  * bounds = device int32 [n_out][2] (first input index, tap count), coeffs = device int32 [n_out][ksize] (22-bit fixed point,
  * computed by the host exactly as Pillow's precompute_coeffs / normalize_coeffs_8bpc do).
  * dg_op_clip_normalize: crop [top, top+n) x [left, left+n), (v / 255 - mean) / std, -> fp16 [B, 3, n, n]. */
+/* Mask compositing of filteration/get_clip_score.py:133-146 (--use_mask): out = mask > 128 ? img : 1 on [B, H, W, 3] uint8 images
+ * with [B, H, W] uint8 masks; count[b] (device uint32, zeroed here) = number of mask pixels > 128 (area = count / (H*W)). */
+int32_t dg_op_mask_composite_u8(dg_ctx* ctx, const void* img_u8, const void* mask_u8, void* out_u8, uint32_t* count, int32_t B,
+                                int32_t H, int32_t W, void* stream);
 int32_t dg_op_resample_u8(dg_ctx* ctx, const void* in_u8, void* out_u8, int32_t B, int32_t Hin, int32_t Win, int32_t C, int32_t Hout,
                           int32_t Wout, const int32_t* bounds, const int32_t* coeffs, int32_t ksize, int32_t axis, void* stream);
 int32_t dg_op_clip_normalize(dg_ctx* ctx, const void* in_u8, void* out, int32_t B, int32_t H, int32_t W, int32_t top, int32_t left, int32_t n,

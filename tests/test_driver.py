@@ -102,8 +102,87 @@ def test_category_layout_rejects_unknown_ids():
 
 
 def test_clip_score_text_is_the_filteration_prompt():
-    """clip_scores_for builds `'a photo of a single {}'.format(' '.join(category_name.split('_')))` (get_clip_score.py:175)."""
-    import inspect
-    from divergen_b200 import generate
-    src = inspect.getsource(generate.clip_scores_for)
-    assert "\"a photo of a single {}\".format(\" \".join(category_name.split(\"_\")))" in src
+    """`text='a photo of a single {}'.format(' '.join(category_name.split('_')))` (get_clip_score.py:175)."""
+    from divergen_b200.generate import clip_prompt_text
+    assert clip_prompt_text("aerosol_can") == "a photo of a single aerosol can"
+    assert clip_prompt_text("alligator") == "a photo of a single alligator"
+    assert clip_prompt_text("bow_(decorative_ribbons)") == "a photo of a single bow (decorative ribbons)"
+
+
+def test_pack_calls_keeps_order_indices_and_limits():
+    """Packing across prompts (the gpt-prompt recipe: `--n_samples 8` on 8 ranks = 1 image per prompt per rank): groups are
+    consecutive, never split a call, never exceed max_batch_size, and together are exactly the unpacked call sequence."""
+    from divergen_b200.generate import iter_calls, pack_calls, plan_batches
+    lines = ["prompt {}".format(k) for k in range(11)]
+    plan = plan_batches(8, 8, 4)                                   # 1 image per prompt per rank
+    calls = list(iter_calls(lines, plan, rank=3, n_samples=8, offset=1024))
+    groups = list(pack_calls(calls, 4))
+    assert [len(g) for g in groups] == [4, 4, 3]
+    assert [c for g in groups for c in g] == calls
+    assert all(sum(c.num_images for c in g) <= 4 for g in groups)
+    # remainder batches: 6 images per prompt per rank at max_batch_size 4 -> calls of 2, 4, 2, 4, ...; a group holds one
+    # 4-call or a 2-call alone (2 + 4 > 4), i.e. packing never reorders or splits
+    plan = plan_batches(6, 1, 4)
+    calls = list(iter_calls(["a", "b"], plan, rank=0, n_samples=6, offset=0))
+    assert [c.num_images for c in calls] == [2, 4, 2, 4]
+    groups = list(pack_calls(calls, 4))
+    assert [[c.num_images for c in g] for g in groups] == [[2], [4], [2], [4]]
+    groups = list(pack_calls(calls, 8))
+    assert [[c.num_images for c in g] for g in groups] == [[2, 4, 2], [4]]
+    assert [n for g in groups for c in g for n in c.counts] == [n for c in calls for n in c.counts]
+    assert list(pack_calls([], 4)) == []
+
+
+def test_writer_surfaces_save_errors_early(tmp_path):
+    """A failed save raises at a later submit / close instead of only after the whole run; back-pressure bounds the queue."""
+    import numpy as np
+    from divergen_b200.generate import AsyncImageWriter
+
+    class FakeImages:                       # stands in for a device tensor: AsyncImageWriter only copies and records an event
+        pass
+
+    w = AsyncImageWriter(workers=1, max_in_flight=2)
+    import concurrent.futures as cf
+    # drive the reaping logic directly with futures (no GPU here)
+    ok = cf.Future(); ok.set_result(2)
+    bad = cf.Future(); bad.set_exception(OSError("disk full"))
+    w._pending = [ok, bad]
+    with pytest.raises(OSError):
+        w._reap(0)
+    assert w._written == 2
+    w._pending = []
+    assert w.close() == 2
+
+
+def test_clip_score_job_helpers(tmp_path):
+    """filteration/get_clip_score.py bookkeeping: stage directories (:87-101), mask paths (:134-137), rank striding (:113-115),
+    index-sorted merge of the gathered scores (:192-200)."""
+    from types import SimpleNamespace
+    from divergen_b200.clip_score import build_parser, mask_path_for, merge_gathered, picked_for_rank, stage_dirs
+    a = SimpleNamespace(indir="in", outdir="out", use_mask=False, in_mask_dir="m", seg_name="sam")
+    assert stage_dirs(a, "sd") == ("in", "out") and stage_dirs(a, "III") == (os.path.join("in", "III"), os.path.join("out", "III"))
+    a.use_mask = True
+    assert stage_dirs(a, "sd") == ("in", os.path.join("out", "sam"))
+    assert stage_dirs(a, "III") == (os.path.join("in", "III"), os.path.join("out", "III", "sam"))
+    assert mask_path_for(a, "sd", "cat", "/x/y/1_0000001.png") == os.path.join("m", "sam", "cat", "1_0000001.png")
+    assert mask_path_for(a, "III", "cat", "/x/y/1_0000001.png") == os.path.join("m", "III", "sam", "cat", "1_0000001.png")
+    paths = ["p{}".format(i) for i in range(7)]
+    got = [picked_for_rank(paths, r, 3) for r in range(3)]
+    assert [[i for i, _ in g] for g in got] == [[0, 3, 6], [1, 4], [2, 5]]
+    merged = merge_gathered([[0, 3, 6], [1, 4], [2, 5]], [[0.0, 3.0, 6.0], [1.0, 4.0], [2.0, 5.0]])
+    assert merged == [float(i) for i in range(7)]
+    p = build_parser().parse_args(["--indir", "i", "--outdir", "o", "--use_mask", "--in_mask_dir", "m", "--seg_name", "s", "--dist",
+                                   "--n_samples", "1024", "1280", "--max_batch_size", "8", "--stages", "sd"])
+    assert p.n_samples == [1024, 1280] and p.use_mask and p.max_batch_size == 8
+
+
+def test_gather_clip_results_single_rank(tmp_path):
+    """The fused-scoring job leaves the reference's results.json: the category list with `clip_scores` in sorted-file order."""
+    import json
+    from divergen_b200.generate import gather_clip_results
+    cats = tmp_path / "cats.json"
+    cats.write_text(json.dumps([{"id": 1, "name": "aerosol_can"}, {"id": 7, "name": "alligator"}]))
+    scores = {"7": {"7_0000002.png": 2.0, "7_0000000.png": 0.5, "7_0000001.png": 1.0}}
+    data = gather_clip_results(scores, {1: "aerosol_can", 7: "alligator"}, str(cats), str(tmp_path / "results.json"), 0, 1)
+    assert json.load(open(tmp_path / "results.json")) == data
+    assert data[0]["clip_scores"] == [] and data[1]["clip_scores"] == [0.5, 1.0, 2.0]

@@ -244,3 +244,73 @@ def test_sd15_full_size_loop_equals_stepwise():
     print(f"sd15 full-size loop vs step-by-step: max diff {d:.4g}, absmax {want.abs().max().item():.4g}")
     assert torch.isfinite(got).all()
     assert d <= 2e-2 * want.abs().max().item() + 5e-3
+
+
+# ------------------------------------------------------------------ full-width parity at the BENCHMARKED shapes (round 2)
+def _full_width_forward(cfg, B, hw, ctx_dim, t, seed, name):
+    oracle, unet = _models(cfg, seed=0)
+    g = torch.Generator().manual_seed(seed)
+    x, ehs = torch.randn(B, 4, hw, hw, generator=g).half(), torch.randn(B, 77, ctx_dim, generator=g).half()
+    with torch.no_grad():
+        o = oracle.to(DEV)
+        ref32 = o(x.to(DEV).float(), torch.tensor([t], device=DEV), ehs.to(DEV).float()).sample.cpu()
+        o = o.half()
+        ref16 = o(x.to(DEV), torch.tensor([t], device=DEV), ehs.to(DEV)).sample.cpu()
+        del o
+    torch.cuda.empty_cache()
+    got = unet(x.to(DEV), t, ehs.to(DEV)).sample
+    torch.cuda.synchronize()
+    _check(got, ref32, ref16, name)
+
+
+def test_sd15_forward_full_width_batch8():
+    """BASELINE config 2's exact UNet shape -- batch 8 (4 images x CFG) at 64x64, SD-1.5 full width -- against the fp32 oracle
+    (run on the GPU as the checker).  Tile scheduling, wave counts and the split-K choices differ from the batch-2 case above;
+    this is the shape bench.py times."""
+    _need_gpu()
+    from oracle.unet_oracle import UNetConfig
+    _full_width_forward(UNetConfig.sd15(), 8, 64, 768, 981, 44, "sd15 full width batch 8")
+
+
+def test_sd21_forward_full_width_batch4():
+    """BASELINE config 4's per-GPU UNet shape -- batch 4 (2 images x CFG) at 96x96, SD-2.1 (768-v) full width."""
+    _need_gpu()
+    from oracle.unet_oracle import UNetConfig
+    _full_width_forward(UNetConfig.sd21(), 4, 96, 1024, 961, 45, "sd21 full width batch 4 96x96")
+
+
+def test_sd15_50_step_loop_vs_oracle_full_width():
+    """The whole 50-step CFG loop of ONE image at SD-1.5 full width: device loop (`dg_denoise_loop`) against the fp32 oracle
+    loop (checker, on the GPU), with the oracle's own fp16 eager run of the same loop beside it.  Random-init weights make
+    the trajectory sensitive to rounding (errors compound over 100 UNet evaluations), so the statement is relative: the
+    kernel path's final latents must agree with the fp32 trajectory at cosine >= 0.99, or at least as well as torch fp16
+    does (cosine >= cos_torch16 - 0.005); cosine and PSNR of both are printed."""
+    _need_gpu()
+    from divergen_b200 import DDIMScheduler, StableDiffusionPipeline
+    from oracle.ddim_oracle import DDIMOracle, denoise_loop
+    from oracle.unet_oracle import UNetConfig
+    oracle, unet = _models(UNetConfig.sd15(), seed=0)
+    g = torch.Generator().manual_seed(46)
+    lat = torch.randn(1, 4, 64, 64, generator=g).half()
+    pos, neg = torch.randn(1, 77, 768, generator=g).half(), torch.randn(1, 77, 768, generator=g).half()
+    o = oracle.to(DEV)
+    ref32 = denoise_loop(o, DDIMOracle(), lat.to(DEV).float(), pos.to(DEV).float(), neg.to(DEV).float(), num_inference_steps=50).cpu()
+    o = o.half()
+    ref16 = denoise_loop(o, DDIMOracle(), lat.to(DEV), pos.to(DEV), neg.to(DEV), num_inference_steps=50).float().cpu()
+    del o
+    torch.cuda.empty_cache()
+    pipe = StableDiffusionPipeline(unet, DDIMScheduler())
+    got = pipe(prompt_embeds=pos, negative_prompt_embeds=neg, latents=lat, num_inference_steps=50, guidance_scale=7.5,
+               output_type="latent").images.float().cpu()
+
+    def stats(a):
+        cos = torch.nn.functional.cosine_similarity(a.flatten(), ref32.flatten(), dim=0).item()
+        mse = (a - ref32).pow(2).mean().item()
+        psnr = 10 * torch.log10(ref32.abs().max() ** 2 / max(mse, 1e-20)).item()
+        return cos, psnr
+    cos_new, psnr_new = stats(got)
+    cos_t16, psnr_t16 = stats(ref16)
+    print(f"50-step loop, SD-1.5 full width: kernel path cosine {cos_new:.5f} PSNR {psnr_new:.1f} dB | "
+          f"torch fp16 oracle cosine {cos_t16:.5f} PSNR {psnr_t16:.1f} dB | ref absmax {ref32.abs().max().item():.3g}")
+    assert torch.isfinite(got).all()
+    assert cos_new >= min(0.99, cos_t16 - 0.005), (cos_new, cos_t16)
