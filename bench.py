@@ -1,6 +1,9 @@
 #!/usr/bin/env python
 """bench.py -- BASELINE.json metric: 512x512 images/sec @ 50 DDIM steps (SD-1.5 UNet, CFG 7.5, batch 4 per GPU).
 
+  python bench.py --config sd21 ...                         # BASELINE configs[3]: SD-2.1 768x768, UNet batch 4 per GPU
+  (the default run also carries two secondary blocks: `e2e_png` = VAE + uint8 + PNG-on-disk rate, `c4` = the sd21 shape)
+
   python bench.py --gpus N --steps K --warmup W            # this repo's sm_100a path
   python bench.py --impl reference --gpus N --steps K ...  # the reference-side CPU path (oracle port; diffusers absent)
 
@@ -24,14 +27,42 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 METRIC = "512x512 images/sec @50 DDIM steps"
-FLOP_PER_SAMPLE_FORWARD = 0.8033e12  # SD-1.5 @64x64 latent (SURVEY.md 8d / BASELINE.md 3)
-IMAGES_PER_GPU = 4
-# DRAM traffic of the GEMM family: mean of dram__bytes_read.sum + dram__bytes_write.sum over the 210 gemm2 launches of one
-# batch-8 forward (one ncu pass, cold caches), see the file named here.
-GEMM_DRAM_BYTES_PER_LAUNCH = 27955415   # read 27.04 MB + write 0.92 MB (outputs mostly stay in the 126 MB L2)
-GEMM_DRAM_SOURCE = "profiles/r01_gemm2_dram.csv"
 DDIM_STEPS = 50
 GUIDANCE = 7.5
+# BASELINE.json configs: sd15 = configs[1] (N = 1) / configs[2] (N > 1, weak scaling); sd21 = configs[3] (SD-2.1 768x768, batch 16
+# over 8 GPUs = 2 images = UNet batch 4 per GPU).  FLOP per sample-forward: SURVEY.md 8d / BASELINE.md 3.
+CONFIGS = {
+    "sd15": dict(model="sd15", images_per_gpu=4, latent=64, ctx_dim=768, prediction="epsilon", flop_per_sample_forward=0.8033e12,
+                 label="configs[1]: SD-1.5 UNet 512x512, 50 DDIM steps, CFG 7.5, batch 4 per GPU (UNet batch 8)",
+                 label_multi="configs[2] weak scaling", metric=METRIC),
+    "sd21": dict(model="sd21", images_per_gpu=2, latent=96, ctx_dim=1024, prediction="v_prediction", flop_per_sample_forward=2.1491e12,
+                 label="configs[3]: SD-2.1 UNet 768x768 (v-prediction), 50 DDIM steps, CFG 7.5, batch 2 per GPU (UNet batch 4)",
+                 label_multi="batch 16 over 8 GPUs", metric="768x768 images/sec @50 DDIM steps"),
+}
+
+
+def gemm_dram_traffic():
+    """DRAM bytes per launch of the GEMM family = mean over the launches of (dram__bytes_read.sum + dram__bytes_write.sum) in the
+    NEWEST `profiles/r??_gemm2_dram.csv` (one `ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum` pass over a batch-8
+    forward, regenerated every round with tools/gemm_dram.sh).  Returns (bytes, file) or (None, None)."""
+    import csv
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r[0-9][0-9]_gemm2_dram.csv")))
+    if not files:
+        return None, None
+    lines = open(files[-1]).read().splitlines()
+    try:
+        start = next(k for k, l in enumerate(lines) if l.startswith('"ID"'))
+    except StopIteration:
+        return None, None
+    per = {}
+    for r in csv.DictReader(lines[start:]):
+        if "gemm2_kernel" in r["Kernel Name"] and r["Metric Name"] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            v = float(r["Metric Value"]) * {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(r["Metric Unit"], 1.0)
+            per[r["ID"]] = per.get(r["ID"], 0.0) + v
+    if not per:
+        return None, None
+    return int(sum(per.values()) / len(per)), os.path.relpath(files[-1], ROOT)
 
 
 def peaks():
@@ -99,6 +130,131 @@ def fast_state_dict(expected_shapes, seed=0):
     return sd
 
 
+class Workload:
+    """One BASELINE config on this rank's GPU: random-init UNet of that architecture, seeded latents / embeddings resident in
+    HBM plus pinned host copies for the end-to-end arm."""
+
+    def __init__(self, cfg, dev, rank, world, dist):
+        import torch
+        from divergen_b200 import SD15_CONFIG, SD21_CONFIG, DDIMScheduler, StableDiffusionPipeline, UNet2DConditionModel
+        self.cfg, self.dev = cfg, dev
+        mc = SD15_CONFIG if cfg["model"] == "sd15" else SD21_CONFIG
+        self.unet = UNet2DConditionModel(device=dev, **{k: v for k, v in mc.items() if k != "time_cond_proj_dim"})
+        self.unet.load_state_dict(fast_state_dict(self.unet.expected_state_dict_shapes(), seed=0))
+        self.sched = DDIMScheduler(prediction_type=cfg["prediction"])
+        self.pipe = StableDiffusionPipeline(self.unet, self.sched)
+        n, hw, d = cfg["images_per_gpu"], cfg["latent"], cfg["ctx_dim"]
+        self.n = n
+        # text embeddings: produced once on rank 0 (synthetic stand-in for CLIP output) and broadcast -- the path's only
+        # data-carrying collective (SURVEY.md 8e); seeds follow the reference's seed + rank (txt2img_...py:200).
+        emb = torch.empty(2, 77, d, dtype=torch.float16, device=dev)
+        if rank == 0:
+            emb.copy_(torch.randn(2, 77, d, generator=torch.Generator().manual_seed(1234)).half())
+        if world > 1:
+            dist.broadcast(emb, src=0)
+        self.pos_h = emb[0:1].repeat(n, 1, 1).cpu().pin_memory()
+        self.neg_h = emb[1:2].repeat(n, 1, 1).cpu().pin_memory()
+        self.lat_h = torch.randn(n, 4, hw, hw, generator=torch.Generator().manual_seed(42 + rank)).half().pin_memory()
+        self.out_h = torch.empty(n, 4, hw, hw, dtype=torch.float16).pin_memory()
+        self.sched.set_timesteps(DDIM_STEPS)
+        self.ts = [int(t) for t in self.sched.timesteps]
+        al = [self.sched.alphas_for(t) for t in self.ts]
+        self.a_t, self.a_prev = [a for a, _ in al], [p for _, p in al]
+        self.ehs = torch.cat([self.neg_h, self.pos_h]).to(dev)
+        self.lat0 = self.lat_h.to(dev)
+        self.lat = self.lat0.clone()
+
+    def device_step(self):
+        self.lat.copy_(self.lat0)
+        self.unet.denoise_loop(self.lat, self.ehs, self.ts, self.a_t, self.a_prev, GUIDANCE, self.cfg["prediction"])
+
+    def e2e_step(self):
+        import torch
+        res = self.pipe(prompt_embeds=self.pos_h, negative_prompt_embeds=self.neg_h, latents=self.lat_h,
+                        num_inference_steps=DDIM_STEPS, guidance_scale=GUIDANCE, output_type="latent").images
+        self.out_h.copy_(res, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+
+def family_times(w, reps=5):
+    """Per-family device time of ONE UNet forward at the workload's shape, two ways:
+      graph: the forward captured with only that family's kernels (dg_unet_set_family_mask) and replayed -- the launch chain
+             (programmatic dependent launch, no host gaps) is the timed loop's; this is what `roofline.achieved` uses;
+      eager: one event pair around every launch of a full eager forward (dg_unet_profile_forward) -- serialised, no overlap."""
+    import torch
+    from divergen_b200 import _lib
+    lib = _lib.load()
+    unet, n, hw = w.unet, w.n, w.cfg["latent"]
+    x_in = torch.cat([w.lat0, w.lat0])
+    out = torch.empty_like(x_in)
+    arrs = [(C.c_double * 4)() for _ in range(3)]
+    launches_f = (C.c_int64 * 4)()
+    total_ms = C.c_double()
+    tarr = (C.c_float * 1)(float(w.ts[0]))
+    best = None
+    for _ in range(3):
+        _lib.check(lib.dg_unet_profile_forward(
+            unet._h, C.c_void_p(x_in.data_ptr()), tarr, 1, C.c_void_p(w.ehs.data_ptr()), 77, C.c_void_p(out.data_ptr()),
+            2 * n, hw, hw, C.c_void_p(torch.cuda.current_stream().cuda_stream), arrs[0], arrs[1], arrs[2], launches_f,
+            C.byref(total_ms)), "dg_unet_profile_forward")
+        cur = dict(ms=list(arrs[0]), flops=list(arrs[1]), bytes=list(arrs[2]), launches=list(launches_f), total_ms=total_ms.value)
+        if best is None or cur["total_ms"] < best["total_ms"]:
+            best = cur
+    graph_ms = {}
+    try:
+        for name, mask in (("all", 15), ("gemm", 1), ("attn", 2), ("norm", 4), ("other", 8)):
+            _lib.check(lib.dg_unet_set_family_mask(unet._h, mask))
+            for _ in range(2):
+                unet(x_in, w.ts[0], w.ehs, out=out)          # capture + one replay
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(reps):
+                unet(x_in, w.ts[0], w.ehs, out=out)
+            e1.record()
+            torch.cuda.synchronize()
+            graph_ms[name] = e0.elapsed_time(e1) / reps
+    finally:
+        _lib.check(lib.dg_unet_set_family_mask(unet._h, 15))
+    return best, graph_ms
+
+
+def png_e2e(w, dev, steps):
+    """images/s of the whole image path through the public API: pinned-host embeddings + latents in, 50-step loop, VAE decode,
+    device uint8 conversion, asynchronous D2H + PNG encode to disk (generate.AsyncImageWriter) -- SD-1.5 512x512 only."""
+    import shutil
+    import tempfile
+    import torch
+    from divergen_b200 import AutoencoderKL, StableDiffusionPipeline
+    from divergen_b200.generate import AsyncImageWriter
+    vae = AutoencoderKL(device=dev)
+    vae.load_state_dict(fast_state_dict(vae.expected_state_dict_shapes(), seed=1))
+    pipe = StableDiffusionPipeline(w.unet, w.sched, vae=vae)
+    tmp = tempfile.mkdtemp(prefix="dg_bench_png_")
+    try:
+        def one(k, writer):
+            img = pipe(prompt_embeds=w.pos_h, negative_prompt_embeds=w.neg_h, latents=w.lat_h, num_inference_steps=DDIM_STEPS,
+                       guidance_scale=GUIDANCE, output_type="uint8").images
+            writer.submit(img, [os.path.join(tmp, "{}_{:07d}.png".format(k, j)) for j in range(w.n)])
+        wr = AsyncImageWriter(4)
+        one(0, wr)
+        wr.close()
+        torch.cuda.synchronize()
+        wr = AsyncImageWriter(4)
+        t0 = time.perf_counter()
+        for k in range(steps):
+            one(k + 1, wr)
+        wrote = wr.close()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        nbytes = sum(os.path.getsize(os.path.join(tmp, f)) for f in os.listdir(tmp))
+        return {"value": round(wrote / dt, 4), "unit": "images/s", "images": wrote, "png_bytes_per_image": int(nbytes / max(1, len(os.listdir(tmp)))),
+                "d2h_bytes_per_step": int(w.n * 512 * 512 * 3), "png_workers": 4,
+                "api": "StableDiffusionPipeline.__call__(..., output_type='uint8') + generate.AsyncImageWriter (VAE decode, uint8, PNG on disk)"}
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -112,44 +268,9 @@ def run_ours(args):
     assert args.gpus == world, f"--gpus {args.gpus} but WORLD_SIZE={world} (launch with torch.distributed.run)"
     torch.cuda.set_device(local_rank)
     dev = torch.device(f"cuda:{local_rank}")
-    from divergen_b200 import DDIMScheduler, StableDiffusionPipeline, UNet2DConditionModel, _lib
-
-    unet = UNet2DConditionModel(device=dev)  # SD-1.5 config
-    unet.load_state_dict(fast_state_dict(unet.expected_state_dict_shapes(), seed=0))
-    sched = DDIMScheduler()
-    pipe = StableDiffusionPipeline(unet, sched)
-
-    n = IMAGES_PER_GPU
-    # text embeddings: produced once on rank 0 (synthetic stand-in for CLIP output) and broadcast -- the path's only
-    # data-carrying collective; seeds follow the reference's seed + rank (txt2img_...py:200).
-    emb = torch.empty(2, 77, 768, dtype=torch.float16, device=dev)
-    if rank == 0:
-        emb.copy_(torch.randn(2, 77, 768, generator=torch.Generator().manual_seed(1234)).half())
-    if world > 1:
-        dist.broadcast(emb, src=0)
-    pos_h = emb[0:1].repeat(n, 1, 1).cpu().pin_memory()
-    neg_h = emb[1:2].repeat(n, 1, 1).cpu().pin_memory()
-    gen = torch.Generator().manual_seed(42 + rank)
-    lat_h = torch.randn(n, 4, 64, 64, generator=gen).half().pin_memory()
-    out_h = torch.empty(n, 4, 64, 64, dtype=torch.float16).pin_memory()
-
-    sched.set_timesteps(DDIM_STEPS)
-    ts = [int(t) for t in sched.timesteps]
-    al = [sched.alphas_for(t) for t in ts]
-    a_t, a_prev = [a for a, _ in al], [p for _, p in al]
-    ehs = torch.cat([neg_h, pos_h]).to(dev)
-    lat0 = lat_h.to(dev)
-    lat = lat0.clone()
-
-    def device_step():
-        lat.copy_(lat0)
-        unet.denoise_loop(lat, ehs, ts, a_t, a_prev, GUIDANCE, "epsilon")
-
-    def e2e_step():
-        res = pipe(prompt_embeds=pos_h, negative_prompt_embeds=neg_h, latents=lat_h, num_inference_steps=DDIM_STEPS,
-                   guidance_scale=GUIDANCE, output_type="latent").images
-        out_h.copy_(res, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
+    cfg = CONFIGS[args.config]
+    w = Workload(cfg, dev, rank, world, dist)
+    n = w.n
 
     def barrier():
         if world > 1:
@@ -157,6 +278,7 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     def timed(fn, k):
+        """-> (max over ranks of the device time, max wall time, [every rank's device time])."""
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0 = time.perf_counter()
@@ -166,22 +288,25 @@ def run_ours(args):
         e1.record()
         barrier()
         wall = (time.perf_counter() - t0) * 1e3
-        ms = torch.tensor([e0.elapsed_time(e1), wall], device=dev)
+        mine = torch.tensor([e0.elapsed_time(e1), wall], device=dev)
+        allr = [mine]
         if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return ms[0].item(), ms[1].item()
+            allr = [torch.empty_like(mine) for _ in range(world)]
+            dist.all_gather(allr, mine)
+        per_rank = [float(t[0]) for t in allr]
+        return max(per_rank), max(float(t[1]) for t in allr), per_rank
 
     for _ in range(args.warmup):
-        device_step()
+        w.device_step()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    ms_dev, _ = timed(device_step, args.steps)
-    launches = unet.last_launch_count * args.steps + args.steps  # + the latent reset copy per step
+    ms_dev, _, per_rank = timed(w.device_step, args.steps)
+    launches = w.unet.last_launch_count * args.steps + args.steps  # + the latent reset copy per step
     clocks = sampler.stop() if rank == 0 else None
     for _ in range(max(1, args.warmup // 2)):
-        e2e_step()
-    ms_e2e_dev, ms_e2e_wall = timed(e2e_step, args.steps)
+        w.e2e_step()
+    ms_e2e_dev, ms_e2e_wall, _ = timed(w.e2e_step, args.steps)
 
     total_images = n * world * args.steps
     value = total_images / (ms_dev / 1e3)
@@ -190,61 +315,85 @@ def run_ours(args):
     result = None
     if rank == 0:
         pk = peaks()
-        # ---- per-kernel roofline: one eager forward with an event pair around every launch (live, this process)
-        x_in = torch.cat([lat0, lat0])
-        out = torch.empty_like(x_in)
-        arrs = [(C.c_double * 4)() for _ in range(3)]
-        launches_f = (C.c_int64 * 4)()
-        total_ms = C.c_double()
-        tarr = (C.c_float * 1)(float(ts[0]))
-        best = None
-        for _ in range(3):
-            _lib.check(_lib.load().dg_unet_profile_forward(
-                unet._h, C.c_void_p(x_in.data_ptr()), tarr, 1, C.c_void_p(ehs.data_ptr()), 77, C.c_void_p(out.data_ptr()),
-                2 * n, 64, 64, C.c_void_p(torch.cuda.current_stream().cuda_stream), arrs[0], arrs[1], arrs[2], launches_f,
-                C.byref(total_ms)), "dg_unet_profile_forward")
-            cur = dict(ms=list(arrs[0]), flops=list(arrs[1]), bytes=list(arrs[2]), launches=list(launches_f), total_ms=total_ms.value)
-            if best is None or cur["total_ms"] < best["total_ms"]:
-                best = cur
+        flop_sf = cfg["flop_per_sample_forward"]
+        best, graph_ms = family_times(w)
         fam = ["gemm2_kernel(linear+conv)", "attn_tc_kernel", "groupnorm-apply", "other"]
-        gemm_tf = best["flops"][0] / (best["ms"][0] * 1e-3) / 1e12
-        attn_tf = best["flops"][1] / (best["ms"][1] * 1e-3) / 1e12 if best["ms"][1] else 0.0
-        norm_gbs = best["bytes"][2] / (best["ms"][2] * 1e-3) / 1e9 if best["ms"][2] else 0.0
+        gemm_tf_eager = best["flops"][0] / (best["ms"][0] * 1e-3) / 1e12
+        gemm_tf = best["flops"][0] / (graph_ms["gemm"] * 1e-3) / 1e12
+        attn_tf = best["flops"][1] / (graph_ms["attn"] * 1e-3) / 1e12 if graph_ms["attn"] else 0.0
+        norm_gbs = best["bytes"][2] / (graph_ms["norm"] * 1e-3) / 1e9 if graph_ms["norm"] else 0.0
         fwd_ms_graph = ms_dev / args.steps / DDIM_STEPS
-        whole_tf = FLOP_PER_SAMPLE_FORWARD * 2 * n / (fwd_ms_graph * 1e-3) / 1e12
+        whole_tf = flop_sf * 2 * n / (fwd_ms_graph * 1e-3) / 1e12
+        traffic, traffic_src = gemm_dram_traffic() if args.config == "sd15" else (None, None)
+        nl = max(1, best["launches"][0])
         roofline = {
-            "bound": "tensor", "kernel": "gemm2_kernel<cta_group 2, tile N 160|320> (all 210 Linear / conv1x1 / conv3x3 launches of one UNet forward)",
+            "bound": "tensor", "kernel": "gemm2_kernel<cta_group 2, tile N 160|320> (every Linear / conv1x1 / conv3x3 launch of one UNet forward)",
             "achieved": round(gemm_tf, 1), "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": round(gemm_tf / pk["tf_sustained"], 4),
+            "how": "algorithmic FLOPs of the family's launches / device time of a replayed CUDA graph holding ONLY those launches "
+                   "(dg_unet_set_family_mask; same launch chain as the timed loop), CUDA events, mean of 5 replays",
             "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({pk['src']}; kernel timed inside a long step)",
-            "traffic": GEMM_DRAM_BYTES_PER_LAUNCH, "traffic_source": GEMM_DRAM_SOURCE,
-            "algorithmic_flops_per_launch": round(best["flops"][0] / max(1, best["launches"][0]) / 1e9, 2),
-            "algorithmic_bytes_per_launch": round(best["bytes"][0] / max(1, best["launches"][0]) / 1e6, 2),
-            "launches_per_forward": best["launches"][0], "avg_launch_us": round(best["ms"][0] * 1e3 / max(1, best["launches"][0]), 2),
-            "share_of_forward": round(best["ms"][0] / best["total_ms"], 4),
-            "families": {fam[i]: {"ms": round(best["ms"][i], 4), "launches": best["launches"][i],
-                                  "share": round(best["ms"][i] / best["total_ms"], 4)} for i in range(4)},
+            "traffic": traffic, "traffic_source": traffic_src,
+            "algorithmic_flops_per_launch": round(best["flops"][0] / nl / 1e9, 2),
+            "algorithmic_bytes_per_launch": round(best["bytes"][0] / nl / 1e6, 2),
+            "launches_per_forward": best["launches"][0], "avg_launch_us": round(graph_ms["gemm"] * 1e3 / nl, 2),
+            "share_of_forward": round(graph_ms["gemm"] / graph_ms["all"], 4),
+            "graph_family_ms": {k: round(v, 4) for k, v in graph_ms.items()},
+            "eager": {"achieved": round(gemm_tf_eager, 1), "frac": round(gemm_tf_eager / pk["tf_sustained"], 4),
+                      "forward_ms": round(best["total_ms"], 3),
+                      "families": {fam[i]: {"ms": round(best["ms"][i], 4), "launches": best["launches"][i]} for i in range(4)},
+                      "how": "one event pair around every launch of an eager forward (serialised, no programmatic overlap)"},
             "attn_tc_tflops": round(attn_tf, 1), "attn_frac_of_peak": round(attn_tf / pk["tf_sustained"], 4),
             "norm_gbs": round(norm_gbs, 1), "norm_frac_of_hbm_peak": round(norm_gbs / pk["hbm"], 4),
-            "eager_forward_ms": round(best["total_ms"], 3), "graph_forward_ms": round(fwd_ms_graph, 3),
+            "graph_forward_ms": round(fwd_ms_graph, 3),
             "whole_unet_tflops": round(whole_tf, 1), "whole_unet_frac": round(whole_tf / pk["tf_sustained"], 4),
         }
         # CPU baseline on rank 0 at N = 1 only (under torchrun OMP_NUM_THREADS=1 would cripple it; the reference arm reports it)
-        cpu = cpu_baseline_sample(max_seconds=30.0) if world == 1 else None
+        cpu = cpu_baseline_sample(max_seconds=30.0) if (world == 1 and args.config == "sd15") else None
+        per_rank_ms = sorted(t / args.steps for t in per_rank)
+        roof_ips = pk["tf_sustained"] * 1e12 / (flop_sf * 2 * DDIM_STEPS)
         result = {
-            "metric": METRIC, "value": round(value, 4), "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "metric": cfg["metric"], "value": round(value, 4), "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": round(ms_dev / args.steps, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f16 (fp32 accumulate / statistics / softmax)", "data": "synthetic (seeded N(0,1) latents + embeddings, random-init SD-1.5 weights)",
-            "config": {"workload": "configs[1]: SD-1.5 UNet 512x512, 50 DDIM steps, CFG 7.5, batch 4 per GPU (UNet batch 8)"
-                                   + (f"; x{world} GPUs = configs[2] weak scaling" if world > 1 else ""),
+            "dtype": "f16 (fp32 accumulate / statistics / softmax)",
+            "data": f"synthetic (seeded N(0,1) latents + embeddings, random-init {cfg['model']} weights)",
+            "config": {"workload": cfg["label"] + (f"; x{world} GPUs = {cfg['label_multi']}" if world > 1 else ""),
                        "images_per_gpu": n, "ddim_steps": DDIM_STEPS, "guidance_scale": GUIDANCE,
-                       "l2": "inputs larger than L2: 1.72 GB of weights + activations stream per forward (L2 = 126 MB)",
+                       "l2": "inputs larger than L2: 1.7 GB of weights + activations stream per forward (L2 = 126 MB)",
                        "step": "one full 50-step denoising loop over the batch"},
-            "e2e": {"value": round(e2e_value, 4), "unit": "images/s", "h2d_bytes_per_step": int(pos_h.nbytes + neg_h.nbytes + lat_h.nbytes),
-                    "d2h_bytes_per_step": int(out_h.nbytes), "ms_per_step_wall": round(ms_e2e_wall / args.steps, 3),
+            "e2e": {"value": round(e2e_value, 4), "unit": "images/s",
+                    "h2d_bytes_per_step": int(w.pos_h.nbytes + w.neg_h.nbytes + w.lat_h.nbytes),
+                    "d2h_bytes_per_step": int(w.out_h.nbytes), "ms_per_step_wall": round(ms_e2e_wall / args.steps, 3),
                     "api": "StableDiffusionPipeline.__call__(prompt_embeds=, negative_prompt_embeds=, latents=<pinned host>, output_type='latent')"},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
-            "tensor_frac_of_roofline_images_per_s": round(value / world / (pk["tf_sustained"] * 1e12 / (FLOP_PER_SAMPLE_FORWARD * 100)), 4),
+            "per_rank_ms_per_step": {"min": round(per_rank_ms[0], 3), "median": round(per_rank_ms[len(per_rank_ms) // 2], 3),
+                                     "max": round(per_rank_ms[-1], 3)},
+            "tensor_frac_of_roofline_images_per_s": round(value / world / roof_ips, 4),
+            "roofline_images_per_s_per_gpu": round(roof_ips, 2),
         }
+    # ---- secondary figures (default run): the PNG-inclusive end-to-end rate, and BASELINE config 4's shape (SD-2.1 768x768)
+    if args.config == "sd15" and not args.no_extras:
+        if world == 1:
+            png = png_e2e(w, dev, max(2, args.steps))
+            if rank == 0:
+                result["e2e_png"] = png
+        del w
+        torch.cuda.empty_cache()
+        c4cfg = CONFIGS["sd21"]
+        w4 = Workload(c4cfg, dev, rank, world, dist)
+        for _ in range(2):
+            w4.device_step()
+        k4 = max(3, args.steps)
+        ms4, _, per4 = timed(w4.device_step, k4)
+        if rank == 0:
+            pk = peaks()
+            v4 = w4.n * world * k4 / (ms4 / 1e3)
+            roof4 = pk["tf_sustained"] * 1e12 / (c4cfg["flop_per_sample_forward"] * 2 * DDIM_STEPS)
+            _, g4 = family_times(w4, reps=3)
+            result["c4"] = {"metric": c4cfg["metric"], "value": round(v4, 4), "unit": "images/s", "n_gpus": world, "loops": k4,
+                            "ms_per_loop": round(ms4 / k4, 3), "workload": c4cfg["label"],
+                            "frac_of_roofline": round(v4 / world / roof4, 4), "roofline_images_per_s_per_gpu": round(roof4, 2),
+                            "graph_forward_ms": round(ms4 / k4 / DDIM_STEPS, 3),
+                            "graph_family_ms": {k: round(v, 4) for k, v in g4.items()}}
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -254,11 +403,11 @@ def run_ours(args):
         print(json.dumps(result), flush=True)
 
 
-def _oracle_sd15():
+def _oracle_model(which="sd15"):
     import torch
     from oracle.unet_oracle import UNet2DConditionOracle, UNetConfig
     torch.manual_seed(0)
-    cfg = UNetConfig.sd15()
+    cfg = UNetConfig.sd15() if which == "sd15" else UNetConfig.sd21()
     with torch.device("meta"):
         m = UNet2DConditionOracle(cfg)
     m = m.to_empty(device="cpu").eval()
@@ -273,19 +422,22 @@ def _oracle_sd15():
     return m
 
 
-def cpu_baseline_sample(max_seconds=30.0, model=None, images=1, reps=None):
+def cpu_baseline_sample(max_seconds=30.0, model=None, images=1, reps=None, which="sd15"):
     """The reference-side CPU path (oracle port: diffusers itself is not installable here) on a bounded sample:
-    DDIM steps of ONE image (a CFG pair through the UNet, fp32, all host threads), extrapolated x50 steps."""
+    DDIM steps of ONE image (a CFG pair through the UNet, fp32, all host threads), extrapolated x50 steps.
+    NOTE the sample runs at UNet batch 2 (one image), not the GPU arm's batch 8: the CPU's per-image time does not improve with
+    batch size (it is compute-bound at batch 2 already), so images/s extrapolates linearly."""
     import torch
     from oracle.ddim_oracle import DDIMOracle
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    m = model or _oracle_sd15()
-    s = DDIMOracle()
+    cfg = CONFIGS[which]
+    m = model or _oracle_model(which)
+    s = DDIMOracle(prediction_type=cfg["prediction"])
     s.set_timesteps(DDIM_STEPS)
     g = torch.Generator().manual_seed(42)
-    lat = torch.randn(images, 4, 64, 64, generator=g)
-    ehs = torch.randn(2 * images, 77, 768, generator=g)
+    lat = torch.randn(images, 4, cfg["latent"], cfg["latent"], generator=g)
+    ehs = torch.randn(2 * images, 77, cfg["ctx_dim"], generator=g)
 
     def one_step(i):
         nonlocal lat
@@ -316,9 +468,9 @@ def cpu_baseline_sample(max_seconds=30.0, model=None, images=1, reps=None):
     except Exception:
         pass
     return {"value": round(ips, 6), "unit": "images/s", "cores": cores, "kind": "port",
-            "sample": f"{len(times)} DDIM step(s) of {images} image (UNet batch {2 * images}, CFG, fp32 torch CPU oracle, SD-1.5 full width), "
-                      f"{per_step:.2f} s/step, extrapolated x{DDIM_STEPS} steps", "cpu_model": cpu_model,
-            "note": "oracle restatement; upstream diffusers unavailable, parity unpinned"}
+            "sample": f"{len(times)} DDIM step(s) of {images} image (UNet batch {2 * images}, NOT the GPU arm's batch {2 * cfg['images_per_gpu']}; "
+                      f"CFG, fp32 torch CPU oracle, {which} full width), {per_step:.2f} s/step, extrapolated x{DDIM_STEPS} steps",
+            "cpu_model": cpu_model, "note": "oracle restatement; upstream diffusers unavailable, parity unpinned"}
 
 
 def run_reference(args):
@@ -330,14 +482,15 @@ def run_reference(args):
     # torchrun exports OMP_NUM_THREADS=1; this arm is the CPU implementation and uses every host core (before torch loads)
     os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
     os.environ["MKL_NUM_THREADS"] = str(os.cpu_count() or 1)
-    m = _oracle_sd15()
+    cfg = CONFIGS[args.config]
+    m = _oracle_model(args.config)
     t0 = time.perf_counter()
-    cpu = cpu_baseline_sample(model=m, reps=max(1, args.steps))
+    cpu = cpu_baseline_sample(model=m, reps=max(1, args.steps), which=args.config)
     wall = time.perf_counter() - t0
-    out = {"impl": "reference", "metric": METRIC, "value": cpu["value"], "unit": "images/s", "n_gpus": args.gpus, "steps": args.steps,
+    out = {"impl": "reference", "metric": cfg["metric"], "value": cpu["value"], "unit": "images/s", "n_gpus": args.gpus, "steps": args.steps,
            "warmup": args.warmup, "ms_per_step": round(1e3 * 1.0 / (cpu["value"] * DDIM_STEPS), 3), "higher_is_better": True, "scaling": "weak",
            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-           "config": {"workload": "configs[1]: SD-1.5 UNet 512x512, 50 DDIM steps, CFG 7.5 (bounded sample: per-DDIM-step cost of one image, extrapolated)"},
+           "config": {"workload": cfg["label"] + " -- CPU arm: bounded sample = per-DDIM-step cost of ONE image (UNet batch 2), extrapolated x50"},
            "cpu_baseline": cpu, "e2e": {"value": cpu["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0, "wall_s": round(wall, 1)}
     print(json.dumps(out), flush=True)
@@ -349,6 +502,8 @@ if __name__ == "__main__":
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="sd15", choices=sorted(CONFIGS), help="sd15 = BASELINE configs[1]/[2] (the headline), sd21 = configs[3]")
+    ap.add_argument("--no_extras", action="store_true", help="skip the secondary e2e_png / c4 figures of the default run")
     a = ap.parse_args()
     if a.impl == "reference":
         run_reference(a)

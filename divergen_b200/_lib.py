@@ -62,6 +62,7 @@ SIGNATURES = {
     "dg_unet_forward": (_I, [_P, _P, C.POINTER(_F), _I, _P, _I, _P, _I, _I, _I, _P]),
     "dg_unet_set_graphs": (_I, [_P, _I]),
     "dg_unet_last_launch_count": (_L, [_P]),
+    "dg_unet_set_family_mask": (_I, [_P, _I]),
     "dg_unet_profile_forward": (_I, [_P, _P, C.POINTER(_F), _I, _P, _I, _P, _I, _I, _I, _P, C.POINTER(C.c_double),
                                      C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(_L), C.POINTER(C.c_double)]),
     "dg_cfg_ddim_step": (_I, [_P, _P, _P, _I, _L, _F, _F, _F, _I, _P]),

@@ -92,10 +92,10 @@ struct T4 {
 };
 
 struct GraphKey {
-  int batch, h, w, tokens; const void* sample; const void* ehs; void* out; int hoisted;
+  int batch, h, w, tokens; const void* sample; const void* ehs; void* out; int hoisted; int fam_mask;
   bool operator==(const GraphKey& o) const {
     return batch == o.batch && h == o.h && w == o.w && tokens == o.tokens && sample == o.sample && ehs == o.ehs && out == o.out &&
-           hoisted == o.hoisted;
+           hoisted == o.hoisted && fam_mask == o.fam_mask;
   }
 };
 
@@ -141,6 +141,10 @@ struct dg_unet : WeightStore {
   bool finalized = false;     // LayerNorm folds are up to date with the loaded weights
   // graphs
   bool use_graphs = true;
+  // measurement only (dg_unet_set_family_mask): kernel families that run_forward enqueues (bit = 1 << Family).  With a family
+  // switched off the result is garbage, the timing of the others is not: bench.py times the GEMM family alone as a replayed
+  // graph (programmatic launch chain intact) instead of eager launches separated by events.
+  int fam_mask = 15;
   cudaStream_t cap_stream = nullptr;
   struct CachedGraph { GraphKey key; cudaGraphExec_t exec; long long launches; };
   std::vector<CachedGraph> graphs;
@@ -327,6 +331,7 @@ struct Fwd {
 
 #define FW(expr) do { if (err == DG_OK) err = (expr); } while (0)
 
+  bool on(int fam) const { return (u->fam_mask >> fam) & 1; }
   bool fuse_gn() const { return u->gn_blk > 0; }
   bool fuse_ln() const { return u->ctx->fuse_ln != 0; }
   // fused GroupNorm block sums [B_][H*W/32][C/blk] float2 for a tensor about to be produced by a 3x3 conv (conv = true:
@@ -351,6 +356,7 @@ struct Fwd {
   }
 
   void gn(const T4& x0, const T4* x1, const Norm& n, float eps, int silu, T4& out) {
+    if (!on(FAM_NORM)) return;
     if (fuse_gn() && x0.gst && (!x1 || x1->gst) && (x0.C + (x1 ? x1->C : 0)) / u->gn_blk <= 256)
       FW(launch_groupnorm_fused(s, sms, x0.p, x0.C, x0.gst, x1 ? x1->p : nullptr, x1 ? x1->C : 0, x1 ? x1->gst : nullptr,
                                 u->gn_blk, n.g, n.b, out.p, x0.B, x0.H * x0.W, u->cfg.norm_num_groups, eps, silu));
@@ -363,7 +369,7 @@ struct Fwd {
     GemmArgs a; a.a0 = x.p; a.c0 = x.C; a.B = x.B; a.H = x.H; a.W = x.W; a.taps = 9; a.w = w.w; a.n_w = w.rows;
     a.n_out = w.out; a.bias = w.b; a.rowvec = rowvec; a.ld_rowvec = temb_ld; a.residual = residual; a.ld_res = w.out;
     a.out = out.p; a.ldo = w.out; a.gn_stats_out = out.gst; a.gn_blk = u->gn_blk;
-    FW(launch_gemm(s, u->ctx->gemm, a));
+    if (on(FAM_GEMM)) FW(launch_gemm(s, u->ctx->gemm, a));
   }
   struct LinOpt {
     const __half* residual = nullptr; int geglu = 0;
@@ -380,7 +386,7 @@ struct Fwd {
       a.w = w.wf; a.bias = nullptr; a.bias32 = w.b32; a.colsum = w.cs; a.ln_stats = o.ln_in; a.ln_parts = gemm_row_parts(o.ln_c);
       a.ln_c = o.ln_c; a.ln_eps = 1e-5f;
     }
-    FW(launch_gemm(s, u->ctx->gemm, a));
+    if (on(FAM_GEMM)) FW(launch_gemm(s, u->ctx->gemm, a));
   }
   void linear(const __half* x0, int c0, const __half* x1, int c1, int rows, const Lin& w, const __half* residual, int geglu,
               __half* out) {
@@ -427,10 +433,10 @@ struct Fwd {
     __half* qkv = alloc((size_t)rows * 3 * C * 2);
     if (fl) { LinOpt o; o.ln_in = rs; o.ln_c = C; linear(h.p, C, nullptr, 0, rows, x.qkv, qkv, o); }
     else {
-      FW(launch_layernorm(s, h.p, x.ln1.g, x.ln1.b, xn.p, rows, C, 1e-5f));
+      if (on(FAM_NORM)) FW(launch_layernorm(s, h.p, x.ln1.g, x.ln1.b, xn.p, rows, C, 1e-5f));
       linear(xn.p, C, nullptr, 0, rows, x.qkv, nullptr, 0, qkv);
     }
-    if (err == DG_OK) FW(launch_attention(s, qkv, 3 * C, qkv + C, 3 * C, qkv + 2 * C, 3 * C, xn.p, B_, x.heads, S, S, d));
+    if (err == DG_OK && on(FAM_ATTN)) FW(launch_attention(s, qkv, 3 * C, qkv + C, 3 * C, qkv + 2 * C, 3 * C, xn.p, B_, x.heads, S, S, d));
     free_(qkv);
     rs = ln_alloc(rows, C);
     { LinOpt o; o.residual = h.p; o.rows_out = rs; linear(xn.p, C, nullptr, 0, rows, x.o1, h.p, o); }
@@ -438,7 +444,7 @@ struct Fwd {
     __half* q = alloc((size_t)rows * C * 2);
     if (fl) { LinOpt o; o.ln_in = rs; o.ln_c = C; linear(h.p, C, nullptr, 0, rows, x.q2, q, o); }
     else {
-      FW(launch_layernorm(s, h.p, x.ln2.g, x.ln2.b, xn.p, rows, C, 1e-5f));
+      if (on(FAM_NORM)) FW(launch_layernorm(s, h.p, x.ln2.g, x.ln2.b, xn.p, rows, C, 1e-5f));
       linear(xn.p, C, nullptr, 0, rows, x.q2, nullptr, 0, q);
     }
     __half* kv;
@@ -449,7 +455,7 @@ struct Fwd {
       kv = alloc((size_t)B_ * tokens * 2 * C * 2);
       linear(ehs, u->cfg.cross_attention_dim, nullptr, 0, B_ * tokens, x.kv2, nullptr, 0, kv);
     }
-    if (err == DG_OK) FW(launch_attention(s, q, C, kv, 2 * C, kv + C, 2 * C, xn.p, B_, x.heads, S, tokens, d));
+    if (err == DG_OK && on(FAM_ATTN)) FW(launch_attention(s, q, C, kv, 2 * C, kv + C, 2 * C, xn.p, B_, x.heads, S, tokens, d));
     free_(q);
     if (!u->kv_ready) free_(kv);
     rs = ln_alloc(rows, C);
@@ -458,7 +464,7 @@ struct Fwd {
     __half* g = alloc((size_t)rows * x.ff_inner * 2);
     if (fl) { LinOpt o; o.ln_in = rs; o.ln_c = C; o.geglu = 1; linear(h.p, C, nullptr, 0, rows, x.ff1, g, o); }
     else {
-      FW(launch_layernorm(s, h.p, x.ln3.g, x.ln3.b, xn.p, rows, C, 1e-5f));
+      if (on(FAM_NORM)) FW(launch_layernorm(s, h.p, x.ln3.g, x.ln3.b, xn.p, rows, C, 1e-5f));
       linear(xn.p, C, nullptr, 0, rows, x.ff1, nullptr, 1, g);
     }
     linear(g, x.ff_inner, nullptr, 0, rows, x.ff2, h.p, 0, h.p);
@@ -490,9 +496,11 @@ int run_forward(dg_unet* u, cudaStream_t s, const __half* sample, const __half* 
   f.temb_all = f.alloc((size_t)B * u->temb_total * 2);
   f.temb_ld = u->temb_total;
   if (f.err) return f.err;
+  if (f.on(FAM_OTHER)) {
   timestep_sinusoid_kernel<<<(B * c0 / 2 + 127) / 128, 128, 0, s>>>(u->d_t, tsin, B, c0, cf.freq_shift, cf.flip_sin_to_cos);
   DG_LAUNCH_CHECK();
-  for (int b0 = 0; b0 < B; b0 += 8) {
+  }
+  for (int b0 = 0; b0 < B && f.on(FAM_OTHER); b0 += 8) {
     const int nb = std::min(8, B - b0);
     DG_TRY(launch_gemv(s, tsin + (size_t)b0 * c0, c0, u->time1.w, u->time1.b, t1 + (size_t)b0 * u->temb_dim, u->temb_dim, nb, u->temb_dim, c0, 0, 1));
     DG_TRY(launch_gemv(s, t1 + (size_t)b0 * u->temb_dim, u->temb_dim, u->time2.w, u->time2.b, emb + (size_t)b0 * u->temb_dim, u->temb_dim, nb, u->temb_dim, u->temb_dim, 0, 0));
@@ -506,8 +514,10 @@ int run_forward(dg_unet* u, cudaStream_t s, const __half* sample, const __half* 
   if (f.err) return f.err;
   {
     const size_t items = (size_t)B * h * w * 64;
-    im2col_conv_in_kernel<<<grid_for(items, 256, sms), 256, 0, s>>>(sample, col, B, cf.in_channels, h, w, 64);
-    DG_LAUNCH_CHECK();
+    if (f.on(FAM_OTHER)) {
+      im2col_conv_in_kernel<<<grid_for(items, 256, sms), 256, 0, s>>>(sample, col, B, cf.in_channels, h, w, 64);
+      DG_LAUNCH_CHECK();
+    }
     x.gst = f.gn_alloc(B, h, w, c0, false);
     { Fwd::LinOpt o; o.gn_out = x.gst; o.hw = h * w; f.linear(col, 64, nullptr, 0, B * h * w, u->conv_in, x.p, o); }
     f.free_(col);
@@ -528,8 +538,10 @@ int run_forward(dg_unet* u, cudaStream_t s, const __half* sample, const __half* 
       T4 y = f.talloc(x.B, Ho, Wo, x.C);
       if (f.err) break;
       const size_t items = (size_t)x.B * Ho * Wo * 9 * (x.C / 8);
-      im2col3x3_nhwc_kernel<<<grid_for(items, 256, sms), 256, 0, s>>>(x.p, c2, x.B, x.H, x.W, x.C, 2, Ho, Wo);
-      DG_LAUNCH_CHECK();
+      if (f.on(FAM_OTHER)) {
+        im2col3x3_nhwc_kernel<<<grid_for(items, 256, sms), 256, 0, s>>>(x.p, c2, x.B, x.H, x.W, x.C, 2, Ho, Wo);
+        DG_LAUNCH_CHECK();
+      }
       y.gst = f.gn_alloc(x.B, Ho, Wo, x.C, false);
       { Fwd::LinOpt o; o.gn_out = y.gst; o.hw = Ho * Wo; f.linear(c2, 9 * x.C, nullptr, 0, x.B * Ho * Wo, d.down, y.p, o); }
       f.free_(c2);
@@ -558,8 +570,10 @@ int run_forward(dg_unet* u, cudaStream_t s, const __half* sample, const __half* 
       T4 y = f.talloc(x.B, x.H * 2, x.W * 2, x.C);
       if (f.err) break;
       const size_t items = (size_t)x.B * 4 * x.H * x.W * (x.C / 8);
-      upsample2x_nhwc_kernel<<<grid_for(items, 256, sms), 256, 0, s>>>(x.p, upx.p, x.B, x.H, x.W, x.C);
-      DG_LAUNCH_CHECK();
+      if (f.on(FAM_OTHER)) {
+        upsample2x_nhwc_kernel<<<grid_for(items, 256, sms), 256, 0, s>>>(x.p, upx.p, x.B, x.H, x.W, x.C);
+        DG_LAUNCH_CHECK();
+      }
       y.gst = f.gn_alloc(x.B, x.H * 2, x.W * 2, x.C, true);
       f.conv3(upx, b.up, nullptr, nullptr, y);
       f.free_(upx); f.free_(x);
@@ -576,10 +590,10 @@ int run_forward(dg_unet* u, cudaStream_t s, const __half* sample, const __half* 
   {
     GemmArgs a; a.a0 = xn.p; a.c0 = xn.C; a.B = B; a.H = h; a.W = w; a.taps = 9; a.w = u->conv_out.w; a.n_w = u->conv_out.rows;
     a.n_out = cf.out_channels; a.bias = u->conv_out.b; a.out = o.p; a.ldo = opitch;
-    if (f.err == DG_OK) f.err = launch_gemm(s, u->ctx->gemm, a);
+    if (f.err == DG_OK && f.on(FAM_GEMM)) f.err = launch_gemm(s, u->ctx->gemm, a);
   }
   if (f.err) return f.err;
-  {
+  if (f.on(FAM_OTHER)) {
     const size_t n = (size_t)B * cf.out_channels * h * w;
     nhwc_to_nchw_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(o.p, out, B, cf.out_channels, h * w, opitch);
     DG_LAUNCH_CHECK();
@@ -613,7 +627,7 @@ int forward_maybe_graph(dg_unet* u, cudaStream_t s, const __half* sample, const 
     u->last_launches += g_launch_counter - c0;
     return DG_OK;
   }
-  GraphKey key{B, h, w, tokens, sample, ehs, out, (u->kv_ready ? 1 : 0) | (u->temb_ready ? 2 : 0)};
+  GraphKey key{B, h, w, tokens, sample, ehs, out, (u->kv_ready ? 1 : 0) | (u->temb_ready ? 2 : 0), u->fam_mask};
   for (auto& g : u->graphs) {
     if (g.key == key) {
       DG_CUDA(cudaGraphLaunch(g.exec, s));
@@ -1197,6 +1211,11 @@ int32_t dg_unet_set_graphs(dg_unet* u, int32_t enabled) {
   return DG_OK;
 }
 int64_t dg_unet_last_launch_count(dg_unet* u) { return u ? u->last_launches : 0; }
+int32_t dg_unet_set_family_mask(dg_unet* u, int32_t mask) {
+  if (!u) return fail(DG_E_ARG, "null");
+  u->fam_mask = mask & 15;
+  return DG_OK;
+}
 
 int32_t dg_unet_forward(dg_unet* u, const void* sample, const float* t_host, int32_t n_t, const void* ehs,
                         int32_t tokens, void* out, int32_t batch, int32_t h, int32_t w, void* stream) {

@@ -465,7 +465,15 @@ inline int launch_attention(cudaStream_t stream, const __half* q, int ldq, const
       if (var == 2) return launch_attn_t<40, 64, 6, 1, 4>(stream, q, ldq, k, ldk, v, ldv, out, B, heads, Sq, Sk);
       return launch_attn_t<40, 64, 6, 1, 4, 2>(stream, q, ldq, k, ldk, v, ldv, out, B, heads, Sq, Sk);
     }
-    case 64: return launch_attn_t<64, 128, 3, 1>(stream, q, ldq, k, ldk, v, ldv, out, B, heads, Sq, Sk, causal);
+    case 64: {
+      // DG_ATTN64_VAR: 0 = 2 query tiles x 128 keys (8 softmax warps), 1 = 4 query tiles x 64 keys (16 softmax warps; the d = 40
+      // kernel's best shape).  Causal (CLIP text, 77 tokens) and short sequences stay on variant 0.
+      static int var64 = -1;
+      if (var64 < 0) { const char* e = getenv("DG_ATTN64_VAR"); var64 = e ? atoi(e) : 0; }
+      if (var64 == 1 && !causal && Sq >= 512)
+        return launch_attn_t<64, 64, 6, 1, 4>(stream, q, ldq, k, ldk, v, ldv, out, B, heads, Sq, Sk);
+      return launch_attn_t<64, 128, 3, 1>(stream, q, ldq, k, ldk, v, ldv, out, B, heads, Sq, Sk, causal);
+    }
     case 80: return launch_attn_t<80, 128, 2, 1>(stream, q, ldq, k, ldk, v, ldv, out, B, heads, Sq, Sk);
     case 160: return launch_attn_t<160, 64, 2, 1>(stream, q, ldq, k, ldk, v, ldv, out, B, heads, Sq, Sk);
     default: return fail(DG_E_UNSUPPORTED, "attention: head dim %d not built (32/40/64/80/160)", d);
@@ -516,6 +524,7 @@ inline int init_kernel_attributes() {
   DG_TRY((init_attn_attr<40, 64, 6, 1, 4>()));
   DG_TRY((init_attn_attr<40, 64, 6, 1, 4, 2>()));
   DG_TRY((init_attn_attr<64, 128, 3>()));
+  DG_TRY((init_attn_attr<64, 64, 6, 1, 4>()));
   DG_TRY((init_attn_attr<80, 128, 2>()));
   DG_TRY((init_attn_attr<160, 64, 2>()));
   return DG_OK;

@@ -85,6 +85,10 @@ int32_t dg_unet_forward(dg_unet* unet, const void* sample, const float* timestep
 int32_t dg_unet_set_graphs(dg_unet* unet, int32_t enabled);
 /* kernels launched by the last dg_unet_forward / dg_denoise_loop call (graph replays count their kernel nodes). */
 int64_t dg_unet_last_launch_count(dg_unet* unet);
+/* Measurement only: bit mask of the kernel families a forward enqueues (1 GEMM/conv, 2 attention, 4 normalisation, 8 other;
+ * default 15).  With a family switched off the output is meaningless but the others' timing is not: bench.py uses it to time
+ * one family as a replayed CUDA graph.  Never set it in production code. */
+int32_t dg_unet_set_family_mask(dg_unet* unet, int32_t mask);
 
 /* One eager (non-graph) forward with a CUDA-event pair around every launch: per kernel family
  * {0: tcgen05 GEMM/conv, 1: tcgen05 attention, 2: Group/LayerNorm, 3: other} accumulated device ms, algorithmic FLOPs,
