@@ -88,7 +88,7 @@ def score_category(scorer, tokenizer, device, category_name: str, picked, max_ba
                 m = np.stack([np.asarray(Image.open(mask_paths[chunk[k][0]]).convert("L")) for k in g])
                 x, a = mask_composite(x, torch.from_numpy(m).to(device))
                 areas.extend(a.tolist())
-            clips.extend(scorer(clip_preprocess(x), ids).view(-1).cpu().tolist())
+            clips.extend(scorer(clip_preprocess(x, n_px=scorer.vision_config.image_size), ids).view(-1).cpu().tolist())
     return clips, areas
 
 

@@ -17,6 +17,9 @@ struct dg_ctx {
   GemmRes gemm;               // split-K workspace, tickets, persistent grid size
   int fuse_ln = 1;            // DG_FUSE_LN=0: stand-alone LayerNorm kernels instead of the folded GEMM epilogue
   int fuse_gn = 1;            // DG_FUSE_GN=0: stand-alone GroupNorm statistics kernels instead of epilogue sums
+  int fuse_xf = 1;            // DG_FUSE_XF=0: stand-alone GroupNorm-apply (+SiLU) pass instead of the transform inside the consuming conv
+  __half* xf_tab = nullptr;   // scratch table for the stand-alone fused-GroupNorm operators (tests)
+  size_t xf_tab_cap = 0;
 };
 
 // ================================================================== arena allocator (deterministic, graph friendly)
@@ -130,6 +133,7 @@ struct dg_unet : WeightStore {
   // fused-statistics scratch: bump-allocated per forward in launch order (graph-stable addresses)
   float* gn_arena = nullptr; size_t gn_cap = 0, gn_off = 0;   // GroupNorm slab/block sums (fully overwritten, never zeroed)
   float* ln_arena = nullptr; size_t ln_cap = 0, ln_off = 0;   // LayerNorm row partials (fully overwritten, never zeroed)
+  __half* xf_arena = nullptr; size_t xf_cap = 0, xf_off = 0;  // (mean_h, scale', shift') tables of the GroupNorms applied inside convs
   int gn_blk = 0;             // channel-block width of the fused GroupNorm sums (block_out_channels[0] / groups), 0 = off
   // step-invariant work hoisted out of the denoising loop (dg_denoise_loop): cross-attention K/V of the text embedding
   // (one buffer per transformer block, in forward order) and the per-step time-embedding projections
@@ -355,6 +359,21 @@ struct Fwd {
     return p;
   }
 
+  // GroupNorm (+ SiLU) applied inside the consuming conv (gemm2_kernel<..., kXf>): possible when both sources carry fused
+  // block sums.  Returns the (mean_h, scale', shift') table the conv reads, or nullptr (the caller then runs the stand-alone pass).
+  const __half* gn_fold(const T4& x0, const T4* x1, const Norm& n, float eps, int silu) {
+    if (!u->ctx->fuse_xf || u->ctx->gemm.cta_mode == 1 || !fuse_gn() || !x0.gst || (x1 && !x1->gst)) return nullptr;
+    const int C = x0.C + (x1 ? x1->C : 0);
+    if (C / u->gn_blk > 256 || (x0.H * x0.W) % 32) return nullptr;
+    const size_t nh = (size_t)x0.B * 3 * C;
+    if (u->xf_off + nh > u->xf_cap) { if (err == DG_OK) err = fail(DG_E_NOMEM, "GroupNorm table arena exhausted"); return nullptr; }
+    __half* tab = u->xf_arena + u->xf_off;
+    u->xf_off += (nh + 7) & ~size_t(7);
+    if (on(FAM_NORM))
+      FW(launch_gn_fold(s, x0.C, x0.gst, x1 ? x1->C : 0, x1 ? x1->gst : nullptr, u->gn_blk, n.g, n.b, tab, x0.B, x0.H * x0.W,
+                        u->cfg.norm_num_groups, eps, silu));
+    return tab;
+  }
   void gn(const T4& x0, const T4* x1, const Norm& n, float eps, int silu, T4& out) {
     if (!on(FAM_NORM)) return;
     if (fuse_gn() && x0.gst && (!x1 || x1->gst) && (x0.C + (x1 ? x1->C : 0)) / u->gn_blk <= 256)
@@ -365,8 +384,11 @@ struct Fwd {
                           x0.H * x0.W, u->cfg.norm_num_groups, eps, silu));
   }
   // 3x3 conv; `out.gst` (if the caller allocated it) receives the fused GroupNorm sums of the result
-  void conv3(const T4& x, const Lin& w, const __half* rowvec, const __half* residual, T4& out) {
+  void conv3(const T4& x, const Lin& w, const __half* rowvec, const __half* residual, T4& out, const T4* x1 = nullptr,
+             const __half* xf_tab = nullptr) {
     GemmArgs a; a.a0 = x.p; a.c0 = x.C; a.B = x.B; a.H = x.H; a.W = x.W; a.taps = 9; a.w = w.w; a.n_w = w.rows;
+    if (x1) { a.a1 = x1->p; a.c1 = x1->C; }
+    a.xf_tab = xf_tab; a.xf_silu = 1;
     a.n_out = w.out; a.bias = w.b; a.rowvec = rowvec; a.ld_rowvec = temb_ld; a.residual = residual; a.ld_res = w.out;
     a.out = out.p; a.ldo = w.out; a.gn_stats_out = out.gst; a.gn_blk = u->gn_blk;
     if (on(FAM_GEMM)) FW(launch_gemm(s, u->ctx->gemm, a));
@@ -396,15 +418,17 @@ struct Fwd {
 
   T4 resnet(const Res& r, const T4& x0, const T4* x1) {
     const int B_ = x0.B, H = x0.H, W = x0.W;
-    T4 hn = talloc(B_, H, W, r.cin);
-    gn(x0, x1, r.n1, u->cfg.norm_eps, 1, hn);
+    // conv1(silu(norm1(x))): normalisation + activation inside the conv's operand path when the statistics are fused
     T4 h1 = talloc(B_, H, W, r.cout);
     h1.gst = gn_alloc(B_, H, W, r.cout, true);
-    conv3(hn, r.c1, temb_all + r.temb_off, nullptr, h1);
-    free_(hn);
-    T4 h2n = talloc(B_, H, W, r.cout);
-    gn(h1, nullptr, r.n2, u->cfg.norm_eps, 1, h2n);
-    free_(h1);
+    if (const __half* tab1 = gn_fold(x0, x1, r.n1, u->cfg.norm_eps, 1)) {
+      conv3(x0, r.c1, temb_all + r.temb_off, nullptr, h1, x1, tab1);
+    } else {
+      T4 hn = talloc(B_, H, W, r.cin);
+      gn(x0, x1, r.n1, u->cfg.norm_eps, 1, hn);
+      conv3(hn, r.c1, temb_all + r.temb_off, nullptr, h1);
+      free_(hn);
+    }
     T4 out = talloc(B_, H, W, r.cout);
     out.gst = gn_alloc(B_, H, W, r.cout, true);
     const __half* resid = x0.p;
@@ -414,8 +438,15 @@ struct Fwd {
       linear(x0.p, x0.C, x1 ? x1->p : nullptr, x1 ? x1->C : 0, B_ * H * W, r.sc, nullptr, 0, sc.p);
       resid = sc.p;
     }
-    conv3(h2n, r.c2, nullptr, resid, out);
-    free_(h2n);
+    if (const __half* tab2 = gn_fold(h1, nullptr, r.n2, u->cfg.norm_eps, 1)) {
+      conv3(h1, r.c2, nullptr, resid, out, nullptr, tab2);
+    } else {
+      T4 h2n = talloc(B_, H, W, r.cout);
+      gn(h1, nullptr, r.n2, u->cfg.norm_eps, 1, h2n);
+      conv3(h2n, r.c2, nullptr, resid, out);
+      free_(h2n);
+    }
+    free_(h1);
     if (r.has_sc) free_(sc);
     return out;
   }
@@ -482,7 +513,7 @@ int run_forward(dg_unet* u, cudaStream_t s, const __half* sample, const __half* 
   const dg_unet_config& cf = u->cfg;
   const int sms = u->ctx->num_sms;
   u->arena.reset();
-  u->gn_off = 0; u->ln_off = 0;
+  u->gn_off = 0; u->ln_off = 0; u->xf_off = 0;
   Fwd f{u, s, sms, B, tokens, ehs, nullptr};
 
   // ---- time embedding: sinusoid -> MLP -> all time_emb_proj(SiLU(emb)) in one GEMV
@@ -581,15 +612,19 @@ int run_forward(dg_unet* u, cudaStream_t s, const __half* sample, const __half* 
     }
   }
   if (f.err) return f.err;
-  // ---- out
-  T4 xn = f.talloc(B, h, w, c0);
-  f.gn(x, nullptr, u->norm_out, cf.norm_eps, 1, xn);
+  // ---- out: conv_out(silu(conv_norm_out(x))), the normalisation inside the conv when the statistics are fused
   // conv_out writes rows padded to 8 channels (TMA store needs a 16-byte row pitch); the NCHW exit kernel reads that pitch
   const int opitch = (cf.out_channels + 7) / 8 * 8;
   T4 o = f.talloc(B, h, w, opitch);
   {
-    GemmArgs a; a.a0 = xn.p; a.c0 = xn.C; a.B = B; a.H = h; a.W = w; a.taps = 9; a.w = u->conv_out.w; a.n_w = u->conv_out.rows;
-    a.n_out = cf.out_channels; a.bias = u->conv_out.b; a.out = o.p; a.ldo = opitch;
+    const __half* tabo = f.gn_fold(x, nullptr, u->norm_out, cf.norm_eps, 1);
+    T4 xn{};
+    if (!tabo) {
+      xn = f.talloc(B, h, w, c0);
+      f.gn(x, nullptr, u->norm_out, cf.norm_eps, 1, xn);
+    }
+    GemmArgs a; a.a0 = tabo ? x.p : xn.p; a.c0 = c0; a.B = B; a.H = h; a.W = w; a.taps = 9; a.w = u->conv_out.w; a.n_w = u->conv_out.rows;
+    a.n_out = cf.out_channels; a.bias = u->conv_out.b; a.out = o.p; a.ldo = opitch; a.xf_tab = tabo; a.xf_silu = 1;
     if (f.err == DG_OK && f.on(FAM_GEMM)) f.err = launch_gemm(s, u->ctx->gemm, a);
   }
   if (f.err) return f.err;
@@ -1048,12 +1083,13 @@ int32_t dg_ctx_create(int32_t device, dg_ctx** out) {
   if (env_int("DG_SPLITK", 1) == 0) { cudaFree(c->gemm.ws); c->gemm.ws = nullptr; }
   c->fuse_ln = env_int("DG_FUSE_LN", 1);
   c->fuse_gn = env_int("DG_FUSE_GN", 1);
+  c->fuse_xf = env_int("DG_FUSE_XF", 1);
   *out = c;
   return DG_OK;
 }
 void dg_ctx_destroy(dg_ctx* ctx) {
   if (!ctx) return;
-  cudaFree(ctx->gn_stats); cudaFree(ctx->gemm.ws); cudaFree(ctx->gemm.tickets);
+  cudaFree(ctx->gn_stats); cudaFree(ctx->gemm.ws); cudaFree(ctx->gemm.tickets); cudaFree(ctx->xf_tab);
   delete ctx;
 }
 
@@ -1089,7 +1125,7 @@ void dg_unet_destroy(dg_unet* u) {
   if (u->cap_stream) cudaStreamDestroy(u->cap_stream);
   for (void* p : u->owned) cudaFree(p);
   cudaFree(u->arena.base); cudaFree(u->d_t); cudaFree(u->gn_stats); cudaFree(u->d_coef); cudaFree(u->d_step);
-  cudaFree(u->loop_in); cudaFree(u->loop_out); cudaFree(u->gn_arena); cudaFree(u->ln_arena);
+  cudaFree(u->loop_in); cudaFree(u->loop_out); cudaFree(u->gn_arena); cudaFree(u->ln_arena); cudaFree(u->xf_arena);
   cudaFree(u->temb_cur); cudaFree(u->temb_table);
   for (__half* p : u->kv_cache) cudaFree(p);
   delete u;
@@ -1200,6 +1236,10 @@ int32_t dg_unet_prepare(dg_unet* u, int32_t max_batch, int32_t h, int32_t w, int
     u->ln_cap = (size_t)pix * 64 * (2 + c0 / 80) + ((size_t)1 << 20);   // >= 3x the sum over blocks of rows*parts*2
     DG_CUDA(cudaMalloc((void**)&u->gn_arena, u->gn_cap * sizeof(float)));
     DG_CUDA(cudaMalloc((void**)&u->ln_arena, u->ln_cap * sizeof(float)));
+    // one (mean_h, scale', shift') table per GroupNorm applied inside a conv: <= 48 of them, each B x 3 x (<= 8 c0) halves
+    cudaFree(u->xf_arena); u->xf_arena = nullptr;
+    u->xf_cap = (size_t)64 * max_batch * 3 * 8 * c0;
+    DG_CUDA(cudaMalloc((void**)&u->xf_arena, u->xf_cap * sizeof(__half)));
   }
   u->max_batch = max_batch; u->ws_h = h; u->ws_w = w; u->ws_tokens = ctx_tokens;
   return DG_OK;
@@ -1413,6 +1453,28 @@ int32_t dg_op_conv3x3(dg_ctx* ctx, const void* x0, int32_t C0, const void* x1, i
   a.w = (const __half*)Wp; a.n_w = N; a.n_out = N; a.bias = (const __half*)bias; a.rowvec = (const __half*)rowvec; a.ld_rowvec = ld_rowvec;
   a.residual = (const __half*)residual; a.ld_res = ldo; a.out = (__half*)out; a.ldo = ldo;
   return launch_gemm((cudaStream_t)stream, ctx->gemm, a);
+}
+int32_t dg_op_conv3x3_gn(dg_ctx* ctx, const void* x0, int32_t C0, const float* stats0, const void* x1, int32_t C1, const float* stats1,
+                         int32_t blk, const void* gamma, const void* beta, int32_t groups, float eps, int32_t silu, const void* Wp,
+                         const void* bias, const void* residual, void* out, int32_t B, int32_t H, int32_t Wd, int32_t N, int32_t ldo,
+                         int32_t taps, void* stream) {
+  if (!ctx || !x0 || !stats0 || !gamma || !beta || !Wp || !out || (x1 && !stats1)) return fail(DG_E_ARG, "null argument");
+  if (taps != 1 && taps != 9) return fail(DG_E_ARG, "taps must be 1 or 9");
+  cudaStream_t s = (cudaStream_t)stream;
+  const size_t need = (size_t)B * 3 * (C0 + C1);
+  if (need > ctx->xf_tab_cap) {
+    DG_CUDA(cudaStreamSynchronize(s));
+    cudaFree(ctx->xf_tab); ctx->xf_tab = nullptr; ctx->xf_tab_cap = 0;
+    DG_CUDA(cudaMalloc((void**)&ctx->xf_tab, need * sizeof(__half)));
+    ctx->xf_tab_cap = need;
+  }
+  DG_TRY(launch_gn_fold(s, C0, stats0, x1 ? C1 : 0, stats1, blk, (const __half*)gamma, (const __half*)beta, ctx->xf_tab, B, H * Wd, groups, eps, silu));
+  GemmArgs a; a.a0 = (const __half*)x0; a.c0 = C0; a.a1 = (const __half*)x1; a.c1 = x1 ? C1 : 0; a.B = B; a.H = H; a.W = Wd; a.taps = taps;
+  a.hw = H * Wd;
+  if (ldo <= 0) ldo = N;
+  a.w = (const __half*)Wp; a.n_w = N; a.n_out = N; a.bias = (const __half*)bias; a.residual = (const __half*)residual; a.ld_res = ldo;
+  a.out = (__half*)out; a.ldo = ldo; a.xf_tab = ctx->xf_tab; a.xf_silu = silu;
+  return launch_gemm(s, ctx->gemm, a);
 }
 int32_t dg_op_attention(dg_ctx* ctx, const void* q, int32_t ldq, const void* k, int32_t ldk, const void* v, int32_t ldv, void* out,
                         int32_t B, int32_t heads, int32_t Sq, int32_t Sk, int32_t d, void* stream) {

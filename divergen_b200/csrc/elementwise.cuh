@@ -256,6 +256,62 @@ __global__ void gn_apply_blk_kernel(const __half* __restrict__ x0, int C0, const
   }
 }
 
+// Statistics fold for the GroupNorm that is applied INSIDE the consuming GEMM (gemm2_kernel<..., kXf = true>): the producers'
+// block sums -> per (sample, channel) fp16 planes tab[b][0..2][C] = (mean_h, scale', shift') with
+//   mean_h = fp16(mean_g),  scale' = k * rstd_g * gamma_c,  shift' = k * (beta_c - (mean_g - mean_h) * rstd_g * gamma_c),
+// k = 1/2 when SiLU follows (silu(y) = y/2 * (1 + tanh(y/2))), else 1.  One CTA per sample; same fold order as
+// gn_apply_blk_kernel (deterministic).  A few microseconds: B CTAs reading B * slots * nb float2.
+__global__ void gn_fold_kernel(int C0, int C1, int HW, int groups, float eps, const float* __restrict__ stats0,
+                               const float* __restrict__ stats1, int blk, int slots, const __half* __restrict__ gamma,
+                               const __half* __restrict__ beta, int do_silu, __half* __restrict__ tab) {
+  __shared__ float2 s_col[8][256];
+  __shared__ float s_mean[64], s_rstd[64];
+  griddep_launch();
+  const int C = C0 + C1, cpg = C / groups;
+  const int b = blockIdx.x;
+  const float inv_n = 1.0f / ((float)cpg * (float)HW);
+  griddep_wait();
+  {
+    const int nb0 = C0 / blk, nb1 = C1 / blk, nb = nb0 + nb1, bpg = cpg / blk;
+    const int ncol = min(nb, 256);
+    const int nstripe = max(1, min(8, 256 / ncol));
+    const int stripe = threadIdx.x / ncol;
+    if (stripe < nstripe) {
+      const int cb = threadIdx.x % ncol;
+      const float2* src = (cb < nb0) ? reinterpret_cast<const float2*>(stats0) + (size_t)b * slots * nb0 + cb
+                                     : reinterpret_cast<const float2*>(stats1) + (size_t)b * slots * nb1 + (cb - nb0);
+      const int ld = (cb < nb0) ? nb0 : nb1;
+      float a = 0.f, q = 0.f;
+#pragma unroll 8
+      for (int sl = stripe; sl < slots; sl += nstripe) { const float2 v = __ldg(src + (size_t)sl * ld); a += v.x; q += v.y; }
+      s_col[stripe][cb] = make_float2(a, q);
+    }
+    __syncthreads();
+    if ((int)threadIdx.x < groups) {
+      const int g = threadIdx.x;
+      float a = 0.f, q = 0.f;
+      for (int i = 0; i < bpg; ++i) {
+        const int cb = g * bpg + i;
+        for (int st = 0; st < nstripe; ++st) { a += s_col[st][cb].x; q += s_col[st][cb].y; }
+      }
+      const float mean = a * inv_n;
+      const float var = fmaxf(q * inv_n - mean * mean, 0.f);
+      s_mean[g] = mean; s_rstd[g] = rsqrtf(var + eps);
+    }
+  }
+  __syncthreads();
+  const float k = do_silu ? 0.5f : 1.0f;
+  __half* t0 = tab + (size_t)b * 3 * C;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const int g = c / cpg;
+    const float mean = s_mean[g], sc = s_rstd[g] * __half2float(__ldg(gamma + c));
+    const __half mh = __float2half_rn(mean);
+    t0[c] = mh;
+    t0[C + c] = __float2half_rn(k * sc);
+    t0[2 * C + c] = __float2half_rn(k * (__half2float(__ldg(beta + c)) - (mean - __half2float(mh)) * sc));
+  }
+}
+
 // ------------------------------------------------------------------ LayerNorm fold (one-off, at weight finalisation)
 // LN(x) W^T + b  ==  rstd * (x Wf^T - mean * colsum) + b32   with  Wf[n,c] = W[n,c]*gamma[c],
 // colsum[n] = sum_c Wf[n,c] (of the ROUNDED fp16 Wf, so the mean term cancels exactly what the GEMM accumulates),

@@ -35,6 +35,15 @@
 //   16 KB per 32-column chunk); the last arriver (atomic ticket) bulk-loads the sum into the idle operand stages, re-zeroes
 //   the workspace and runs the epilogue.  (fp32 addition order varies run to run: reproducible to fp32 rounding.)
 //
+// Fused GroupNorm + SiLU on the A operand (kXf = true; ResnetBlock2D's `conv(act(norm(x)))`): the activation tensor is read RAW.
+//   The A tile of a stage lands on a CTA-LOCAL barrier (a_full); the 8 epilogue warps -- idle during the main loop of a
+//   single-accumulator-stage tile -- rewrite it in place, smem -> registers -> smem: 4 rows x one 16-byte (8-channel) chunk per
+//   thread and k-block, h = (x - mean_h) * scale' + shift' in packed fp16 (the subtraction of the fp16-rounded group mean first:
+//   no cancellation between x * scale and the shift), SiLU as h + h * tanh.approx.f16x2(h) (one MUFU op per channel pair),
+//   fence.proxy.async, then one arrive per warp on the LEADER's full barrier, which now counts the weight bytes of both CTAs
+//   plus 8 transform warps per CTA.  Rows that a tap shifts outside the image stay the zeros TMA filled in (the padding of
+//   conv(act(norm(x))) is applied AFTER the activation).  Tiles then run strictly transform -> MMA -> epilogue per CTA.
+//
 // Replaces (reference side): torch.nn.Conv2d / Linear / LayerNorm / GroupNorm statistics inside diffusers ResnetBlock2D,
 // Attention, FeedForward, Transformer2DModel, reached from DiverGen/generation/txt2img_diffusers_stages_from_txt.py:255-259.
 #pragma once
@@ -74,6 +83,13 @@ struct Gemm2Params {
   int* tickets;            // [m_tile*tiles_n + nt], zero on entry, zero on exit
   int sk_bulk;             // split-K launch with one tile per CTA (host-checked): partials travel as bulk shared->global reductions
   float inv_splits, inv_tiles_n, inv_tiles_x, inv_tiles_y;   // host-computed 1/d for the unit decomposition (fast_div)
+  // Fused GroupNorm (+ SiLU) on the A operand (kXf kernels): per (sample, concatenated input channel) fp16 planes
+  // [B][3][xf_c] = (mean_h, scale', shift') written by gn_fold_kernel; A element x becomes h = (x - mean_h) * scale' + shift'
+  // and, with xf_silu, h + h * tanh(h) (scale' / shift' then carry the factor 1/2: silu(y) = y/2 * (1 + tanh(y/2))).
+  const __half* xf_tab;
+  int xf_c, xf_silu;
+  int xf_one;              // every row of an M tile belongs to one sample (conv: bn == 1; plain GEMM: 128 | hw)
+  int bw_log2, bh_log2;    // box sides are powers of two
   long long* dbg;          // optional (DG_GEMM_DBG=1): clock64() stamps of CTA 0's first unit, see DG_STAMP sites
 };
 // Clock stamps are compiled in only for instrumented builds (DG_NVCC_EXTRA=-DDG_GEMM_STAMPS): their predicates otherwise
@@ -286,7 +302,19 @@ __device__ __forceinline__ Unit unit_coord(const Gemm2Params& p, int u, int cta_
   return t;
 }
 
-template <int kCta, int kBN, int kStages, bool kGeglu>
+// two packed channels of the fused GroupNorm (+ SiLU) transform
+__device__ __forceinline__ uint32_t xf_half2(uint32_t x, uint32_t m, uint32_t sc, uint32_t sh, int silu) {
+  __half2 h = __hfma2(__hsub2(*reinterpret_cast<__half2*>(&x), *reinterpret_cast<__half2*>(&m)), *reinterpret_cast<__half2*>(&sc),
+                      *reinterpret_cast<__half2*>(&sh));
+  if (silu) {
+    uint32_t hu = *reinterpret_cast<uint32_t*>(&h), tu;
+    asm("tanh.approx.f16x2 %0, %1;" : "=r"(tu) : "r"(hu));
+    h = __hfma2(h, *reinterpret_cast<__half2*>(&tu), h);
+  }
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+template <int kCta, int kBN, int kStages, bool kGeglu, bool kXf = false>
 __global__ void __launch_bounds__(384, 1)
 gemm2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
              const __grid_constant__ CUtensorMap mapW, const __grid_constant__ CUtensorMap mapO,
@@ -319,7 +347,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
   uint64_t* chunk_ready = buf_free + S::kRing;   // [kRing]  staging buffer written by all 8 epilogue warps (-> store warp)
   uint64_t* res_full = chunk_ready + S::kRing;   // [kRing]  residual tile landed in the staging buffer (TMA -> epilogue warps)
   uint64_t* sk_full = res_full + S::kRing;       // [1]      split-K: the summed fp32 tile landed in the (idle) operand stages
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sk_full + 1);
+  uint64_t* a_full = sk_full + 1;                // [kStages] kXf: this CTA's raw A tile landed (local; -> transform warps)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_full + kStages);
   volatile uint32_t* ticket_slot = tmem_slot + 1;
   volatile int* chunk_info = reinterpret_cast<volatile int*>(tmem_slot + 2);   // [kRing][5]: col, x0, y0, b0, flags (1 store, 2 stop)
 
@@ -335,7 +364,9 @@ gemm2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
     if (p.residual) tma_prefetch_desc(&mapR);
   }
   if (warp == 1 && lane == 0) {
-    for (int i = 0; i < kStages; ++i) { mbar_init(&full[i], kCta); mbar_init(&empty[i], 1); }
+    // full: one arrive per producer (+ expect_tx of the bytes that complete on it) and, with the fused transform, one per
+    // transform warp of either CTA
+    for (int i = 0; i < kStages; ++i) { mbar_init(&full[i], kXf ? kCta * 9 : kCta); mbar_init(&empty[i], 1); mbar_init(&a_full[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], kCta * 8); }
     for (int i = 0; i < S::kRing; ++i) { mbar_init(&buf_free[i], 1); mbar_init(&chunk_ready[i], 8); mbar_init(&res_full[i], 1); }
     mbar_init(sk_full, 1);
@@ -410,10 +441,19 @@ gemm2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
           mbar_wait_parked(&empty[stage], phase ^ 1);
           uint8_t* sa = smem + stage * S::kStageBytes;
           uint8_t* sb = sa + S::kABytes;
+          if constexpr (kXf) {
+            // raw A -> this CTA's own barrier (the transform warps pass it on); only the weights complete on the leader's
+            if (leader) mbar_arrive_expect_tx(&full[stage], kCta * S::kBBytes);
+            else mbar_arrive_cluster(full0_leader + stage * 8);
+            mbar_arrive_expect_tx(&a_full[stage], S::kABytes);
+            if (kb < p.kb0) tma_load_4d(sa, &mapA0, &a_full[stage], kb * 64, t.x0 + dx, t.y0 + dy, t.b0);
+            else            tma_load_4d(sa, &mapA1, &a_full[stage], (kb - p.kb0) * 64, t.x0 + dx, t.y0 + dy, t.b0);
+          } else {
           if (leader) mbar_arrive_expect_tx(&full[stage], kCta * S::kStageBytes);
           else mbar_arrive_cluster(full0_leader + stage * 8);
           if (kb < p.kb0) tma_load_4d_pair<kCta>(sa, &mapA0, &full[stage], kb * 64, t.x0 + dx, t.y0 + dy, t.b0);
           else            tma_load_4d_pair<kCta>(sa, &mapA1, &full[stage], (kb - p.kb0) * 64, t.x0 + dx, t.y0 + dy, t.b0);
+          }
           const int kcol = kbi * 64;
 #pragma unroll
           for (int g = 0; g < S::kNumAcc; ++g)
@@ -530,6 +570,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
     const bool has_ln = p.colsum != nullptr;
     int as = 0; uint32_t acc_phase = 0;
     uint32_t chunk_ctr = 0;             // staging-ring chunk counter (final epilogues only)
+    int xstage = 0; uint32_t xphase = 0;   // kXf: operand stage / phase of the next A tile to transform
+    const uint32_t full0_leader_x = mapa_rank(smem_u32(&full[0]), 0);
 
     // first tile column of this thread's piece of chunk j (accumulator columns == output columns for plain tiles)
     // plain tiles: each warp owns a contiguous column half (160 or 80 columns) in 5 pieces; GEGLU: chunk j = outputs
@@ -540,6 +582,66 @@ gemm2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
       if (et == 0 && u == pair_id + num_pairs) DG_STAMP(30);      // second tile: loop top
       const Unit t = unit_at(u, uk);
       const int nt = t.nt;
+      if constexpr (kXf) {
+        // ===== fused GroupNorm (+ SiLU) on this unit's A tiles, k-block by k-block, in place (see the header comment) =====
+        const int xrow0 = et >> 3;                   // this thread's rows: xrow0 + 32 i, i = 0..3 (same row & 7: same swizzle phase)
+        const int xchunk = et & 7;                   // its 16-byte chunk = 8 consecutive channels of the k-block
+        const uint32_t xoff = (uint32_t)xrow0 * 128u + ((uint32_t)(xchunk ^ (xrow0 & 7)) << 4);
+        const bool plain = p.taps == 1 && p.H == 1 && p.B == 1;
+        const __half* tabc = p.xf_tab + xchunk * 8;
+        const size_t plane = (size_t)p.xf_c;
+        int tap = t.kb_begin / kb_per_tap;
+        int kb = t.kb_begin - tap * kb_per_tap;
+        const int b_tile = plain ? (p.hw > 0 ? t.x0 / p.hw : 0) : t.b0;
+        for (int kbi = t.kb_begin; kbi < t.kb_end; ++kbi) {
+          const int dx = (p.taps == 9) ? (tap % 3 - 1) : 0;
+          const int dy = (p.taps == 9) ? (tap / 3 - 1) : 0;
+          uint4 tm = make_uint4(0, 0, 0, 0), ts = tm, tf = tm;
+          if (p.xf_one) {                            // (mean_h, scale', shift') of this thread's 8 channels: in flight during the wait
+            const __half* tp = tabc + (size_t)b_tile * 3 * plane + kb * 64;
+            tm = __ldg(reinterpret_cast<const uint4*>(tp));
+            ts = __ldg(reinterpret_cast<const uint4*>(tp + plane));
+            tf = __ldg(reinterpret_cast<const uint4*>(tp + 2 * plane));
+          }
+          mbar_wait(&a_full[xstage], xphase);
+          const uint32_t sa = smem_u32(smem) + (uint32_t)xstage * S::kStageBytes + xoff;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int row = xrow0 + 32 * i;
+            bool ok;
+            int bb;
+            if (plain) {
+              const int gr = t.x0 + row;
+              ok = t.valid_m && gr < p.W;
+              bb = (!p.xf_one && p.hw > 0) ? gr / p.hw : b_tile;
+            } else {
+              const int xx = t.x0 + (row & (p.bw - 1)) + dx, yy = t.y0 + ((row >> p.bw_log2) & (p.bh - 1)) + dy;
+              bb = t.b0 + (row >> (p.bw_log2 + p.bh_log2));
+              ok = t.valid_m && (unsigned)xx < (unsigned)p.W && (unsigned)yy < (unsigned)p.H && bb < p.B;
+            }
+            if (ok) {
+              if (!p.xf_one) {
+                const __half* tp = tabc + (size_t)bb * 3 * plane + kb * 64;
+                tm = __ldg(reinterpret_cast<const uint4*>(tp));
+                ts = __ldg(reinterpret_cast<const uint4*>(tp + plane));
+                tf = __ldg(reinterpret_cast<const uint4*>(tp + 2 * plane));
+              }
+              const uint32_t a_ = sa + (uint32_t)i * 4096u;
+              const uint4 v = lds_u4(a_);
+              sts_u4(a_, xf_half2(v.x, tm.x, ts.x, tf.x, p.xf_silu), xf_half2(v.y, tm.y, ts.y, tf.y, p.xf_silu),
+                     xf_half2(v.z, tm.z, ts.z, tf.z, p.xf_silu), xf_half2(v.w, tm.w, ts.w, tf.w, p.xf_silu));
+            }
+          }
+          fence_proxy_async();                       // the rewritten tile is visible to the tensor core's (async-proxy) reads
+          __syncwarp();
+          if (lane == 0) {
+            if (leader) mbar_arrive(&full[xstage]);
+            else mbar_arrive_cluster(full0_leader_x + xstage * 8);
+          }
+          if (++kb == kb_per_tap) { kb = 0; ++tap; }
+          if (++xstage == kStages) { xstage = 0; xphase ^= 1; }
+        }
+      }
       const uint32_t t_row = tmem_base + as * S::kAccStride + ((uint32_t)(q * 32) << 16);
       // ---- this thread's output row
       int bb;

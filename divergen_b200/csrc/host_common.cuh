@@ -213,6 +213,8 @@ struct GemmArgs {
   float* row_stats_out = nullptr;          // [rows][2*tiles_n][2]
   float* gn_stats_out = nullptr; int gn_blk = 0;   // [B][HW/32][n_out/gn_blk][2] (see gn_stats_supported)
   __half* out = nullptr; int ldo = 0;
+  // fused GroupNorm (+ SiLU) on the A operand: [B][3][c0 + c1] fp16 planes from launch_gn_fold (nullptr: A is used as is)
+  const __half* xf_tab = nullptr; int xf_silu = 0;
 };
 
 // LayerNorm row partials are always produced by 160-wide tiles: two column halves per tile.
@@ -260,10 +262,10 @@ inline int choose_splits(int units, int num_kb, int slots, size_t ws_floats_per_
   return best;
 }
 
-template <int kCta, int kBN, int kStages, bool kGeglu>
+template <int kCta, int kBN, int kStages, bool kGeglu, bool kXf = false>
 inline cudaError_t launch_gemm2_t(cudaStream_t stream, int grid_ctas, const CUtensorMap& mA0, const CUtensorMap& mA1,
                                   const CUtensorMap& mW, const CUtensorMap& mO, const CUtensorMap& mR, const Gemm2Params& p) {
-  return launch_pdl(gemm2_kernel<kCta, kBN, kStages, kGeglu>, dim3((unsigned)grid_ctas), dim3(384),
+  return launch_pdl(gemm2_kernel<kCta, kBN, kStages, kGeglu, kXf>, dim3((unsigned)grid_ctas), dim3(384),
                     (size_t)Gemm2Cfg<kCta, kBN, kStages>::kTotal, stream, kCta, mA0, mA1, mW, mO, mR, p);
 }
 
@@ -278,6 +280,7 @@ inline int launch_gemm(cudaStream_t stream, const GemmRes& res, const GemmArgs& 
   if (a.geglu && (a.residual || a.rowvec || a.row_stats_out || a.gn_stats_out)) return fail(DG_E_ARG, "gemm: geglu epilogue takes bias / LayerNorm fold only");
   if (a.colsum && (!a.ln_stats || !a.bias32 || a.ln_c <= 0)) return fail(DG_E_ARG, "gemm: LayerNorm fold needs ln_stats, bias32 and ln_c");
   if (a.row_stats_out && a.taps != 1) return fail(DG_E_ARG, "gemm: row statistics are produced by plain GEMMs only");
+  if (a.xf_tab && (a.geglu || res.cta_mode == 1)) return fail(DG_E_ARG, "gemm: the fused GroupNorm transform is built for CTA-pair, non-GEGLU tiles");
   if (a.gn_stats_out && !gn_stats_supported(a.taps == 1 ? (a.hw > 0 ? a.hw : a.H * a.W) : a.H * a.W, a.taps == 9 ? a.W : 0,
                                             a.taps == 9 ? a.H : 0, a.gn_blk, a.n_out))
     return fail(DG_E_SHAPE, "gemm: fused GroupNorm statistics unsupported for this shape (hw %d, blk %d, n_out %d)", a.H * a.W, a.gn_blk, a.n_out);
@@ -325,6 +328,9 @@ inline int launch_gemm(cudaStream_t stream, const GemmRes& res, const GemmArgs& 
   p.gn_stats_out = a.gn_stats_out; p.gn_blk = a.gn_blk; p.gn_nblk = a.gn_blk > 0 ? a.n_out / a.gn_blk : 0;
   p.gn_slots = (a.taps == 1 ? (a.hw > 0 ? a.hw : a.H * a.W) : a.H * a.W) / 32;
   p.ws = res.ws; p.tickets = res.tickets;
+  p.xf_tab = a.xf_tab; p.xf_c = a.c0 + a.c1; p.xf_silu = a.xf_silu;
+  p.xf_one = (a.taps == 1) ? (p.hw > 0 && p.hw % 128 == 0) : (p.bn == 1);
+  { int l = 0; while ((1 << l) < p.bw) ++l; p.bw_log2 = l; l = 0; while ((1 << l) < p.bh) ++l; p.bh_log2 = l; }
   if (a.geglu && !a.bias && !a.bias32) return fail(DG_E_ARG, "gemm: geglu epilogue needs a packed bias");
 
   const int m_tiles = p.tiles_x * p.tiles_y * p.tiles_b;
@@ -390,6 +396,8 @@ inline int launch_gemm(cudaStream_t stream, const GemmRes& res, const GemmArgs& 
   cudaError_t e;
   if (kcta == 2) {
     if (a.geglu) e = launch_gemm2_t<2, kGegluTile, kGegluTile == 320 ? kStages_2_320 : kStages_2_160, true>(stream, grid_units * 2, mA0, mA1, mW, mO, mR, p);
+    else if (a.xf_tab && kbn == 320) e = launch_gemm2_t<2, 320, kStages_2_320, false, true>(stream, grid_units * 2, mA0, mA1, mW, mO, mR, p);
+    else if (a.xf_tab) e = launch_gemm2_t<2, 160, kStages_2_160, false, true>(stream, grid_units * 2, mA0, mA1, mW, mO, mR, p);
     else if (kbn == 320) e = launch_gemm2_t<2, 320, kStages_2_320, false>(stream, grid_units * 2, mA0, mA1, mW, mO, mR, p);
     else e = launch_gemm2_t<2, 160, kStages_2_160, false>(stream, grid_units * 2, mA0, mA1, mW, mO, mR, p);
   } else {
@@ -488,9 +496,9 @@ inline int init_attn_attr() {
   DG_CUDA(cudaFuncSetAttribute(attn_tc_kernel<kD, kKV, kStages, 2, kSBuf, kQ, kSplit>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnCfg<kD, kKV, kStages, kSBuf, kQ, kSplit>::kSmem));
   return DG_OK;
 }
-template <int kCta, int kBN, int kStages, bool kGeglu>
+template <int kCta, int kBN, int kStages, bool kGeglu, bool kXf = false>
 inline int init_gemm_attr() {
-  DG_CUDA(cudaFuncSetAttribute(gemm2_kernel<kCta, kBN, kStages, kGeglu>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  DG_CUDA(cudaFuncSetAttribute(gemm2_kernel<kCta, kBN, kStages, kGeglu, kXf>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                Gemm2Cfg<kCta, kBN, kStages>::kTotal));
   return DG_OK;
 }
@@ -518,6 +526,8 @@ inline int init_kernel_attributes() {
   DG_TRY((init_gemm_attr<2, 320, kStages_2_320, false>()));
   DG_TRY((init_gemm_attr<2, 320, kStages_2_320, true>()));
   DG_TRY((init_gemm_attr<2, 160, kStages_2_160, false>()));
+  DG_TRY((init_gemm_attr<2, 320, kStages_2_320, false, true>()));
+  DG_TRY((init_gemm_attr<2, 160, kStages_2_160, false, true>()));
   DG_TRY((init_attn_attr<32, 128, 4>()));
   DG_TRY((init_attn_attr<40, 128, 4>()));
   DG_TRY((init_attn_attr<40, 64, 6, 2>()));
@@ -585,6 +595,22 @@ inline int launch_groupnorm_fused(cudaStream_t s, int num_sms, const __half* x0,
                                HW / 32, gamma, beta, silu, out);
     if (e != cudaSuccess) return fail(DG_E_CUDA, "groupnorm launch failed: %s", cudaGetErrorString(e));
   }
+  return DG_OK;
+}
+
+// Statistics fold for a GroupNorm applied inside the consuming GEMM (GemmArgs::xf_tab): tab = [B][3][C0 + C1] fp16.
+inline int launch_gn_fold(cudaStream_t s, int C0, const float* st0, int C1, const float* st1, int blk, const __half* gamma,
+                          const __half* beta, __half* tab, int B, int HW, int groups, float eps, int silu) {
+  if (HW % 32) return fail(DG_E_SHAPE, "groupnorm(fold): HW=%d must be a multiple of 32", HW);
+  const int C = C0 + C1;
+  if (C % groups || C0 % 64 || C1 % 64 || groups > 64) return fail(DG_E_SHAPE, "groupnorm(fold): C=%d+%d groups=%d", C0, C1, groups);
+  if (blk <= 0 || (C / groups) % blk || C0 % blk || C1 % blk || C / blk > 256)
+    return fail(DG_E_SHAPE, "groupnorm(fold): block %d does not tile C=%d+%d (at most 256 blocks)", blk, C0, C1);
+  ProfScope prof_(FAM_NORM, s, 0.0, 8.0 * B * (HW / 32) * (double)(C / blk) + 6.0 * B * C);
+  ++g_launch_counter;
+  cudaError_t e = launch_pdl(gn_fold_kernel, dim3((unsigned)B), dim3(256), (size_t)0, s, 1, C0, C1, HW, groups, eps, st0, st1, blk, HW / 32,
+                             gamma, beta, silu, tab);
+  if (e != cudaSuccess) return fail(DG_E_CUDA, "groupnorm fold launch failed: %s", cudaGetErrorString(e));
   return DG_OK;
 }
 

@@ -258,7 +258,7 @@ def clip_scores_for(scorer, tokenizer, images_u8, category_name: str):
     text = clip_prompt_text(category_name)
     ids = tokenizer([text], padding="max_length", max_length=getattr(tokenizer, "model_max_length", 77), truncation=True,
                     return_tensors="pt").input_ids
-    return scorer(clip_preprocess(images_u8), ids).view(-1).cpu().tolist()
+    return scorer(clip_preprocess(images_u8, n_px=scorer.vision_config.image_size), ids).view(-1).cpu().tolist()
 
 
 def load_clip_scorer(clip_dir: str, device):

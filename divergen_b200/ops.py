@@ -218,6 +218,32 @@ def groupnorm_fused_nhwc(x, stats, gamma, beta, groups: int, eps: float, silu: b
     return out
 
 
+def conv_gn(x, stats, gamma, beta, groups: int, eps: float, silu: bool, blk: int, weight, bias=None, x1=None, stats1=None,
+            residual=None):
+    """conv(act(norm(x))) with the GroupNorm (+ SiLU) applied inside the GEMM's operand path (dg_op_conv3x3_gn).
+    weight [O, I, 3, 3] -> 3x3 conv; weight [O, I] -> 1x1 conv / Linear over the pixels.  stats / stats1: block sums
+    [B, H*W // 32, C // blk, 2] of x / x1 (any assignment of a sample's pixels to its 32-pixel slabs)."""
+    _chk16(x, gamma, beta, weight, bias, x1, residual)
+    lib, ctx, s = _env(x)
+    B, H, W, C0 = x.shape
+    C1 = x1.shape[3] if x1 is not None else 0
+    O, I = weight.shape[:2]
+    assert I == C0 + C1
+    taps = 9 if weight.dim() == 4 else 1
+    if taps == 9:
+        wp = torch.empty((O, 9 * I), dtype=torch.float16, device=x.device)
+        _lib.check(lib.dg_op_pack_conv3x3(ctx, _p(weight), _p(wp), O, I, s), "dg_op_pack_conv3x3")
+    else:
+        wp = weight.contiguous()
+    ldo = (O + 7) // 8 * 8   # TMA store needs a 16-byte row pitch
+    if residual is not None and ldo != O:
+        raise ValueError("residual needs an output width that is a multiple of 8")
+    out = torch.zeros((B, H, W, ldo), dtype=torch.float16, device=x.device)
+    _lib.check(lib.dg_op_conv3x3_gn(ctx, _p(x), C0, _pf(stats), _p(x1), C1, _pf(stats1), blk, _p(gamma), _p(beta), groups, eps,
+                                    int(silu), _p(wp), _p(bias), _p(residual), _p(out), B, H, W, O, ldo, taps, s), "dg_op_conv3x3_gn")
+    return out[..., :O]
+
+
 def image_to_uint8(images):
     """[B, C, H, W] fp16 in [-1, 1] -> [B, H, W, C] uint8 on the device: diffusers.utils.pt_to_pil's arithmetic
     (`(x / 2 + 0.5).clamp(0, 1)`, `* 255`, round) without the host round trip of the float image."""

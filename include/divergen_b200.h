@@ -227,6 +227,15 @@ int32_t dg_op_pack_conv3x3(dg_ctx* ctx, const void* w_oihw, void* w_out, int32_t
 int32_t dg_op_conv3x3(dg_ctx* ctx, const void* x0, int32_t C0, const void* x1, int32_t C1, const void* Wp,
                       const void* bias, const void* rowvec, int32_t ld_rowvec, const void* residual, void* out,
                       int32_t B, int32_t H, int32_t Wd, int32_t N, int32_t ldo, void* stream);
+/* conv3x3 (taps = 9) or 1x1 / Linear (taps = 1) over GroupNorm(x) [+ SiLU], the normalisation applied INSIDE the GEMM's operand
+ * path (diffusers ResnetBlock2D: conv(act(norm(x)))): x0 / x1 are the RAW NHWC sources (x1 optional: channel concat), stats0 /
+ * stats1 their fused block sums [B][H*W/32][C/blk] float2 as written by dg_op_conv3x3_stats / the GEMM epilogues, Wp the packed
+ * weight, out [B, H, W, ldo] (row pitch ldo >= N, a multiple of 8; 0 = N).  Equals dg_op_groupnorm_fused followed by
+ * dg_op_conv3x3 up to fp16 rounding. */
+int32_t dg_op_conv3x3_gn(dg_ctx* ctx, const void* x0, int32_t C0, const float* stats0, const void* x1, int32_t C1, const float* stats1,
+                         int32_t blk, const void* gamma, const void* beta, int32_t groups, float eps, int32_t silu, const void* Wp,
+                         const void* bias, const void* residual, void* out, int32_t B, int32_t H, int32_t Wd, int32_t N, int32_t ldo,
+                         int32_t taps, void* stream);
 int32_t dg_op_attention(dg_ctx* ctx, const void* q, int32_t ldq, const void* k, int32_t ldk, const void* v, int32_t ldv,
                         void* out, int32_t B, int32_t heads, int32_t Sq, int32_t Sk, int32_t d, void* stream);
 int32_t dg_op_groupnorm(dg_ctx* ctx, const void* x0, int32_t C0, const void* x1, int32_t C1, const void* gamma,

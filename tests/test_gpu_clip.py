@@ -16,7 +16,9 @@ def _models(seed=0, **cfg_kw):
     from transformers import CLIPTextConfig
     from transformers import CLIPTextModel as HFCLIPTextModel
     from divergen_b200 import CLIPTextModel
-    cfg = CLIPTextConfig(hidden_act="quick_gelu", layer_norm_eps=1e-5, **cfg_kw)
+    cfg_kw = dict(cfg_kw)
+    cfg = CLIPTextConfig(hidden_act=cfg_kw.pop("hidden_act", "quick_gelu"), layer_norm_eps=1e-5, **cfg_kw)
+    cfg_kw["hidden_act"] = cfg.hidden_act
     torch.manual_seed(seed)
     ref = HFCLIPTextModel(cfg).eval()
     sd = {k: v.half().float() for k, v in ref.state_dict().items() if not k.endswith("position_ids")}
@@ -80,6 +82,21 @@ def test_sd_clip_text_encoder_full_width():
         ref16 = ref.half().to(DEV)(input_ids=ids.to(DEV)).last_hidden_state
     got = ours(ids).last_hidden_state
     _check(got, ref32, ref16, name="clip sd 2x77")
+
+
+def test_sd21_text_encoder_activation():
+    """SD-2.x's OpenCLIP text tower uses erf GELU (`hidden_act: "gelu"`): same kernels, other activation (tiny width here;
+    the full 23 x 1024 configuration is SD21_CLIP_CONFIG)."""
+    _need_gpu()
+    ref, ours = _models(5, hidden_act="gelu", **TINY)
+    ids = _ids(2, 77, TINY["vocab_size"], 9)
+    with torch.no_grad():
+        ref32 = ref(input_ids=ids).last_hidden_state
+        ref16 = ref.half().to(DEV)(input_ids=ids.to(DEV)).last_hidden_state
+    _check(ours(ids).last_hidden_state, ref32, ref16, name="clip tiny gelu")
+    ref_q, _ = _models(5, **TINY)                 # the activation really is different from quick_gelu
+    with torch.no_grad():
+        assert (ref_q(input_ids=ids).last_hidden_state - ref32).abs().max().item() > 1e-2
 
 
 def test_clip_errors():

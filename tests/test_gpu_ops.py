@@ -197,6 +197,59 @@ def test_conv3x3_groupnorm_fused(ops, B, H, W, C, N, blk):
     _report("groupnorm from fused sums", got, ref, 4e-3, 4e-3)
 
 
+def _block_sums(x, blk):
+    """[B, H*W // 32, C // blk, 2] (sum, sum of squares) of an NHWC tensor: what the GEMM epilogues leave for the next GroupNorm."""
+    B, H, W, C = x.shape
+    xb = x.float().view(B, H * W // 32, 32, C // blk, blk)
+    return torch.stack([xb.sum((2, 4)), (xb * xb).sum((2, 4))], -1).contiguous()
+
+
+@pytest.mark.parametrize("B,H,W,C0,C1,N,blk,silu,taps", [
+    (2, 64, 64, 320, 0, 320, 10, True, 9),        # level-0 resnet conv (320-wide tiles, one sample per tile)
+    (2, 32, 32, 640, 320, 640, 10, True, 9),      # up-block conv over cat([x, skip]): two sources, groups span both
+    (2, 16, 16, 1280, 0, 1280, 40, True, 9),      # few-tile level: 160-wide tiles
+    (3, 8, 8, 1280, 1280, 1280, 40, True, 9),     # 8x8 level: a tile holds two samples, split-K
+    (8, 8, 8, 1280, 0, 1280, 40, True, 9),        # batch 8 at the bottom of the U (the benchmarked shape)
+    (2, 64, 64, 320, 0, 4, 10, True, 9),          # conv_norm_out -> conv_out (4 output channels)
+    (5, 4, 8, 64, 0, 64, 2, True, 9),             # tiny-UNet level: 32 pixels per sample, four samples per tile, ragged batch
+    (2, 24, 24, 128, 0, 128, 4, True, 9),         # 96x96 latents' 24x24 level: boxes that do not divide the image evenly
+    (2, 32, 32, 320, 0, 320, 10, False, 1),       # transformer GroupNorm (no SiLU) -> proj_in as a 1x1 conv
+    (3, 8, 8, 128, 0, 256, 4, False, 1),          # ... with several samples per 128-row tile
+])
+def test_conv_groupnorm_silu_fused_into_operand_path(ops, B, H, W, C0, C1, N, blk, silu, taps):
+    """conv(act(norm(x))) with GroupNorm + SiLU applied inside the GEMM's A-operand path (gemm2_kernel<..., kXf>) against
+    the fp32 torch reference, and against the two-kernel path (GroupNorm apply, then conv) it replaces."""
+    x0 = _rand(B, H, W, C0, seed=70) * 1.5 + 0.7            # a mean well away from zero: exercises the mean_h subtraction
+    x1 = (_rand(B, H, W, C1, seed=71) * 0.5 - 1.0) if C1 else None
+    C = C0 + C1
+    gamma, beta = _rand(C, seed=72) * 0.2 + 1, _rand(C, seed=73) * 0.1
+    if taps == 9:
+        w = _rand(N, C, 3, 3, scale=1 / math.sqrt(9 * C), seed=74)
+    else:
+        w = _rand(N, C, scale=1 / math.sqrt(C), seed=74)
+    bias = _rand(N, scale=0.1, seed=75)
+    res = _rand(B, H, W, N, seed=76) if N % 8 == 0 else None
+    got = ops.conv_gn(x0, _block_sums(x0, blk), gamma, beta, 32, 1e-5, silu, blk, w, bias, x1, _block_sums(x1, blk) if C1 else None, res)
+    x = torch.cat([x0, x1], -1) if C1 else x0
+    hn = F.group_norm(x.float().permute(0, 3, 1, 2), 32, gamma.float(), beta.float(), 1e-5)
+    hn = F.silu(hn) if silu else hn
+    wf = w.float() if taps == 9 else w.float()[:, :, None, None]
+    ref = F.conv2d(hn, wf, bias.float(), padding=1 if taps == 9 else 0).permute(0, 2, 3, 1)
+    if res is not None:
+        ref = ref + res.float()
+    _report(f"conv_gn {B}x{H}x{W}x{C}->{N} taps {taps}", got, ref, 8e-3, 6e-3)
+    # the path it replaces, for scale: GroupNorm apply kernel -> conv kernel
+    hn16 = ops.groupnorm_fused_nhwc(x0, _block_sums(x0, blk), gamma, beta, 32, 1e-5, silu, blk, x1, _block_sums(x1, blk) if C1 else None)
+    if taps == 9:
+        old = ops.conv3x3_nhwc(hn16, w, bias, None, None, res)
+    else:
+        old = ops.linear(hn16.view(-1, C), w, bias, res.view(-1, N) if res is not None else None).view(B, H, W, N)
+    e_new = (got.float() - ref).pow(2).mean().sqrt().item()
+    e_old = (old.float() - ref).pow(2).mean().sqrt().item()
+    print(f"conv_gn {B}x{H}x{W}x{C}->{N}: rms error fused {e_new:.3g} vs two-kernel {e_old:.3g} (ref rms {ref.pow(2).mean().sqrt().item():.3g})")
+    assert e_new <= 3 * e_old + 1e-4
+
+
 @pytest.mark.parametrize("B,H,W,C0,C1,N", [(1, 64, 64, 64, 0, 160), (2, 64, 64, 320, 0, 320), (2, 32, 32, 640, 320, 640),
                                            (2, 16, 16, 1280, 0, 1280), (2, 8, 8, 1280, 1280, 1280), (3, 8, 8, 64, 0, 64),
                                            (2, 64, 64, 320, 0, 4), (1, 24, 24, 128, 0, 128), (2, 4, 4, 128, 0, 128)])

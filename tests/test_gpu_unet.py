@@ -294,9 +294,12 @@ def test_sd15_50_step_loop_vs_oracle_full_width():
     lat = torch.randn(1, 4, 64, 64, generator=g).half()
     pos, neg = torch.randn(1, 77, 768, generator=g).half(), torch.randn(1, 77, 768, generator=g).half()
     o = oracle.to(DEV)
-    ref32 = denoise_loop(o, DDIMOracle(), lat.to(DEV).float(), pos.to(DEV).float(), neg.to(DEV).float(), num_inference_steps=50).cpu()
+
+    def on_dev(x, t, e):                       # the scheduler's timesteps live on the host
+        return o(x, torch.as_tensor(t).reshape(1).to(DEV), e)
+    ref32 = denoise_loop(on_dev, DDIMOracle(), lat.to(DEV).float(), pos.to(DEV).float(), neg.to(DEV).float(), num_inference_steps=50).cpu()
     o = o.half()
-    ref16 = denoise_loop(o, DDIMOracle(), lat.to(DEV), pos.to(DEV), neg.to(DEV), num_inference_steps=50).float().cpu()
+    ref16 = denoise_loop(on_dev, DDIMOracle(), lat.to(DEV), pos.to(DEV), neg.to(DEV), num_inference_steps=50).float().cpu()
     del o
     torch.cuda.empty_cache()
     pipe = StableDiffusionPipeline(unet, DDIMScheduler())
