@@ -11,7 +11,8 @@ import subprocess
 import sys
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libdivergen_b200.so")
+# DG_LIB_PATH: load another build of the same sources (A/B runs of compile-time switches); the default is the in-tree library
+LIB_PATH = os.environ.get("DG_LIB_PATH") or os.path.join(_HERE, "libdivergen_b200.so")
 CSRC = os.path.join(_HERE, "csrc")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]

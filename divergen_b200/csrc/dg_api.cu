@@ -17,7 +17,8 @@ struct dg_ctx {
   GemmRes gemm;               // split-K workspace, tickets, persistent grid size
   int fuse_ln = 1;            // DG_FUSE_LN=0: stand-alone LayerNorm kernels instead of the folded GEMM epilogue
   int fuse_gn = 1;            // DG_FUSE_GN=0: stand-alone GroupNorm statistics kernels instead of epilogue sums
-  int fuse_xf = 1;            // DG_FUSE_XF=0: stand-alone GroupNorm-apply (+SiLU) pass instead of the transform inside the consuming conv
+  int fuse_xf = 1;            // DG_FUSE_XF=0: stand-alone GroupNorm-apply (+SiLU) pass instead of the transform inside the consuming conv;
+                              // 2: also the transformer's GroupNorm inside proj_in
   __half* xf_tab = nullptr;   // scratch table for the stand-alone fused-GroupNorm operators (tests)
   size_t xf_tab_cap = 0;
 };
@@ -398,12 +399,14 @@ struct Fwd {
     float* gn_out = nullptr; int hw = 0;         // fused GroupNorm sums of the result (rows per sample = hw)
     float* rows_out = nullptr;                   // LayerNorm row partials of the result
     const float* ln_in = nullptr; int ln_c = 0;  // LayerNorm-folded GEMM: row partials of the input (w must carry wf/cs/b32)
+    const __half* xf_tab = nullptr;              // GroupNorm (no activation) applied to the input inside the GEMM (needs hw)
   };
   // plain GEMM over rows = B*H*W of x (optionally 2-source concat along channels)
   void linear(const __half* x0, int c0, const __half* x1, int c1, int rows, const Lin& w, __half* out, const LinOpt& o) {
     GemmArgs a; a.a0 = x0; a.c0 = c0; a.a1 = x1; a.c1 = c1; a.B = 1; a.H = 1; a.W = rows; a.taps = 1; a.w = w.w; a.n_w = w.rows;
     a.n_out = w.out; a.bias = w.b; a.residual = o.residual; a.ld_res = w.out; a.geglu = o.geglu; a.out = out; a.ldo = w.out;
     a.gn_stats_out = o.gn_out; a.gn_blk = u->gn_blk; a.hw = o.hw; a.row_stats_out = o.rows_out;
+    a.xf_tab = o.xf_tab; a.xf_silu = 0;
     if (o.ln_in) {
       a.w = w.wf; a.bias = nullptr; a.bias32 = w.b32; a.colsum = w.cs; a.ln_stats = o.ln_in; a.ln_parts = gemm_row_parts(o.ln_c);
       a.ln_c = o.ln_c; a.ln_eps = 1e-5f;
@@ -455,11 +458,16 @@ struct Fwd {
     const int B_ = in.B, S = in.H * in.W, C = x.c, rows = B_ * S;
     const int d = C / x.heads;
     const bool fl = fuse_ln();
-    T4 xn = talloc(B_, in.H, in.W, C);
-    gn(in, nullptr, x.gn, 1e-6f, 0, xn);
+    T4 xn = talloc(B_, in.H, in.W, C);      // (also the attention outputs' buffer below)
     T4 h = talloc(B_, in.H, in.W, C);
     float* rs = ln_alloc(rows, C);
-    { LinOpt o; o.rows_out = rs; linear(xn.p, C, nullptr, 0, rows, x.proj_in, h.p, o); }
+    // proj_in(norm(x)): the GroupNorm (eps 1e-6, no activation) inside the GEMM's operand path when the statistics are fused
+    if (const __half* tabn = u->ctx->fuse_xf >= 2 ? gn_fold(in, nullptr, x.gn, 1e-6f, 0) : nullptr) {
+      LinOpt o; o.rows_out = rs; o.xf_tab = tabn; o.hw = S; linear(in.p, C, nullptr, 0, rows, x.proj_in, h.p, o);
+    } else {
+      gn(in, nullptr, x.gn, 1e-6f, 0, xn);
+      LinOpt o; o.rows_out = rs; linear(xn.p, C, nullptr, 0, rows, x.proj_in, h.p, o);
+    }
     // self-attention: LayerNorm folded into the QKV projection (or a stand-alone LayerNorm pass when fusion is off)
     __half* qkv = alloc((size_t)rows * 3 * C * 2);
     if (fl) { LinOpt o; o.ln_in = rs; o.ln_c = C; linear(h.p, C, nullptr, 0, rows, x.qkv, qkv, o); }

@@ -35,6 +35,13 @@
 //   16 KB per 32-column chunk); the last arriver (atomic ticket) bulk-loads the sum into the idle operand stages, re-zeroes
 //   the workspace and runs the epilogue.  (fp32 addition order varies run to run: reproducible to fp32 rounding.)
 //
+// Two epilogue sets (kSets = 2; 160-wide tiles, whose accumulator is double-buffered in TMEM): 16 epilogue warps, set s owns
+//   TMEM stage s, staging slot s and the CTA's tiles s, s + 2, ...  -- two tiles' epilogues are in flight at once, each exactly
+//   the 8-warp epilogue described above.  For K <= 1280 the epilogue of a 128 x 160 tile (~4 k cycles + ~1.2 k between tiles,
+//   latency-bound: 2 warps per scheduler) outlasts its MMA (1.6 k cycles at K = 320); a second set doubles the epilogue rate
+//   without touching the per-tile code.  Registers: 640 threads start at 96 each; the role warpgroup drops to 32 and the four
+//   epilogue warpgroups rise to 112 (setmaxnreg; the two amounts must balance).
+//
 // Fused GroupNorm + SiLU on the A operand (kXf = true; ResnetBlock2D's `conv(act(norm(x)))`): the activation tensor is read RAW.
 //   The A tile of a stage lands on a CTA-LOCAL barrier (a_full); the 8 epilogue warps -- idle during the main loop of a
 //   single-accumulator-stage tile -- rewrite it in place, smem -> registers -> smem: 4 rows x one 16-byte (8-channel) chunk per
@@ -105,12 +112,14 @@ struct Gemm2Params {
 #define DG_STAMP_C1(slot) do { } while (0)
 #endif
 
-template <int kCta, int kBN, int kStages>
+template <int kCta, int kBN, int kStages, int kSets = 1>
 struct Gemm2Cfg {
-  static_assert(kBN == 320 || kBN == 160, "tile N is one or two 160-wide accumulators");
-  static constexpr int kNI = 160;                       // N of one MMA instruction
+  static_assert(kBN == 320 || kBN == 160 || kBN == 256, "tile N: one or two 160-wide accumulators, or two 128-wide ones (GEGLU)");
+  static constexpr int kNI = kBN == 256 ? 128 : 160;    // N of one MMA instruction
   static constexpr int kNumAcc = kBN / kNI;             // accumulators per tile
-  static constexpr int kAccStages = kNumAcc == 1 ? 2 : 1;   // a 160-wide tile double-buffers in TMEM: epilogue(i) overlaps mainloop(i+1)
+  // 160- and 256-wide tiles double-buffer in TMEM (2 x 160 / 2 x 256 of 512 columns): epilogue(i) overlaps mainloop(i+1)
+  static constexpr int kAccStages = kBN == 320 ? 1 : 2;
+  static constexpr bool kWholeSlots = kAccStages == 2;  // output staging: whole-tile slots (one hand-off per tile) vs a chunk ring
   static constexpr int kAccStride = 256;                // TMEM columns between accumulator stages
   static constexpr int kABytes = 128 * 64 * 2;          // 16 KB: 128 pixels x 64 channels
   static constexpr int kBRows = kNI / kCta;             // weight rows this CTA loads per accumulator
@@ -119,13 +128,15 @@ struct Gemm2Cfg {
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kSubBytes = 128 * 64;            // staging sub-tile [128 rows][32 cols fp16], 64-byte swizzle
   // output staging ring, drained by the store warp.  320-wide tiles: 4 slots of one 32-column chunk per column half;
-  // 160-wide tiles: 2 slots of a WHOLE tile (5 sub-tiles) -- one wait / fence / hand-off per tile instead of per chunk
-  static constexpr int kRing = kNumAcc == 1 ? 2 : 4;
-  static constexpr int kSlotSubs = kNumAcc == 1 ? 5 : 2;
+  // 160- / 256-wide tiles: 2 slots of a WHOLE tile (5 / 4 sub-tiles) -- one wait / fence / hand-off per tile instead of per chunk
+  static constexpr int kRing = kWholeSlots ? 2 : 4;
+  static constexpr int kSlotSubs = kBN == 160 ? 5 : kBN == 256 ? 4 : 2;   // 256-wide GEGLU tiles produce 128 output columns
   static constexpr int kRingBytes = kRing * kSlotSubs * kSubBytes;
-  static constexpr int kVecBytes = 2 * 2 * 320 * 4;     // 2 generations of (bias, colsum), fp32
-  static constexpr int kColBufBytes = 8 * (kBN / 2) * 8;   // per epilogue warp: (sum, sumsq) of each of its kBN / 2 columns
-  static constexpr int kUnitTab = 32;                   // this CTA's first tiles, decomposed once in the prologue
+  static_assert(kSets == 1 || (kSets == 2 && kAccStages == 2), "two epilogue sets need the double-buffered accumulator");
+  static constexpr int kThreads = 128 + kSets * 256;    // 4 role warps + 8 epilogue warps per set
+  static constexpr int kVecBytes = kSets * 2 * 2 * kBN * 4;   // per set: 2 generations of (bias, colsum), fp32
+  static constexpr int kColBufBytes = kSets * 8 * (kBN / 2) * 8;   // per epilogue warp: (sum, sumsq) of each of its kBN / 2 columns
+  static constexpr int kUnitTab = kSets == 2 ? 12 : 32;   // this CTA's first tiles, decomposed once in the prologue
   static constexpr int kBarBytes = 512 + kUnitTab * 40;
   static constexpr int kTotal = kStages * kStageBytes + kRingBytes + kVecBytes + kColBufBytes + kBarBytes + 1024 /*align slack*/;
   static_assert(kBHalfBytes % 1024 == 0 && kStageBytes % 1024 == 0, "operand tiles must keep 1024-byte alignment");
@@ -314,19 +325,21 @@ __device__ __forceinline__ uint32_t xf_half2(uint32_t x, uint32_t m, uint32_t sc
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
-template <int kCta, int kBN, int kStages, bool kGeglu, bool kXf = false>
-__global__ void __launch_bounds__(384, 1)
+template <int kCta, int kBN, int kStages, bool kGeglu, bool kXf = false, int kSets = 1>
+__global__ void __launch_bounds__(128 + kSets * 256, 1)
 gemm2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
              const __grid_constant__ CUtensorMap mapW, const __grid_constant__ CUtensorMap mapO,
              const __grid_constant__ CUtensorMap mapR, const Gemm2Params p) {
-  using S = Gemm2Cfg<kCta, kBN, kStages>;
+  using S = Gemm2Cfg<kCta, kBN, kStages, kSets>;
+  static_assert(!(kXf && kSets > 1), "the operand transform is built for one epilogue set");
   // GEGLU tiles: 320-wide [160 value | 160 gate] (one TMEM stage) or 160-wide [64 value | 64 gate | 32 zero rows] -- the
   // latter wastes a fifth of the MMA columns but runs on the double-buffered accumulator, so the packed-GELU epilogue
   // (~3x the MMA time of a K = 320 tile) overlaps the next tile's MMA instead of serialising with it.
-  constexpr int kGateOff = (kBN == 320) ? S::kNI : 64;   // accumulator column of the gate half
+  static_assert(kBN != 256 || kGeglu, "256-wide tiles are the GEGLU layout [128 value | 128 gate]");
+  constexpr int kGateOff = (kBN == 160) ? 64 : S::kNI;   // accumulator column of the gate half
   constexpr uint32_t kTmemCols = 512;
   constexpr int kEpiThreads = 256;
-  constexpr int kChunks = (kGeglu && kBN == 160) ? 2 : 5;
+  constexpr int kChunks = !kGeglu ? 5 : (kBN == 160 ? 2 : kBN == 256 ? 4 : 5);
   // columns one epilogue thread converts per chunk: 320-wide tiles give each column-half warp 32 consecutive columns,
   // 160-wide tiles (and GEGLU outputs) give the two warps of a TMEM quadrant the two 16-column halves of a 32-column chunk
   constexpr int kCW = (kBN == 320 && !kGeglu) ? 32 : 16;
@@ -336,8 +349,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sRing = smem + kStages * S::kStageBytes;                       // 1024-aligned
-  float* sVec = reinterpret_cast<float*>(sRing + S::kRingBytes);           // [2 generations][bias 320 | colsum 320]
-  float2* sColBuf = reinterpret_cast<float2*>(sRing + S::kRingBytes + S::kVecBytes);   // [8 warps][160]
+  float* sVec = reinterpret_cast<float*>(sRing + S::kRingBytes);           // [set][2 generations][bias kBN | colsum kBN]
+  float2* sColBuf = reinterpret_cast<float2*>(sRing + S::kRingBytes + S::kVecBytes);   // [8 warps per set][kBN / 2]
   uint64_t* bars = reinterpret_cast<uint64_t*>(sRing + S::kRingBytes + S::kVecBytes + S::kColBufBytes);
   uint64_t* full = bars;                    // [kStages]  (leader's are the live ones)
   uint64_t* empty = bars + kStages;         // [kStages]
@@ -349,8 +362,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
   uint64_t* sk_full = res_full + S::kRing;       // [1]      split-K: the summed fp32 tile landed in the (idle) operand stages
   uint64_t* a_full = sk_full + 1;                // [kStages] kXf: this CTA's raw A tile landed (local; -> transform warps)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_full + kStages);
-  volatile uint32_t* ticket_slot = tmem_slot + 1;
-  volatile int* chunk_info = reinterpret_cast<volatile int*>(tmem_slot + 2);   // [kRing][5]: col, x0, y0, b0, flags (1 store, 2 stop)
+  volatile uint32_t* ticket_slots = tmem_slot + 1;   // [2] one per epilogue set
+  volatile int* chunk_info = reinterpret_cast<volatile int*>(tmem_slot + 3);   // [kRing][5]: col, x0, y0, b0, flags (1 store, 2 stop)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -405,10 +418,10 @@ gemm2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
   auto unit_at = [&](int u, int k) -> Unit {
     return k < S::kUnitTab ? sUnits[k] : unit_coord<kCta>(p, u, cta_rank, m_tiles, num_kb);
   };
-  constexpr bool kWholeT = (kBN == 160);
+  constexpr bool kWholeT = S::kWholeSlots;
   // (one thread) residual of unit `tt` -> slot sl: whole-tile slots take all 5 sub-tiles, ring slots chunk j's two halves
   auto issue_res = [&](uint32_t sl, int j, const Unit& tt) {
-    constexpr int kSubs = kWholeT ? 5 : 2;
+    constexpr int kSubs = kWholeT ? S::kSlotSubs : 2;
     const int col0 = tt.nt * kOutW + (kWholeT ? 0 : j * 32);
     const int cstep = kWholeT ? 32 : S::kNI;
     int nsub = 0;
@@ -424,6 +437,11 @@ gemm2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
   // epilogue issues it itself)
   const bool res_loader = p.residual != nullptr && p.splits == 1 && !kGeglu;
 
+  if (warp < 4) {
+  // 640 threads (two epilogue sets) start with 96 registers each.  The pool setmaxnreg.inc draws from holds only what the
+  // CTA's own warps released: the role warpgroup gives up 128 x (96 - 32) = 8192 registers, exactly the 4 x 128 x (112 - 96)
+  // the epilogue warpgroups take (an unbalanced pair spins forever in USETMAXREG.TRY_ALLOC -- it did, once).
+  if constexpr (kSets == 2) asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");
   if (warp == 0) {
     // ===================== TMA producer (one elected lane; elect.sync lets the compiler keep TMA operands in uniform
     // registers -- a `lane == 0` test costs an ELECT / R2UR.BROADCAST waterfall loop per UTMALDG, profiles/r01_ncu_pair_v2.txt)
@@ -521,7 +539,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
     // residual into its slot while it works on the current one (ring) / prime the next tile's slot (whole-tile slots).
     // Whole-tile slots (160-wide tiles, 2 slots): both start free and a slot is handed back as soon as ITS store has been
     // read out of shared memory, so the epilogue can prime the next tile's residual while it converts the current tile.
-    constexpr bool kWholeSlots = (kBN == 160);
+    constexpr bool kWholeSlots = S::kWholeSlots;
     constexpr uint32_t kFreeAhead = kWholeSlots ? S::kRing : 2;
     if (elect_one()) {
       for (uint32_t i = 0; i < kFreeAhead; ++i) mbar_arrive(&buf_free[i]);   // the first slots start free
@@ -532,10 +550,10 @@ gemm2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
         const int b0 = chunk_info[buf * 5 + 3], flags = chunk_info[buf * 5 + 4];
         if (flags & 2) break;
         if (flags & 1) {
-          if constexpr (kBN == 160) {
+          if constexpr (kWholeSlots) {
 #pragma unroll
             for (int k = 0; k < kOutW / 32; ++k)
-              if (col + k * 32 < p.n_out) tma_store_4d(&mapO, sRing + (buf * 5 + k) * S::kSubBytes, col + k * 32, x0, y0, b0);
+              if (col + k * 32 < p.n_out) tma_store_4d(&mapO, sRing + (buf * S::kSlotSubs + k) * S::kSubBytes, col + k * 32, x0, y0, b0);
           } else if constexpr (kCW == 32) {
 #pragma unroll
             for (int h2 = 0; h2 < 2; ++h2)
@@ -552,13 +570,18 @@ gemm2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
       tma_store_wait_all();
       DG_STAMP(11);                     // all stores complete
     }
-  } else if (warp >= 4) {
-    // ===================== epilogue (8 warps) =====================
-    const int ew = warp - 4;
+  }
+  } else {
+    if constexpr (kSets == 2) asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
+    // ===================== epilogue (8 warps per set) =====================
+    const int eset = (kSets == 2) ? (warp - 4) >> 3 : 0;   // epilogue set: owns TMEM stage / staging slot / tiles eset, eset + 2, ...
+    const int ew = (warp - 4) & 7;
     const int q = ew & 3;               // TMEM lane quadrant (== warp index % 4)
     const int hf = ew >> 2;             // which column half (320-wide) / chunk half (160-wide, GEGLU) this warp owns
     const int r = q * 32 + lane;        // accumulator row within this CTA's tile
-    const int et = threadIdx.x - 128;   // 0..255
+    const int et = threadIdx.x - 128 - eset * 256;   // 0..255 within the set
+    const uint32_t set_bar = 1u + (uint32_t)eset;    // named barrier of this set's 256 threads
+    volatile uint32_t* ticket_slot = ticket_slots + eset;
     const int box_xy = p.bw * p.bh;
     const uint32_t row_sw = (uint32_t)((r >> 1) & 3);   // 64-byte swizzle phase of this row
     const uint32_t acc_empty_leader = mapa_rank(smem_u32(&acc_empty[0]), 0);
@@ -568,8 +591,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
     const int row_rb = r / box_xy, row_ry = (r - row_rb * box_xy) / p.bw, row_rx = (r - row_rb * box_xy) % p.bw;
     int vec_nt = -1, vec_gen = 1;       // column tile they hold; reloaded (into the other generation) only when it changes
     const bool has_ln = p.colsum != nullptr;
-    int as = 0; uint32_t acc_phase = 0;
-    uint32_t chunk_ctr = 0;             // staging-ring chunk counter (final epilogues only)
+    int as = eset; uint32_t acc_phase = 0;
+    uint32_t chunk_ctr = (uint32_t)eset;   // staging-ring chunk counter (final epilogues only); two sets: the CTA's tile index
     int xstage = 0; uint32_t xphase = 0;   // kXf: operand stage / phase of the next A tile to transform
     const uint32_t full0_leader_x = mapa_rank(smem_u32(&full[0]), 0);
 
@@ -578,7 +601,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
     // [32j, 32j+32), 16 per warp half
     auto chunk_col = [&](int j) { return kCW == 32 ? hf * S::kNI + j * 32 : (kBN == 160 ? (kGeglu ? hf * 32 + j * 16 : hf * 80 + j * 16) : j * 32 + hf * 16); };
 
-    for (int u = pair_id, uk = 0; u < total_units; u += num_pairs, ++uk) {
+    for (int u = pair_id + eset * num_pairs, uk = eset; u < total_units; u += kSets * num_pairs, uk += kSets) {
       if (et == 0 && u == pair_id + num_pairs) DG_STAMP(30);      // second tile: loop top
       const Unit t = unit_at(u, uk);
       const int nt = t.nt;
@@ -668,7 +691,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
       const bool vec_reload = nt != vec_nt;
       if (vec_reload) {
         vec_nt = nt; vec_gen ^= 1;
-        float* dstv = sVec + vec_gen * 640;
+        float* dstv = sVec + (eset * 2 + vec_gen) * (2 * kBN);
         for (int i = et; i < kBN; i += kEpiThreads) {
           const int n = nt * kBN + i;
           float bv = 0.f, cv = 0.f;
@@ -677,9 +700,9 @@ gemm2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
             else if (p.bias) bv = __half2float(__ldg(p.bias + n));
             if (p.colsum) cv = __ldg(p.colsum + n);
           }
-          dstv[i] = bv; dstv[320 + i] = cv;
+          dstv[i] = bv; dstv[kBN + i] = cv;
         }
-        sBias_a = smem_u32(dstv); sCs_a = sBias_a + 320 * 4;
+        sBias_a = smem_u32(dstv); sCs_a = sBias_a + kBN * 4;
       }
       // ---- LayerNorm fold: this row's mean / rstd from the producer's partials
       float ln_a = 1.f, ln_b = 0.f;     // value = ln_a * acc + ln_b * colsum[n] + bias[n]
@@ -700,12 +723,12 @@ gemm2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
       // one 16-byte shared load per 8 columns.  (Per-thread 16-byte cp.async copies of 640-byte-strided rows cost ~4k
       // cycles per 40 KB tile: 32 half-used sectors per instruction.)
       constexpr int kRV = kCW / 8;      // 16-byte vectors per chunk piece
-      constexpr bool kWhole = (kBN == 160);
+      constexpr bool kWhole = S::kWholeSlots;
       // shared address of 16-byte vector i of this thread's piece of chunk j in ring slot `sl`
       auto stage_addr = [&](uint32_t sl, int j, int i) -> uint32_t {
         if constexpr (kWhole) {
           const int c = chunk_col(j);
-          return sRing_a + (sl * 5 + (c >> 5)) * S::kSubBytes + r * 64 + (((uint32_t)(((c & 31) >> 3) + i) ^ row_sw) << 4);
+          return sRing_a + (sl * S::kSlotSubs + (c >> 5)) * S::kSubBytes + r * 64 + (((uint32_t)(((c & 31) >> 3) + i) ^ row_sw) << 4);
         } else {
           return sRing_a + (sl * 2 + hf) * S::kSubBytes + r * 64 + (((uint32_t)i ^ row_sw) << 4);
         }
@@ -717,7 +740,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
       tc_fence_after();
       if (u == pair_id && et == 0) DG_STAMP(3);        // first accumulator complete
       if (et == 0 && (u - pair_id) / num_pairs < 4) DG_STAMP(22 + 2 * ((u - pair_id) / num_pairs));   // unit k: accumulator complete
-      if (vec_reload) asm volatile("bar.sync 1, 256;" ::: "memory");   // the new generation of bias / colsum is visible
+      if (vec_reload) asm volatile("bar.sync %0, 256;" ::"r"(set_bar) : "memory");   // the new generation of bias / colsum is visible
       auto release_acc = [&]() {        // every TMEM read of this unit has completed: hand the accumulator back
         tc_fence_before();
         __syncwarp();
@@ -745,7 +768,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
         }
         release_acc();
         fence_proxy_async();
-        asm volatile("bar.sync 1, 256;" ::: "memory");
+        asm volatile("bar.sync %0, 256;" ::"r"(set_bar) : "memory");
         if (et == 0) {
 #pragma unroll
           for (int cc = 0; cc < 5; ++cc) bulk_reduce_add_f32(ws_tile + cc * 4096, sRing + cc * 16384, 16384u);
@@ -754,7 +777,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
           __threadfence();
           *ticket_slot = (uint32_t)atomicAdd(p.tickets + t.ctile, 1);
         }
-        asm volatile("bar.sync 1, 256;" ::: "memory");
+        asm volatile("bar.sync %0, 256;" ::"r"(set_bar) : "memory");
         do_final = (*ticket_slot == (uint32_t)(p.splits - 1));
         if (do_final) {
           // last arriver: pull the summed tile into the operand stages (this CTA's only tile is done with them), then zero
@@ -799,9 +822,9 @@ gemm2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
         }
         release_acc();
         __threadfence();
-        asm volatile("bar.sync 1, 256;" ::: "memory");
+        asm volatile("bar.sync %0, 256;" ::"r"(set_bar) : "memory");
         if (ew == 0 && elect_one()) *ticket_slot = (uint32_t)atomicAdd(p.tickets + t.ctile, 1);
-        asm volatile("bar.sync 1, 256;" ::: "memory");
+        asm volatile("bar.sync %0, 256;" ::"r"(set_bar) : "memory");
         do_final = (*ticket_slot == (uint32_t)(p.splits - 1));
         if (do_final) {
           __threadfence();
@@ -817,7 +840,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
         // each lane folds one gn_blk-column block and stores it to the warp's slab entry.  No shuffles, no atomics.
         const bool gn_on = p.gn_stats_out != nullptr;
         float2* gn_dst = nullptr;       // this warp's slab: [gn_nblk] (sum, sumsq) pairs
-        const uint32_t colbuf_a = smem_u32(sColBuf) + (uint32_t)ew * (kBN / 2) * 8;
+        const uint32_t colbuf_a = smem_u32(sColBuf) + (uint32_t)(eset * 8 + ew) * (kBN / 2) * 8;
         if (gn_on) {
           const int r0 = q * 32;        // first row of this warp within the tile
           int slab;
@@ -1004,14 +1027,14 @@ gemm2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
           for (int i = 0; i < kCW / 2; ++i) pk[i] = cvt_pack_half2(f[2 * i], f[2 * i + 1]);
           if constexpr (kWhole) {
             DG_STAMP_C1(18);
-            const uint32_t sub = sRing_a + (slot * 5 + (ocol >> 5)) * S::kSubBytes + r * 64;
+            const uint32_t sub = sRing_a + (slot * S::kSlotSubs + (ocol >> 5)) * S::kSubBytes + r * 64;
             const uint32_t k0 = (uint32_t)((ocol & 31) >> 3);
 #pragma unroll
             for (int i = 0; i < 2; ++i) sts_u4(sub + (((k0 + i) ^ row_sw) << 4), pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
             if (gn_on) {      // transposed read-back: lane = (row half, column of the 16)
               __syncwarp();
               const int col = lane & 15, rh = lane >> 4;
-              const uint32_t slab_a = sRing_a + (slot * 5 + (ocol >> 5)) * S::kSubBytes + (uint32_t)(q * 32 + rh * 16) * 64;
+              const uint32_t slab_a = sRing_a + (slot * S::kSlotSubs + (ocol >> 5)) * S::kSubBytes + (uint32_t)(q * 32 + rh * 16) * 64;
               const uint32_t kc = k0 + (uint32_t)(col >> 3);
               float cs = 0.f, css = 0.f;
 #pragma unroll
@@ -1082,7 +1105,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
             if (u == pair_id && ew == 0) DG_STAMP(8);
             if (ew == 0 && (u - pair_id) / num_pairs < 4) DG_STAMP(23 + 2 * ((u - pair_id) / num_pairs));   // unit k handed to the store warp
           }
-          ++chunk_ctr;
+          chunk_ctr += kSets;
         }
         if (gn_on) {          // fold this warp's columns into gn_blk-channel blocks (fixed order) and store the slab entries
           __syncwarp();
@@ -1102,9 +1125,12 @@ gemm2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
         if (p.row_stats_out && row_ok)
           reinterpret_cast<float2*>(p.row_stats_out)[grow * p.row_parts + nt * 2 + hf] = make_float2(rs, rss);
       }
-      if (++as == S::kAccStages) { as = 0; acc_phase ^= 1; }
+      if constexpr (kSets == 2) { acc_phase ^= 1; }            // this set's stage every time
+      else if (++as == S::kAccStages) { as = 0; acc_phase ^= 1; }
     }
-    {   // tell the store warp to stop
+    // tell the store warp to stop: the slot after the CTA's last tile (two sets: posted by the set that would own that tile)
+    const int my_tiles = pair_id < total_units ? (total_units - pair_id + num_pairs - 1) / num_pairs : 0;
+    if (kSets == 1 || chunk_ctr == (uint32_t)my_tiles) {
       const uint32_t buf = chunk_ctr % S::kRing;
       mbar_wait(&buf_free[buf], (chunk_ctr / S::kRing) & 1);
       if (lane == 0) {

@@ -172,16 +172,26 @@ constexpr int kGemmTileN = 320;     // widest tile: two 160-wide accumulators
 // the 320-wide kernel.  DG_NVCC_EXTRA=-DDG_GEGLU_NARROW builds 160/64 on the double-buffered 160-wide kernel (epilogue
 // overlaps the next tile's MMA) -- measured SLOWER on the whole forward (10.20 vs 9.95 ms): 2.5x more tiles, each paying
 // the ~1.2 k-cycle gap between tiles, and a fifth of the MMA columns wasted.
-#ifdef DG_GEGLU_NARROW
+// Round 2: 256/128 -- two 128-wide accumulators, DOUBLE-buffered in TMEM (2 x 256 of 512 columns) with two epilogue sets: the
+// packed-GELU epilogue (~2x the MMA time of a K = 320 tile) overlaps the next tile's main loop, and two tiles' epilogues run
+// at once.  DG_NVCC_EXTRA=-DDG_GEGLU_WIDE builds round 1's 320/160 single-stage layout for A/B runs.
+#if defined(DG_GEGLU_NARROW)
 constexpr int kGegluTile = 160, kGegluHalf = 64;
-#else
+#elif defined(DG_GEGLU_WIDE)
 constexpr int kGegluTile = 320, kGegluHalf = 160;
+#else
+constexpr int kGegluTile = 256, kGegluHalf = 128;
 #endif
+constexpr int kGegluSets = kGegluTile == 320 ? 1 : 2;
 // smem ring depths per (CTAs per tile, tile N): stage bytes are 16 KB of A + 10/20/40 KB of B; + 64 KB output staging ring
 constexpr int kStages_2_320 = 4;    // 4 x 36 KB
 constexpr int kStages_2_160 = 5;    // 5 x 26 KB (+ 80 KB: two whole-tile staging slots)
 constexpr int kStages_1_320 = 2;    // 2 x 56 KB (single-CTA variants: bring-up / A-B runs only, DG_GEMM_CTA=1)
 constexpr int kStages_1_160 = 3;    // 3 x 36 KB
+constexpr int kStages_2_256 = 4;    // 4 x 32 KB (+ 64 KB: two whole-tile staging slots of 128 output columns)
+constexpr int kStages_1_256 = 3;    // 3 x 48 KB
+constexpr int kStagesGeglu2 = kGegluTile == 320 ? kStages_2_320 : kGegluTile == 256 ? kStages_2_256 : kStages_2_160;
+constexpr int kStagesGeglu1 = kGegluTile == 320 ? kStages_1_320 : kGegluTile == 256 ? kStages_1_256 : kStages_1_160;
 constexpr size_t kSplitWsFloats = (size_t)8 << 20;    // 32 MB of fp32 split-K tile accumulators (zero between launches)
 constexpr int kSplitTickets = 1 << 16;
 
@@ -262,11 +272,18 @@ inline int choose_splits(int units, int num_kb, int slots, size_t ws_floats_per_
   return best;
 }
 
-template <int kCta, int kBN, int kStages, bool kGeglu, bool kXf = false>
+inline bool gemm_two_sets() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("DG_GEMM_SETS"); v = (e && e[0] == '1') ? 0 : 1; }
+  return v == 1;
+}
+
+template <int kCta, int kBN, int kStages, bool kGeglu, bool kXf = false, int kSets = 1>
 inline cudaError_t launch_gemm2_t(cudaStream_t stream, int grid_ctas, const CUtensorMap& mA0, const CUtensorMap& mA1,
                                   const CUtensorMap& mW, const CUtensorMap& mO, const CUtensorMap& mR, const Gemm2Params& p) {
-  return launch_pdl(gemm2_kernel<kCta, kBN, kStages, kGeglu, kXf>, dim3((unsigned)grid_ctas), dim3(384),
-                    (size_t)Gemm2Cfg<kCta, kBN, kStages>::kTotal, stream, kCta, mA0, mA1, mW, mO, mR, p);
+  using Cfg = Gemm2Cfg<kCta, kBN, kStages, kSets>;
+  return launch_pdl(gemm2_kernel<kCta, kBN, kStages, kGeglu, kXf, kSets>, dim3((unsigned)grid_ctas), dim3(Cfg::kThreads),
+                    (size_t)Cfg::kTotal, stream, kCta, mA0, mA1, mW, mO, mR, p);
 }
 
 inline int launch_gemm(cudaStream_t stream, const GemmRes& res, const GemmArgs& a) {
@@ -359,7 +376,7 @@ inline int launch_gemm(cudaStream_t stream, const GemmRes& res, const GemmArgs& 
       mA1 = mA0;
     }
     const uint64_t ktot = (uint64_t)a.taps * (a.c0 + a.c1);
-    DG_TRY(make_map_2d(&mW, a.w, ktot, (uint64_t)a.n_w, ktot * 2, 64, 160 / kcta));   // one accumulator's rows per CTA
+    DG_TRY(make_map_2d(&mW, a.w, ktot, (uint64_t)a.n_w, ktot * 2, 64, (kbn == 256 ? 128 : 160) / kcta));   // one accumulator's rows per CTA
     // output tiles: {n_out, W, H, B} boxes of 32 columns x 128 pixels, 64-byte swizzle in smem
     uint64_t od[4] = {(uint64_t)a.n_out, (uint64_t)W, (uint64_t)H, (uint64_t)B};
     uint64_t os[3] = {(uint64_t)a.ldo * 2, (uint64_t)W * a.ldo * 2, (uint64_t)H * W * a.ldo * 2};
@@ -395,13 +412,17 @@ inline int launch_gemm(cudaStream_t stream, const GemmRes& res, const GemmArgs& 
   if (dbg_on) { cudaMemsetAsync(dbg_dev, 0, 40 * 8, stream); p.dbg = dbg_dev; }
   cudaError_t e;
   if (kcta == 2) {
-    if (a.geglu) e = launch_gemm2_t<2, kGegluTile, kGegluTile == 320 ? kStages_2_320 : kStages_2_160, true>(stream, grid_units * 2, mA0, mA1, mW, mO, mR, p);
+    if (a.geglu && kGegluSets == 2 && p.splits == 1 && gemm_two_sets())
+      e = launch_gemm2_t<2, kGegluTile, kStagesGeglu2, true, false, kGegluSets>(stream, grid_units * 2, mA0, mA1, mW, mO, mR, p);
+    else if (a.geglu) e = launch_gemm2_t<2, kGegluTile, kStagesGeglu2, true>(stream, grid_units * 2, mA0, mA1, mW, mO, mR, p);
     else if (a.xf_tab && kbn == 320) e = launch_gemm2_t<2, 320, kStages_2_320, false, true>(stream, grid_units * 2, mA0, mA1, mW, mO, mR, p);
     else if (a.xf_tab) e = launch_gemm2_t<2, 160, kStages_2_160, false, true>(stream, grid_units * 2, mA0, mA1, mW, mO, mR, p);
     else if (kbn == 320) e = launch_gemm2_t<2, 320, kStages_2_320, false>(stream, grid_units * 2, mA0, mA1, mW, mO, mR, p);
+    // 160-wide tiles without split-K: two epilogue sets (16 epilogue warps, two tiles' epilogues in flight); DG_GEMM_SETS=1: one
+    else if (p.splits == 1 && gemm_two_sets()) e = launch_gemm2_t<2, 160, kStages_2_160, false, false, 2>(stream, grid_units * 2, mA0, mA1, mW, mO, mR, p);
     else e = launch_gemm2_t<2, 160, kStages_2_160, false>(stream, grid_units * 2, mA0, mA1, mW, mO, mR, p);
   } else {
-    if (a.geglu) e = launch_gemm2_t<1, kGegluTile, kGegluTile == 320 ? kStages_1_320 : kStages_1_160, true>(stream, grid_units, mA0, mA1, mW, mO, mR, p);
+    if (a.geglu) e = launch_gemm2_t<1, kGegluTile, kStagesGeglu1, true>(stream, grid_units, mA0, mA1, mW, mO, mR, p);
     else if (kbn == 320) e = launch_gemm2_t<1, 320, kStages_1_320, false>(stream, grid_units, mA0, mA1, mW, mO, mR, p);
     else e = launch_gemm2_t<1, 160, kStages_1_160, false>(stream, grid_units, mA0, mA1, mW, mO, mR, p);
   }
@@ -496,10 +517,10 @@ inline int init_attn_attr() {
   DG_CUDA(cudaFuncSetAttribute(attn_tc_kernel<kD, kKV, kStages, 2, kSBuf, kQ, kSplit>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnCfg<kD, kKV, kStages, kSBuf, kQ, kSplit>::kSmem));
   return DG_OK;
 }
-template <int kCta, int kBN, int kStages, bool kGeglu, bool kXf = false>
+template <int kCta, int kBN, int kStages, bool kGeglu, bool kXf = false, int kSets = 1>
 inline int init_gemm_attr() {
-  DG_CUDA(cudaFuncSetAttribute(gemm2_kernel<kCta, kBN, kStages, kGeglu, kXf>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               Gemm2Cfg<kCta, kBN, kStages>::kTotal));
+  DG_CUDA(cudaFuncSetAttribute(gemm2_kernel<kCta, kBN, kStages, kGeglu, kXf, kSets>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               Gemm2Cfg<kCta, kBN, kStages, kSets>::kTotal));
   return DG_OK;
 }
 // Co-resident CTA pairs of the pair kernels (persistent grid size; every variant is one CTA per SM).
@@ -519,15 +540,15 @@ inline int query_max_pairs(int* out) {
 }
 inline int init_kernel_attributes() {
   DG_TRY((init_gemm_attr<1, 320, kStages_1_320, false>()));
-  DG_TRY((init_gemm_attr<1, 320, kStages_1_320, true>()));
   DG_TRY((init_gemm_attr<1, 160, kStages_1_160, false>()));
-  DG_TRY((init_gemm_attr<1, 160, kStages_1_160, true>()));
-  DG_TRY((init_gemm_attr<2, 160, kStages_2_160, true>()));
+  DG_TRY((init_gemm_attr<1, kGegluTile, kStagesGeglu1, true>()));
+  DG_TRY((init_gemm_attr<2, kGegluTile, kStagesGeglu2, true>()));
+  if constexpr (kGegluSets == 2) DG_TRY((init_gemm_attr<2, kGegluTile, kStagesGeglu2, true, false, kGegluSets>()));
   DG_TRY((init_gemm_attr<2, 320, kStages_2_320, false>()));
-  DG_TRY((init_gemm_attr<2, 320, kStages_2_320, true>()));
   DG_TRY((init_gemm_attr<2, 160, kStages_2_160, false>()));
   DG_TRY((init_gemm_attr<2, 320, kStages_2_320, false, true>()));
   DG_TRY((init_gemm_attr<2, 160, kStages_2_160, false, true>()));
+  DG_TRY((init_gemm_attr<2, 160, kStages_2_160, false, false, 2>()));
   DG_TRY((init_attn_attr<32, 128, 4>()));
   DG_TRY((init_attn_attr<40, 128, 4>()));
   DG_TRY((init_attn_attr<40, 64, 6, 2>()));
