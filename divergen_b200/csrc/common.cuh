@@ -65,20 +65,30 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
-// Long waits of single-thread roles (TMA producer, MMA issuer): the hardware parks the thread for up to the hinted time
-// instead of re-issuing try_wait -- a hot spin loop costs ~6 issue slots per probe on a scheduler it shares with math warps.
+// Long waits of single-thread roles (TMA producer, MMA issuer): the hardware may park the thread for up to the hinted time
+// (try_wait with a suspend-time hint compiles to SYNCS.PHASECHK.TRYWAIT + NANOSLEEP.SYNCS) instead of re-issuing try_wait -- a
+// hot spin loop costs ~6 issue slots per probe on a scheduler it shares with math warps.  DG_PARK_NS (compile time): the
+// hint in nanoseconds; 0 = plain spinning.  (Round 2: the wake-up of a parked thread is what paces short-K GEMMs, whose MMA
+// issuer is AHEAD of the data on every k-block -- see profiles/r02_ab.md.)
+#ifndef DG_PARK_NS
+#define DG_PARK_NS 10000000
+#endif
 __device__ __forceinline__ void mbar_wait_parked(uint64_t* bar, uint32_t parity) {
+#if DG_PARK_NS == 0
+  mbar_wait(bar, parity);
+#else
   uint32_t spins = 0;
   for (;;) {
     uint32_t ok;
     asm volatile(
         "{\n\t.reg .pred P;\n\tmbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, P;\n\t}\n"
         : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity), "r"(0x989680u)
+        : "r"(smem_u32(bar)), "r"(parity), "r"((uint32_t)DG_PARK_NS)
         : "memory");
     if (ok) return;
-    if (++spins > (1u << 22)) { __trap(); }
+    if (++spins > (1u << 26)) { __trap(); }
   }
+#endif
 }
 
 // Bulk (non-tensor) async copies: shared -> global reduction (fp32 add performed at L2, line granularity) and global -> shared load.

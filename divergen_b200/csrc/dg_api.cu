@@ -17,8 +17,9 @@ struct dg_ctx {
   GemmRes gemm;               // split-K workspace, tickets, persistent grid size
   int fuse_ln = 1;            // DG_FUSE_LN=0: stand-alone LayerNorm kernels instead of the folded GEMM epilogue
   int fuse_gn = 1;            // DG_FUSE_GN=0: stand-alone GroupNorm statistics kernels instead of epilogue sums
-  int fuse_xf = 1;            // DG_FUSE_XF=0: stand-alone GroupNorm-apply (+SiLU) pass instead of the transform inside the consuming conv;
+  int fuse_xf = 0;            // DG_FUSE_XF=0: stand-alone GroupNorm-apply (+SiLU) pass instead of the transform inside the consuming conv;
                               // 2: also the transformer's GroupNorm inside proj_in
+  int up_phases = 1;          // DG_UPCONV_PHASES=0: materialise the nearest-x2 tensor and run the 9-tap conv on it (round 1)
   __half* xf_tab = nullptr;   // scratch table for the stand-alone fused-GroupNorm operators (tests)
   size_t xf_tab_cap = 0;
 };
@@ -69,6 +70,7 @@ struct Slot {
   std::vector<int64_t> shape;  // expected PyTorch shape
   PackKind kind;
   __half* dst = nullptr;       // destination base
+  __half* dst2 = nullptr;      // PK_CONV3 of an upsampler: also the four phase matrices [4][O][4*I] (pack_upconv_kernel)
   int64_t row_off = 0;         // PK_ROWS: destination row offset (fused QKV / KV / time_emb_proj tables)
   int a = 0, b = 0;            // kind-specific dims
   bool set = false;
@@ -77,6 +79,7 @@ struct Slot {
 struct Norm { __half* g = nullptr; __half* b = nullptr; int c = 0; };
 struct Lin {
   __half* w = nullptr; __half* b = nullptr; int in = 0, out = 0; int rows = 0;
+  __half* wph = nullptr;       // upsampler convs: phase-decomposed weights [4][out][4*in] (see pack_upconv_kernel)
   // LayerNorm-folded copy (finalize_weights): wf = w * gamma, cs = row sums of wf, b32 = b + w . beta
   __half* wf = nullptr; float* cs = nullptr; float* b32 = nullptr;
 };
@@ -193,11 +196,15 @@ int make_linear(WeightStore* u, const std::string& pfx, int in, int out, bool bi
   }
   return DG_OK;
 }
-int make_conv3(WeightStore* u, const std::string& pfx, int in, int out, Lin* l) {
+int make_conv3(WeightStore* u, const std::string& pfx, int in, int out, Lin* l, bool upsampler = false) {
   l->in = in; l->out = out; l->rows = out;
   DG_TRY(dev_alloc(u, (void**)&l->w, (size_t)in * 9 * out * 2));
   DG_TRY(dev_alloc(u, (void**)&l->b, out * 2));
   add_slot(u, pfx + ".weight", {out, in, 3, 3}, PK_CONV3, l->w, 0, out, in);
+  if (upsampler) {
+    DG_TRY(dev_alloc(u, (void**)&l->wph, (size_t)16 * in * out * 2));
+    u->slots.back().dst2 = l->wph;
+  }
   add_slot(u, pfx + ".bias", {out}, PK_COPY, l->b);
   return DG_OK;
 }
@@ -296,7 +303,7 @@ int build_modules(dg_unet* u) {
       if (attn) DG_TRY(make_xf(u, pfx + ".attentions." + std::to_string(j), cout, cf.num_heads[3 - i], &b.xf[j]));
     }
     b.has_up = i != 3;
-    if (b.has_up) DG_TRY(make_conv3(u, pfx + ".upsamplers.0.conv", cout, cout, &b.up));
+    if (b.has_up) DG_TRY(make_conv3(u, pfx + ".upsamplers.0.conv", cout, cout, &b.up, true));
   }
   DG_TRY(make_norm(u, "conv_norm_out", ch[0], &u->norm_out));
   DG_TRY(make_conv3(u, "conv_out", ch[0], cf.out_channels, &u->conv_out));
@@ -375,11 +382,19 @@ struct Fwd {
                         u->cfg.norm_num_groups, eps, silu));
     return tab;
   }
+  // per-(sample, group) totals of one GroupNorm (two-step apply): a slice of the table arena
+  float* gt_alloc(int B_) {
+    const size_t nh = (size_t)B_ * u->cfg.norm_num_groups * 2 * 2;     // floats, counted in halves
+    if (u->xf_off + nh > u->xf_cap) return nullptr;
+    float* p = reinterpret_cast<float*>(u->xf_arena + u->xf_off);
+    u->xf_off += (nh + 7) & ~size_t(7);
+    return p;
+  }
   void gn(const T4& x0, const T4* x1, const Norm& n, float eps, int silu, T4& out) {
     if (!on(FAM_NORM)) return;
     if (fuse_gn() && x0.gst && (!x1 || x1->gst) && (x0.C + (x1 ? x1->C : 0)) / u->gn_blk <= 256)
       FW(launch_groupnorm_fused(s, sms, x0.p, x0.C, x0.gst, x1 ? x1->p : nullptr, x1 ? x1->C : 0, x1 ? x1->gst : nullptr,
-                                u->gn_blk, n.g, n.b, out.p, x0.B, x0.H * x0.W, u->cfg.norm_num_groups, eps, silu));
+                                u->gn_blk, n.g, n.b, out.p, x0.B, x0.H * x0.W, u->cfg.norm_num_groups, eps, silu, gt_alloc(x0.B)));
     else
       FW(launch_groupnorm(s, sms, x0.p, x0.C, x1 ? x1->p : nullptr, x1 ? x1->C : 0, n.g, n.b, out.p, u->gn_stats, x0.B,
                           x0.H * x0.W, u->cfg.norm_num_groups, eps, silu));
@@ -393,6 +408,19 @@ struct Fwd {
     a.n_out = w.out; a.bias = w.b; a.rowvec = rowvec; a.ld_rowvec = temb_ld; a.residual = residual; a.ld_res = w.out;
     a.out = out.p; a.ldo = w.out; a.gn_stats_out = out.gst; a.gn_blk = u->gn_blk;
     if (on(FAM_GEMM)) FW(launch_gemm(s, u->ctx->gemm, a));
+  }
+  // Upsample2D: nearest x2 + conv3x3 as four 2x2 phase convolutions on the low-resolution input (pack_upconv_kernel): 2.25x
+  // fewer multiply-adds than the 9-tap conv on the upsampled tensor, which is never materialised.  `out` is [B, 2H, 2W, N]; its
+  // fused GroupNorm sums (if allocated) are filled phase by phase (a quarter of each sample's slabs per launch).
+  void upconv(const T4& x, const Lin& w, T4& out) {
+    const bool stats = out.gst && gn_stats_supported(x.H * x.W, x.W, x.H, u->gn_blk, w.out);
+    if (!stats) out.gst = nullptr;              // the consumer falls back to the stand-alone statistics kernel
+    for (int ph = 0; ph < 4; ++ph) {
+      GemmArgs a; a.a0 = x.p; a.c0 = x.C; a.B = x.B; a.H = x.H; a.W = x.W; a.taps = 4; a.phase_y = ph >> 1; a.phase_x = ph & 1;
+      a.w = w.wph + (size_t)ph * w.out * 4 * w.in; a.n_w = w.rows; a.n_out = w.out; a.bias = w.b; a.out = out.p; a.ldo = w.out;
+      if (stats) { a.gn_stats_out = out.gst; a.gn_blk = u->gn_blk; a.gn_slot0 = ph * (x.H * x.W / 32); a.gn_slots = 4 * (x.H * x.W / 32); }
+      if (on(FAM_GEMM)) FW(launch_gemm(s, u->ctx->gemm, a));
+    }
   }
   struct LinOpt {
     const __half* residual = nullptr; int geglu = 0;
@@ -605,17 +633,23 @@ int run_forward(dg_unet* u, cudaStream_t s, const __half* sample, const __half* 
       x = y;
     }
     if (b.has_up) {
-      T4 upx = f.talloc(x.B, x.H * 2, x.W * 2, x.C);
       T4 y = f.talloc(x.B, x.H * 2, x.W * 2, x.C);
       if (f.err) break;
-      const size_t items = (size_t)x.B * 4 * x.H * x.W * (x.C / 8);
-      if (f.on(FAM_OTHER)) {
-        upsample2x_nhwc_kernel<<<grid_for(items, 256, sms), 256, 0, s>>>(x.p, upx.p, x.B, x.H, x.W, x.C);
-        DG_LAUNCH_CHECK();
-      }
       y.gst = f.gn_alloc(x.B, x.H * 2, x.W * 2, x.C, true);
-      f.conv3(upx, b.up, nullptr, nullptr, y);
-      f.free_(upx); f.free_(x);
+      if (u->ctx->up_phases && u->ctx->gemm.cta_mode != 1) {
+        f.upconv(x, b.up, y);
+      } else {
+        T4 upx = f.talloc(x.B, x.H * 2, x.W * 2, x.C);
+        if (f.err) break;
+        const size_t items = (size_t)x.B * 4 * x.H * x.W * (x.C / 8);
+        if (f.on(FAM_OTHER)) {
+          upsample2x_nhwc_kernel<<<grid_for(items, 256, sms), 256, 0, s>>>(x.p, upx.p, x.B, x.H, x.W, x.C);
+          DG_LAUNCH_CHECK();
+        }
+        f.conv3(upx, b.up, nullptr, nullptr, y);
+        f.free_(upx);
+      }
+      f.free_(x);
       x = y;
     }
   }
@@ -852,7 +886,7 @@ int build_vae(dg_vae* v) {
     const std::string pfx = "decoder.up_blocks." + std::to_string(i);
     for (int j = 0; j <= v->layers; ++j) DG_TRY(make_vres(v, pfx + ".resnets." + std::to_string(j), j == 0 ? cin : cout, cout, &u.res[j]));
     u.has_up = i != 3;
-    if (u.has_up) DG_TRY(make_conv3(v, pfx + ".upsamplers.0.conv", cout, cout, &u.up));
+    if (u.has_up) DG_TRY(make_conv3(v, pfx + ".upsamplers.0.conv", cout, cout, &u.up, true));
     cin = cout;
   }
   DG_TRY(make_norm(v, "decoder.conv_norm_out", ch[0], &v->norm_out));
@@ -1091,7 +1125,10 @@ int32_t dg_ctx_create(int32_t device, dg_ctx** out) {
   if (env_int("DG_SPLITK", 1) == 0) { cudaFree(c->gemm.ws); c->gemm.ws = nullptr; }
   c->fuse_ln = env_int("DG_FUSE_LN", 1);
   c->fuse_gn = env_int("DG_FUSE_GN", 1);
-  c->fuse_xf = env_int("DG_FUSE_XF", 1);
+  // off by default: measured SLOWER (13.2 vs 9.7 ms per forward, profiles/r02_ab.md) -- the activation is re-evaluated for
+  // each of the 9 taps and one MUFU.TANH per element (512 cycles per k-block per SM) does not fit under the MMA time
+  c->fuse_xf = env_int("DG_FUSE_XF", 0);
+  c->up_phases = env_int("DG_UPCONV_PHASES", 1);
   *out = c;
   return DG_OK;
 }
@@ -1178,6 +1215,10 @@ static int store_set_weight(WeightStore* u, const char* key, const void* src, in
     case PK_CONV3:
       pack_conv3x3_kernel<<<grid_for(n, 256, sms), 256>>>(w, s.dst, s.a, s.b, s.b);
       DG_LAUNCH_CHECK();
+      if (s.dst2) {
+        pack_upconv_kernel<<<grid_for((size_t)16 * s.a * s.b, 256, sms), 256>>>(w, s.dst2, s.a, s.b);
+        DG_LAUNCH_CHECK();
+      }
       break;
     case PK_CONV_IN:
       pack_conv_in_kernel<<<grid_for((size_t)s.a * 64, 256, sms), 256>>>(w, s.dst, s.a, s.b, 64);
@@ -1484,6 +1525,24 @@ int32_t dg_op_conv3x3_gn(dg_ctx* ctx, const void* x0, int32_t C0, const float* s
   a.out = (__half*)out; a.ldo = ldo; a.xf_tab = ctx->xf_tab; a.xf_silu = silu;
   return launch_gemm(s, ctx->gemm, a);
 }
+int32_t dg_op_upsample_conv3x3(dg_ctx* ctx, const void* x, int32_t C, const void* w_oihw, const void* bias, void* out, int32_t B, int32_t H,
+                               int32_t Wd, int32_t N, float* gn_stats_out, int32_t gn_blk, void* stream) {
+  if (!ctx || !x || !w_oihw || !out) return fail(DG_E_ARG, "null argument");
+  cudaStream_t s = (cudaStream_t)stream;
+  __half* wph = nullptr;
+  DG_CUDA(cudaMalloc((void**)&wph, (size_t)16 * C * N * 2));
+  pack_upconv_kernel<<<grid_for((size_t)16 * C * N, 256, ctx->num_sms), 256, 0, s>>>((const __half*)w_oihw, wph, N, C);
+  int r = DG_OK;
+  for (int ph = 0; ph < 4 && r == DG_OK; ++ph) {
+    GemmArgs a; a.a0 = (const __half*)x; a.c0 = C; a.B = B; a.H = H; a.W = Wd; a.taps = 4; a.phase_y = ph >> 1; a.phase_x = ph & 1;
+    a.w = wph + (size_t)ph * N * 4 * C; a.n_w = N; a.n_out = N; a.bias = (const __half*)bias; a.out = (__half*)out; a.ldo = N;
+    if (gn_stats_out) { a.gn_stats_out = gn_stats_out; a.gn_blk = gn_blk; a.gn_slot0 = ph * (H * Wd / 32); a.gn_slots = 4 * (H * Wd / 32); }
+    r = launch_gemm(s, ctx->gemm, a);
+  }
+  cudaStreamSynchronize(s);
+  cudaFree(wph);
+  return r;
+}
 int32_t dg_op_attention(dg_ctx* ctx, const void* q, int32_t ldq, const void* k, int32_t ldk, const void* v, int32_t ldv, void* out,
                         int32_t B, int32_t heads, int32_t Sq, int32_t Sk, int32_t d, void* stream) {
   if (!ctx || !q || !k || !v || !out) return fail(DG_E_ARG, "null argument");
@@ -1602,13 +1661,24 @@ int32_t dg_vae_decode(dg_vae* v, const void* latents, float scale, void* out, in
     VUp& u = v->up[i];
     for (size_t j = 0; j < u.res.size() && !f.err; ++j) x = f.resnet(u.res[j], x);
     if (u.has_up && !f.err) {
-      T4 upx = f.talloc(x.B, x.H * 2, x.W * 2, x.C);
       T4 y = f.talloc(x.B, x.H * 2, x.W * 2, x.C);
       if (f.err) break;
-      upsample2x_nhwc_kernel<<<grid_for((size_t)x.B * 4 * x.H * x.W * (x.C / 8), 256, sms), 256, 0, s>>>(x.p, upx.p, x.B, x.H, x.W, x.C);
-      DG_LAUNCH_CHECK();
-      f.conv3(upx, u.up, nullptr, y);
-      f.free_(upx); f.free_(x);
+      if (v->ctx->up_phases && v->ctx->gemm.cta_mode != 1) {
+        // nearest x2 + conv3x3 as four 2x2 phase convolutions on the low-resolution tensor (see Fwd::upconv)
+        for (int ph = 0; ph < 4 && !f.err; ++ph) {
+          GemmArgs a; a.a0 = x.p; a.c0 = x.C; a.B = x.B; a.H = x.H; a.W = x.W; a.taps = 4; a.phase_y = ph >> 1; a.phase_x = ph & 1;
+          a.w = u.up.wph + (size_t)ph * u.up.out * 4 * u.up.in; a.n_w = u.up.rows; a.n_out = u.up.out; a.bias = u.up.b; a.out = y.p; a.ldo = u.up.out;
+          f.err = launch_gemm(s, v->ctx->gemm, a);
+        }
+      } else {
+        T4 upx = f.talloc(x.B, x.H * 2, x.W * 2, x.C);
+        if (f.err) break;
+        upsample2x_nhwc_kernel<<<grid_for((size_t)x.B * 4 * x.H * x.W * (x.C / 8), 256, sms), 256, 0, s>>>(x.p, upx.p, x.B, x.H, x.W, x.C);
+        DG_LAUNCH_CHECK();
+        f.conv3(upx, u.up, nullptr, y);
+        f.free_(upx);
+      }
+      f.free_(x);
       x = y;
     }
   }

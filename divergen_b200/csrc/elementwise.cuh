@@ -126,6 +126,8 @@ __global__ void gn_apply_kernel(const __half* __restrict__ x0, int C0, const __h
   const int p1 = min(HW, p0 + pix_per_block);
   const float inv_n = 1.0f / ((float)cpg * (float)HW);
   const GnThreadMap tm(nvec);
+  griddep_launch();
+  griddep_wait();            // (returns at once when the kernel was not launched as a programmatic dependent)
   for (int v = tm.v0; v < nvec; v += tm.vstep) {
     const int c = v * 8;
     float sc[8], sf[8], g[8], be[8];
@@ -253,6 +255,42 @@ __global__ void gn_apply_blk_kernel(const __half* __restrict__ x0, int C0, const
       }
       store8(out + pix * C + c, f);
     }
+  }
+}
+
+// Fold of the producers' block sums into per-(sample, group) totals {sum, sumsq} -- the input of gn_apply_kernel.  One CTA per
+// sample (B x slots x nb float2 read ONCE, instead of once per apply CTA as gn_apply_blk_kernel does); fixed order.
+__global__ void gn_fold_groups_kernel(int C0, int C1, int groups, const float* __restrict__ stats0, const float* __restrict__ stats1,
+                                      int blk, int slots, float* __restrict__ out) {
+  __shared__ float2 s_col[8][256];
+  griddep_launch();
+  const int C = C0 + C1, cpg = C / groups;
+  const int b = blockIdx.x;
+  const int nb0 = C0 / blk, nb1 = C1 / blk, nb = nb0 + nb1, bpg = cpg / blk;
+  const int ncol = min(nb, 256);
+  const int nstripe = max(1, min(8, 256 / ncol));
+  const int stripe = threadIdx.x / ncol;
+  griddep_wait();
+  if (stripe < nstripe) {
+    const int cb = threadIdx.x % ncol;
+    const float2* src = (cb < nb0) ? reinterpret_cast<const float2*>(stats0) + (size_t)b * slots * nb0 + cb
+                                   : reinterpret_cast<const float2*>(stats1) + (size_t)b * slots * nb1 + (cb - nb0);
+    const int ld = (cb < nb0) ? nb0 : nb1;
+    float a = 0.f, q = 0.f;
+#pragma unroll 8
+    for (int sl = stripe; sl < slots; sl += nstripe) { const float2 v = __ldg(src + (size_t)sl * ld); a += v.x; q += v.y; }
+    s_col[stripe][cb] = make_float2(a, q);
+  }
+  __syncthreads();
+  if ((int)threadIdx.x < groups) {
+    const int g = threadIdx.x;
+    float a = 0.f, q = 0.f;
+    for (int i = 0; i < bpg; ++i) {
+      const int cb = g * bpg + i;
+      for (int st = 0; st < nstripe; ++st) { a += s_col[st][cb].x; q += s_col[st][cb].y; }
+    }
+    out[((size_t)b * groups + g) * 2] = a;
+    out[((size_t)b * groups + g) * 2 + 1] = q;
   }
 }
 
@@ -553,6 +591,31 @@ __global__ void pack_conv3x3_kernel(const __half* __restrict__ w, __half* __rest
   }
 }
 // conv_in: OIHW [O, I, 3, 3] -> [O, Kpad] with k = tap*I + c.
+// Nearest-x2 upsampling followed by a 3x3 convolution (diffusers Upsample2D) as four 2x2 convolutions on the LOW-resolution
+// tensor, one per output phase (py, px) = parity of the output pixel: the 3 kernel rows that touch output row 2y + py read only
+// two distinct input rows (py = 0: {y-1: ky 0; y: ky 1, 2}; py = 1: {y: ky 0, 1; y+1: ky 2}), likewise along x, so their
+// weights can be summed beforehand -- 16 C N instead of 36 C N multiply-adds per low-resolution pixel, and the upsampled
+// tensor is never written.  out[ph][n][(ty*2 + tx) * I + c] = sum_{ky in S(py,ty)} sum_{kx in S(px,tx)} w[n][c][ky][kx]
+// (fp32 sum, rounded once to fp16), ph = py*2 + px.
+__global__ void pack_upconv_kernel(const __half* __restrict__ w, __half* __restrict__ out, int O, int I) {
+  const size_t total = (size_t)4 * O * 4 * I;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % I);
+    size_t r = i / I;
+    const int tap = (int)(r % 4); r /= 4;
+    const int n = (int)(r % O);
+    const int ph = (int)(r / O);
+    const int py = ph >> 1, px = ph & 1, ty = tap >> 1, tx = tap & 1;
+    // S(0,0) = {0}, S(0,1) = {1,2}, S(1,0) = {0,1}, S(1,1) = {2}
+    const int ky0 = (py == 0) ? (ty == 0 ? 0 : 1) : (ty == 0 ? 0 : 2), ky1 = (py == 0) ? (ty == 0 ? 0 : 2) : (ty == 0 ? 1 : 2);
+    const int kx0 = (px == 0) ? (tx == 0 ? 0 : 1) : (tx == 0 ? 0 : 2), kx1 = (px == 0) ? (tx == 0 ? 0 : 2) : (tx == 0 ? 1 : 2);
+    float acc = 0.f;
+    for (int ky = ky0; ky <= ky1; ++ky)
+      for (int kx = kx0; kx <= kx1; ++kx) acc += __half2float(w[(((size_t)n * I + c) * 3 + ky) * 3 + kx]);
+    out[i] = __float2half_rn(acc);
+  }
+}
+
 __global__ void pack_conv_in_kernel(const __half* __restrict__ w, __half* __restrict__ out, int O, int I, int Kpad) {
   const size_t total = (size_t)O * Kpad;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {

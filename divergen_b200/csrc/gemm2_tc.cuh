@@ -62,7 +62,10 @@ struct Gemm2Params {
   // problem
   int n_out;        // valid output columns (after GEGLU halving if enabled)
   int n_gemm;       // rows of Wt that are meaningful
-  int taps;         // 1 or 9
+  int taps;         // 1, 9 (3x3: tap offsets -1..1) or 4 (2x2 phase of an upsample conv: offsets tap_x0 + {0,1}, tap_y0 + {0,1})
+  int tap_x0, tap_y0;
+  int out_mul, out_ox, out_oy;   // output pixel of box pixel (x, y): (x * out_mul + out_ox, y * out_mul + out_oy) -- 2 / phase for taps == 4
+  int gn_slot0;     // first GroupNorm slab of this launch within a sample's gn_slots (taps == 4: phase * slabs per phase)
   int kb0, kb1;     // 64-channel k-blocks taken from source 0 / source 1 per tap
   int splits;       // K splits per tile (>= 1)
   // M tiling (pixels)
@@ -454,9 +457,10 @@ gemm2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
         int kb = t.kb_begin - tap * kb_per_tap;
         const int wrow = t.nt * kBN + cta_rank * S::kBRows;
         for (int kbi = t.kb_begin; kbi < t.kb_end; ++kbi) {
-          const int dx = (p.taps == 9) ? (tap % 3 - 1) : 0;
-          const int dy = (p.taps == 9) ? (tap / 3 - 1) : 0;
+          const int dx = (p.taps == 9) ? (tap % 3 - 1) : (p.taps == 4) ? (tap & 1) + p.tap_x0 : 0;
+          const int dy = (p.taps == 9) ? (tap / 3 - 1) : (p.taps == 4) ? (tap >> 1) + p.tap_y0 : 0;
           mbar_wait_parked(&empty[stage], phase ^ 1);
+          if (kbi == t.kb_begin && uk < 4) DG_STAMP(32 + uk);            // tile uk: its first operand stage is free, loads go out
           uint8_t* sa = smem + stage * S::kStageBytes;
           uint8_t* sb = sa + S::kABytes;
           if constexpr (kXf) {
@@ -512,6 +516,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
             }
             umma_commit_pair<kCta>(&empty[stage]);
             if (kbi == kb_end - 1) umma_commit_pair<kCta>(&acc_full[as]);
+            if (kbi == kb_end - 1 && uk < 4) DG_STAMP(36 + uk);         // tile uk: last MMA issued
           }
           __syncwarp();
           if (++stage == kStages) { stage = 0; phase ^= 1; }
@@ -546,7 +551,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
       for (uint32_t c = 0;; ++c) {
         const uint32_t buf = c % S::kRing;
         mbar_wait_parked(&chunk_ready[buf], (c / S::kRing) & 1);
-        const int col = chunk_info[buf * 5 + 0], x0 = chunk_info[buf * 5 + 1], y0 = chunk_info[buf * 5 + 2];
+        const int col = chunk_info[buf * 5 + 0];
+        const int x0 = chunk_info[buf * 5 + 1] * p.out_mul + p.out_ox, y0 = chunk_info[buf * 5 + 2] * p.out_mul + p.out_oy;   // (strided map for taps == 4)
         const int b0 = chunk_info[buf * 5 + 3], flags = chunk_info[buf * 5 + 4];
         if (flags & 2) break;
         if (flags & 1) {
@@ -567,7 +573,9 @@ gemm2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
         mbar_arrive(&buf_free[(buf + kFreeAhead) % S::kRing]);     // ... which chunk c + kFreeAhead uses (whole-tile: its own)
       }
       DG_STAMP(10);                     // stop seen by the store warp
-      tma_store_wait_all();
+      // only the shared-memory reads of the last stores must be over before the CTA tears down; the writes themselves
+      // complete with the grid (the dependent kernel's griddepcontrol.wait covers them)
+      tma_store_wait_read<0>();
       DG_STAMP(11);                     // all stores complete
     }
   }
@@ -617,8 +625,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
         int kb = t.kb_begin - tap * kb_per_tap;
         const int b_tile = plain ? (p.hw > 0 ? t.x0 / p.hw : 0) : t.b0;
         for (int kbi = t.kb_begin; kbi < t.kb_end; ++kbi) {
-          const int dx = (p.taps == 9) ? (tap % 3 - 1) : 0;
-          const int dy = (p.taps == 9) ? (tap / 3 - 1) : 0;
+          const int dx = (p.taps == 9) ? (tap % 3 - 1) : (p.taps == 4) ? (tap & 1) + p.tap_x0 : 0;
+          const int dy = (p.taps == 9) ? (tap / 3 - 1) : (p.taps == 4) ? (tap >> 1) + p.tap_y0 : 0;
           uint4 tm = make_uint4(0, 0, 0, 0), ts = tm, tf = tm;
           if (p.xf_one) {                            // (mean_h, scale', shift') of this thread's 8 channels: in flight during the wait
             const __half* tp = tabc + (size_t)b_tile * 3 * plane + kb * 64;
@@ -628,33 +636,37 @@ gemm2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
           }
           mbar_wait(&a_full[xstage], xphase);
           const uint32_t sa = smem_u32(smem) + (uint32_t)xstage * S::kStageBytes + xoff;
+          // all four rows are loaded before any is rewritten (the shared-memory round trips overlap instead of chaining)
+          bool ok[4];
+          uint4 v[4];
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             const int row = xrow0 + 32 * i;
-            bool ok;
-            int bb;
             if (plain) {
-              const int gr = t.x0 + row;
-              ok = t.valid_m && gr < p.W;
-              bb = (!p.xf_one && p.hw > 0) ? gr / p.hw : b_tile;
+              ok[i] = t.valid_m && t.x0 + row < p.W;
             } else {
               const int xx = t.x0 + (row & (p.bw - 1)) + dx, yy = t.y0 + ((row >> p.bw_log2) & (p.bh - 1)) + dy;
-              bb = t.b0 + (row >> (p.bw_log2 + p.bh_log2));
-              ok = t.valid_m && (unsigned)xx < (unsigned)p.W && (unsigned)yy < (unsigned)p.H && bb < p.B;
+              ok[i] = t.valid_m && (unsigned)xx < (unsigned)p.W && (unsigned)yy < (unsigned)p.H && t.b0 + (row >> (p.bw_log2 + p.bh_log2)) < p.B;
             }
-            if (ok) {
-              if (!p.xf_one) {
-                const __half* tp = tabc + (size_t)bb * 3 * plane + kb * 64;
-                tm = __ldg(reinterpret_cast<const uint4*>(tp));
-                ts = __ldg(reinterpret_cast<const uint4*>(tp + plane));
-                tf = __ldg(reinterpret_cast<const uint4*>(tp + 2 * plane));
-              }
-              const uint32_t a_ = sa + (uint32_t)i * 4096u;
-              const uint4 v = lds_u4(a_);
-              sts_u4(a_, xf_half2(v.x, tm.x, ts.x, tf.x, p.xf_silu), xf_half2(v.y, tm.y, ts.y, tf.y, p.xf_silu),
-                     xf_half2(v.z, tm.z, ts.z, tf.z, p.xf_silu), xf_half2(v.w, tm.w, ts.w, tf.w, p.xf_silu));
-            }
+            v[i] = make_uint4(0, 0, 0, 0);
+            if (ok[i]) v[i] = lds_u4(sa + (uint32_t)i * 4096u);
           }
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            if (!p.xf_one && ok[i]) {                // rows of several samples in one tile: this row's own table entries
+              const int row = xrow0 + 32 * i;
+              const int bb = plain ? (p.hw > 0 ? (t.x0 + row) / p.hw : 0) : t.b0 + (row >> (p.bw_log2 + p.bh_log2));
+              const __half* tp = tabc + (size_t)bb * 3 * plane + kb * 64;
+              tm = __ldg(reinterpret_cast<const uint4*>(tp));
+              ts = __ldg(reinterpret_cast<const uint4*>(tp + plane));
+              tf = __ldg(reinterpret_cast<const uint4*>(tp + 2 * plane));
+            }
+            v[i].x = xf_half2(v[i].x, tm.x, ts.x, tf.x, p.xf_silu); v[i].y = xf_half2(v[i].y, tm.y, ts.y, tf.y, p.xf_silu);
+            v[i].z = xf_half2(v[i].z, tm.z, ts.z, tf.z, p.xf_silu); v[i].w = xf_half2(v[i].w, tm.w, ts.w, tf.w, p.xf_silu);
+          }
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            if (ok[i]) sts_u4(sa + (uint32_t)i * 4096u, v[i].x, v[i].y, v[i].z, v[i].w);
           fence_proxy_async();                       // the rewritten tile is visible to the tensor core's (async-proxy) reads
           __syncwarp();
           if (lane == 0) {
@@ -845,7 +857,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
           const int r0 = q * 32;        // first row of this warp within the tile
           int slab;
           if (p.taps == 1 && p.H == 1 && p.B == 1) slab = (int)(((size_t)t.x0 + r0) % p.hw) >> 5;
-          else slab = (((t.y0 / p.bh) * p.tiles_x + t.x0 / p.bw) * box_xy + r0 % box_xy) >> 5;
+          else slab = p.gn_slot0 + ((((t.y0 / p.bh) * p.tiles_x + t.x0 / p.bw) * box_xy + r0 % box_xy) >> 5);
           const int b_w = __shfl_sync(0xffffffffu, bb, 0);
           const bool ok_w = __shfl_sync(0xffffffffu, row_ok ? 1 : 0, 0) != 0;
           if (ok_w) gn_dst = reinterpret_cast<float2*>(p.gn_stats_out) + ((size_t)b_w * p.gn_slots + slab) * p.gn_nblk;

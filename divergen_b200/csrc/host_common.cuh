@@ -126,14 +126,16 @@ inline PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
 
 // rank-4 fp16 map, 128-byte swizzle, zero OOB fill.  dims/box innermost first; strides (bytes) for dims 1..3.
 inline int make_map_4d(CUtensorMap* m, const void* ptr, const uint64_t dims[4], const uint64_t strides[3],
-                       const uint32_t box[4], bool weights = false, bool swizzle64 = false) {
+                       const uint32_t box[4], bool weights = false, bool swizzle64 = false, uint32_t pixel_stride = 1) {
   (void)weights;
   auto fn = get_encode_fn();
   if (!fn) return fail(DG_E_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
   cuuint64_t gd[4] = {dims[0], dims[1], dims[2], dims[3]};
   cuuint64_t gs[3] = {strides[0], strides[1], strides[2]};
-  cuuint32_t bx[4] = {box[0], box[1], box[2], box[3]};
-  cuuint32_t es[4] = {1, 1, 1, 1};
+  // pixel_stride 2: the box takes every second pixel along W and H (boxDim counts the span in the tensor, the tile in shared
+  // memory is box[1] x box[2] pixels) -- the output map of one phase of an upsample convolution
+  cuuint32_t bx[4] = {box[0], box[1] * pixel_stride, box[2] * pixel_stride, box[3]};
+  cuuint32_t es[4] = {1, pixel_stride, pixel_stride, 1};
   CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(ptr), gd, gs, bx, es,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
                   weights ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -208,7 +210,9 @@ struct GemmArgs {
   const __half* a0 = nullptr; int c0 = 0;  // source 0: NHWC [B,H,W,c0]
   const __half* a1 = nullptr; int c1 = 0;  // optional source 1 (channel concat)
   int B = 1, H = 1, W = 1;                 // plain GEMM: B = H = 1, W = M
-  int taps = 1;                            // 1 (Linear / 1x1) or 9 (3x3, stride 1, pad 1)
+  int taps = 1;                            // 1 (Linear / 1x1), 9 (3x3, stride 1, pad 1) or 4 (one 2x2 phase of nearest-x2 + conv3x3)
+  int phase_x = 0, phase_y = 0;            // taps == 4: output pixels (2x + phase_x, 2y + phase_y) of a [B, 2H, 2W, n_out] tensor
+  int gn_slot0 = 0, gn_slots = 0;          // taps == 4: this phase's first GroupNorm slab / slabs per sample of the whole output
   int hw = 0;                              // plain GEMM: rows per sample (needed for gn_stats)
   const __half* w = nullptr;               // packed [n_w, taps*(c0+c1)]
   int n_w = 0;                             // rows of w
@@ -272,11 +276,16 @@ inline int choose_splits(int units, int num_kb, int slots, size_t ws_floats_per_
   return best;
 }
 
-inline bool gemm_two_sets() {
+// Two epilogue sets (gemm2_kernel<..., kSets = 2>) pay off only when a CTA works through many tiles: measured per shape
+// (profiles/r02_ab.md) 32768x960x320 41.0 -> 36.0 us, GEGLU 32768x2560x320 89.7 -> 82.7, 8192x5120x640 57.7 -> 52.4, but
+// +1..2 us on every launch with <= 4 tiles per CTA (640-thread CTAs, 112-register epilogue, idle second set).
+// DG_GEMM_SETS=2: whenever the kernel allows it; default (and 1): never.
+inline bool gemm_two_sets(int total_units, int slots) {
   static int v = -1;
-  if (v < 0) { const char* e = getenv("DG_GEMM_SETS"); v = (e && e[0] == '1') ? 0 : 1; }
-  return v == 1;
-}
+  if (v < 0) { const char* e = getenv("DG_GEMM_SETS"); v = (e && e[0]) ? atoi(e) : 0; }
+  (void)total_units; (void)slots;
+  return v == 2;        // default: one set -- on the whole forward the selective rule (>= 6 tiles per CTA) measured 9.58-9.68 ms
+}                       // against 9.53-9.58 ms with one set everywhere (same box, three alternations)
 
 template <int kCta, int kBN, int kStages, bool kGeglu, bool kXf = false, int kSets = 1>
 inline cudaError_t launch_gemm2_t(cudaStream_t stream, int grid_ctas, const CUtensorMap& mA0, const CUtensorMap& mA1,
@@ -288,7 +297,8 @@ inline cudaError_t launch_gemm2_t(cudaStream_t stream, int grid_ctas, const CUte
 
 inline int launch_gemm(cudaStream_t stream, const GemmRes& res, const GemmArgs& a) {
   if (a.c0 % 64 || a.c1 % 64 || a.c0 <= 0) return fail(DG_E_SHAPE, "gemm: channel counts must be multiples of 64 (%d,%d)", a.c0, a.c1);
-  if (a.taps != 1 && a.taps != 9) return fail(DG_E_ARG, "gemm: taps must be 1 or 9");
+  if (a.taps != 1 && a.taps != 9 && a.taps != 4) return fail(DG_E_ARG, "gemm: taps must be 1, 9 or 4");
+  if (a.taps == 4 && (a.residual || a.rowvec || a.xf_tab || a.geglu)) return fail(DG_E_ARG, "gemm: an upsample phase takes bias / GroupNorm sums only");
   if ((reinterpret_cast<uintptr_t>(a.a0) | reinterpret_cast<uintptr_t>(a.w) | reinterpret_cast<uintptr_t>(a.out) |
        reinterpret_cast<uintptr_t>(a.residual) | reinterpret_cast<uintptr_t>(a.a1) | reinterpret_cast<uintptr_t>(a.rowvec)) & 15)
     return fail(DG_E_ARG, "gemm: pointers must be 16-byte aligned");
@@ -298,8 +308,8 @@ inline int launch_gemm(cudaStream_t stream, const GemmRes& res, const GemmArgs& 
   if (a.colsum && (!a.ln_stats || !a.bias32 || a.ln_c <= 0)) return fail(DG_E_ARG, "gemm: LayerNorm fold needs ln_stats, bias32 and ln_c");
   if (a.row_stats_out && a.taps != 1) return fail(DG_E_ARG, "gemm: row statistics are produced by plain GEMMs only");
   if (a.xf_tab && (a.geglu || res.cta_mode == 1)) return fail(DG_E_ARG, "gemm: the fused GroupNorm transform is built for CTA-pair, non-GEGLU tiles");
-  if (a.gn_stats_out && !gn_stats_supported(a.taps == 1 ? (a.hw > 0 ? a.hw : a.H * a.W) : a.H * a.W, a.taps == 9 ? a.W : 0,
-                                            a.taps == 9 ? a.H : 0, a.gn_blk, a.n_out))
+  if (a.gn_stats_out && !gn_stats_supported(a.taps == 1 ? (a.hw > 0 ? a.hw : a.H * a.W) : a.H * a.W, a.taps != 1 ? a.W : 0,
+                                            a.taps != 1 ? a.H : 0, a.gn_blk, a.n_out))
     return fail(DG_E_SHAPE, "gemm: fused GroupNorm statistics unsupported for this shape (hw %d, blk %d, n_out %d)", a.H * a.W, a.gn_blk, a.n_out);
   const int kcta = res.cta_mode == 1 ? 1 : 2;
   Gemm2Params p{};
@@ -344,6 +354,11 @@ inline int launch_gemm(cudaStream_t stream, const GemmRes& res, const GemmArgs& 
   p.row_stats_out = a.row_stats_out; p.row_parts = 2 * p.tiles_n;
   p.gn_stats_out = a.gn_stats_out; p.gn_blk = a.gn_blk; p.gn_nblk = a.gn_blk > 0 ? a.n_out / a.gn_blk : 0;
   p.gn_slots = (a.taps == 1 ? (a.hw > 0 ? a.hw : a.H * a.W) : a.H * a.W) / 32;
+  p.gn_slot0 = 0; p.tap_x0 = p.tap_y0 = 0; p.out_mul = 1; p.out_ox = p.out_oy = 0;
+  if (a.taps == 4) {
+    p.tap_x0 = a.phase_x - 1; p.tap_y0 = a.phase_y - 1; p.out_mul = 2; p.out_ox = a.phase_x; p.out_oy = a.phase_y;
+    if (a.gn_stats_out) { p.gn_slot0 = a.gn_slot0; p.gn_slots = a.gn_slots; }
+  }
   p.ws = res.ws; p.tickets = res.tickets;
   p.xf_tab = a.xf_tab; p.xf_c = a.c0 + a.c1; p.xf_silu = a.xf_silu;
   p.xf_one = (a.taps == 1) ? (p.hw > 0 && p.hw % 128 == 0) : (p.bn == 1);
@@ -378,10 +393,11 @@ inline int launch_gemm(cudaStream_t stream, const GemmRes& res, const GemmArgs& 
     const uint64_t ktot = (uint64_t)a.taps * (a.c0 + a.c1);
     DG_TRY(make_map_2d(&mW, a.w, ktot, (uint64_t)a.n_w, ktot * 2, 64, (kbn == 256 ? 128 : 160) / kcta));   // one accumulator's rows per CTA
     // output tiles: {n_out, W, H, B} boxes of 32 columns x 128 pixels, 64-byte swizzle in smem
-    uint64_t od[4] = {(uint64_t)a.n_out, (uint64_t)W, (uint64_t)H, (uint64_t)B};
-    uint64_t os[3] = {(uint64_t)a.ldo * 2, (uint64_t)W * a.ldo * 2, (uint64_t)H * W * a.ldo * 2};
+    const uint64_t om = a.taps == 4 ? 2 : 1;      // an upsample phase scatters into the [B, 2H, 2W, n_out] output
+    uint64_t od[4] = {(uint64_t)a.n_out, (uint64_t)W * om, (uint64_t)H * om, (uint64_t)B};
+    uint64_t os[3] = {(uint64_t)a.ldo * 2, (uint64_t)W * om * a.ldo * 2, (uint64_t)H * om * W * om * a.ldo * 2};
     uint32_t obox[4] = {32, (uint32_t)p.bw, (uint32_t)p.bh, (uint32_t)p.bn};
-    DG_TRY(make_map_4d(&mO, a.out, od, os, obox, false, true));
+    DG_TRY(make_map_4d(&mO, a.out, od, os, obox, false, true, (uint32_t)om));
     if (a.residual) {     // same boxes over the residual tensor: the TMA load lands where the TMA store will read
       uint64_t rs[3] = {(uint64_t)a.ld_res * 2, (uint64_t)W * a.ld_res * 2, (uint64_t)H * W * a.ld_res * 2};
       DG_TRY(make_map_4d(&mR, a.residual, od, rs, obox, false, true));
@@ -412,14 +428,14 @@ inline int launch_gemm(cudaStream_t stream, const GemmRes& res, const GemmArgs& 
   if (dbg_on) { cudaMemsetAsync(dbg_dev, 0, 40 * 8, stream); p.dbg = dbg_dev; }
   cudaError_t e;
   if (kcta == 2) {
-    if (a.geglu && kGegluSets == 2 && p.splits == 1 && gemm_two_sets())
+    if (a.geglu && kGegluSets == 2 && p.splits == 1 && gemm_two_sets(total_units, slots))
       e = launch_gemm2_t<2, kGegluTile, kStagesGeglu2, true, false, kGegluSets>(stream, grid_units * 2, mA0, mA1, mW, mO, mR, p);
     else if (a.geglu) e = launch_gemm2_t<2, kGegluTile, kStagesGeglu2, true>(stream, grid_units * 2, mA0, mA1, mW, mO, mR, p);
     else if (a.xf_tab && kbn == 320) e = launch_gemm2_t<2, 320, kStages_2_320, false, true>(stream, grid_units * 2, mA0, mA1, mW, mO, mR, p);
     else if (a.xf_tab) e = launch_gemm2_t<2, 160, kStages_2_160, false, true>(stream, grid_units * 2, mA0, mA1, mW, mO, mR, p);
     else if (kbn == 320) e = launch_gemm2_t<2, 320, kStages_2_320, false>(stream, grid_units * 2, mA0, mA1, mW, mO, mR, p);
-    // 160-wide tiles without split-K: two epilogue sets (16 epilogue warps, two tiles' epilogues in flight); DG_GEMM_SETS=1: one
-    else if (p.splits == 1 && gemm_two_sets()) e = launch_gemm2_t<2, 160, kStages_2_160, false, false, 2>(stream, grid_units * 2, mA0, mA1, mW, mO, mR, p);
+    // 160-wide tiles without split-K, many tiles per CTA: two epilogue sets (16 epilogue warps, two tiles' epilogues in flight)
+    else if (p.splits == 1 && gemm_two_sets(total_units, slots)) e = launch_gemm2_t<2, 160, kStages_2_160, false, false, 2>(stream, grid_units * 2, mA0, mA1, mW, mO, mR, p);
     else e = launch_gemm2_t<2, 160, kStages_2_160, false>(stream, grid_units * 2, mA0, mA1, mW, mO, mR, p);
   } else {
     if (a.geglu) e = launch_gemm2_t<1, kGegluTile, kStagesGeglu1, true>(stream, grid_units, mA0, mA1, mW, mO, mR, p);
@@ -438,6 +454,10 @@ inline int launch_gemm(cudaStream_t stream, const GemmRes& res, const GemmArgs& 
     fprintf(stderr, " | units (acc, handed):");
     for (int i = 0; i < 4; ++i) if (h[22 + 2 * i]) fprintf(stderr, " (+%lld, +%lld)", h[22 + 2 * i] - h[0], h[23 + 2 * i] - h[0]);
     fprintf(stderr, " | tile 1: loop top +%lld, setup done +%lld", h[30] - h[0], h[31] - h[0]);
+    fprintf(stderr, " | producer (tile k loads go out):");
+    for (int i = 0; i < 4; ++i) if (h[32 + i]) fprintf(stderr, " +%lld", h[32 + i] - h[0]);
+    fprintf(stderr, " | MMA (tile k last issue):");
+    for (int i = 0; i < 4; ++i) if (h[36 + i]) fprintf(stderr, " +%lld", h[36 + i] - h[0]);
     fprintf(stderr, " | stop +%lld | stores done +%lld | at teardown +%lld | passed +%lld | tmem freed +%lld\n", h[10] - h[0],
             h[11] - h[0], h[12] - h[0], h[13] - h[0], h[14] - h[0]);
   }
@@ -480,6 +500,14 @@ inline int launch_attn_t(cudaStream_t stream, const __half* q, int ldq, const __
   return DG_OK;
 }
 
+inline bool attn_x96() {
+  // measured SLOWER (S = 4096 x 77, d = 40: 42.2 vs 36.6 us; forward 9.67-9.73 vs 9.61-9.64 ms): 8 softmax warps on the masked
+  // per-element path lose more than the second, mostly empty key tile costs.  DG_ATTN_X96=1 enables it.
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("DG_ATTN_X96"); v = (e && e[0] == '1') ? 1 : 0; }
+  return v == 1;
+}
+
 inline int launch_attention(cudaStream_t stream, const __half* q, int ldq, const __half* k, int ldk, const __half* v,
                             int ldv, __half* out, int B, int heads, int Sq, int Sk, int d, int causal = 0) {
   if (causal && d != 64) return fail(DG_E_UNSUPPORTED, "attention: causal mask is built for head dim 64 only");
@@ -487,6 +515,8 @@ inline int launch_attention(cudaStream_t stream, const __half* q, int ldq, const
   switch (d) {
     case 32: return launch_attn_t<32, 128, 4, 1>(stream, q, ldq, k, ldk, v, ldv, out, B, heads, Sq, Sk);
     case 40: {
+      // cross-attention (77 text tokens): ONE 96-key tile instead of two 64-key tiles (64 + 13 valid keys); DG_ATTN_X96=0: off
+      if (attn_x96() && Sk <= 96 && !causal) return launch_attn_t<40, 96, 2, 1, 2>(stream, q, ldq, k, ldk, v, ldv, out, B, heads, Sq, Sk);
       static int var = -1;     // DG_ATTN_VAR: 0 = 2 query tiles x 128 keys, 1 = 2 x 64 keys double-buffered scores, 2 = 4 query tiles x 64 keys
       if (var < 0) { const char* e = getenv("DG_ATTN_VAR"); var = e ? atoi(e) : 2; }   // 3 = 2 query tiles x 2 key-tile streams (measured equal to 2 at batch 8; better wave fit at small batch)
       if (var == 0) return launch_attn_t<40, 128, 4, 1>(stream, q, ldq, k, ldk, v, ldv, out, B, heads, Sq, Sk);
@@ -499,6 +529,7 @@ inline int launch_attention(cudaStream_t stream, const __half* q, int ldq, const
       // kernel's best shape).  Causal (CLIP text, 77 tokens) and short sequences stay on variant 0.
       static int var64 = -1;
       if (var64 < 0) { const char* e = getenv("DG_ATTN64_VAR"); var64 = e ? atoi(e) : 0; }
+      if (attn_x96() && Sk <= 96 && !causal && Sq >= 256) return launch_attn_t<64, 96, 2, 1, 2>(stream, q, ldq, k, ldk, v, ldv, out, B, heads, Sq, Sk);
       if (var64 == 1 && !causal && Sq >= 512)
         return launch_attn_t<64, 64, 6, 1, 4>(stream, q, ldq, k, ldk, v, ldv, out, B, heads, Sq, Sk);
       return launch_attn_t<64, 128, 3, 1>(stream, q, ldq, k, ldk, v, ldv, out, B, heads, Sq, Sk, causal);
@@ -556,6 +587,8 @@ inline int init_kernel_attributes() {
   DG_TRY((init_attn_attr<40, 64, 6, 1, 4, 2>()));
   DG_TRY((init_attn_attr<64, 128, 3>()));
   DG_TRY((init_attn_attr<64, 64, 6, 1, 4>()));
+  DG_TRY((init_attn_attr<40, 96, 2, 1, 2>()));
+  DG_TRY((init_attn_attr<64, 96, 2, 1, 2>()));
   DG_TRY((init_attn_attr<80, 128, 2>()));
   DG_TRY((init_attn_attr<160, 64, 2>()));
   return DG_OK;
@@ -600,7 +633,7 @@ inline int launch_groupnorm(cudaStream_t s, int num_sms, const __half* x0, int C
 // GroupNorm apply with statistics already accumulated by the producing GEMM epilogues (block sums per source).
 inline int launch_groupnorm_fused(cudaStream_t s, int num_sms, const __half* x0, int C0, const float* st0, const __half* x1,
                                   int C1, const float* st1, int blk, const __half* gamma, const __half* beta, __half* out,
-                                  int B, int HW, int groups, float eps, int silu) {
+                                  int B, int HW, int groups, float eps, int silu, float* group_totals = nullptr) {
   if (HW % 32) return fail(DG_E_SHAPE, "groupnorm(fused): HW=%d must be a multiple of 32", HW);
   const int C = C0 + C1;
   if (C % groups || C0 % 8 || C1 % 8 || groups > 64) return fail(DG_E_SHAPE, "groupnorm: C=%d+%d groups=%d", C0, C1, groups);
@@ -610,6 +643,20 @@ inline int launch_groupnorm_fused(cudaStream_t s, int num_sms, const __half* x0,
   int ppb, pstride;
   gn_launch_geometry(C, B, HW, num_sms, &ppb, &pstride);
   dim3 grid((HW + ppb - 1) / ppb, B);
+  // DG_GN_TWO_STEP=1: fold the block sums once (one CTA per sample) into group totals, then the lean apply kernel -- instead of
+  // every apply CTA folding its sample's slabs x blocks itself (as many bytes as the activations it then touches)
+  static int two_step = -1;
+  if (two_step < 0) { const char* e = getenv("DG_GN_TWO_STEP"); two_step = (e && e[0] == '1') ? 1 : 0; }
+  if (two_step && group_totals) {
+    g_launch_counter += 2;
+    cudaError_t e = launch_pdl(gn_fold_groups_kernel, dim3((unsigned)B), dim3(256), (size_t)0, s, 1, C0, C1, groups, st0, st1, blk, HW / 32,
+                               group_totals);
+    if (e == cudaSuccess)
+      e = launch_pdl(gn_apply_kernel, grid, dim3(256), (size_t)0, s, 1, x0, C0, x1, C1, HW, groups, eps, ppb, (const float*)group_totals, gamma,
+                     beta, silu, out);
+    if (e != cudaSuccess) return fail(DG_E_CUDA, "groupnorm launch failed: %s", cudaGetErrorString(e));
+    return DG_OK;
+  }
   {
     ++g_launch_counter;
     cudaError_t e = launch_pdl(gn_apply_blk_kernel, grid, dim3(256), (size_t)0, s, 1, x0, C0, x1, C1, HW, groups, eps, ppb, st0, st1, blk,

@@ -244,6 +244,20 @@ def conv_gn(x, stats, gamma, beta, groups: int, eps: float, silu: bool, blk: int
     return out[..., :O]
 
 
+def upsample_conv3x3(x, weight_oihw, bias, gn_blk: int = 0):
+    """Upsample2D (nearest x2 + conv3x3) on NHWC x [B, H, W, C] -> [B, 2H, 2W, N] through the four-phase decomposition
+    (dg_op_upsample_conv3x3); with gn_blk also the GroupNorm block sums [B, 4*H*W // 32, N // gn_blk, 2] of the result."""
+    _chk16(x, weight_oihw, bias)
+    lib, ctx, s = _env(x)
+    B, H, W, Cin = x.shape
+    O = weight_oihw.shape[0]
+    out = torch.empty((B, 2 * H, 2 * W, O), dtype=torch.float16, device=x.device)
+    gs = torch.full((B, 4 * H * W // 32, O // gn_blk, 2), float("nan"), dtype=torch.float32, device=x.device) if gn_blk else None
+    _lib.check(lib.dg_op_upsample_conv3x3(ctx, _p(x), Cin, _p(weight_oihw.contiguous()), _p(bias), _p(out), B, H, W, O, _pf(gs), gn_blk, s),
+               "dg_op_upsample_conv3x3")
+    return (out, gs) if gn_blk else out
+
+
 def image_to_uint8(images):
     """[B, C, H, W] fp16 in [-1, 1] -> [B, H, W, C] uint8 on the device: diffusers.utils.pt_to_pil's arithmetic
     (`(x / 2 + 0.5).clamp(0, 1)`, `* 255`, round) without the host round trip of the float image."""

@@ -236,6 +236,11 @@ int32_t dg_op_conv3x3_gn(dg_ctx* ctx, const void* x0, int32_t C0, const float* s
                          int32_t blk, const void* gamma, const void* beta, int32_t groups, float eps, int32_t silu, const void* Wp,
                          const void* bias, const void* residual, void* out, int32_t B, int32_t H, int32_t Wd, int32_t N, int32_t ldo,
                          int32_t taps, void* stream);
+/* diffusers Upsample2D: nearest x2 followed by conv3x3 (pad 1), computed as four 2x2 "phase" convolutions on the LOW-resolution
+ * NHWC input x [B, H, W, C] (weights summed per phase: 2.25x fewer multiply-adds, no upsampled tensor).  w_oihw [N, C, 3, 3] is
+ * the ordinary conv weight; out [B, 2H, 2W, N].  gn_stats_out (optional): block sums [B][4*H*W/32][N/gn_blk] float2 of out. */
+int32_t dg_op_upsample_conv3x3(dg_ctx* ctx, const void* x, int32_t C, const void* w_oihw, const void* bias, void* out, int32_t B, int32_t H,
+                               int32_t Wd, int32_t N, float* gn_stats_out, int32_t gn_blk, void* stream);
 int32_t dg_op_attention(dg_ctx* ctx, const void* q, int32_t ldq, const void* k, int32_t ldk, const void* v, int32_t ldv,
                         void* out, int32_t B, int32_t heads, int32_t Sq, int32_t Sk, int32_t d, void* stream);
 int32_t dg_op_groupnorm(dg_ctx* ctx, const void* x0, int32_t C0, const void* x1, int32_t C1, const void* gamma,

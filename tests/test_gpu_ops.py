@@ -265,6 +265,25 @@ def test_conv3x3(ops, B, H, W, C0, C1, N):
     _report(f"conv3x3 {B}x{H}x{W}x{C}->{N}", got, ref, 5e-3, 4e-3)
 
 
+@pytest.mark.parametrize("B,H,W,C,N,blk", [(2, 32, 32, 640, 640, 20), (8, 8, 8, 1280, 1280, 40), (3, 16, 16, 128, 64, 2),
+                                           (1, 8, 16, 64, 192, 0), (2, 2, 2, 64, 64, 0), (2, 64, 64, 128, 128, 4)])
+def test_upsample_conv3x3_phases(ops, B, H, W, C, N, blk):
+    """Upsample2D (nearest x2 + conv3x3) as four 2x2 phase convolutions on the low-resolution input vs the torch fp32 reference;
+    the fused GroupNorm block sums cover the whole upsampled output."""
+    x = _rand(B, H, W, C, seed=80)
+    w, bias = _rand(N, C, 3, 3, scale=1 / math.sqrt(9 * C), seed=81), _rand(N, scale=0.1, seed=82)
+    res = ops.upsample_conv3x3(x, w, bias, blk)
+    out, gs = res if blk else (res, None)
+    up = F.interpolate(x.float().permute(0, 3, 1, 2), scale_factor=2.0, mode="nearest")
+    ref = F.conv2d(up, w.float(), bias.float(), padding=1).permute(0, 2, 3, 1)
+    _report(f"upsample conv {B}x{H}x{W}x{C}->{N}", out, ref, 6e-3, 5e-3)     # (phase weights are sums of up to 4 fp16 weights, rounded once)
+    if blk:
+        ob = out.float().reshape(B, 4 * H * W, N // blk, blk)
+        want = torch.stack([ob.sum((1, 3)), (ob * ob).sum((1, 3))], -1)
+        assert torch.isfinite(gs).all()
+        assert torch.allclose(gs.sum(1), want, rtol=2e-3, atol=1e-1), (gs.sum(1) - want).abs().max().item()
+
+
 def test_conv3x3_temb_residual(ops):
     B, H, W, C, N = 2, 32, 32, 320, 320
     x = _rand(B, H, W, C, seed=34)
