@@ -601,17 +601,27 @@ int run_forward(dg_unet* u, cudaStream_t s, const __half* sample, const __half* 
     }
     if (d.has_down) {
       const int Ho = (x.H - 1) / 2 + 1, Wo = (x.W - 1) / 2 + 1;
-      __half* c2 = f.alloc((size_t)x.B * Ho * Wo * 9 * x.C * 2);
       T4 y = f.talloc(x.B, Ho, Wo, x.C);
       if (f.err) break;
-      const size_t items = (size_t)x.B * Ho * Wo * 9 * (x.C / 8);
-      if (f.on(FAM_OTHER)) {
-        im2col3x3_nhwc_kernel<<<grid_for(items, 256, sms), 256, 0, s>>>(x.p, c2, x.B, x.H, x.W, x.C, 2, Ho, Wo);
-        DG_LAUNCH_CHECK();
+      if (u->ctx->up_phases && u->ctx->gemm.cta_mode != 1 && x.H % 2 == 0 && x.W % 2 == 0) {
+        // Downsample2D (conv3x3, stride 2, pad 1): the 9-tap implicit GEMM over the OUTPUT grid, its operand boxes taking every
+        // second input pixel through a strided tensor map (no materialised im2col tensor)
+        y.gst = f.gn_alloc(x.B, Ho, Wo, x.C, true);
+        GemmArgs a; a.a0 = x.p; a.c0 = x.C; a.B = x.B; a.H = Ho; a.W = Wo; a.taps = 9; a.in_stride = 2; a.w = d.down.w; a.n_w = d.down.rows;
+        a.n_out = d.down.out; a.bias = d.down.b; a.out = y.p; a.ldo = d.down.out; a.gn_stats_out = y.gst; a.gn_blk = u->gn_blk;
+        if (f.on(FAM_GEMM)) f.err = launch_gemm(s, u->ctx->gemm, a);
+      } else {
+        __half* c2 = f.alloc((size_t)x.B * Ho * Wo * 9 * x.C * 2);
+        if (f.err) break;
+        const size_t items = (size_t)x.B * Ho * Wo * 9 * (x.C / 8);
+        if (f.on(FAM_OTHER)) {
+          im2col3x3_nhwc_kernel<<<grid_for(items, 256, sms), 256, 0, s>>>(x.p, c2, x.B, x.H, x.W, x.C, 2, Ho, Wo);
+          DG_LAUNCH_CHECK();
+        }
+        y.gst = f.gn_alloc(x.B, Ho, Wo, x.C, false);
+        { Fwd::LinOpt o; o.gn_out = y.gst; o.hw = Ho * Wo; f.linear(c2, 9 * x.C, nullptr, 0, x.B * Ho * Wo, d.down, y.p, o); }
+        f.free_(c2);
       }
-      y.gst = f.gn_alloc(x.B, Ho, Wo, x.C, false);
-      { Fwd::LinOpt o; o.gn_out = y.gst; o.hw = Ho * Wo; f.linear(c2, 9 * x.C, nullptr, 0, x.B * Ho * Wo, d.down, y.p, o); }
-      f.free_(c2);
       x = y; skips.push_back(x);
     }
   }
@@ -1400,9 +1410,10 @@ int32_t dg_denoise_loop(dg_unet* u, void* latents, const void* ehs, int32_t toke
   std::vector<float4> cf(n_steps);
   for (int i = 0; i < n_steps; ++i) cf[i] = make_float4(sqrtf(a_t[i]), sqrtf(1.f - a_t[i]), sqrtf(a_prev[i]), sqrtf(1.f - a_prev[i]));
   float* d_ttab = (float*)(u->d_coef + n_steps);
+  // (pageable sources: cudaMemcpyAsync returns once they have been copied to the driver's staging memory, so the host buffers
+  // may go out of scope -- and the host may run a whole call ahead of the GPU: no synchronisation here)
   DG_CUDA(cudaMemcpyAsync(u->d_coef, cf.data(), sizeof(float4) * n_steps, cudaMemcpyHostToDevice, s));
   DG_CUDA(cudaMemcpyAsync(d_ttab, t_host, sizeof(float) * n_steps, cudaMemcpyHostToDevice, s));
-  DG_CUDA(cudaStreamSynchronize(s));  // host staging buffers go out of scope
   u->last_launches = 0;
   const long long c_h = g_launch_counter;
   DG_TRY(hoist_loop_invariants(u, s, (const __half*)ehs, tokens, B, d_ttab, n_steps));
@@ -1524,6 +1535,14 @@ int32_t dg_op_conv3x3_gn(dg_ctx* ctx, const void* x0, int32_t C0, const float* s
   a.w = (const __half*)Wp; a.n_w = N; a.n_out = N; a.bias = (const __half*)bias; a.residual = (const __half*)residual; a.ld_res = ldo;
   a.out = (__half*)out; a.ldo = ldo; a.xf_tab = ctx->xf_tab; a.xf_silu = silu;
   return launch_gemm(s, ctx->gemm, a);
+}
+int32_t dg_op_conv3x3_stride2(dg_ctx* ctx, const void* x, int32_t C, const void* Wp, const void* bias, void* out, int32_t B, int32_t Hout,
+                              int32_t Wout, int32_t N, float* gn_stats_out, int32_t gn_blk, void* stream) {
+  if (!ctx || !x || !Wp || !out) return fail(DG_E_ARG, "null argument");
+  GemmArgs a; a.a0 = (const __half*)x; a.c0 = C; a.B = B; a.H = Hout; a.W = Wout; a.taps = 9; a.in_stride = 2;
+  a.w = (const __half*)Wp; a.n_w = N; a.n_out = N; a.bias = (const __half*)bias; a.out = (__half*)out; a.ldo = N;
+  a.gn_stats_out = gn_stats_out; a.gn_blk = gn_blk;
+  return launch_gemm((cudaStream_t)stream, ctx->gemm, a);
 }
 int32_t dg_op_upsample_conv3x3(dg_ctx* ctx, const void* x, int32_t C, const void* w_oihw, const void* bias, void* out, int32_t B, int32_t H,
                                int32_t Wd, int32_t N, float* gn_stats_out, int32_t gn_blk, void* stream) {

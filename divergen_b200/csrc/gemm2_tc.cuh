@@ -64,6 +64,7 @@ struct Gemm2Params {
   int n_gemm;       // rows of Wt that are meaningful
   int taps;         // 1, 9 (3x3: tap offsets -1..1) or 4 (2x2 phase of an upsample conv: offsets tap_x0 + {0,1}, tap_y0 + {0,1})
   int tap_x0, tap_y0;
+  int in_mul;       // input pixel of box pixel (x, y) and tap (dx, dy): (x * in_mul + dx, y * in_mul + dy) -- 2 for a stride-2 conv
   int out_mul, out_ox, out_oy;   // output pixel of box pixel (x, y): (x * out_mul + out_ox, y * out_mul + out_oy) -- 2 / phase for taps == 4
   int gn_slot0;     // first GroupNorm slab of this launch within a sample's gn_slots (taps == 4: phase * slabs per phase)
   int kb0, kb1;     // 64-channel k-blocks taken from source 0 / source 1 per tap
@@ -473,8 +474,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
           } else {
           if (leader) mbar_arrive_expect_tx(&full[stage], kCta * S::kStageBytes);
           else mbar_arrive_cluster(full0_leader + stage * 8);
-          if (kb < p.kb0) tma_load_4d_pair<kCta>(sa, &mapA0, &full[stage], kb * 64, t.x0 + dx, t.y0 + dy, t.b0);
-          else            tma_load_4d_pair<kCta>(sa, &mapA1, &full[stage], (kb - p.kb0) * 64, t.x0 + dx, t.y0 + dy, t.b0);
+          if (kb < p.kb0) tma_load_4d_pair<kCta>(sa, &mapA0, &full[stage], kb * 64, t.x0 * p.in_mul + dx, t.y0 * p.in_mul + dy, t.b0);
+          else            tma_load_4d_pair<kCta>(sa, &mapA1, &full[stage], (kb - p.kb0) * 64, t.x0 * p.in_mul + dx, t.y0 * p.in_mul + dy, t.b0);
           }
           const int kcol = kbi * 64;
 #pragma unroll

@@ -211,6 +211,7 @@ struct GemmArgs {
   const __half* a1 = nullptr; int c1 = 0;  // optional source 1 (channel concat)
   int B = 1, H = 1, W = 1;                 // plain GEMM: B = H = 1, W = M
   int taps = 1;                            // 1 (Linear / 1x1), 9 (3x3, stride 1, pad 1) or 4 (one 2x2 phase of nearest-x2 + conv3x3)
+  int in_stride = 1;                       // taps == 9: 2 = stride-2 conv (Downsample2D): B/H/W are the OUTPUT grid, the source is [B, 2H, 2W, c0]
   int phase_x = 0, phase_y = 0;            // taps == 4: output pixels (2x + phase_x, 2y + phase_y) of a [B, 2H, 2W, n_out] tensor
   int gn_slot0 = 0, gn_slots = 0;          // taps == 4: this phase's first GroupNorm slab / slabs per sample of the whole output
   int hw = 0;                              // plain GEMM: rows per sample (needed for gn_stats)
@@ -299,6 +300,7 @@ inline int launch_gemm(cudaStream_t stream, const GemmRes& res, const GemmArgs& 
   if (a.c0 % 64 || a.c1 % 64 || a.c0 <= 0) return fail(DG_E_SHAPE, "gemm: channel counts must be multiples of 64 (%d,%d)", a.c0, a.c1);
   if (a.taps != 1 && a.taps != 9 && a.taps != 4) return fail(DG_E_ARG, "gemm: taps must be 1, 9 or 4");
   if (a.taps == 4 && (a.residual || a.rowvec || a.xf_tab || a.geglu)) return fail(DG_E_ARG, "gemm: an upsample phase takes bias / GroupNorm sums only");
+  if (a.in_stride != 1 && (a.in_stride != 2 || a.taps != 9 || a.xf_tab || a.c1)) return fail(DG_E_ARG, "gemm: in_stride 2 is the single-source stride-2 3x3 conv");
   if ((reinterpret_cast<uintptr_t>(a.a0) | reinterpret_cast<uintptr_t>(a.w) | reinterpret_cast<uintptr_t>(a.out) |
        reinterpret_cast<uintptr_t>(a.residual) | reinterpret_cast<uintptr_t>(a.a1) | reinterpret_cast<uintptr_t>(a.rowvec)) & 15)
     return fail(DG_E_ARG, "gemm: pointers must be 16-byte aligned");
@@ -354,7 +356,7 @@ inline int launch_gemm(cudaStream_t stream, const GemmRes& res, const GemmArgs& 
   p.row_stats_out = a.row_stats_out; p.row_parts = 2 * p.tiles_n;
   p.gn_stats_out = a.gn_stats_out; p.gn_blk = a.gn_blk; p.gn_nblk = a.gn_blk > 0 ? a.n_out / a.gn_blk : 0;
   p.gn_slots = (a.taps == 1 ? (a.hw > 0 ? a.hw : a.H * a.W) : a.H * a.W) / 32;
-  p.gn_slot0 = 0; p.tap_x0 = p.tap_y0 = 0; p.out_mul = 1; p.out_ox = p.out_oy = 0;
+  p.gn_slot0 = 0; p.tap_x0 = p.tap_y0 = 0; p.out_mul = 1; p.out_ox = p.out_oy = 0; p.in_mul = a.in_stride;
   if (a.taps == 4) {
     p.tap_x0 = a.phase_x - 1; p.tap_y0 = a.phase_y - 1; p.out_mul = 2; p.out_ox = a.phase_x; p.out_oy = a.phase_y;
     if (a.gn_stats_out) { p.gn_slot0 = a.gn_slot0; p.gn_slots = a.gn_slots; }
@@ -379,10 +381,11 @@ inline int launch_gemm(cudaStream_t stream, const GemmRes& res, const GemmArgs& 
   p.inv_tiles_x = 1.0f / (float)p.tiles_x; p.inv_tiles_y = 1.0f / (float)p.tiles_y;
   CUtensorMap mA0, mA1, mW, mO, mR;
   {
-    uint64_t dims[4] = {(uint64_t)a.c0, (uint64_t)W, (uint64_t)H, (uint64_t)B};
-    uint64_t st[3] = {(uint64_t)a.c0 * 2, (uint64_t)W * a.c0 * 2, (uint64_t)H * W * a.c0 * 2};
+    const uint64_t im = (uint64_t)a.in_stride;    // stride-2 conv: the source is the [B, 2H, 2W, c0] tensor, every second pixel per box
+    uint64_t dims[4] = {(uint64_t)a.c0, (uint64_t)W * im, (uint64_t)H * im, (uint64_t)B};
+    uint64_t st[3] = {(uint64_t)a.c0 * 2, (uint64_t)W * im * a.c0 * 2, (uint64_t)H * im * W * im * a.c0 * 2};
     uint32_t box[4] = {64, (uint32_t)p.bw, (uint32_t)p.bh, (uint32_t)p.bn};
-    DG_TRY(make_map_4d(&mA0, a.a0, dims, st, box));
+    DG_TRY(make_map_4d(&mA0, a.a0, dims, st, box, false, false, (uint32_t)im));
     if (a.c1 > 0) {
       uint64_t d1[4] = {(uint64_t)a.c1, (uint64_t)W, (uint64_t)H, (uint64_t)B};
       uint64_t s1[3] = {(uint64_t)a.c1 * 2, (uint64_t)W * a.c1 * 2, (uint64_t)H * W * a.c1 * 2};

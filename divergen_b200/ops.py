@@ -244,6 +244,20 @@ def conv_gn(x, stats, gamma, beta, groups: int, eps: float, silu: bool, blk: int
     return out[..., :O]
 
 
+def conv3x3_stride2(x, weight_oihw, bias):
+    """Downsample2D: conv3x3 / stride 2 / pad 1 on NHWC x [B, H, W, C] (H, W even) -> [B, H/2, W/2, N] (dg_op_conv3x3_stride2)."""
+    _chk16(x, weight_oihw, bias)
+    lib, ctx, s = _env(x)
+    B, H, W, Cin = x.shape
+    O = weight_oihw.shape[0]
+    wp = torch.empty((O, 9 * Cin), dtype=torch.float16, device=x.device)
+    _lib.check(lib.dg_op_pack_conv3x3(ctx, _p(weight_oihw), _p(wp), O, Cin, s), "dg_op_pack_conv3x3")
+    out = torch.empty((B, H // 2, W // 2, O), dtype=torch.float16, device=x.device)
+    _lib.check(lib.dg_op_conv3x3_stride2(ctx, _p(x), Cin, _p(wp), _p(bias), _p(out), B, H // 2, W // 2, O, _pf(None), 0, s),
+               "dg_op_conv3x3_stride2")
+    return out
+
+
 def upsample_conv3x3(x, weight_oihw, bias, gn_blk: int = 0):
     """Upsample2D (nearest x2 + conv3x3) on NHWC x [B, H, W, C] -> [B, 2H, 2W, N] through the four-phase decomposition
     (dg_op_upsample_conv3x3); with gn_blk also the GroupNorm block sums [B, 4*H*W // 32, N // gn_blk, 2] of the result."""

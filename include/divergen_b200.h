@@ -236,6 +236,10 @@ int32_t dg_op_conv3x3_gn(dg_ctx* ctx, const void* x0, int32_t C0, const float* s
                          int32_t blk, const void* gamma, const void* beta, int32_t groups, float eps, int32_t silu, const void* Wp,
                          const void* bias, const void* residual, void* out, int32_t B, int32_t H, int32_t Wd, int32_t N, int32_t ldo,
                          int32_t taps, void* stream);
+/* diffusers Downsample2D: conv3x3, stride 2, pad 1 on NHWC x [B, 2*Hout, 2*Wout, C] with the packed weight of dg_op_pack_conv3x3;
+ * out [B, Hout, Wout, N].  The operand boxes take every second input pixel through a strided tensor map (no im2col tensor). */
+int32_t dg_op_conv3x3_stride2(dg_ctx* ctx, const void* x, int32_t C, const void* Wp, const void* bias, void* out, int32_t B, int32_t Hout,
+                              int32_t Wout, int32_t N, float* gn_stats_out, int32_t gn_blk, void* stream);
 /* diffusers Upsample2D: nearest x2 followed by conv3x3 (pad 1), computed as four 2x2 "phase" convolutions on the LOW-resolution
  * NHWC input x [B, H, W, C] (weights summed per phase: 2.25x fewer multiply-adds, no upsampled tensor).  w_oihw [N, C, 3, 3] is
  * the ordinary conv weight; out [B, 2H, 2W, N].  gn_stats_out (optional): block sums [B][4*H*W/32][N/gn_blk] float2 of out. */

@@ -284,6 +284,17 @@ def test_upsample_conv3x3_phases(ops, B, H, W, C, N, blk):
         assert torch.allclose(gs.sum(1), want, rtol=2e-3, atol=1e-1), (gs.sum(1) - want).abs().max().item()
 
 
+@pytest.mark.parametrize("B,H,W,C,N", [(2, 64, 64, 320, 320), (8, 16, 16, 1280, 1280), (3, 8, 8, 64, 128), (2, 4, 4, 64, 64),
+                                       (1, 96, 96, 64, 64)])
+def test_conv3x3_stride2(ops, B, H, W, C, N):
+    """Downsample2D (conv3x3, stride 2, pad 1) through the strided operand map vs the torch fp32 reference."""
+    x = _rand(B, H, W, C, seed=85)
+    w, bias = _rand(N, C, 3, 3, scale=1 / math.sqrt(9 * C), seed=86), _rand(N, scale=0.1, seed=87)
+    got = ops.conv3x3_stride2(x, w, bias)
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.float(), bias.float(), stride=2, padding=1).permute(0, 2, 3, 1)
+    _report(f"conv3x3 stride 2 {B}x{H}x{W}x{C}->{N}", got, ref, 5e-3, 4e-3)
+
+
 def test_conv3x3_temb_residual(ops):
     B, H, W, C, N = 2, 32, 32, 320, 320
     x = _rand(B, H, W, C, seed=34)

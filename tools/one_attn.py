@@ -1,14 +1,13 @@
-"""One self-attention call at the SD-1.5 64x64 level (for ncu captures): python tools/one_attn.py [reps]"""
-import os
+"""One attention shape, a few launches (for ncu): python tools/one_attn.py [reps] [B heads S Sk d]"""
 import sys
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
+sys.path.insert(0, ".")
 from divergen_b200 import ops
-
 reps = int(sys.argv[1]) if len(sys.argv) > 1 else 3
-B, heads, S, d = 8, 8, 4096, 40
+B, heads, S, Sk, d = (int(v) for v in sys.argv[2:7]) if len(sys.argv) > 6 else (8, 8, 4096, 4096, 40)
 g = torch.Generator().manual_seed(0)
-q, k, v = (torch.randn(B, S, heads * d, generator=g).half().cuda() for _ in range(3))
+q = torch.randn(B, S, heads * d, generator=g).half().cuda()
+k, v = (torch.randn(B, Sk, heads * d, generator=g).half().cuda() for _ in range(2))
 for _ in range(reps):
     o = ops.attention(q, k, v, heads)
 torch.cuda.synchronize()
