@@ -159,6 +159,10 @@ __global__ void gn_apply_kernel(const __half* __restrict__ x0, int C0, const __h
   }
 }
 
+#ifndef DG_GN_FOLD_UNROLL
+#define DG_GN_FOLD_UNROLL 16
+#endif
+constexpr int kGnFoldUnroll = DG_GN_FOLD_UNROLL;
 // Same apply pass, statistics taken from the producers' fused epilogue sums: stats{0,1}[b][slots][C{0,1}/blk] float2 hold
 // (sum, sum of squares) over blk-channel blocks of each 32-pixel slab of each source (gemm2_tc.cuh).  A group of the
 // concatenated tensor is a union of whole blocks; each CTA first folds slabs x blocks into 32 (mean, rstd) pairs in shared
@@ -202,7 +206,8 @@ __global__ void gn_apply_blk_kernel(const __half* __restrict__ x0, int C0, const
                                      : reinterpret_cast<const float2*>(stats1) + (size_t)b * slots * nb1 + (cb - nb0);
       const int ld = (cb < nb0) ? nb0 : nb1;
       float a = 0.f, q = 0.f;
-#pragma unroll 4
+      // (all of a thread's slab loads in flight together: this fold is a latency chain at the head of every CTA)
+#pragma unroll kGnFoldUnroll
       for (int sl = stripe; sl < slots; sl += nstripe) { const float2 v = __ldg(src + (size_t)sl * ld); a += v.x; q += v.y; }
       s_col[stripe][cb] = make_float2(a, q);
     }

@@ -85,7 +85,7 @@ struct Gemm2Params {
   int ld_rowvec;
   const __half* residual;  // same geometry as out (row pitch ld_res) or nullptr
   int ld_res;
-  float* row_stats_out;    // [rows][row_parts][2]; this launch writes part nt*2 + hf   (plain GEMM only)
+  float* row_stats_out;    // [rows][row_parts][2], row_parts = 2 * ceil(n_out / 160)   (plain GEMM only)
   int row_parts;
   float* gn_stats_out;     // [B][gn_slots][gn_nblk][2]: (sum, sumsq) over gn_blk-channel blocks of each 32-pixel slab,
   int gn_blk, gn_nblk;     //   every entry written exactly once by one epilogue warp (plain stores: no atomics, no memset)
@@ -1135,8 +1135,18 @@ gemm2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
           }
           __syncwarp();
         }
-        if (p.row_stats_out && row_ok)
-          reinterpret_cast<float2*>(p.row_stats_out)[grow * p.row_parts + nt * 2 + hf] = make_float2(rs, rss);
+        if (p.row_stats_out && row_ok) {
+          // parts are 80 columns wide whatever the tile width (the consumer just sums gemm_row_parts(n) of them): a 160-wide tile
+          // writes one part per column half, a 320-wide tile puts a half's 160 columns into the first of its two parts
+          float2* rp = reinterpret_cast<float2*>(p.row_stats_out) + grow * p.row_parts;
+          if constexpr (kBN == 160) {
+            rp[nt * 2 + hf] = make_float2(rs, rss);
+          } else {
+            const int part = nt * 4 + hf * 2;
+            if (part < p.row_parts) rp[part] = make_float2(rs, rss);
+            if (part + 1 < p.row_parts) rp[part + 1] = make_float2(0.f, 0.f);
+          }
+        }
       }
       if constexpr (kSets == 2) { acc_phase ^= 1; }            // this set's stage every time
       else if (++as == S::kAccStages) { as = 0; acc_phase ^= 1; }

@@ -232,7 +232,7 @@ struct GemmArgs {
   const __half* xf_tab = nullptr; int xf_silu = 0;
 };
 
-// LayerNorm row partials are always produced by 160-wide tiles: two column halves per tile.
+// LayerNorm row partials: 80-column parts, whatever tile width produced them.
 inline int gemm_row_parts(int n_out) { return 2 * ((n_out + 159) / 160); }
 
 inline int largest_pow2_divisor(int x, int cap) {
@@ -333,7 +333,9 @@ inline int launch_gemm(cudaStream_t stream, const GemmRes& res, const GemmArgs& 
   static int forced_bn = -1;
   if (forced_bn < 0) { const char* e = getenv("DG_GEMM_BN"); forced_bn = e && e[0] ? atoi(e) : 0; }
   static int kb_thresh = -1;
-  if (kb_thresh < 0) { const char* e = getenv("DG_GEMM_KB_THRESH"); kb_thresh = e ? atoi(e) : 24; }
+  // round 2: 4 (was 24).  Layers with K = 320..1536 and N > 160 are operand-supply-bound, not epilogue-bound: a 320-wide tile
+  // reads its activation rows once instead of once per 160-wide column tile (forward 9.57 -> 9.35-9.46 ms, profiles/r02_ab.md)
+  if (kb_thresh < 0) { const char* e = getenv("DG_GEMM_KB_THRESH"); kb_thresh = e ? atoi(e) : 4; }
   int kbn = a.geglu ? kGegluTile : (num_kb > kb_thresh && a.n_w > 160) ? 320 : 160;
   {
     // few-tile layers (the 8x8 / 16x16 levels): 320-wide tiles would leave most SMs idle -- measured on 512x11520x1280:
@@ -342,9 +344,17 @@ inline int launch_gemm(cudaStream_t stream, const GemmRes& res, const GemmArgs& 
     const int units320 = ((m_tiles_ + kcta - 1) / kcta) * ((a.n_w + 319) / 320);
     const int slots_ = kcta == 2 ? res.max_pairs : res.num_sms;
     if (!a.geglu && kbn == 320 && units320 * 2 <= slots_) kbn = 160;
+    // K <= 1536: the 320-wide tile's only advantage is reading its activation rows once (~15 % per tile, measured on
+    // 32768x960x320 and 32768x320x1280); it loses when the tile count quantises badly against the persistent grid
+    // (2048x3840x1280: 96 tiles on 74 CTA pairs, 30.1 vs 26.5 us)
+    if (!a.geglu && kbn == 320 && num_kb <= 24) {
+      const int units160 = ((m_tiles_ + kcta - 1) / kcta) * ((a.n_w + 159) / 160);
+      const int w320 = (units320 + slots_ - 1) / slots_, w160 = (units160 + slots_ - 1) / slots_;
+      if (1.7 * w320 > (double)w160) kbn = 160;
+    }
   }
   if (forced_bn == 160 || forced_bn == 320) kbn = a.geglu ? kGegluTile : forced_bn;
-  if (a.row_stats_out) kbn = 160;
+  if (a.row_stats_out && a.geglu) return fail(DG_E_ARG, "gemm: row statistics are not produced by GEGLU tiles");
   p.tiles_n = (a.n_w + kbn - 1) / kbn;
   p.n_out = a.n_out;
   p.taps = a.taps;
@@ -353,7 +363,7 @@ inline int launch_gemm(cudaStream_t stream, const GemmRes& res, const GemmArgs& 
   p.ln_stats = a.ln_stats; p.ln_parts = a.ln_parts; p.ln_inv_c = a.ln_c > 0 ? 1.0f / (float)a.ln_c : 0.f; p.ln_eps = a.ln_eps;
   p.rowvec = a.rowvec; p.ld_rowvec = a.ld_rowvec;
   p.residual = a.residual; p.ld_res = a.ld_res;
-  p.row_stats_out = a.row_stats_out; p.row_parts = 2 * p.tiles_n;
+  p.row_stats_out = a.row_stats_out; p.row_parts = gemm_row_parts(a.n_out);
   p.gn_stats_out = a.gn_stats_out; p.gn_blk = a.gn_blk; p.gn_nblk = a.gn_blk > 0 ? a.n_out / a.gn_blk : 0;
   p.gn_slots = (a.taps == 1 ? (a.hw > 0 ? a.hw : a.H * a.W) : a.H * a.W) / 32;
   p.gn_slot0 = 0; p.tap_x0 = p.tap_y0 = 0; p.out_mul = 1; p.out_ox = p.out_oy = 0; p.in_mul = a.in_stride;
@@ -533,6 +543,8 @@ inline int launch_attention(cudaStream_t stream, const __half* q, int ldq, const
       static int var64 = -1;
       if (var64 < 0) { const char* e = getenv("DG_ATTN64_VAR"); var64 = e ? atoi(e) : 0; }
       if (attn_x96() && Sk <= 96 && !causal && Sq >= 256) return launch_attn_t<64, 96, 2, 1, 2>(stream, q, ldq, k, ldk, v, ldv, out, B, heads, Sq, Sk);
+      if (var64 == 2 && !causal && Sq >= 512)     // 2 query tiles x 64 keys, double-buffered scores
+        return launch_attn_t<64, 64, 6, 2>(stream, q, ldq, k, ldk, v, ldv, out, B, heads, Sq, Sk);
       if (var64 == 1 && !causal && Sq >= 512)
         return launch_attn_t<64, 64, 6, 1, 4>(stream, q, ldq, k, ldk, v, ldv, out, B, heads, Sq, Sk);
       return launch_attn_t<64, 128, 3, 1>(stream, q, ldq, k, ldk, v, ldv, out, B, heads, Sq, Sk, causal);
@@ -590,6 +602,7 @@ inline int init_kernel_attributes() {
   DG_TRY((init_attn_attr<40, 64, 6, 1, 4, 2>()));
   DG_TRY((init_attn_attr<64, 128, 3>()));
   DG_TRY((init_attn_attr<64, 64, 6, 1, 4>()));
+  DG_TRY((init_attn_attr<64, 64, 6, 2>()));
   DG_TRY((init_attn_attr<40, 96, 2, 1, 2>()));
   DG_TRY((init_attn_attr<64, 96, 2, 1, 2>()));
   DG_TRY((init_attn_attr<80, 128, 2>()));
