@@ -110,6 +110,7 @@ SIGNATURES = {
     "dg_op_pack_conv3x3": (_I, [_P, _P, _P, _I, _I, _P]),
     "dg_op_conv3x3": (_I, [_P, _P, _I, _P, _I, _P, _P, _P, _I, _P, _P, _I, _I, _I, _I, _I, _P]),
     "dg_op_conv3x3_gn": (_I, [_P, _P, _I, _P, _P, _I, _P, _I, _P, _P, _I, _F, _I, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
+    "dg_op_conv3x3_shortcut": (_I, [_P, _P, _I, _P, _P, _P, _I, _P, _I, _P, _I, _I, _I, _I, _P]),
     "dg_op_conv3x3_stride2": (_I, [_P, _P, _I, _P, _P, _P, _I, _I, _I, _I, _P, _I, _P]),
     "dg_op_upsample_conv3x3": (_I, [_P, _P, _I, _P, _P, _P, _I, _I, _I, _I, _P, _I, _P]),
     "dg_op_attention": (_I, [_P, _P, _I, _P, _I, _P, _I, _P, _I, _I, _I, _I, _I, _P]),

@@ -19,6 +19,8 @@ struct dg_ctx {
   int fuse_gn = 1;            // DG_FUSE_GN=0: stand-alone GroupNorm statistics kernels instead of epilogue sums
   int fuse_xf = 0;            // DG_FUSE_XF=0: stand-alone GroupNorm-apply (+SiLU) pass instead of the transform inside the consuming conv;
                               // 2: also the transformer's GroupNorm inside proj_in
+  int cfg_dedup = 1;          // DG_CFG_DEDUP=0: the guidance loop runs the identical prefix of the two CFG halves twice (round 1)
+  int fuse_sc = 1;            // DG_FUSE_SC=0: conv_shortcut as its own 1x1 GEMM whose output conv2 adds as a residual (round 1)
   int up_phases = 1;          // DG_UPCONV_PHASES=0: materialise the nearest-x2 tensor and run the 9-tap conv on it (round 1)
   __half* xf_tab = nullptr;   // scratch table for the stand-alone fused-GroupNorm operators (tests)
   size_t xf_tab_cap = 0;
@@ -83,7 +85,10 @@ struct Lin {
   // LayerNorm-folded copy (finalize_weights): wf = w * gamma, cs = row sums of wf, b32 = b + w . beta
   __half* wf = nullptr; float* cs = nullptr; float* b32 = nullptr;
 };
-struct Res { Norm n1, n2; Lin c1, c2, sc; bool has_sc = false; int cin = 0, cout = 0; int temb_off = 0; };
+struct Res {
+  Norm n1, n2; Lin c1, c2, sc; bool has_sc = false; int cin = 0, cout = 0; int temb_off = 0;
+  Lin c2x;       // has_sc: [conv2 | conv_shortcut] weights per row + summed bias (finalize_weights): the shortcut runs inside conv2's K loop
+};
 struct Xf {
   Norm gn, ln1, ln2, ln3;
   Lin proj_in, qkv, o1, q2, kv2, o2, ff1, ff2, proj_out;
@@ -146,6 +151,11 @@ struct dg_unet : WeightStore {
   __half* temb_table = nullptr; int temb_table_rows = 0;   // [n_steps, temb_total]
   __half* temb_cur = nullptr;                               // [temb_total]: row of the current step (set_step_kernel)
   bool temb_ready = false;    // the forward reads temb_cur (same row for every sample) instead of running the MLP
+  // classifier-free guidance inside dg_denoise_loop: rows [0, B/2) and [B/2, B) of the UNet input are the SAME latents at the same
+  // timestep, and nothing before the first cross-attention sees the text embeddings -- conv_in, the first ResnetBlock2D and the
+  // first transformer block up to its self-attention out-projection run on B/2 rows and are then duplicated (exact: identical
+  // inputs give identical outputs; DG_CFG_DEDUP=0 switches it off)
+  bool cfg_pairs = false;
   bool finalized = false;     // LayerNorm folds are up to date with the loaded weights
   // graphs
   bool use_graphs = true;
@@ -447,6 +457,23 @@ struct Fwd {
     linear(x0, c0, x1, c1, rows, w, out, o);
   }
 
+  // [Bh, ...] -> [2 Bh, ...]: both halves = the source (fp16 tensors; fp32 statistics are copied as raw 16-byte vectors)
+  void dup_rows(const void* src, void* dst, size_t bytes) {
+    if (!src || !dst || err != DG_OK || !on(FAM_OTHER)) return;
+    dup_latents_kernel<<<grid_for(bytes / 16, 256, sms), 256, 0, s>>>((const __half*)src, (__half*)dst, bytes / 16, 2);
+    ++g_launch_counter;
+    if (cudaGetLastError() != cudaSuccess) err = fail(DG_E_CUDA, "dup_rows launch failed");
+  }
+  T4 expand2(const T4& t, bool conv_stats) {
+    T4 o = talloc(2 * t.B, t.H, t.W, t.C);
+    dup_rows(t.p, o.p, t.bytes());
+    if (t.gst) {
+      o.gst = gn_alloc(2 * t.B, t.H, t.W, t.C, conv_stats);
+      if (o.gst) dup_rows(t.gst, o.gst, (size_t)t.B * (t.H * t.W / 32) * (t.C / u->gn_blk) * 2 * sizeof(float));
+    }
+    return o;
+  }
+
   T4 resnet(const Res& r, const T4& x0, const T4* x1) {
     const int B_ = x0.B, H = x0.H, W = x0.W;
     // conv1(silu(norm1(x))): normalisation + activation inside the conv's operand path when the statistics are fused
@@ -464,26 +491,44 @@ struct Fwd {
     out.gst = gn_alloc(B_, H, W, r.cout, true);
     const __half* resid = x0.p;
     T4 sc{};
-    if (r.has_sc) {
+    const bool sc_in_conv = r.has_sc && u->ctx->fuse_sc && r.c2x.w;
+    if (r.has_sc && !sc_in_conv) {
       sc = talloc(B_, H, W, r.cout);
       linear(x0.p, x0.C, x1 ? x1->p : nullptr, x1 ? x1->C : 0, B_ * H * W, r.sc, nullptr, 0, sc.p);
       resid = sc.p;
     }
-    if (const __half* tab2 = gn_fold(h1, nullptr, r.n2, u->cfg.norm_eps, 1)) {
-      conv3(h1, r.c2, nullptr, resid, out, nullptr, tab2);
+    auto conv2 = [&](const T4& in, const __half* tab) {
+      if (sc_in_conv) {
+        // out = conv2(in) + conv_shortcut(cat[x0, x1]) + (b2 + bs): the 1x1 shortcut is two more sources of conv2's K loop
+        GemmArgs a; a.a0 = in.p; a.c0 = in.C; a.B = B_; a.H = H; a.W = W; a.taps = 9; a.w = r.c2x.w; a.n_w = r.c2x.rows; a.n_out = r.c2x.out;
+        a.bias = r.c2x.b; a.x0 = x0.p; a.cx0 = x0.C; a.x1 = x1 ? x1->p : nullptr; a.cx1 = x1 ? x1->C : 0;
+        a.out = out.p; a.ldo = r.c2x.out; a.gn_stats_out = out.gst; a.gn_blk = u->gn_blk; a.xf_tab = nullptr;
+        (void)tab;
+        if (on(FAM_GEMM)) FW(launch_gemm(s, u->ctx->gemm, a));
+      } else {
+        conv3(in, r.c2, nullptr, resid, out, nullptr, tab);
+      }
+    };
+    const __half* tab2 = sc_in_conv ? nullptr : gn_fold(h1, nullptr, r.n2, u->cfg.norm_eps, 1);
+    if (tab2) {
+      conv2(h1, tab2);
     } else {
       T4 h2n = talloc(B_, H, W, r.cout);
       gn(h1, nullptr, r.n2, u->cfg.norm_eps, 1, h2n);
-      conv3(h2n, r.c2, nullptr, resid, out);
+      conv2(h2n, nullptr);
       free_(h2n);
     }
     free_(h1);
-    if (r.has_sc) free_(sc);
+    if (sc.p) free_(sc);
     return out;
   }
 
-  T4 transformer(const Xf& x, const T4& in) {
-    const int B_ = in.B, S = in.H * in.W, C = x.c, rows = B_ * S;
+  // `expand`: `in_` holds B/2 samples whose duplicates form the real batch (cfg_pairs): everything up to the self-attention
+  // out-projection runs on the half, then h (+ its LayerNorm partials) and the block input are duplicated
+  T4 transformer(const Xf& x, const T4& in_, bool expand = false) {
+    T4 in = in_;
+    int B_ = in.B, rows = B_ * in.H * in.W;
+    const int S = in.H * in.W, C = x.c;
     const int d = C / x.heads;
     const bool fl = fuse_ln();
     T4 xn = talloc(B_, in.H, in.W, C);      // (also the attention outputs' buffer below)
@@ -507,6 +552,19 @@ struct Fwd {
     free_(qkv);
     rs = ln_alloc(rows, C);
     { LinOpt o; o.residual = h.p; o.rows_out = rs; linear(xn.p, C, nullptr, 0, rows, x.o1, h.p, o); }
+    T4 in_full{};
+    if (expand) {
+      T4 h2 = talloc(2 * B_, in.H, in.W, C);
+      dup_rows(h.p, h2.p, h.bytes());
+      float* rs2 = ln_alloc(2 * rows, C);
+      if (rs && rs2) dup_rows(rs, rs2, (size_t)rows * gemm_row_parts(C) * 2 * sizeof(float));
+      in_full = talloc(2 * B_, in.H, in.W, C);
+      dup_rows(in.p, in_full.p, in.bytes());
+      free_(h); free_(xn);
+      h = h2; rs = rs2; in = in_full;
+      B_ *= 2; rows *= 2;
+      xn = talloc(B_, in.H, in.W, C);
+    }
     // cross-attention
     __half* q = alloc((size_t)rows * C * 2);
     if (fl) { LinOpt o; o.ln_in = rs; o.ln_c = C; linear(h.p, C, nullptr, 0, rows, x.q2, q, o); }
@@ -541,6 +599,7 @@ struct Fwd {
     out.gst = gn_alloc(B_, in.H, in.W, C, false);
     { LinOpt o; o.residual = in.p; o.gn_out = out.gst; o.hw = S; linear(h.p, C, nullptr, 0, rows, x.proj_out, out.p, o); }
     free_(xn); free_(h);
+    if (in_full.p) free_(in_full);
     return out;
   }
 };
@@ -576,27 +635,36 @@ int run_forward(dg_unet* u, cudaStream_t s, const __half* sample, const __half* 
   }
 
   // ---- conv_in (4-channel NCHW gather -> K=64 GEMM)
-  __half* col = f.alloc((size_t)B * h * w * 64 * 2);
-  T4 x = f.talloc(B, h, w, c0);
+  // cfg_pairs: the two halves of the batch are identical until the first cross-attention -- the prefix runs on the first half
+  const bool dedup = u->cfg_pairs && u->ctx->cfg_dedup && B % 2 == 0 && !u->down[0].xf.empty() && u->fam_mask == 15;
+  const int Bp = dedup ? B / 2 : B;
+  __half* col = f.alloc((size_t)Bp * h * w * 64 * 2);
+  T4 x = f.talloc(Bp, h, w, c0);
   if (f.err) return f.err;
   {
-    const size_t items = (size_t)B * h * w * 64;
+    const size_t items = (size_t)Bp * h * w * 64;
     if (f.on(FAM_OTHER)) {
-      im2col_conv_in_kernel<<<grid_for(items, 256, sms), 256, 0, s>>>(sample, col, B, cf.in_channels, h, w, 64);
+      im2col_conv_in_kernel<<<grid_for(items, 256, sms), 256, 0, s>>>(sample, col, Bp, cf.in_channels, h, w, 64);
       DG_LAUNCH_CHECK();
     }
-    x.gst = f.gn_alloc(B, h, w, c0, false);
-    { Fwd::LinOpt o; o.gn_out = x.gst; o.hw = h * w; f.linear(col, 64, nullptr, 0, B * h * w, u->conv_in, x.p, o); }
+    x.gst = f.gn_alloc(Bp, h, w, c0, false);
+    { Fwd::LinOpt o; o.gn_out = x.gst; o.hw = h * w; f.linear(col, 64, nullptr, 0, Bp * h * w, u->conv_in, x.p, o); }
     f.free_(col);
   }
   std::vector<T4> skips;
-  skips.push_back(x);
+  if (!dedup) skips.push_back(x);
   // ---- down
   for (int i = 0; i < 4 && !f.err; ++i) {
     DownBlk& d = u->down[i];
     for (size_t j = 0; j < d.res.size(); ++j) {
+      const bool half = dedup && i == 0 && j == 0;           // x still holds B/2 samples
       T4 y = f.resnet(d.res[j], x, nullptr);
-      if (!d.xf.empty()) { T4 z = f.transformer(d.xf[j], y); f.free_(y); y = z; }
+      if (half) {                                             // the skip connection of conv_in's output needs the whole batch
+        T4 xf_ = f.expand2(x, false);
+        f.free_(x);
+        skips.push_back(xf_);
+      }
+      if (!d.xf.empty()) { T4 z = f.transformer(d.xf[j], y, half); f.free_(y); y = z; }
       x = y; skips.push_back(x);
     }
     if (d.has_down) {
@@ -714,7 +782,7 @@ int forward_maybe_graph(dg_unet* u, cudaStream_t s, const __half* sample, const 
     u->last_launches += g_launch_counter - c0;
     return DG_OK;
   }
-  GraphKey key{B, h, w, tokens, sample, ehs, out, (u->kv_ready ? 1 : 0) | (u->temb_ready ? 2 : 0), u->fam_mask};
+  GraphKey key{B, h, w, tokens, sample, ehs, out, (u->kv_ready ? 1 : 0) | (u->temb_ready ? 2 : 0) | (u->cfg_pairs ? 4 : 0), u->fam_mask};
   for (auto& g : u->graphs) {
     if (g.key == key) {
       DG_CUDA(cudaGraphLaunch(g.exec, s));
@@ -767,6 +835,24 @@ int finalize_weights(dg_unet* u) {
   for (auto& d : u->down) for (auto& x : d.xf) DG_TRY(fold_xf(x));
   DG_TRY(fold_xf(u->mid_xf));
   for (auto& b : u->up) for (auto& x : b.xf) DG_TRY(fold_xf(x));
+  // conv_shortcut inside conv2: [conv2 | shortcut] weight rows and the summed bias
+  auto fuse_sc = [&](Res& r) -> int {
+    if (!r.has_sc) return DG_OK;
+    const int k0 = 9 * r.cout, k1 = r.cin;
+    if (!r.c2x.w) {
+      DG_TRY(dev_alloc(u, (void**)&r.c2x.w, (size_t)r.cout * (k0 + k1) * 2));
+      DG_TRY(dev_alloc(u, (void**)&r.c2x.b, (size_t)r.cout * 2));
+    }
+    r.c2x.in = r.cout; r.c2x.out = r.cout; r.c2x.rows = r.cout;
+    concat_weight_rows_kernel<<<grid_for((size_t)r.cout * (k0 + k1), 256, u->ctx->num_sms), 256>>>(r.c2.w, k0, r.sc.w, k1, r.c2x.w, r.cout);
+    DG_LAUNCH_CHECK();
+    add_bias_kernel<<<(r.cout + 255) / 256, 256>>>(r.c2.b, r.sc.b, r.c2x.b, r.cout);
+    DG_LAUNCH_CHECK();
+    return DG_OK;
+  };
+  for (auto& d : u->down) for (auto& r : d.res) DG_TRY(fuse_sc(r));
+  DG_TRY(fuse_sc(u->mid_r0)); DG_TRY(fuse_sc(u->mid_r1));
+  for (auto& b : u->up) for (auto& r : b.res) DG_TRY(fuse_sc(r));
   DG_CUDA(cudaDeviceSynchronize());
   for (auto& g : u->graphs) cudaGraphExecDestroy(g.exec);   // captured graphs point at stale folds
   u->graphs.clear();
@@ -1139,6 +1225,8 @@ int32_t dg_ctx_create(int32_t device, dg_ctx** out) {
   // each of the 9 taps and one MUFU.TANH per element (512 cycles per k-block per SM) does not fit under the MMA time
   c->fuse_xf = env_int("DG_FUSE_XF", 0);
   c->up_phases = env_int("DG_UPCONV_PHASES", 1);
+  c->fuse_sc = env_int("DG_FUSE_SC", 1);
+  c->cfg_dedup = env_int("DG_CFG_DEDUP", 1);
   *out = c;
   return DG_OK;
 }
@@ -1419,7 +1507,8 @@ int32_t dg_denoise_loop(dg_unet* u, void* latents, const void* ehs, int32_t toke
   DG_TRY(hoist_loop_invariants(u, s, (const __half*)ehs, tokens, B, d_ttab, n_steps));
   u->last_launches += g_launch_counter - c_h;
   u->kv_ready = true; u->temb_ready = true;
-  struct Unhoist { dg_unet* u; ~Unhoist() { u->kv_ready = false; u->temb_ready = false; } } unhoist{u};
+  u->cfg_pairs = cfg_on;      // dup_latents_kernel below makes rows [0, n) and [n, 2n) of the UNet input identical
+  struct Unhoist { dg_unet* u; ~Unhoist() { u->kv_ready = false; u->temb_ready = false; u->cfg_pairs = false; } } unhoist{u};
   for (int i = 0; i < n_steps; ++i) {
     set_step_kernel<<<1, 256, 0, s>>>(u->d_step, u->d_t, d_ttab, i, B, u->temb_table, u->temb_cur, u->temb_total);
     DG_LAUNCH_CHECK();
@@ -1535,6 +1624,14 @@ int32_t dg_op_conv3x3_gn(dg_ctx* ctx, const void* x0, int32_t C0, const float* s
   a.w = (const __half*)Wp; a.n_w = N; a.n_out = N; a.bias = (const __half*)bias; a.residual = (const __half*)residual; a.ld_res = ldo;
   a.out = (__half*)out; a.ldo = ldo; a.xf_tab = ctx->xf_tab; a.xf_silu = silu;
   return launch_gemm(s, ctx->gemm, a);
+}
+int32_t dg_op_conv3x3_shortcut(dg_ctx* ctx, const void* x, int32_t C, const void* Wcat, const void* bias, const void* xs0, int32_t Cs0,
+                               const void* xs1, int32_t Cs1, void* out, int32_t B, int32_t H, int32_t Wd, int32_t N, void* stream) {
+  if (!ctx || !x || !Wcat || !xs0 || !out) return fail(DG_E_ARG, "null argument");
+  GemmArgs a; a.a0 = (const __half*)x; a.c0 = C; a.B = B; a.H = H; a.W = Wd; a.taps = 9; a.w = (const __half*)Wcat; a.n_w = N; a.n_out = N;
+  a.bias = (const __half*)bias; a.x0 = (const __half*)xs0; a.cx0 = Cs0; a.x1 = (const __half*)xs1; a.cx1 = xs1 ? Cs1 : 0;
+  a.out = (__half*)out; a.ldo = N;
+  return launch_gemm((cudaStream_t)stream, ctx->gemm, a);
 }
 int32_t dg_op_conv3x3_stride2(dg_ctx* ctx, const void* x, int32_t C, const void* Wp, const void* bias, void* out, int32_t B, int32_t Hout,
                               int32_t Wout, int32_t N, float* gn_stats_out, int32_t gn_blk, void* stream) {

@@ -596,6 +596,21 @@ __global__ void pack_conv3x3_kernel(const __half* __restrict__ w, __half* __rest
   }
 }
 // conv_in: OIHW [O, I, 3, 3] -> [O, Kpad] with k = tap*I + c.
+// ResnetBlock2D's conv_shortcut (1x1) accumulated inside conv2 (3x3): one weight matrix [N][9*C + Cs] = [conv2 | shortcut] per
+// row and one bias b2 + bs, so that out = conv2(h) + conv_shortcut(x) + biases is a single K loop over two tensors.
+__global__ void concat_weight_rows_kernel(const __half* __restrict__ w0, int k0, const __half* __restrict__ w1, int k1,
+                                          __half* __restrict__ out, int N) {
+  const size_t kt = (size_t)k0 + k1, total = (size_t)N * kt;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t n = i / kt, k = i % kt;
+    out[i] = k < (size_t)k0 ? w0[n * k0 + k] : w1[n * k1 + (k - k0)];
+  }
+}
+__global__ void add_bias_kernel(const __half* __restrict__ a, const __half* __restrict__ b, __half* __restrict__ out, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = __float2half_rn(__half2float(a[i]) + __half2float(b[i]));
+}
+
 // Nearest-x2 upsampling followed by a 3x3 convolution (diffusers Upsample2D) as four 2x2 convolutions on the LOW-resolution
 // tensor, one per output phase (py, px) = parity of the output pixel: the 3 kernel rows that touch output row 2y + py read only
 // two distinct input rows (py = 0: {y-1: ky 0; y: ky 1, 2}; py = 1: {y: ky 0, 1; y+1: ky 2}), likewise along x, so their

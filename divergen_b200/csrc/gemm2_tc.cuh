@@ -68,6 +68,8 @@ struct Gemm2Params {
   int out_mul, out_ox, out_oy;   // output pixel of box pixel (x, y): (x * out_mul + out_ox, y * out_mul + out_oy) -- 2 / phase for taps == 4
   int gn_slot0;     // first GroupNorm slab of this launch within a sample's gn_slots (taps == 4: phase * slabs per phase)
   int kb0, kb1;     // 64-channel k-blocks taken from source 0 / source 1 per tap
+  int kbx0, kbx1;   // extra k-blocks AFTER the taps, read at tap offset (0, 0) from two more sources (mapX0 / mapX1): a 1x1
+                    //   convolution of another tensor accumulated into the same tile -- ResnetBlock2D's conv_shortcut inside conv2
   int splits;       // K splits per tile (>= 1)
   // M tiling (pixels)
   int W, H, B;      // logical A dims (plain GEMM: W = M, H = B = 1)
@@ -333,7 +335,8 @@ template <int kCta, int kBN, int kStages, bool kGeglu, bool kXf = false, int kSe
 __global__ void __launch_bounds__(128 + kSets * 256, 1)
 gemm2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
              const __grid_constant__ CUtensorMap mapW, const __grid_constant__ CUtensorMap mapO,
-             const __grid_constant__ CUtensorMap mapR, const Gemm2Params p) {
+             const __grid_constant__ CUtensorMap mapR, const __grid_constant__ CUtensorMap mapX0,
+             const __grid_constant__ CUtensorMap mapX1, const Gemm2Params p) {
   using S = Gemm2Cfg<kCta, kBN, kStages, kSets>;
   static_assert(!(kXf && kSets > 1), "the operand transform is built for one epilogue set");
   // GEGLU tiles: 320-wide [160 value | 160 gate] (one TMEM stage) or 160-wide [64 value | 64 gate | 32 zero rows] -- the
@@ -379,6 +382,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&mapA0); tma_prefetch_desc(&mapA1); tma_prefetch_desc(&mapW); tma_prefetch_desc(&mapO);
     if (p.residual) tma_prefetch_desc(&mapR);
+    if (p.kbx0) tma_prefetch_desc(&mapX0);
+    if (p.kbx1) tma_prefetch_desc(&mapX1);
   }
   if (warp == 1 && lane == 0) {
     // full: one arrive per producer (+ expect_tx of the bytes that complete on it) and, with the fused transform, one per
@@ -397,7 +402,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
     const int m_tiles_ = p.tiles_x * p.tiles_y * p.tiles_b;
     const int total_ = ((m_tiles_ + kCta - 1) / kCta) * p.tiles_n * p.splits;
     const int u = pair_id + lane * num_pairs;
-    if (lane < S::kUnitTab && u < total_) sUnits[lane] = unit_coord<kCta>(p, u, cta_rank, m_tiles_, p.taps * (p.kb0 + p.kb1));
+    if (lane < S::kUnitTab && u < total_) sUnits[lane] = unit_coord<kCta>(p, u, cta_rank, m_tiles_, p.taps * (p.kb0 + p.kb1) + p.kbx0 + p.kbx1);
   }
   tc_fence_before();
   __syncthreads();                     // TMEM address, tile table and barrier init are visible CTA-wide (shared-memory ordering)
@@ -416,7 +421,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
   const int m_pairs = (m_tiles + kCta - 1) / kCta;
   const int total_units = m_pairs * p.tiles_n * p.splits;
   const int kb_per_tap = p.kb0 + p.kb1;
-  const int num_kb = p.taps * kb_per_tap;
+  const int kb_main = p.taps * kb_per_tap;             // k-blocks of the taps; [kb_main, num_kb) are the extra 1x1 sources
+  const int num_kb = kb_main + p.kbx0 + p.kbx1;
 
   // k-th tile of this CTA (u = pair_id + k * num_pairs)
   auto unit_at = [&](int u, int k) -> Unit {
@@ -474,6 +480,11 @@ gemm2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
           } else {
           if (leader) mbar_arrive_expect_tx(&full[stage], kCta * S::kStageBytes);
           else mbar_arrive_cluster(full0_leader + stage * 8);
+          if (kbi >= kb_main) {       // extra 1x1 source (conv_shortcut): no tap offset
+            const int e = kbi - kb_main;
+            if (e < p.kbx0) tma_load_4d_pair<kCta>(sa, &mapX0, &full[stage], e * 64, t.x0, t.y0, t.b0);
+            else            tma_load_4d_pair<kCta>(sa, &mapX1, &full[stage], (e - p.kbx0) * 64, t.x0, t.y0, t.b0);
+          } else
           if (kb < p.kb0) tma_load_4d_pair<kCta>(sa, &mapA0, &full[stage], kb * 64, t.x0 * p.in_mul + dx, t.y0 * p.in_mul + dy, t.b0);
           else            tma_load_4d_pair<kCta>(sa, &mapA1, &full[stage], (kb - p.kb0) * 64, t.x0 * p.in_mul + dx, t.y0 * p.in_mul + dy, t.b0);
           }

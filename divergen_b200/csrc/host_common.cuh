@@ -209,6 +209,8 @@ struct GemmRes {
 struct GemmArgs {
   const __half* a0 = nullptr; int c0 = 0;  // source 0: NHWC [B,H,W,c0]
   const __half* a1 = nullptr; int c1 = 0;  // optional source 1 (channel concat)
+  const __half* x0 = nullptr; int cx0 = 0; // extra 1x1 sources (same B, H, W): their channels follow the taps in K -- the weight is
+  const __half* x1 = nullptr; int cx1 = 0; //   [n_w, taps*(c0+c1) + cx0 + cx1]; ResnetBlock2D's conv_shortcut accumulated inside conv2
   int B = 1, H = 1, W = 1;                 // plain GEMM: B = H = 1, W = M
   int taps = 1;                            // 1 (Linear / 1x1), 9 (3x3, stride 1, pad 1) or 4 (one 2x2 phase of nearest-x2 + conv3x3)
   int in_stride = 1;                       // taps == 9: 2 = stride-2 conv (Downsample2D): B/H/W are the OUTPUT grid, the source is [B, 2H, 2W, c0]
@@ -281,6 +283,9 @@ inline int choose_splits(int units, int num_kb, int slots, size_t ws_floats_per_
 // (profiles/r02_ab.md) 32768x960x320 41.0 -> 36.0 us, GEGLU 32768x2560x320 89.7 -> 82.7, 8192x5120x640 57.7 -> 52.4, but
 // +1..2 us on every launch with <= 4 tiles per CTA (640-thread CTAs, 112-register epilogue, idle second set).
 // DG_GEMM_SETS=2: whenever the kernel allows it; default (and 1): never.
+// tensor maps of the extra 1x1 sources of the launch being enqueued (set by launch_gemm just before launch_gemm2_t reads them)
+inline thread_local CUtensorMap g_mapX[2];
+
 inline bool gemm_two_sets(int total_units, int slots) {
   static int v = -1;
   if (v < 0) { const char* e = getenv("DG_GEMM_SETS"); v = (e && e[0]) ? atoi(e) : 0; }
@@ -293,11 +298,13 @@ inline cudaError_t launch_gemm2_t(cudaStream_t stream, int grid_ctas, const CUte
                                   const CUtensorMap& mW, const CUtensorMap& mO, const CUtensorMap& mR, const Gemm2Params& p) {
   using Cfg = Gemm2Cfg<kCta, kBN, kStages, kSets>;
   return launch_pdl(gemm2_kernel<kCta, kBN, kStages, kGeglu, kXf, kSets>, dim3((unsigned)grid_ctas), dim3(Cfg::kThreads),
-                    (size_t)Cfg::kTotal, stream, kCta, mA0, mA1, mW, mO, mR, p);
+                    (size_t)Cfg::kTotal, stream, kCta, mA0, mA1, mW, mO, mR, g_mapX[0], g_mapX[1], p);
 }
 
 inline int launch_gemm(cudaStream_t stream, const GemmRes& res, const GemmArgs& a) {
-  if (a.c0 % 64 || a.c1 % 64 || a.c0 <= 0) return fail(DG_E_SHAPE, "gemm: channel counts must be multiples of 64 (%d,%d)", a.c0, a.c1);
+  if (a.c0 % 64 || a.c1 % 64 || a.c0 <= 0 || a.cx0 % 64 || a.cx1 % 64) return fail(DG_E_SHAPE, "gemm: channel counts must be multiples of 64 (%d,%d,%d,%d)", a.c0, a.c1, a.cx0, a.cx1);
+  if ((a.cx0 || a.cx1) && (a.taps != 9 || a.in_stride != 1 || a.xf_tab || a.geglu || !a.x0 || (a.cx1 && !a.x1)))
+    return fail(DG_E_ARG, "gemm: extra 1x1 sources go with the plain stride-1 3x3 conv");
   if (a.taps != 1 && a.taps != 9 && a.taps != 4) return fail(DG_E_ARG, "gemm: taps must be 1, 9 or 4");
   if (a.taps == 4 && (a.residual || a.rowvec || a.xf_tab || a.geglu)) return fail(DG_E_ARG, "gemm: an upsample phase takes bias / GroupNorm sums only");
   if (a.in_stride != 1 && (a.in_stride != 2 || a.taps != 9 || a.xf_tab || a.c1)) return fail(DG_E_ARG, "gemm: in_stride 2 is the single-source stride-2 3x3 conv");
@@ -327,7 +334,7 @@ inline int launch_gemm(cudaStream_t stream, const GemmRes& res, const GemmArgs& 
   p.tiles_b = (B + p.bn - 1) / p.bn;
   p.hw = a.taps == 1 ? (a.hw > 0 ? a.hw : a.H * a.W) : 0;
   p.n_gemm = a.n_w;
-  const int num_kb = a.taps * (a.c0 / 64 + a.c1 / 64);
+  const int num_kb = a.taps * (a.c0 / 64 + a.c1 / 64) + a.cx0 / 64 + a.cx1 / 64;
   // tile width: 320 (two accumulators, single TMEM stage: best operand reuse) for long-K layers; 160 (double-buffered TMEM:
   // the epilogue overlaps the next main loop, twice the tiles for wave balance) for short-K / epilogue-bound layers
   static int forced_bn = -1;
@@ -358,7 +365,7 @@ inline int launch_gemm(cudaStream_t stream, const GemmRes& res, const GemmArgs& 
   p.tiles_n = (a.n_w + kbn - 1) / kbn;
   p.n_out = a.n_out;
   p.taps = a.taps;
-  p.kb0 = a.c0 / 64; p.kb1 = a.c1 / 64;
+  p.kb0 = a.c0 / 64; p.kb1 = a.c1 / 64; p.kbx0 = a.cx0 / 64; p.kbx1 = a.cx1 / 64;
   p.bias = a.bias; p.bias32 = a.bias32; p.colsum = a.colsum;
   p.ln_stats = a.ln_stats; p.ln_parts = a.ln_parts; p.ln_inv_c = a.ln_c > 0 ? 1.0f / (float)a.ln_c : 0.f; p.ln_eps = a.ln_eps;
   p.rowvec = a.rowvec; p.ld_rowvec = a.ld_rowvec;
@@ -403,7 +410,18 @@ inline int launch_gemm(cudaStream_t stream, const GemmRes& res, const GemmArgs& 
     } else {
       mA1 = mA0;
     }
-    const uint64_t ktot = (uint64_t)a.taps * (a.c0 + a.c1);
+    g_mapX[0] = mA0; g_mapX[1] = mA0;
+    if (a.cx0) {
+      uint64_t dx_[4] = {(uint64_t)a.cx0, (uint64_t)W, (uint64_t)H, (uint64_t)B};
+      uint64_t sx_[3] = {(uint64_t)a.cx0 * 2, (uint64_t)W * a.cx0 * 2, (uint64_t)H * W * a.cx0 * 2};
+      DG_TRY(make_map_4d(&g_mapX[0], a.x0, dx_, sx_, box));
+    }
+    if (a.cx1) {
+      uint64_t dx_[4] = {(uint64_t)a.cx1, (uint64_t)W, (uint64_t)H, (uint64_t)B};
+      uint64_t sx_[3] = {(uint64_t)a.cx1 * 2, (uint64_t)W * a.cx1 * 2, (uint64_t)H * W * a.cx1 * 2};
+      DG_TRY(make_map_4d(&g_mapX[1], a.x1, dx_, sx_, box));
+    }
+    const uint64_t ktot = (uint64_t)a.taps * (a.c0 + a.c1) + a.cx0 + a.cx1;
     DG_TRY(make_map_2d(&mW, a.w, ktot, (uint64_t)a.n_w, ktot * 2, 64, (kbn == 256 ? 128 : 160) / kcta));   // one accumulator's rows per CTA
     // output tiles: {n_out, W, H, B} boxes of 32 columns x 128 pixels, 64-byte swizzle in smem
     const uint64_t om = a.taps == 4 ? 2 : 1;      // an upsample phase scatters into the [B, 2H, 2W, n_out] output
@@ -422,13 +440,13 @@ inline int launch_gemm(cudaStream_t stream, const GemmRes& res, const GemmArgs& 
   const int grid_units = total_units < slots ? total_units : slots;
   if (trace_on())
     fprintf(stderr, "DG_TRACE gemm M=%d N=%d K=%d taps=%d c0=%d c1=%d bn=%d units=%d splits=%d grid=%dx%d geglu=%d ln=%d res=%d gn=%d rs=%d\n",
-            a.B * a.H * a.W, a.n_w, a.taps * (a.c0 + a.c1), a.taps, a.c0, a.c1, kbn, units, p.splits, grid_units, kcta, a.geglu,
+            a.B * a.H * a.W, a.n_w, a.taps * (a.c0 + a.c1) + a.cx0 + a.cx1, a.taps, a.c0, a.c1, kbn, units, p.splits, grid_units, kcta, a.geglu,
             a.colsum != nullptr, a.residual != nullptr, a.gn_stats_out != nullptr, a.row_stats_out != nullptr);
-  const double rows_ = (double)a.B * a.H * a.W, ktot_ = (double)a.taps * (a.c0 + a.c1);
+  const double rows_ = (double)a.B * a.H * a.W, ktot_ = (double)a.taps * (a.c0 + a.c1) + a.cx0 + a.cx1;
   // algorithmic work: a GEGLU projection has 2 * n_out weight rows (the packing's zero rows are not work)
   const double n_alg_ = a.geglu ? 2.0 * a.n_out : (double)a.n_w;
   ProfScope prof_(FAM_GEMM, stream, 2.0 * rows_ * ktot_ * n_alg_,
-                  2.0 * (rows_ * (a.c0 + a.c1) + ktot_ * n_alg_ + rows_ * a.n_out));
+                  2.0 * (rows_ * (a.c0 + a.c1 + a.cx0 + a.cx1) + ktot_ * n_alg_ + rows_ * a.n_out));
   static int dbg_on = -1;
   static long long* dbg_dev = nullptr;
   if (dbg_on < 0) {

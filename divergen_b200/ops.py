@@ -244,6 +244,23 @@ def conv_gn(x, stats, gamma, beta, groups: int, eps: float, silu: bool, blk: int
     return out[..., :O]
 
 
+def conv3x3_shortcut(x, weight_oihw, bias, xs0, shortcut_weight, shortcut_bias, xs1=None):
+    """conv3x3(x) + conv1x1(cat[xs0, xs1]) + biases in one K loop (dg_op_conv3x3_shortcut): ResnetBlock2D's conv2 with its
+    conv_shortcut.  shortcut_weight [N, Cs0 + Cs1]."""
+    _chk16(x, weight_oihw, bias, xs0, shortcut_weight, shortcut_bias, xs1)
+    lib, ctx, s = _env(x)
+    B, H, W, Cin = x.shape
+    O = weight_oihw.shape[0]
+    wp = torch.empty((O, 9 * Cin), dtype=torch.float16, device=x.device)
+    _lib.check(lib.dg_op_pack_conv3x3(ctx, _p(weight_oihw), _p(wp), O, Cin, s), "dg_op_pack_conv3x3")
+    wcat = torch.cat([wp, shortcut_weight.reshape(O, -1)], dim=1).contiguous()
+    b = (bias.float() + shortcut_bias.float()).half()
+    out = torch.empty((B, H, W, O), dtype=torch.float16, device=x.device)
+    _lib.check(lib.dg_op_conv3x3_shortcut(ctx, _p(x), Cin, _p(wcat), _p(b), _p(xs0), xs0.shape[3], _p(xs1),
+                                          xs1.shape[3] if xs1 is not None else 0, _p(out), B, H, W, O, s), "dg_op_conv3x3_shortcut")
+    return out
+
+
 def conv3x3_stride2(x, weight_oihw, bias):
     """Downsample2D: conv3x3 / stride 2 / pad 1 on NHWC x [B, H, W, C] (H, W even) -> [B, H/2, W/2, N] (dg_op_conv3x3_stride2)."""
     _chk16(x, weight_oihw, bias)

@@ -236,6 +236,11 @@ int32_t dg_op_conv3x3_gn(dg_ctx* ctx, const void* x0, int32_t C0, const float* s
                          int32_t blk, const void* gamma, const void* beta, int32_t groups, float eps, int32_t silu, const void* Wp,
                          const void* bias, const void* residual, void* out, int32_t B, int32_t H, int32_t Wd, int32_t N, int32_t ldo,
                          int32_t taps, void* stream);
+/* ResnetBlock2D tail: out = conv3x3(x) + conv1x1(cat[xs0, xs1]) + bias in ONE K loop (the conv_shortcut is two more operand
+ * sources after the nine taps).  Wcat [N, 9*C + Cs0 + Cs1] = [dg_op_pack_conv3x3 layout | shortcut weight [N, Cs0 + Cs1]] per row;
+ * bias = conv bias + shortcut bias; x [B, H, W, C], xs0 / xs1 [B, H, W, Cs0 / Cs1] (xs1 optional); out [B, H, W, N]. */
+int32_t dg_op_conv3x3_shortcut(dg_ctx* ctx, const void* x, int32_t C, const void* Wcat, const void* bias, const void* xs0, int32_t Cs0,
+                               const void* xs1, int32_t Cs1, void* out, int32_t B, int32_t H, int32_t Wd, int32_t N, void* stream);
 /* diffusers Downsample2D: conv3x3, stride 2, pad 1 on NHWC x [B, 2*Hout, 2*Wout, C] with the packed weight of dg_op_pack_conv3x3;
  * out [B, Hout, Wout, N].  The operand boxes take every second input pixel through a strided tensor map (no im2col tensor). */
 int32_t dg_op_conv3x3_stride2(dg_ctx* ctx, const void* x, int32_t C, const void* Wp, const void* bias, void* out, int32_t B, int32_t Hout,

@@ -295,6 +295,23 @@ def test_conv3x3_stride2(ops, B, H, W, C, N):
     _report(f"conv3x3 stride 2 {B}x{H}x{W}x{C}->{N}", got, ref, 5e-3, 4e-3)
 
 
+@pytest.mark.parametrize("B,H,W,C,N,Cs0,Cs1", [(2, 32, 32, 640, 640, 640, 320), (2, 64, 64, 320, 320, 320, 320), (8, 8, 8, 1280, 1280, 1280, 1280),
+                                               (3, 16, 16, 128, 128, 64, 0), (2, 16, 16, 1280, 1280, 640, 0)])
+def test_conv3x3_with_shortcut_in_the_k_loop(ops, B, H, W, C, N, Cs0, Cs1):
+    """ResnetBlock2D tail: conv2(h) + conv_shortcut(cat[x, skip]) as one GEMM whose K loop runs over the nine taps of h and then
+    over the channels of x / skip (no shortcut tensor, no residual read) vs the torch fp32 reference."""
+    h = _rand(B, H, W, C, seed=90)
+    x0 = _rand(B, H, W, Cs0, seed=91)
+    x1 = _rand(B, H, W, Cs1, seed=92) if Cs1 else None
+    w, bias = _rand(N, C, 3, 3, scale=1 / math.sqrt(9 * C), seed=93), _rand(N, scale=0.1, seed=94)
+    ws, bs = _rand(N, Cs0 + Cs1, scale=1 / math.sqrt(Cs0 + Cs1), seed=95), _rand(N, scale=0.1, seed=96)
+    got = ops.conv3x3_shortcut(h, w, bias, x0, ws, bs, x1)
+    xs = torch.cat([x0, x1], -1) if Cs1 else x0
+    ref = F.conv2d(h.float().permute(0, 3, 1, 2), w.float(), bias.float(), padding=1).permute(0, 2, 3, 1)
+    ref = ref + xs.float() @ ws.float().T + bs.float()
+    _report(f"conv3x3 + shortcut {B}x{H}x{W} {C}+{Cs0}+{Cs1}->{N}", got, ref, 6e-3, 4e-3)
+
+
 def test_conv3x3_temb_residual(ops):
     B, H, W, C, N = 2, 32, 32, 320, 320
     x = _rand(B, H, W, C, seed=34)

@@ -1,0 +1,12 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 150 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
+timeout 300 python -m pytest tests/test_gpu_ops.py -q -k "shortcut or gemm" 2>&1 | tail -2
+timeout 400 python -m pytest tests/test_gpu_unet.py tests/test_golden.py tests/test_gpu_edges.py -q -m gpu 2>&1 | tail -2
+{
+for rep in 1 2 3; do
+echo "== default (shortcut inside conv2)"; timeout 120 python tools/time_forward.py 2>&1 | tail -1
+echo "== DG_FUSE_SC=0"; DG_FUSE_SC=0 timeout 120 python tools/time_forward.py 2>&1 | tail -1
+done
+} > gpurun_out/r02_run14_ab.log 2>&1
+cat gpurun_out/r02_run14_ab.log
