@@ -336,6 +336,8 @@ int build_modules(dg_unet* u) {
 }
 
 // ================================================================== forward
+__global__ void dup_latents_kernel(const __half* __restrict__ lat, __half* __restrict__ dst, size_t n_vec8, int copies);
+
 struct Fwd {
   dg_unet* u; cudaStream_t s; int sms; int B; int tokens; const __half* ehs; __half* temb_all;
   int err = DG_OK;
