@@ -47,6 +47,11 @@ struct AttnParams {
   float scale_log2;  // d^-1/2 * log2(e)
   int causal;        // 1: key t is visible to query row r only if t <= r (CLIP text encoder); kSplit == 1 variants only
   __half* out;       // [B, Sq, heads*d]
+  // Wave-balanced grid (plan_attn_grid, host): 1-D grid; the (batch, head) pairs form two groups -- the first n_g1 pairs are cut
+  // into a1 CTAs of kQTiles query tiles + b1 CTAs of kQTiles - 1, the others into a2 + b2 -- and every full-size CTA comes
+  // before every short one in block order (longest first), so the block scheduler packs the SMs to within one tile:
+  // 64 x 32 tiles on 148 one-CTA SMs take 14 tile times instead of 4 waves x 4 tiles.  part_on = 0: grid (x, head, batch).
+  int part_on, n_bh, n_g1, a1, b1, a2, b2;
 };
 
 // kQ = softmax streams per CTA (one 4-warp group, one score buffer set and one O accumulator each).  kSplit = 1: every
@@ -96,9 +101,19 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int q_row0 = blockIdx.x * (C::kQTiles * 128);
-  const int head = blockIdx.y;
-  const int batch = blockIdx.z;
+  int q_row0 = blockIdx.x * (C::kQTiles * 128);
+  int head = blockIdx.y;
+  int batch = blockIdx.z;
+  int nq = C::kQTiles;                     // query tiles this CTA works on (the streams of the others stay idle)
+  if (p.part_on) {
+    int idx = blockIdx.x, bh, tile0;
+    const int f1 = p.n_g1 * p.a1, f2 = (p.n_bh - p.n_g1) * p.a2, t1 = p.n_g1 * p.b1;
+    if (idx < f1) { bh = idx / p.a1; tile0 = (idx % p.a1) * C::kQTiles; }
+    else if (idx < f1 + f2) { idx -= f1; bh = p.n_g1 + idx / p.a2; tile0 = (idx % p.a2) * C::kQTiles; }
+    else if (idx < f1 + f2 + t1) { idx -= f1 + f2; bh = idx / p.b1; tile0 = p.a1 * C::kQTiles + (idx % p.b1) * (C::kQTiles - 1); nq = C::kQTiles - 1; }
+    else { idx -= f1 + f2 + t1; bh = p.n_g1 + idx / p.b2; tile0 = p.a2 * C::kQTiles + (idx % p.b2) * (C::kQTiles - 1); nq = C::kQTiles - 1; }
+    q_row0 = tile0 * 128; head = bh % p.heads; batch = bh / p.heads;
+  }
   const int nkv = (p.Sk + kKV - 1) / kKV;
 
   if (warp == 0 && lane == 0) {
@@ -176,7 +191,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
     for (int t = 0; t < kAhead && t < nkv; ++t) {
       ensure(t);
       if (elect_one()) {
-        for (int qq = 0; qq < C::kQTiles; ++qq)
+        for (int qq = 0; qq < nq; ++qq)
           issue_S(qq * kSplit + t % kSplit, (t / kSplit) % kSBuf, smem_u32(sKV + (t % kStages) * C::kStageBytes));
       }
       __syncwarp();
@@ -190,7 +205,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
       if (has_next) ensure(tn);
       const uint32_t sk_next = smem_u32(sKV + (tn % kStages) * C::kStageBytes);
       const bool last = (j + kSplit >= nkv); // the stream's last tile
-      for (int qq = 0; qq < C::kQTiles; ++qq) {
+      for (int qq = 0; qq < nq; ++qq) {
         const int st = qq * kSplit + j % kSplit;
         mbar_wait_parked(&p_full[st * kSBuf + b], (jj / kSBuf) & 1);
         tc_fence_after();
@@ -198,7 +213,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
           issue_PV(st, b, sv_addr, jj > 0);
           umma_commit(last ? &o_done[st] : &pv_done[st]);
           if (has_next) issue_S(st, b, sk_next);
-          if (qq == C::kQTiles - 1) umma_commit(&kv_empty[stage]);
+          if (qq == nq - 1) umma_commit(&kv_empty[stage]);
         }
         __syncwarp();
       }
@@ -208,6 +223,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
     const int q = (warp - 4) >> 2;       // stream handled by this warp group
     const int qt = q / kSplit;           // its query tile
     const int h = q % kSplit;            // its share of the key tiles: j % kSplit == h
+    const bool active = qt < nq;         // (a short CTA of the wave-balanced grid leaves its last query tile's streams idle)
+    const int nkv_s = active ? nkv : 0;
     const int quad = warp & 3;           // TMEM lane quadrant
     const int row = quad * 32 + lane;    // row within the 128-row tile
     const uint32_t lane_off = (uint32_t)(quad * 32) << 16;
@@ -218,7 +235,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
     constexpr bool kPre = kQ <= 2;
     float m_run = -INFINITY;  // running max (log2 domain, already scaled)
     float l_run = 0.f;
-    for (int jj = 0, j = h; j < nkv; ++jj, j += kSplit) {
+    for (int jj = 0, j = h; j < nkv_s; ++jj, j += kSplit) {
       const uint32_t tS = tS_q + (uint32_t)((jj % kSBuf) * kKV);
       mbar_wait(&s_full[q * kSBuf + jj % kSBuf], (jj / kSBuf) & 1);
       tc_fence_after();
@@ -352,7 +369,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
       mbar_arrive(&p_full[q * kSBuf + jj % kSBuf]);
     }
     // epilogue: O / l -> fp16 global
-    const bool has_tiles = h < nkv;      // (a second stream has nothing to do when there is a single key tile)
+    const bool has_tiles = h < nkv_s;    // (a second stream has nothing to do when there is a single key tile)
     if (has_tiles) { mbar_wait(&o_done[q], 0); tc_fence_after(); }
     const int qrow = q_row0 + qt * 128 + row;
     // O = sum(P' V) with P' = 2^112 v (truncated), l = sum(v):  out = O * 2^-112 / l, corrected for the truncation bias
@@ -386,6 +403,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
 #pragma unroll
     for (int c = 0; c < C::kDPad; c += 16) {
       if (kSplit == 2 && h == 1) break;  // the partner stream writes the merged rows
+      if (!active) break;
       uint32_t o[16];
       tmem_ld16(tO + c, o);
       tmem_ld_wait();

@@ -7,11 +7,14 @@
 #include <cuda_runtime.h>
 #include <cudaTypedefs.h>
 
+#include <algorithm>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <string>
+#include <tuple>
 #include <vector>
 
 #include "../../include/divergen_b200.h"
@@ -497,6 +500,66 @@ inline int launch_gemm(cudaStream_t stream, const GemmRes& res, const GemmArgs& 
 }
 
 // ------------------------------------------------------------------ attention launcher
+// Wave-balanced attention grid.  Every attention CTA owns an SM (shared memory + all 512 TMEM columns), so a grid of n_bh * T / big
+// equal CTAs (T = 128-row query tiles per (batch, head) pair, big = query tiles per CTA) runs in ceil(ctas / SMs) waves: SD-1.5's
+// 64 x 64 level at UNet batch 8 is 512 CTAs = 3.46 waves, i.e. 16 tile times where 2048 tiles / 148 SMs = 13.84 would do.  The plan
+// cuts each pair into a CTAs of `big` tiles and b of `big - 1` (big * a + (big - 1) * b = T; two groups of pairs with their own
+// (a, b)), orders the grid longest-first and simulates the block scheduler (next CTA -> first free SM); it is used only when the
+// simulated makespan beats the uniform grid by >= 3 % (a short CTA is charged 4 % extra per tile).  DG_ATTN_PART=0: off.
+inline int attn_part_min_keys() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("DG_ATTN_PART_MIN_KEYS"); v = e ? atoi(e) : 512; }
+  return v;
+}
+struct AttnPlan { int on = 0, n_g1 = 0, a1 = 0, b1 = 0, a2 = 0, b2 = 0, ctas = 0; double makespan = 0, uniform = 0; };
+inline double attn_plan_makespan(int sms, int n_big, int n_small, double c_big, double c_small) {
+  std::vector<double> heap(sms, 0.0);                       // min-heap of SM free times
+  auto cmp = [](double x, double y) { return x > y; };
+  double end = 0;
+  for (int i = 0; i < n_big + n_small; ++i) {
+    std::pop_heap(heap.begin(), heap.end(), cmp);
+    double t = heap.back() + (i < n_big ? c_big : c_small);
+    heap.back() = t;
+    end = t > end ? t : end;
+    std::push_heap(heap.begin(), heap.end(), cmp);
+  }
+  return end;
+}
+inline AttnPlan plan_attn_grid(int n_bh, int T, int big, int sms) {
+  static std::map<std::tuple<int, int, int, int>, AttnPlan> cache;
+  static int enabled = -1;
+  if (enabled < 0) { const char* e = getenv("DG_ATTN_PART"); enabled = (e && e[0] == '0') ? 0 : 1; }
+  AttnPlan best;
+  if (!enabled || big < 2 || T < big || sms <= 0) return best;
+  const auto key = std::make_tuple(n_bh, T, big, sms);
+  auto it = cache.find(key);
+  if (it != cache.end()) return it->second;
+  const int small = big - 1;
+  const double c_big = big, c_small = small * 1.04;
+  const long uniform_ctas = (long)n_bh * ((T + big - 1) / big);
+  best.uniform = (double)((uniform_ctas + sms - 1) / sms) * c_big;
+  best.makespan = best.uniform;
+  std::vector<std::pair<int, int>> opts;                    // (a, b): the (up to 6) splits of a pair with the most full-size CTAs
+  for (int a = T / big; a >= 0 && opts.size() < 6; --a)
+    if ((T - big * a) % small == 0) opts.push_back({a, (T - big * a) / small});
+  for (auto& o1 : opts)
+    for (auto& o2 : opts)
+      for (int g1 = (o1 == o2 ? n_bh : 1); g1 <= n_bh; ++g1) {
+        if (o1 == o2 && g1 != n_bh) continue;
+        if (o1 != o2 && g1 == n_bh) continue;               // (covered by o1 == o2)
+        const int g2 = n_bh - g1;
+        const int nb = g1 * o1.first + g2 * o2.first, ns = g1 * o1.second + g2 * o2.second;
+        const double m = attn_plan_makespan(sms, nb, ns, c_big, c_small);
+        if (m < best.makespan - 1e-9 || (best.on && m < best.makespan + 1e-9 && nb + ns < best.ctas)) {
+          best.on = 1; best.makespan = m; best.n_g1 = g1; best.a1 = o1.first; best.b1 = o1.second; best.a2 = o2.first; best.b2 = o2.second;
+          best.ctas = nb + ns;
+        }
+      }
+  if (best.on && best.makespan > 0.97 * best.uniform) best.on = 0;
+  cache[key] = best;
+  return best;
+}
+
 template <int kD, int kKV, int kStages, int kSBuf, int kQ = 2, int kSplit = 1>
 inline int launch_attn_t(cudaStream_t stream, const __half* q, int ldq, const __half* k, int ldk, const __half* v,
                          int ldv, __half* out, int B, int heads, int Sq, int Sk, int causal = 0) {
@@ -520,7 +583,17 @@ inline int launch_attn_t(cudaStream_t stream, const __half* q, int ldq, const __
   auto kern = poly == 0 ? attn_tc_kernel<kD, kKV, kStages, 0, kSBuf, kQ, kSplit>
               : poly == 2 ? attn_tc_kernel<kD, kKV, kStages, 2, kSBuf, kQ, kSplit> : attn_tc_kernel<kD, kKV, kStages, 3, kSBuf, kQ, kSplit>;
   dim3 grid((Sq + C::kQTiles * 128 - 1) / (C::kQTiles * 128), heads, B);
-  if (trace_on()) fprintf(stderr, "DG_TRACE attn B=%d heads=%d Sq=%d Sk=%d d=%d\n", B, heads, Sq, Sk, kD);
+  if (kSplit == 1 && !causal && Sq % 128 == 0 && Sk >= attn_part_min_keys()) {   // (short key sequences: a CTA's time is its fixed cost, not its tiles)
+    static int sms = 0;
+    if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
+    const AttnPlan pl = plan_attn_grid(B * heads, Sq / 128, C::kQTiles, sms);
+    if (pl.on) {
+      p.part_on = 1; p.n_bh = B * heads; p.n_g1 = pl.n_g1; p.a1 = pl.a1; p.b1 = pl.b1; p.a2 = pl.a2; p.b2 = pl.b2;
+      grid = dim3(pl.ctas, 1, 1);
+    }
+  }
+  if (trace_on()) fprintf(stderr, "DG_TRACE attn B=%d heads=%d Sq=%d Sk=%d d=%d grid=%u (%s)\n", B, heads, Sq, Sk, kD, grid.x * grid.y * grid.z,
+                          p.part_on ? "wave-balanced" : "uniform");
   ProfScope prof_(FAM_ATTN, stream, 4.0 * B * heads * (double)Sq * Sk * kD,
                   2.0 * B * heads * kD * (2.0 * Sq + 2.0 * Sk));
   {

@@ -347,7 +347,10 @@ def _attn_ref(q, k, v, heads):
 @pytest.mark.parametrize("B,heads,Sq,Sk,d", [(1, 1, 256, 128, 64), (2, 5, 576, 576, 64), (2, 8, 1024, 1024, 40),
                                              (2, 8, 256, 256, 80), (2, 8, 256, 256, 160), (2, 8, 64, 64, 160),
                                              (2, 8, 1024, 77, 40), (2, 8, 256, 77, 80), (2, 8, 64, 77, 160),
-                                             (1, 2, 256, 256, 32), (1, 4, 16, 77, 32), (1, 8, 4096, 4096, 40)])
+                                             (1, 2, 256, 256, 32), (1, 4, 16, 77, 32), (1, 8, 4096, 4096, 40),
+                                             # wave-balanced grids (plan_attn_grid: CTAs of kQTiles and kQTiles - 1 query tiles)
+                                             (5, 8, 2048, 512, 40), (4, 8, 4096, 640, 40), (5, 8, 1024, 512, 80),
+                                             (10, 10, 384, 512, 64), (25, 2, 896, 577, 160), (8, 8, 4096, 77, 40)])
 def test_attention(ops, B, heads, Sq, Sk, d):
     C = heads * d
     qkv_self = Sq == Sk

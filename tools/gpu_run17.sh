@@ -1,0 +1,18 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 300 python -m pytest tests/test_gpu_ops.py -q -k "attention" -x 2>&1 | tail -3
+{
+for rep in 1 2 3; do
+echo "== wave-balanced grid (default)"; timeout 200 python tools/bench_ops.py attn 2>&1 | head -1
+echo "== DG_ATTN_PART=0"; DG_ATTN_PART=0 timeout 200 python tools/bench_ops.py attn 2>&1 | head -1
+done
+for rep in 1 2 3; do
+echo "== forward, default"; timeout 120 python tools/time_forward.py 2>&1 | tail -1
+echo "== forward, DG_ATTN_PART=0"; DG_ATTN_PART=0 timeout 120 python tools/time_forward.py 2>&1 | tail -1
+done
+for rep in 1 2; do
+echo "== loop, default"; timeout 120 python tools/time_loop.py 2>&1 | tail -1
+echo "== loop, DG_ATTN_PART=0"; DG_ATTN_PART=0 timeout 120 python tools/time_loop.py 2>&1 | tail -1
+done
+} > gpurun_out/r02_run17_attn_part.log 2>&1
+cat gpurun_out/r02_run17_attn_part.log
