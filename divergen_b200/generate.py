@@ -517,6 +517,8 @@ def main(argv: Optional[Sequence[str]] = None) -> int:
             pos = torch.cat([table[row[c.prompt]][None].expand(c.num_images, -1, -1) for c in group])
             neg = table[0][None].expand(pos.shape[0], -1, -1)
             lat = torch.cat([torch.randn((c.num_images, 4, lat_hw, lat_hw), generator=generator, dtype=torch.float16) for c in group])
+            if lat.device.type == "cpu":
+                lat = lat.pin_memory()          # the pipeline copies pinned inputs without blocking: the host stays one call ahead of the GPU
             out = pipe(prompt_embeds=pos, negative_prompt_embeds=neg, latents=lat,
                        output_type="uint8" if vae is not None else "latent",
                        num_images_per_prompt=1, num_inference_steps=args.num_inference_steps,

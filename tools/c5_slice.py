@@ -58,15 +58,16 @@ if __name__ == "__main__":
     ap.add_argument("--gpt_cats", type=int, default=2)
     ap.add_argument("--dist", action="store_true")
     ap.add_argument("--skip_unpacked", action="store_true")
+    ap.add_argument("--max_batch_size", type=int, default=4, help="images per pipeline call (UNet batch = 2x with CFG)")
     ap.add_argument("--only", choices=["lvis", "gpt"], default=None, help="run one recipe (one process group per torchrun launch)")
     a = ap.parse_args()
     world, rank = int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("RANK", 0))
     # one scratch directory shared by the ranks of a node (rank 0's name is passed through the environment by the launcher)
     tmp = os.environ.get("DG_C5_TMP") or tempfile.mkdtemp(prefix="dg_c5_")
     os.makedirs(tmp, exist_ok=True)
-    res = {"world": world, "model": "SD-1.5 512x512, 50 DDIM steps, CFG 7.5, random-init UNet + VAE, PNGs written"}
+    res = {"world": world, "max_batch_size": a.max_batch_size, "model": "SD-1.5 512x512, 50 DDIM steps, CFG 7.5, random-init UNet + VAE, PNGs written"}
     dist_flag = ["--dist"] if a.dist else []
-    common = ["--random_init", "--decode", "--seed", "42", "--offset", "0", "--max_batch_size", "4"] + dist_flag
+    common = ["--random_init", "--decode", "--seed", "42", "--offset", "0", "--max_batch_size", str(a.max_batch_size)] + dist_flag
     # ---- recipe 1.1 (lvis prompts)
     cats = write_prompts(os.path.join(tmp, "lvis_prompt"), a.cats, 1)
     json.dump(cats, open(os.path.join(tmp, "cats.json"), "w"))
