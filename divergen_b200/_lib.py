@@ -49,6 +49,7 @@ class UNetConfigC(C.Structure):
 _P, _I, _L, _F = C.c_void_p, C.c_int32, C.c_int64, C.c_float
 SIGNATURES = {
     "dg_version": (_I, []),
+    "dg_plan_attention_grid": (_I, [_I, _I, _I, _I, C.POINTER(C.c_int32), C.POINTER(C.c_double)]),
     "dg_last_error": (C.c_char_p, []),
     "dg_ctx_create": (_I, [_I, C.POINTER(_P)]),
     "dg_ctx_destroy": (None, [_P]),

@@ -1195,6 +1195,14 @@ int build_clipscore(dg_clipscore* c) {
 extern "C" {
 
 int32_t dg_version(void) { return 100; }
+int32_t dg_plan_attention_grid(int32_t n_bh, int32_t q_tiles, int32_t tiles_per_cta, int32_t sms, int32_t* plan, double* makespan) {
+  if (!plan || !makespan || n_bh <= 0 || q_tiles <= 0 || tiles_per_cta <= 0 || sms <= 0) return fail(DG_E_ARG, "bad argument");
+  const AttnPlan pl = plan_attn_grid(n_bh, q_tiles, tiles_per_cta, sms);
+  plan[0] = pl.on; plan[1] = pl.on ? pl.n_g1 : 0; plan[2] = pl.on ? pl.a1 : 0; plan[3] = pl.on ? pl.b1 : 0;
+  plan[4] = pl.on ? pl.a2 : 0; plan[5] = pl.on ? pl.b2 : 0; plan[6] = pl.on ? pl.ctas : 0;
+  makespan[0] = pl.makespan; makespan[1] = pl.uniform;
+  return DG_OK;
+}
 const char* dg_last_error(void) { return g_last_error.c_str(); }
 
 int32_t dg_ctx_create(int32_t device, dg_ctx** out) {

@@ -252,6 +252,13 @@ int32_t dg_op_upsample_conv3x3(dg_ctx* ctx, const void* x, int32_t C, const void
                                int32_t Wd, int32_t N, float* gn_stats_out, int32_t gn_blk, void* stream);
 int32_t dg_op_attention(dg_ctx* ctx, const void* q, int32_t ldq, const void* k, int32_t ldk, const void* v, int32_t ldv,
                         void* out, int32_t B, int32_t heads, int32_t Sq, int32_t Sk, int32_t d, void* stream);
+/* Host-only (no GPU needed): the wave-balanced grid dg_op_attention / the UNet use for n_bh = B * heads (batch, head) pairs of
+ * q_tiles 128-row query tiles each, with kernels that take tiles_per_cta query tiles per CTA, on `sms` one-CTA SMs.
+ * plan[0] = 1 if a balanced grid beats the uniform one (else 0 and the rest is 0); plan[1] = pairs in group 1;
+ * plan[2], plan[3] = CTAs of tiles_per_cta / tiles_per_cta - 1 tiles per pair of group 1; plan[4], plan[5] = the same for the
+ * remaining pairs; plan[6] = CTAs in the grid (full-size CTAs first); makespan[0] / makespan[1] = simulated / uniform run
+ * time in query-tile units.  (Exported for tests/test_attn_plan.py.) */
+int32_t dg_plan_attention_grid(int32_t n_bh, int32_t q_tiles, int32_t tiles_per_cta, int32_t sms, int32_t* plan, double* makespan);
 int32_t dg_op_groupnorm(dg_ctx* ctx, const void* x0, int32_t C0, const void* x1, int32_t C1, const void* gamma,
                         const void* beta, void* out, int32_t B, int32_t HW, int32_t groups, float eps, int32_t silu,
                         void* stream);
