@@ -156,7 +156,10 @@ struct dg_unet : WeightStore {
   // first transformer block up to its self-attention out-projection run on B/2 rows and are then duplicated (exact: identical
   // inputs give identical outputs; DG_CFG_DEDUP=0 switches it off)
   bool cfg_pairs = false;
+  bool temb_cache = true;     // DG_TEMB_CACHE=0: rebuild the time-embedding table on every call (round-2 start)
   bool finalized = false;     // LayerNorm folds are up to date with the loaded weights
+  std::vector<float> temb_ts; // timesteps the rows of temb_table were computed for (empty: table invalid); every call of a sweep
+                              // uses the same 50 timesteps, so the table (a function of timesteps and weights only) is built once
   // graphs
   bool use_graphs = true;
   // measurement only (dg_unet_set_family_mask): kernel families that run_forward enqueues (bit = 1 << Family).  With a family
@@ -859,6 +862,7 @@ int finalize_weights(dg_unet* u) {
   for (auto& g : u->graphs) cudaGraphExecDestroy(g.exec);   // captured graphs point at stale folds
   u->graphs.clear();
   u->finalized = true;
+  u->temb_ts.clear();         // the time-embedding table was computed from the previous weights
   return DG_OK;
 }
 
@@ -875,7 +879,8 @@ std::vector<Xf*> all_xf(dg_unet* u) {
 //  - cross-attention K/V = to_k / to_v of the text embedding for all 16 transformer blocks (32 of the 210 GEMMs of a forward);
 //  - Timesteps -> TimestepEmbedding -> all 22 time_emb_proj(SiLU(emb)) rows for every step of the schedule.
 // Exact: the same kernels on the same inputs, only not repeated 50 times.
-int hoist_loop_invariants(dg_unet* u, cudaStream_t s, const __half* ehs, int tokens, int B, const float* d_ttab, int n_steps) {
+int hoist_loop_invariants(dg_unet* u, cudaStream_t s, const __half* ehs, int tokens, int B, const float* d_ttab, const float* t_host,
+                          int n_steps) {
   const dg_unet_config& cf = u->cfg;
   u->arena.reset();
   Fwd f{u, s, u->ctx->num_sms, B, tokens, ehs, nullptr};
@@ -886,6 +891,9 @@ int hoist_loop_invariants(dg_unet* u, cudaStream_t s, const __half* ehs, int tok
     f.linear(ehs, cf.cross_attention_dim, nullptr, 0, B * tokens, x.kv2, nullptr, 0, u->kv_cache[i]);
   }
   if (f.err) return f.err;
+  if (u->temb_cache && (int)u->temb_ts.size() == n_steps && memcmp(u->temb_ts.data(), t_host, sizeof(float) * n_steps) == 0)
+    return DG_OK;             // same timesteps, same weights: the table of the previous call stands (stream order keeps it valid)
+  u->temb_ts.clear();
   if (u->temb_table_rows < n_steps) {
     cudaFree(u->temb_table);
     u->temb_table = nullptr; u->temb_table_rows = 0;
@@ -905,6 +913,7 @@ int hoist_loop_invariants(dg_unet* u, cudaStream_t s, const __half* ehs, int tok
     DG_TRY(launch_gemv(s, t1 + (size_t)b0 * u->temb_dim, u->temb_dim, u->time2.w, u->time2.b, emb + (size_t)b0 * u->temb_dim, u->temb_dim, nb, u->temb_dim, u->temb_dim, 0, 0));
     DG_TRY(launch_gemv(s, emb + (size_t)b0 * u->temb_dim, u->temb_dim, u->temb_proj_w, u->temb_proj_b, u->temb_table + (size_t)b0 * u->temb_total, u->temb_total, nb, u->temb_total, u->temb_dim, 1, 0));
   }
+  u->temb_ts.assign(t_host, t_host + n_steps);
   return DG_OK;
 }
 
@@ -1257,6 +1266,7 @@ int32_t dg_unet_create(dg_ctx* ctx, const dg_unet_config* cfg, dg_unet** out) {
   DG_CUDA(cudaSetDevice(ctx->device));
   std::unique_ptr<dg_unet> u(new dg_unet());
   u->ctx = ctx; u->cfg = *cfg;
+  { const char* e = getenv("DG_TEMB_CACHE"); u->temb_cache = !(e && e[0] == '0'); }
   {
     // fused GroupNorm sums are kept per (sample, blk-channel block); every channel count of the UNet is a multiple of
     // block_out_channels[0], so blk = block_out_channels[0] / groups tiles every (concatenated) group exactly.
@@ -1514,7 +1524,7 @@ int32_t dg_denoise_loop(dg_unet* u, void* latents, const void* ehs, int32_t toke
   DG_CUDA(cudaMemcpyAsync(d_ttab, t_host, sizeof(float) * n_steps, cudaMemcpyHostToDevice, s));
   u->last_launches = 0;
   const long long c_h = g_launch_counter;
-  DG_TRY(hoist_loop_invariants(u, s, (const __half*)ehs, tokens, B, d_ttab, n_steps));
+  DG_TRY(hoist_loop_invariants(u, s, (const __half*)ehs, tokens, B, d_ttab, t_host, n_steps));
   u->last_launches += g_launch_counter - c_h;
   u->kv_ready = true; u->temb_ready = true;
   u->cfg_pairs = cfg_on;      // dup_latents_kernel below makes rows [0, n) and [n, 2n) of the UNet input identical

@@ -138,6 +138,40 @@ def test_tiny_denoise_loop(pred):
     assert d <= 3e-2 * ref.abs().max().item() + 5e-3
 
 
+def test_time_embedding_table_is_reused_across_calls_and_rebuilt_when_it_must_be():
+    """dg_denoise_loop keeps the [steps, 22 projections] time-embedding table of the previous call when the timesteps (and the
+    weights) are the same -- every call of a sweep uses the same 50.  Same inputs -> same result on the reusing call; other
+    step counts and reloaded weights rebuild it (each checked against the oracle loop)."""
+    _need_gpu()
+    from divergen_b200 import DDIMScheduler, StableDiffusionPipeline
+    from oracle.ddim_oracle import DDIMOracle, denoise_loop
+    from oracle.unet_oracle import UNetConfig, seeded_state_dict
+    cfg = UNetConfig.tiny()
+    oracle, unet = _models(cfg, seed=5)
+    g = torch.Generator().manual_seed(12)
+    lat = torch.randn(2, 4, 16, 16, generator=g).half()
+    pos, neg = torch.randn(2, 77, 64, generator=g).half(), torch.randn(2, 77, 64, generator=g).half()
+    pipe = StableDiffusionPipeline(unet, DDIMScheduler())
+    run = lambda steps: pipe(prompt_embeds=pos, negative_prompt_embeds=neg, latents=lat, num_inference_steps=steps, guidance_scale=7.5,
+                             height=128, width=128, output_type="latent").images.float().cpu()
+    ref = lambda steps: denoise_loop(oracle, DDIMOracle(), lat.float(), pos.float(), neg.float(), num_inference_steps=steps,
+                                     guidance_scale=7.5)
+    a, b = run(4), run(4)                      # the second call reuses the table
+    r4 = ref(4)
+    tol = lambda r: 5e-2 * r.abs().max().item() + 5e-3
+    assert (a - r4).abs().max().item() <= tol(r4) and (b - r4).abs().max().item() <= tol(r4)
+    assert (a - b).abs().max().item() <= 2e-3 * r4.abs().max().item() + 1e-3
+    c = run(3)                                 # other timesteps: rebuilt
+    r3 = ref(3)
+    assert (c - r3).abs().max().item() <= tol(r3)
+    sd2 = {k: v.half().float() for k, v in seeded_state_dict(cfg, 6).items()}   # other weights, same timesteps: rebuilt
+    oracle.load_state_dict(sd2)
+    unet.load_state_dict(sd2)
+    d = run(3)
+    r3b = ref(3)
+    assert (d - r3b).abs().max().item() <= tol(r3b)
+
+
 def test_sd15_forward_full_width():
     """SD-1.5 at full width, batch 2 (one CFG pair) at 64x64 latent -- BASELINE config 2's per-sample shape.
     The fp32 oracle runs on the GPU here (CPU takes minutes); it is the checker, never the thing measured."""
