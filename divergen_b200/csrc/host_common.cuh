@@ -626,6 +626,7 @@ inline int launch_attention(cudaStream_t stream, const __half* q, int ldq, const
       if (var == 0) return launch_attn_t<40, 128, 4, 1>(stream, q, ldq, k, ldk, v, ldv, out, B, heads, Sq, Sk);
       if (var == 1) return launch_attn_t<40, 64, 6, 2>(stream, q, ldq, k, ldk, v, ldv, out, B, heads, Sq, Sk);
       if (var == 2) return launch_attn_t<40, 64, 6, 1, 4>(stream, q, ldq, k, ldk, v, ldv, out, B, heads, Sq, Sk);
+      if (var == 4) return launch_attn_t<40, 32, 12, 2, 4>(stream, q, ldq, k, ldk, v, ldv, out, B, heads, Sq, Sk);   // 4 query tiles x 32 keys, double-buffered scores (fills TMEM exactly)
       return launch_attn_t<40, 64, 6, 1, 4, 2>(stream, q, ldq, k, ldk, v, ldv, out, B, heads, Sq, Sk);
     }
     case 64: {
@@ -690,6 +691,7 @@ inline int init_kernel_attributes() {
   DG_TRY((init_attn_attr<40, 128, 4>()));
   DG_TRY((init_attn_attr<40, 64, 6, 2>()));
   DG_TRY((init_attn_attr<40, 64, 6, 1, 4>()));
+  DG_TRY((init_attn_attr<40, 32, 12, 2, 4>()));
   DG_TRY((init_attn_attr<40, 64, 6, 1, 4, 2>()));
   DG_TRY((init_attn_attr<64, 128, 3>()));
   DG_TRY((init_attn_attr<64, 64, 6, 1, 4>()));
