@@ -44,7 +44,7 @@ CONFIGS = {
 def gemm_dram_traffic():
     """DRAM bytes per launch of the GEMM family = mean over the launches of (dram__bytes_read.sum + dram__bytes_write.sum) in the
     NEWEST `profiles/r??_gemm2_dram.csv` (one `ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum` pass over a batch-8
-    forward, regenerated every round with tools/gemm_dram.sh).  Returns (bytes, file) or (None, None)."""
+    forward, regenerated every round by tools/final_profile3.sh).  Returns (bytes, file) or (None, None)."""
     import csv
     import glob
     files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r[0-9][0-9]_gemm2_dram.csv")))
