@@ -441,6 +441,18 @@ inline int launch_gemm(cudaStream_t stream, const GemmRes& res, const GemmArgs& 
   }
   const int total_units = units * p.splits;
   const int grid_units = total_units < slots ? total_units : slots;
+  {
+    // DG_GEMM_BLOCKED=0: every GEMM keeps the strided tile assignment; DG_GEMM_VECPRE=0: per-column vectors loaded at the tile's start
+    static int blocked = -1, vecpre = -1;
+    if (blocked < 0) { const char* e = getenv("DG_GEMM_BLOCKED"); blocked = e ? atoi(e) : 1; }   // 2: every multi-column-tile GEMM, not only the LayerNorm-folded ones
+    if (vecpre < 0) { const char* e = getenv("DG_GEMM_VECPRE"); vecpre = (e && e[0] == '0') ? 0 : 1; }
+    p.vec_pre = vecpre;
+    p.blk_np = 0; p.blk_q = 0; p.blk_rem = 0; p.inv_blk_np = 0.f;
+    if (blocked && (a.ln_stats || blocked >= 2) && p.splits == 1 && p.tiles_n > 1 && total_units > grid_units) {
+      p.blk_np = grid_units; p.blk_q = total_units / grid_units; p.blk_rem = total_units % grid_units;
+      p.inv_blk_np = 1.0f / (float)grid_units;
+    }
+  }
   if (trace_on())
     fprintf(stderr, "DG_TRACE gemm M=%d N=%d K=%d taps=%d c0=%d c1=%d bn=%d units=%d splits=%d grid=%dx%d geglu=%d ln=%d res=%d gn=%d rs=%d\n",
             a.B * a.H * a.W, a.n_w, a.taps * (a.c0 + a.c1) + a.cx0 + a.cx1, a.taps, a.c0, a.c1, kbn, units, p.splits, grid_units, kcta, a.geglu,
